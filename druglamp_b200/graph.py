@@ -1,0 +1,107 @@
+"""Graph carrier for the molecular GCN (SURVEY.md section 8b "Graph carrier").
+
+The reference hands ``MolecularGCN.forward`` a batched ``DGLGraph``
+(``model/basic_model.py:147-153``; built by ``handler/dataset.py:212-222`` and
+``utils.py:326-334``).  The B200 path wants the adjacency as CSR *by destination*
+so that one warp owns one destination row of the segment-sum (forward), and CSR
+*by source* for the transposed aggregation in backward.  ``BatchedMolGraph``
+holds both, plus the symmetric-normalisation vectors
+``deg.clamp(min=1) ** -0.5`` of ``GraphConv.forward`` (``basic_model.py:596-603``,
+``:623-630``).  Duplicate edges are kept and counted (App. A5: real atoms carry two
+self loops).
+
+It duck-types the few DGLGraph members the reference touches (``ndata`` with
+``pop``, ``batch_size``, ``num_nodes()``, ``edges()``, ``in_degrees()``,
+``out_degrees()``, ``local_scope()``, ``to()``), so the *reference's own*
+``MolecularGCN`` never sees it but ``model/DrugLAMP*.py`` can pass it through.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+
+
+def _csr(sort_key: torch.Tensor, other: torch.Tensor, n: int):
+    """CSR rows = sort_key; column ids = ``other`` in stable edge order."""
+    order = torch.argsort(sort_key, stable=True)
+    counts = torch.bincount(sort_key, minlength=n)
+    indptr = torch.zeros(n + 1, dtype=torch.int32, device=sort_key.device)
+    indptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return indptr, other[order].to(torch.int32).contiguous(), counts
+
+
+class BatchedMolGraph:
+    is_block = False
+
+    def __init__(self, src: torch.Tensor, dst: torch.Tensor, num_nodes: int,
+                 batch_size: int, h: Optional[torch.Tensor] = None):
+        if src.shape != dst.shape or src.dim() != 1:
+            raise ValueError("src/dst must be 1-D tensors of equal length")
+        self._n = int(num_nodes)
+        self.batch_size = int(batch_size)
+        self.src = src.long()
+        self.dst = dst.long()
+        if self.src.numel() and (int(self.src.max()) >= self._n or int(self.dst.max()) >= self._n
+                                 or int(self.src.min()) < 0 or int(self.dst.min()) < 0):
+            raise ValueError("edge endpoint out of range")
+        self.ndata = {} if h is None else {"h": h}
+        # CSR by destination (forward aggregation) and by source (backward)
+        self.indptr, self.indices, in_counts = _csr(self.dst, self.src, self._n)
+        self.indptr_t, self.indices_t, out_counts = _csr(self.src, self.dst, self._n)
+        self.in_deg = in_counts
+        self.out_deg = out_counts
+        self.norm_dst = in_counts.clamp(min=1).to(torch.float32).pow(-0.5)
+        self.norm_src = out_counts.clamp(min=1).to(torch.float32).pow(-0.5)
+
+    # ---- DGLGraph duck-typing -------------------------------------------------
+    def num_nodes(self) -> int:
+        return self._n
+
+    number_of_nodes = num_nodes
+
+    def num_edges(self) -> int:
+        return int(self.src.numel())
+
+    def edges(self):
+        return self.src, self.dst
+
+    def in_degrees(self):
+        return self.in_deg
+
+    def out_degrees(self):
+        return self.out_deg
+
+    @contextlib.contextmanager
+    def local_scope(self):
+        yield
+
+    @property
+    def device(self):
+        return self.src.device
+
+    def to(self, device, **kw) -> "BatchedMolGraph":
+        g = object.__new__(BatchedMolGraph)
+        g._n, g.batch_size = self._n, self.batch_size
+        for k in ("src", "dst", "indptr", "indices", "indptr_t", "indices_t",
+                  "in_deg", "out_deg", "norm_dst", "norm_src"):
+            setattr(g, k, getattr(self, k).to(device, **kw))
+        g.ndata = {k: v.to(device, **kw) for k, v in self.ndata.items()}
+        return g
+
+    # ---- constructors -----------------------------------------------------------
+    @classmethod
+    def from_dgl(cls, g) -> "BatchedMolGraph":
+        """Accept a real DGLGraph (or anything with edges()/num_nodes()/batch_size/ndata)."""
+        if isinstance(g, cls):
+            return g
+        src, dst = g.edges()
+        h = g.ndata["h"] if "h" in g.ndata else None
+        return cls(src, dst, g.num_nodes(), g.batch_size, h)
+
+    def check_no_zero_in_degree(self) -> None:
+        """Mirror of the DGLError raised at ``basic_model.py:580-590``."""
+        if bool((self.in_deg == 0).any()):
+            raise Exception("There are 0-in-degree nodes in the graph, output for those nodes "
+                            "will be invalid. Adding self-loop on the input graph will resolve the issue.")

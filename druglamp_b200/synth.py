@@ -1,0 +1,135 @@
+"""Synthetic DTI batches laid out exactly as the reference collate delivers them.
+
+Layouts follow ``utils.multimodality_collate_func`` (reference ``utils.py:326-334``),
+``tail_pad``/``repeat_pad`` (``utils.py:304-324``), ``repeat_integer_label_protein``
+(``utils.py:392-412``) and the virtual-node / double self-loop construction in
+``handler/dataset.py:212-222``.  Distributions are the ones SURVEY.md section 8d fixes.
+There is no network, RDKit, ESM or ChemBERTa here, so atom features and LLM
+embeddings are seeded surrogates; padding rows are exact zeros like the reference's.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .graph import BatchedMolGraph
+
+MAX_NODES = 512
+SEQ_LEN = 9 * 256
+NODE_FEATS = 75
+MAX_RESIDUES = 1022
+
+
+@dataclass
+class Batch:
+    graph: BatchedMolGraph
+    vp: torch.Tensor          # (B, 2304) float64 tokens 0..25
+    y: torch.Tensor           # (B,) int64 {0,1}
+    xd: torch.Tensor          # (B, 512, n_drug_feature) f32
+    xp: torch.Tensor          # (B, 2304, n_prot_feature) f32
+    meta: List[dict]
+    n_atoms: np.ndarray
+    prot_len: np.ndarray
+
+    def to(self, device, non_blocking=False):
+        return Batch(self.graph.to(device), self.vp.to(device, non_blocking=non_blocking),
+                     self.y.to(device, non_blocking=non_blocking),
+                     self.xd.to(device, non_blocking=non_blocking),
+                     self.xp.to(device, non_blocking=non_blocking), self.meta,
+                     self.n_atoms, self.prot_len)
+
+    def model_inputs(self):
+        """(vd, vp, xd, xp) in the order ``Model.forward`` takes them (DrugLAMP.py:8)."""
+        return self.graph, self.vp, self.xd, self.xp
+
+
+def _molecule_edges(rng: np.random.Generator, n: int):
+    """Random spanning tree + round(0.1 n) ring closures, both directions."""
+    src, dst = [], []
+    for a in range(1, n):
+        b = int(rng.integers(0, a))
+        src += [a, b]
+        dst += [b, a]
+    for _ in range(int(round(0.1 * n))):
+        a, b = (int(v) for v in rng.integers(0, n, size=2))
+        if a != b:
+            src += [a, b]
+            dst += [b, a]
+    return src, dst
+
+
+def make_batch(batch_size: int, seed: int = 1234, n_drug_feature: int = 384,
+               n_prot_feature: int = 640, n_unique_frac: float = 60 / 64,
+               drugs_per_protein: Optional[float] = None,
+               max_atoms: int = 290, min_prot: int = 50, max_prot: int = MAX_RESIDUES) -> Batch:
+    rng = np.random.default_rng(seed)
+    B = batch_size
+    n_atoms = np.clip(np.round(rng.lognormal(np.log(24.0), 0.45, B)), 4, max_atoms).astype(np.int64)
+    prot_len = np.clip(np.round(rng.lognormal(np.log(480.0), 0.6, B)), min_prot, max_prot).astype(np.int64)
+
+    # identities: draw pair ids so that a batch has ~n_unique_frac unique proteins / drugs;
+    # BindingDB-shaped batches use ~drugs_per_protein drugs per protein.
+    if drugs_per_protein is None:
+        n_p = max(1, int(round(B * n_unique_frac)))
+        n_d = max(1, int(round(B * n_unique_frac)))
+    else:
+        n_p = max(1, int(round(B / drugs_per_protein)))
+        n_d = max(1, int(round(B * n_unique_frac)))
+    pid = rng.integers(0, n_p, B)
+    did = rng.integers(0, n_d, B)
+    # entity-level properties are shared by every occurrence of the same id
+    n_atoms = n_atoms[did]      # n_d, n_p <= B
+    prot_len = prot_len[pid]
+    y = (rng.random(B) < 0.45).astype(np.int64)
+
+    feats = np.zeros((B, MAX_NODES, NODE_FEATS), dtype=np.float32)
+    src_all, dst_all = [], []
+    for b in range(B):
+        ent = np.random.default_rng([seed, 1, int(did[b])])
+        n = int(n_atoms[b])
+        cols = ent.integers(0, 74, size=(n, 8))
+        feats[b, np.arange(n)[:, None], cols] = 1.0
+        feats[b, n:, 74] = 1.0                      # virtual-node bit (dataset.py:219)
+        s, d = _molecule_edges(ent, n)
+        loops_real = list(range(n))                 # smiles_to_bigraph(add_self_loop=True)
+        loops_all = list(range(MAX_NODES))          # v_d.add_self_loop() after padding
+        s = np.asarray(s + loops_real + loops_all, dtype=np.int64) + b * MAX_NODES
+        d = np.asarray(d + loops_real + loops_all, dtype=np.int64) + b * MAX_NODES
+        src_all.append(s)
+        dst_all.append(d)
+    src = torch.from_numpy(np.concatenate(src_all))
+    dst = torch.from_numpy(np.concatenate(dst_all))
+    h = torch.from_numpy(feats.reshape(B * MAX_NODES, NODE_FEATS))
+    graph = BatchedMolGraph(src, dst, B * MAX_NODES, B, h)
+
+    vp = np.zeros((B, SEQ_LEN), dtype=np.float64)
+    xp = torch.zeros(B, SEQ_LEN, n_prot_feature, dtype=torch.float32)
+    xd = torch.zeros(B, MAX_NODES, n_drug_feature, dtype=torch.float32)
+    for b in range(B):
+        L = int(prot_len[b])
+        ent = np.random.default_rng([seed, 2, int(pid[b])])
+        toks = ent.integers(1, 26, L)
+        gp = torch.Generator().manual_seed(int(seed) * 1000003 + 2 * int(pid[b]) + 1)
+        emb = torch.randn(L + 2, n_prot_feature, generator=gp)
+        for i in range(SEQ_LEN // (L + 2)):
+            st = i * (L + 2)
+            vp[b, st + 1: st + 1 + L] = toks       # utils.py:403-407
+            xp[b, st: st + L + 2] = emb            # utils.py:319-323
+        gd = torch.Generator().manual_seed(int(seed) * 1000003 + 2 * int(did[b]))
+        rows = min(int(n_atoms[b]) + 2, MAX_NODES)
+        xd[b, :rows] = torch.randn(rows, n_drug_feature, generator=gd)
+
+    meta = [{"Drug_ID": f"D{int(did[b])}", "Prot_ID": f"P{int(pid[b])}", "Y": int(y[b])}
+            for b in range(B)]
+    # one label per (protein, drug) identity, as in a real dataset
+    seen = {}
+    for b in range(B):
+        key = (meta[b]["Prot_ID"], meta[b]["Drug_ID"])
+        if key in seen:
+            y[b] = seen[key]
+            meta[b]["Y"] = int(y[b])
+        seen[key] = int(y[b])
+    return Batch(graph, torch.from_numpy(vp), torch.from_numpy(y), xd, xp, meta, n_atoms, prot_len)

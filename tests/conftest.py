@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def model_shapes():
+    """state_dict name -> shape of DrugLAMP(384, 640), from the product model
+    (same keys as the reference; checked against the reference in test_state_dict_contract)."""
+    import json
+    path = os.path.join(ROOT, "tests", "golden", "state_shapes.json")
+    with open(path) as f:
+        return {k: tuple(v) for k, v in json.load(f).items()}
