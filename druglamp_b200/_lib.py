@@ -1,0 +1,114 @@
+"""ctypes binding of ``libdruglamp_sm100.so`` (C ABI: ``include/druglamp_sm100.h``).
+
+There is no CPU or PyTorch fallback: if the library cannot be loaded, or a call fails, a
+``RuntimeError`` is raised.  PyTorch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdruglamp_sm100.so")
+
+DL_F32, DL_BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+MUL_NONE, MUL_GELU_GRAD, MUL_RELU_MASK, MUL_VALUE = 0, 1, 2, 3
+
+_lib = None
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p),
+        ("preact_out", C.c_void_p), ("mul_aux", C.c_void_p), ("residual", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+        ("batch_lo", C.c_int64), ("batch_hi", C.c_int64),
+        ("sa_lo", C.c_int64), ("sa_hi", C.c_int64), ("sb_lo", C.c_int64), ("sb_hi", C.c_int64),
+        ("sc_lo", C.c_int64), ("sc_hi", C.c_int64),
+        ("alpha", C.c_float),
+        ("dtype_ab", C.c_int32), ("dtype_c", C.c_int32),
+        ("trans_a", C.c_int32), ("trans_b", C.c_int32),
+        ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32),
+    ]
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m druglamp_b200.build` "
+            "(druglamp_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.dl_version.restype = C.c_int
+    L.dl_last_error.restype = C.c_char_p
+    L.dl_launch_count.restype = C.c_int64
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = sig
+    _lib = L
+    return L
+
+
+_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+_SIGNATURES = {
+    "dl_gemm": [C.POINTER(GemmArgs), _P],
+}
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().dl_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DL_F32
+    if t.dtype == torch.bfloat16:
+        return DL_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("druglamp_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().dl_launch_count())
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
+         lda: int, ldb: int, ldc: int, trans_a: bool = False, trans_b: bool = False,
+         batch_lo: int = 1, batch_hi: int = 1, sa=(0, 0), sb=(0, 0), sc=(0, 0),
+         alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         preact_out: Optional[torch.Tensor] = None, mul_aux: Optional[torch.Tensor] = None,
+         mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, tile_n: int = 0) -> None:
+    """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
+    if A.dtype != B.dtype:
+        raise TypeError("A and B must share a dtype")
+    for t in (preact_out, mul_aux, residual):
+        if t is not None and t.dtype != out.dtype:
+            raise TypeError("epilogue tensors must share C's dtype")
+    if bias is not None and bias.dtype != torch.float32:
+        raise TypeError("bias must be fp32")
+    a = GemmArgs(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(preact_out), ptr(mul_aux), ptr(residual),
+                 M, N, K, lda, ldb, ldc, batch_lo, batch_hi, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
+                 alpha, dt(A), dt(out), int(trans_a), int(trans_b), act, mul_mode, tile_n)
+    check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
