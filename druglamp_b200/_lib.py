@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
+from typing import Optional, Sequence
 
 import torch
 
@@ -19,6 +19,7 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 MUL_NONE, MUL_GELU_GRAD, MUL_RELU_MASK, MUL_VALUE = 0, 1, 2, 3
 
 _lib = None
+_I64x3 = C.c_int64 * 3
 
 
 class GemmArgs(C.Structure):
@@ -27,14 +28,42 @@ class GemmArgs(C.Structure):
         ("preact_out", C.c_void_p), ("mul_aux", C.c_void_p), ("residual", C.c_void_p),
         ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
-        ("batch_lo", C.c_int64), ("batch_hi", C.c_int64),
-        ("sa_lo", C.c_int64), ("sa_hi", C.c_int64), ("sb_lo", C.c_int64), ("sb_hi", C.c_int64),
-        ("sc_lo", C.c_int64), ("sc_hi", C.c_int64),
+        ("batch", _I64x3), ("sa", _I64x3), ("sb", _I64x3), ("sc", _I64x3),
+        ("ldr", C.c_int64), ("sr", _I64x3),
+        ("drop_seed", C.c_uint64), ("drop_p", C.c_float),
         ("alpha", C.c_float),
         ("dtype_ab", C.c_int32), ("dtype_c", C.c_int32),
         ("trans_a", C.c_int32), ("trans_b", C.c_int32),
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32),
     ]
+
+
+_P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
+# name -> argtypes; must list every compute entry point declared in include/druglamp_sm100.h
+SIGNATURES = {
+    "dl_gemm": [C.POINTER(GemmArgs), _P],
+    "dl_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
+    "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
+    "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],
+    "dl_softmax_bwd": [_P, _P, _P, _I64, _I32, _I64, _F, _I32, _P],
+    "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _P],
+    "dl_dropout": [_P, _P, _I64, _F, _U64, _I32, _P],
+    "dl_act_bwd": [_P, _P, _P, _I64, _I32, _F, _U64, _I32, _P],
+    "dl_cast": [_P, _I32, _P, _I32, _I64, _P],
+    "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _I32, _P],
+    "dl_spmm_norm": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
+    "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _I32, _P],
+    "dl_batchnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
+    "dl_fillbit_pool": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P],
+    "dl_site_pool_fwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
+    "dl_site_pool_bwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
+    "dl_mhla_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
+    "dl_mhla_gate_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
+    "dl_cm_triplet_fwd": [_P, _P, _I64, _I64, _F, _P, _P, _P],
+    "dl_cm_triplet_bwd": [_P, _P, _I64, _I64, _F, _P, _P, _P, _P],
+    "dl_bce_fwd": [_P, _P, _P, _P, _I64, _P],
+    "dl_bce_bwd": [_P, _P, _P, _P, _I64, _P],
+}
 
 
 def lib():
@@ -50,18 +79,12 @@ def lib():
     L.dl_version.restype = C.c_int
     L.dl_last_error.restype = C.c_char_p
     L.dl_launch_count.restype = C.c_int64
-    for name, sig in _SIGNATURES.items():
+    for name, sig in SIGNATURES.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = sig
     _lib = L
     return L
-
-
-_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
-_SIGNATURES = {
-    "dl_gemm": [C.POINTER(GemmArgs), _P],
-}
 
 
 def check(rc: int, what: str) -> None:
@@ -70,16 +93,21 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args, stream_ptr()), name)
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def dt(t: torch.Tensor) -> int:
-    if t.dtype == torch.float32:
+def dt(t) -> int:
+    d = t if isinstance(t, torch.dtype) else t.dtype
+    if d == torch.float32:
         return DL_F32
-    if t.dtype == torch.bfloat16:
+    if d == torch.bfloat16:
         return DL_BF16
-    raise TypeError(f"unsupported dtype {t.dtype}")
+    raise TypeError(f"unsupported dtype {d}")
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -94,21 +122,30 @@ def launch_count() -> int:
     return int(lib().dl_launch_count())
 
 
+def _3(v: Sequence[int]):
+    v = tuple(int(x) for x in v)
+    v = v + (0,) * (3 - len(v))
+    return _I64x3(*v)
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
          lda: int, ldb: int, ldc: int, trans_a: bool = False, trans_b: bool = False,
-         batch_lo: int = 1, batch_hi: int = 1, sa=(0, 0), sb=(0, 0), sc=(0, 0),
+         batch=(1, 1, 1), sa=(0, 0, 0), sb=(0, 0, 0), sc=(0, 0, 0),
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          preact_out: Optional[torch.Tensor] = None, mul_aux: Optional[torch.Tensor] = None,
-         mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, tile_n: int = 0) -> None:
+         mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
+         sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
-        raise TypeError("A and B must share a dtype")
+        raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
     for t in (preact_out, mul_aux, residual):
         if t is not None and t.dtype != out.dtype:
             raise TypeError("epilogue tensors must share C's dtype")
     if bias is not None and bias.dtype != torch.float32:
         raise TypeError("bias must be fp32")
+    b = tuple(int(x) for x in batch) + (1,) * (3 - len(batch))
     a = GemmArgs(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(preact_out), ptr(mul_aux), ptr(residual),
-                 M, N, K, lda, ldb, ldc, batch_lo, batch_hi, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
-                 alpha, dt(A), dt(out), int(trans_a), int(trans_b), act, mul_mode, tile_n)
+                 M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
+                 drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
+                 mul_mode, tile_n)
     check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")

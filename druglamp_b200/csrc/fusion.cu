@@ -1,0 +1,546 @@
+// Model-glue kernels of the DrugLAMP hot path that are not GEMMs:
+//   * dl_fillbit_pool   -- fill-bit mask (x.sum(-1)==0), concat and 9-way site mean in ONE pass
+//                          over the LLM embeddings (reference model/DrugLAMP.py:11-19,39-40)
+//   * dl_site_pool_*    -- view(B,9,256,C).mean(1) of the CNN output and its backward (:35-37)
+//   * dl_mhla_gate_ln_* -- MHLA's softmax-over-sequence gating through the memory-reinterpreting
+//                          .view (model/PMMA/encoder.py:127-140) fused with the
+//                          residual add and the following LayerNorm (model/DrugLAMP.py:63-71)
+//   * dl_cm_triplet_*   -- dense form of ccpp_p_tri_loss (model/cross_modality.py:15-47)
+//   * dl_bce_*          -- sigmoid + BCELoss (model/basic_model.py:17-22)
+#include "../../include/druglamp_sm100.h"
+#include "common.cuh"
+
+namespace dl {
+void count_launch(int n = 1);
+namespace {
+
+// ------------------------------------------------------------------ fill bit + concat + site mean
+// x: (B, S*L, C) fp32.  grid (L, B), 256 threads, each thread owns float4 chunks tid, tid+256.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
+                    float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C) {
+  __shared__ float red[32];
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int nchunk = C >> 2;
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  float bit_acc = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const size_t t = (size_t)b * S * L + (size_t)s * L + j;
+    const float* row = x + t * C;
+    float4 v[2];
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int ch = tid + k * 256;
+      v[k] = ch < nchunk ? *reinterpret_cast<const float4*>(row + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      part += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      acc[k].x += v[k].x; acc[k].y += v[k].y; acc[k].z += v[k].z; acc[k].w += v[k].w;
+    }
+    const float total = block_sum(part, red);
+    const float bit = total == 0.f ? 1.f : 0.f;
+    bit_acc += bit;
+    if (tid == 0 && bit_out) bit_out[t] = bit;
+    if (cat_out) {
+      float* crow = cat_out + t * (C + 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int ch = tid + k * 256;
+        if (ch < nchunk) {
+          crow[ch * 4 + 0] = v[k].x; crow[ch * 4 + 1] = v[k].y;
+          crow[ch * 4 + 2] = v[k].z; crow[ch * 4 + 3] = v[k].w;
+        }
+      }
+      if (tid == 0) crow[C] = bit;
+    }
+  }
+  if (pooled) {
+    const float inv = 1.f / (float)S;
+    TO* prow = pooled + ((size_t)b * L + j) * (C + 1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int ch = tid + k * 256;
+      if (ch < nchunk) {
+        stf<TO>(prow, ch * 4 + 0, acc[k].x * inv); stf<TO>(prow, ch * 4 + 1, acc[k].y * inv);
+        stf<TO>(prow, ch * 4 + 2, acc[k].z * inv); stf<TO>(prow, ch * 4 + 3, acc[k].w * inv);
+      }
+    }
+    if (tid == 0) stf<TO>(prow, C, bit_acc * inv);
+  }
+}
+
+// ------------------------------------------------------------------ site pooling
+template <typename T>
+__global__ void site_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int S, long long LC4,
+                                     long long n4, long long ldy4, long long C4) {
+  // y[b, j, c] = mean_s x[b, s*L + j, c];  index in float4 units; y row stride ldy (elements)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / LC4, r = i % LC4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+      const float4 v = ld4<T>(x + ((b * S + s) * LC4 + r) * 4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float inv = 1.f / (float)S;
+    const long long row = (b * LC4 + r) / C4, c4 = r % C4;
+    st4<T>(y + (row * ldy4 + c4) * 4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+  }
+}
+
+template <typename T>
+__global__ void site_pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int S,
+                                     long long LC4, long long n4, long long ldy4, long long C4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / LC4, r = i % LC4;
+    const long long row = (b * LC4 + r) / C4, c4 = r % C4;
+    float4 g = ld4<T>(dy + (row * ldy4 + c4) * 4);
+    const float inv = 1.f / (float)S;
+    g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+    for (int s = 0; s < S; ++s) st4<T>(dx + ((b * S + s) * LC4 + r) * 4, g);
+  }
+}
+
+// ------------------------------------------------------------------ MHLA gate + residual + LN
+// One block (256 threads = 8 warps) per batch element.
+//   p[h, l]  = softmax over l of logits[b, l, h]
+//   u[b,l,e] = v[b,l,e] * (1 + p[hh, ll]),  f = l*E + e, hh = f / (L*hd), ll = (f % (L*hd)) / hd
+//   y        = LayerNorm_E(u) * gamma + beta
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        T* __restrict__ y, float* __restrict__ p_out, float* __restrict__ mean_out,
+                        float* __restrict__ rstd_out, int L, int H, float eps) {
+  constexpr int E = VEC * 128;
+  extern __shared__ float sp[];                 // [H][L]
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int hd = E / H;
+  // phase 1: column softmax, warp per head
+  for (int h = w; h < H; h += 8) {
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, ldf<T>(logits, ((size_t)b * L + l) * H + h));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float e = __expf(ldf<T>(logits, ((size_t)b * L + l) * H + h) - m);
+      sp[h * L + l] = e;
+      s += e;
+    }
+    const float inv = 1.f / warp_sum(s);
+    for (int l = lane; l < L; l += 32) {
+      const float pv = sp[h * L + l] * inv;
+      sp[h * L + l] = pv;
+      if (p_out) p_out[((size_t)b * H + h) * L + l] = pv;
+    }
+  }
+  __syncthreads();
+  // phase 2: gate + residual + LayerNorm, warp per row
+  for (int l = w; l < L; l += 8) {
+    const size_t rbase = ((size_t)b * L + l) * E;
+    float4 u[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int e0 = (j * 32 + lane) * 4;
+      const long long f = (long long)l * E + e0;
+      const int hh = (int)(f / ((long long)L * hd)), ll = (int)((f % ((long long)L * hd)) / hd);
+      const float g = 1.f + sp[hh * L + ll];
+      const float4 x = ld4<T>(v + rbase + e0);
+      u[j] = make_float4(x.x * g, x.y * g, x.z * g, x.w * g);
+      s += u[j].x + u[j].y + u[j].z + u[j].w;
+    }
+    const float mean = warp_sum(s) * (1.f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float a = u[j].x - mean, bb = u[j].y - mean, c = u[j].z - mean, d = u[j].w - mean;
+      q += a * a + bb * bb + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / E) + eps);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int e0 = (j * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + e0);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + e0);
+      st4<T>(y + rbase + e0, make_float4((u[j].x - mean) * rstd * g.x + bt.x,
+                                         (u[j].y - mean) * rstd * g.y + bt.y,
+                                         (u[j].z - mean) * rstd * g.z + bt.z,
+                                         (u[j].w - mean) * rstd * g.w + bt.w));
+    }
+    if (lane == 0) {
+      mean_out[(size_t)b * L + l] = mean;
+      rstd_out[(size_t)b * L + l] = rstd;
+    }
+  }
+}
+
+// backward: dv (direct path), dlogits, dgamma/dbeta (atomics into zeroed buffers)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
+                        const float* __restrict__ p, const float* __restrict__ mean_in,
+                        const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                        T* __restrict__ dv, T* __restrict__ dlogits, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int L, int H) {
+  constexpr int E = VEC * 128;
+  extern __shared__ float smem[];
+  float* sp = smem;                 // [H][L] probabilities
+  float* sdp = smem + H * L;        // [H][L] d(loss)/d(p)
+  float* red = sdp + H * L;         // [8][128] column partial staging
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int hd = E / H;
+  for (int i = threadIdx.x; i < H * L; i += 256) sp[i] = p[(size_t)b * H * L + i];
+  __syncthreads();
+  float4 ag[VEC], ab[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int lanes_per_chunk = hd / 4;           // lanes sharing one (hh, ll) gate
+  for (int l = w; l < L; l += 8) {
+    const size_t rbase = ((size_t)b * L + l) * E;
+    const float mean = mean_in[(size_t)b * L + l], rstd = rstd_in[(size_t)b * L + l];
+    float4 xv[VEC], xh[VEC], dg[VEC];
+    float gate[VEC];
+    int gidx[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int e0 = (j * 32 + lane) * 4;
+      const long long f = (long long)l * E + e0;
+      const int hh = (int)(f / ((long long)L * hd)), ll = (int)((f % ((long long)L * hd)) / hd);
+      gidx[j] = hh * L + ll;
+      gate[j] = 1.f + sp[gidx[j]];
+      xv[j] = ld4<T>(v + rbase + e0);
+      const float4 d = ld4<T>(dy + rbase + e0);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + e0);
+      xh[j] = make_float4((xv[j].x * gate[j] - mean) * rstd, (xv[j].y * gate[j] - mean) * rstd,
+                          (xv[j].z * gate[j] - mean) * rstd, (xv[j].w * gate[j] - mean) * rstd);
+      dg[j] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s1 += dg[j].x + dg[j].y + dg[j].z + dg[j].w;
+      s2 += dg[j].x * xh[j].x + dg[j].y * xh[j].y + dg[j].z * xh[j].z + dg[j].w * xh[j].w;
+      ag[j].x += d.x * xh[j].x; ag[j].y += d.y * xh[j].y; ag[j].z += d.z * xh[j].z; ag[j].w += d.w * xh[j].w;
+      ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
+    }
+    const float c1 = warp_sum(s1) * (1.f / E), c2 = warp_sum(s2) * (1.f / E);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int e0 = (j * 32 + lane) * 4;
+      float4 du;
+      du.x = rstd * (dg[j].x - c1 - xh[j].x * c2);
+      du.y = rstd * (dg[j].y - c1 - xh[j].y * c2);
+      du.z = rstd * (dg[j].z - c1 - xh[j].z * c2);
+      du.w = rstd * (dg[j].w - c1 - xh[j].w * c2);
+      st4<T>(dv + rbase + e0, make_float4(du.x * gate[j], du.y * gate[j], du.z * gate[j], du.w * gate[j]));
+      float t = du.x * xv[j].x + du.y * xv[j].y + du.z * xv[j].z + du.w * xv[j].w;
+      for (int o = 1; o < lanes_per_chunk; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if ((lane % lanes_per_chunk) == 0) sdp[gidx[j]] = t;     // each (hh,ll) is owned by one chunk
+    }
+  }
+  __syncthreads();
+  // softmax-over-L backward, warp per head: dlogit[l,h] = p (dp - sum_l p dp)
+  for (int h = w; h < H; h += 8) {
+    float dot = 0.f;
+    for (int l = lane; l < L; l += 32) dot += sp[h * L + l] * sdp[h * L + l];
+    dot = warp_sum(dot);
+    for (int l = lane; l < L; l += 32)
+      stf<T>(dlogits, ((size_t)b * L + l) * H + h, sp[h * L + l] * (sdp[h * L + l] - dot));
+  }
+  // LayerNorm parameter gradients
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const float4 a = pass == 0 ? ag[j] : ab[j];
+      __syncthreads();
+      red[w * 128 + lane * 4 + 0] = a.x; red[w * 128 + lane * 4 + 1] = a.y;
+      red[w * 128 + lane * 4 + 2] = a.z; red[w * 128 + lane * 4 + 3] = a.w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) t += red[ww * 128 + threadIdx.x];
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + j * 128 + threadIdx.x, t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CrossModality triplet loss
+// cos: (P, D) fp32 cosine similarities of the unit latents, G: (P, D) int8 labels.
+// loss = [ sum_i sum_{p in pos_i} sum_{n in neg_i} relu(s_in - s_ip + m)
+//        + sum_{i: pos_i empty} sum_n relu(s_in - sigmoid(1) + m) ] / max(#terms, 1),  s = sigmoid(cos)
+// acc[0] += sum of hinge terms, acc[1] += number of terms (doubles).
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+cm_triplet_kernel(const float* __restrict__ cos, const int8_t* __restrict__ G, int D, float margin,
+                  double* __restrict__ acc, const float* __restrict__ gout, float* __restrict__ dcos) {
+  extern __shared__ float sm[];
+  float* sig = sm;                          // [D]
+  int* pos = reinterpret_cast<int*>(sm + D);  // [D] compacted positive columns
+  __shared__ int npos_s;
+  __shared__ float red[32];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) npos_s = 0;
+  __syncthreads();
+  for (int j = tid; j < D; j += 256) {
+    sig[j] = 1.f / (1.f + __expf(-cos[(size_t)i * D + j]));
+    if (G[(size_t)i * D + j] == 1) pos[atomicAdd(&npos_s, 1)] = j;
+  }
+  __syncthreads();
+  const int npos = npos_s;
+  const int nneg = D - npos;                // labels are {0,1}: everything not positive is negative
+  const float s_self = 1.f / (1.f + __expf(-1.f));
+  float coef = 0.f;
+  if (BWD) {
+    const double cnt = acc[1];
+    coef = gout[0] / (float)(cnt > 1.0 ? cnt : 1.0);
+  }
+  float local = 0.f;
+  if (nneg > 0) {
+    for (int j = tid; j < D; j += 256) {
+      if (G[(size_t)i * D + j] == 1) continue;
+      const float sn = sig[j];
+      if (npos > 0) {
+        int active = 0;
+        for (int k = 0; k < npos; ++k) {
+          const float t = sn - sig[pos[k]] + margin;
+          if (t > 0.f) { local += t; ++active; }
+        }
+        if (BWD) dcos[(size_t)i * D + j] = coef * (float)active * sn * (1.f - sn);
+      } else {
+        const float t = sn - s_self + margin;
+        if (t > 0.f) local += t;
+        if (BWD) dcos[(size_t)i * D + j] = t > 0.f ? coef * sn * (1.f - sn) : 0.f;
+      }
+    }
+  } else if (BWD) {
+    for (int j = tid; j < D; j += 256) dcos[(size_t)i * D + j] = 0.f;
+  }
+  if (BWD) {
+    // positives: d/ds_ip = -(number of negatives n with s_in - s_ip + m > 0)
+    for (int k = tid; k < npos; k += 256) {
+      const int jp = pos[k];
+      const float sp = sig[jp];
+      int active = 0;
+      if (nneg > 0)
+        for (int j = 0; j < D; ++j)
+          if (G[(size_t)i * D + j] != 1 && sig[j] - sp + margin > 0.f) ++active;
+      dcos[(size_t)i * D + jp] = -coef * (float)active * sp * (1.f - sp);
+    }
+  } else {
+    const float total = block_sum(local, red);
+    if (tid == 0) {
+      atomicAdd(acc, (double)total);
+      const double terms = nneg > 0 ? (npos > 0 ? (double)npos * nneg : (double)nneg) : 0.0;
+      atomicAdd(acc + 1, terms);
+    }
+  }
+}
+
+__global__ void cm_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss) {
+  const double cnt = acc[1] > 1.0 ? acc[1] : 1.0;
+  loss[0] = (float)(acc[0] / cnt);
+}
+
+// ------------------------------------------------------------------ BCE
+__global__ void bce_fwd_kernel(const float* __restrict__ score, const float* __restrict__ y,
+                               float* __restrict__ prob, float* __restrict__ loss, int n) {
+  __shared__ float red[32];
+  float local = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float pr = 1.f / (1.f + expf(-score[i]));
+    prob[i] = pr;
+    const float l1 = fmaxf(logf(pr), -100.f), l0 = fmaxf(logf(1.f - pr), -100.f);
+    local -= y[i] * l1 + (1.f - y[i]) * l0;
+  }
+  const float t = block_sum(local, red);
+  if (threadIdx.x == 0) loss[0] = t / (float)n;
+}
+
+__global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y,
+                               const float* __restrict__ gout, float* __restrict__ dscore, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float pr = prob[i];
+    const float dn = (pr - y[i]) / fmaxf((1.f - pr) * pr, 1e-12f);   // BCELoss backward
+    dscore[i] = gout[0] * dn * pr * (1.f - pr) / (float)n;           // through the sigmoid
+  }
+}
+
+int ew_grid(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+}  // namespace
+}  // namespace dl
+
+using namespace dl;
+
+extern "C" int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, void* pooled,
+                               int32_t pooled_dtype, int64_t B, int32_t S, int32_t L, int32_t C,
+                               void* stream) {
+  DL_REQUIRE(x != nullptr, "dl_fillbit_pool: null input");
+  DL_REQUIRE(B >= 0 && S >= 1 && L >= 1 && C >= 4 && C % 4 == 0 && C <= 2048,
+             "dl_fillbit_pool: need C %% 4 == 0 and C <= 2048 (got B=%lld S=%d L=%d C=%d)", (long long)B, S, L, C);
+  DL_REQUIRE(((uintptr_t)x & 15) == 0, "dl_fillbit_pool: x must be 16-byte aligned");
+  DL_REQUIRE(B <= 65535, "dl_fillbit_pool: B too large");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(L, (unsigned)B);
+  if (pooled_dtype == DL_BF16)
+    fillbit_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C);
+  else
+    fillbit_pool_kernel<float><<<grid, 256, 0, st>>>(x, bit_out, cat_out, (float*)pooled, S, L, C);
+  DL_LAUNCH_CHECK("fillbit_pool_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, int32_t C,
+                                int64_t ldy, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && y && C % 4 == 0 && ldy % 4 == 0 && ldy >= C, "dl_site_pool_fwd: bad arguments");
+  const long long LC4 = (long long)L * C / 4, n4 = B * LC4;
+  if (n4 <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    site_pool_fwd_kernel<__nv_bfloat16><<<ew_grid(n4, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, S, LC4, n4, ldy / 4, C / 4);
+  else
+    site_pool_fwd_kernel<float><<<ew_grid(n4, 256), 256, 0, st>>>((const float*)x, (float*)y, S, LC4, n4, ldy / 4, C / 4);
+  DL_LAUNCH_CHECK("site_pool_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L,
+                                int32_t C, int64_t ldy, int32_t dtype, void* stream) {
+  DL_REQUIRE(dy && dx && C % 4 == 0 && ldy % 4 == 0 && ldy >= C, "dl_site_pool_bwd: bad arguments");
+  const long long LC4 = (long long)L * C / 4, n4 = B * LC4;
+  if (n4 <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    site_pool_bwd_kernel<__nv_bfloat16><<<ew_grid(n4, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, S, LC4, n4, ldy / 4, C / 4);
+  else
+    site_pool_bwd_kernel<float><<<ew_grid(n4, 256), 256, 0, st>>>((const float*)dy, (float*)dx, S, LC4, n4, ldy / 4, C / 4);
+  DL_LAUNCH_CHECK("site_pool_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const float* gamma,
+                                   const float* beta, void* y, float* p_out, float* mean,
+                                   float* rstd, int64_t B, int32_t L, int32_t E, int32_t H,
+                                   float eps, int32_t dtype, void* stream) {
+  DL_REQUIRE(v && logits && gamma && beta && y && p_out && mean && rstd, "dl_mhla_gate_ln_fwd: null pointer");
+  DL_REQUIRE(E % 128 == 0 && E <= 512 && H >= 1 && E % H == 0 && (E / H) % 4 == 0 && 32 % ((E / H) / 4) == 0,
+             "dl_mhla_gate_ln_fwd: unsupported E=%d H=%d", E, H);
+  DL_REQUIRE((long long)H * L * 4 <= 160 * 1024, "dl_mhla_gate_ln_fwd: H*L too large for shared memory");
+  if (B <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)H * L * sizeof(float);
+#define DL_MHLA_FWD(TT, VV)                                                                         \
+  do {                                                                                              \
+    if (smem > 48 * 1024)                                                                           \
+      DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_fwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mhla_gate_ln_fwd_kernel<TT, VV><<<(unsigned)B, 256, smem, st>>>((const TT*)v, (const TT*)logits, gamma, beta, (TT*)y, p_out, mean, rstd, L, H, eps); \
+  } while (0)
+  if (dtype == DL_BF16) {
+    if (E == 128) DL_MHLA_FWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_FWD(__nv_bfloat16, 2);
+    else if (E == 384) DL_MHLA_FWD(__nv_bfloat16, 3); else DL_MHLA_FWD(__nv_bfloat16, 4);
+  } else {
+    if (E == 128) DL_MHLA_FWD(float, 1); else if (E == 256) DL_MHLA_FWD(float, 2);
+    else if (E == 384) DL_MHLA_FWD(float, 3); else DL_MHLA_FWD(float, 4);
+  }
+#undef DL_MHLA_FWD
+  DL_LAUNCH_CHECK("mhla_gate_ln_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_mhla_gate_ln_bwd(const void* dy, const void* v, const float* p, const float* mean,
+                                   const float* rstd, const float* gamma, void* dv, void* dlogits,
+                                   float* dgamma, float* dbeta, int64_t B, int32_t L, int32_t E,
+                                   int32_t H, int32_t dtype, void* stream) {
+  DL_REQUIRE(dy && v && p && mean && rstd && gamma && dv && dlogits, "dl_mhla_gate_ln_bwd: null pointer");
+  DL_REQUIRE(E % 128 == 0 && E <= 512 && H >= 1 && E % H == 0 && (E / H) % 4 == 0 && 32 % ((E / H) / 4) == 0,
+             "dl_mhla_gate_ln_bwd: unsupported E=%d H=%d", E, H);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dgamma) DL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * E, st));
+  if (dbeta) DL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * E, st));
+  if (B <= 0) return 0;
+  const size_t smem = ((size_t)2 * H * L + 8 * 128) * sizeof(float);
+  DL_REQUIRE(smem <= 200 * 1024, "dl_mhla_gate_ln_bwd: H*L too large for shared memory");
+#define DL_MHLA_BWD(TT, VV)                                                                         \
+  do {                                                                                              \
+    if (smem > 48 * 1024)                                                                           \
+      DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_bwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mhla_gate_ln_bwd_kernel<TT, VV><<<(unsigned)B, 256, smem, st>>>((const TT*)dy, (const TT*)v, p, mean, rstd, gamma, (TT*)dv, (TT*)dlogits, dgamma, dbeta, L, H); \
+  } while (0)
+  if (dtype == DL_BF16) {
+    if (E == 128) DL_MHLA_BWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_BWD(__nv_bfloat16, 2);
+    else if (E == 384) DL_MHLA_BWD(__nv_bfloat16, 3); else DL_MHLA_BWD(__nv_bfloat16, 4);
+  } else {
+    if (E == 128) DL_MHLA_BWD(float, 1); else if (E == 256) DL_MHLA_BWD(float, 2);
+    else if (E == 384) DL_MHLA_BWD(float, 3); else DL_MHLA_BWD(float, 4);
+  }
+#undef DL_MHLA_BWD
+  DL_LAUNCH_CHECK("mhla_gate_ln_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
+// acc: 2 doubles of workspace (zeroed here); loss: 1 float
+extern "C" int dl_cm_triplet_fwd(const float* cos, const int8_t* G, int64_t P, int64_t D,
+                                 float margin, double* acc, float* loss, void* stream) {
+  DL_REQUIRE(cos && G && acc && loss, "dl_cm_triplet_fwd: null pointer");
+  DL_REQUIRE(P >= 0 && D >= 1 && D <= 24576, "dl_cm_triplet_fwd: D must be in [1, 24576]");
+  cudaStream_t st = (cudaStream_t)stream;
+  DL_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  const size_t smem = (size_t)D * 8;
+  if (P > 0) {
+    if (smem > 48 * 1024)
+      DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cm_triplet_kernel<false><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, acc, nullptr, nullptr);
+    DL_LAUNCH_CHECK("cm_triplet_kernel");
+    count_launch();
+  }
+  cm_finalize_kernel<<<1, 1, 0, st>>>(acc, loss);
+  DL_LAUNCH_CHECK("cm_finalize_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, int64_t D,
+                                 float margin, const double* acc, const float* gout, float* dcos,
+                                 void* stream) {
+  DL_REQUIRE(cos && G && acc && gout && dcos, "dl_cm_triplet_bwd: null pointer");
+  DL_REQUIRE(P >= 0 && D >= 1 && D <= 24576, "dl_cm_triplet_bwd: D must be in [1, 24576]");
+  if (P == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)D * 8;
+  if (smem > 48 * 1024)
+    DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cm_triplet_kernel<true><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, const_cast<double*>(acc), gout, dcos);
+  DL_LAUNCH_CHECK("cm_triplet_kernel(bwd)");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_bce_fwd(const float* score, const float* y, float* prob, float* loss, int64_t n,
+                          void* stream) {
+  DL_REQUIRE(score && y && prob && loss && n >= 1 && n < (1 << 30), "dl_bce_fwd: bad arguments");
+  bce_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(score, y, prob, loss, (int)n);
+  DL_LAUNCH_CHECK("bce_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_bce_bwd(const float* prob, const float* y, const float* gout, float* dscore,
+                          int64_t n, void* stream) {
+  DL_REQUIRE(prob && y && gout && dscore && n >= 1 && n < (1 << 30), "dl_bce_bwd: bad arguments");
+  bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(prob, y, gout, dscore, (int)n);
+  DL_LAUNCH_CHECK("bce_bwd_kernel");
+  count_launch();
+  return 0;
+}

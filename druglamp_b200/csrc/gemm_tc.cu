@@ -5,10 +5,11 @@
 //   warp 1      allocates TMEM, issues tcgen05.mma (one thread), commits to mbarriers
 //   warps 2..5  epilogue: tcgen05.ld the accumulator quadrant they own (TMEM lanes 32*(warp%4)..),
 //               transpose through shared memory so global traffic is coalesced, apply
-//               bias / activation / auxiliary multiply / residual, store C.
+//               bias / activation / auxiliary multiply / dropout / residual, store C.
 // A K-block is 128 bytes of K (64 bf16 or 32 tf32 values) = four tcgen05.mma instructions.
 // Both operands may be K-major or MN-major (transposed storage); the shared-memory tile is
 // always "rows x 128 B" so only the descriptors and TMA boxes differ (see ptx.cuh).
+// Up to three batch dimensions (e.g. head, query-set, pair) map onto a 5-D tensor map.
 #include <mutex>
 
 #include "../../include/druglamp_sm100.h"
@@ -29,10 +30,13 @@ struct GemmParams {
   void* preact;
   const void* aux;
   const void* res;
-  long long ldc, sc_lo, sc_hi;
+  long long ldc, sc[3];
+  long long ldr, sr[3];
+  unsigned long long drop_seed;
+  float drop_p;
   int M, N, K;
-  int batch_lo;
-  int a_lo_on, a_hi_on, b_lo_on, b_hi_on;  // 0 when that batch stride is a broadcast
+  int nb0, nb1;                 // extents of the two fastest batch dims
+  int a_on[3], b_on[3];         // 0 when that batch stride is a broadcast
   int a_mn, b_mn;
   int c_bf16;
   int act, mul_mode;
@@ -73,7 +77,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int b_lo = blockIdx.z % p.batch_lo, b_hi = blockIdx.z / p.batch_lo;
+  const int b0 = blockIdx.z % p.nb0;
+  const int b1 = (blockIdx.z / p.nb0) % p.nb1;
+  const int b2 = blockIdx.z / (p.nb0 * p.nb1);
   const int nkb = (p.K + C::KE - 1) / C::KE;
 
   if (threadIdx.x == 0) {
@@ -95,8 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      const int ca2 = p.a_lo_on ? b_lo : 0, ca3 = p.a_hi_on ? b_hi : 0;
-      const int cb2 = p.b_lo_on ? b_lo : 0, cb3 = p.b_hi_on ? b_hi : 0;
+      const int a2 = p.a_on[0] ? b0 : 0, a3 = p.a_on[1] ? b1 : 0, a4 = p.a_on[2] ? b2 : 0;
+      const int c2 = p.b_on[0] ? b0 : 0, c3 = p.b_on[1] ? b1 : 0, c4 = p.b_on[2] ? b2 : 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
@@ -106,18 +112,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
         const int k0 = kb * C::KE;
         if (!p.a_mn) {
-          ptx::tma_load_4d(sA, &tmA, full, k0, m0, ca2, ca3);
+          ptx::tma_load_5d(sA, &tmA, full, k0, m0, a2, a3, a4);
         } else {
 #pragma unroll
           for (int blk = 0; blk < BM / C::MNB; ++blk)
-            ptx::tma_load_4d(sA + blk * C::KE * 128, &tmA, full, m0 + blk * C::MNB, k0, ca2, ca3);
+            ptx::tma_load_5d(sA + blk * C::KE * 128, &tmA, full, m0 + blk * C::MNB, k0, a2, a3, a4);
         }
         if (!p.b_mn) {
-          ptx::tma_load_4d(sB, &tmB, full, k0, n0, cb2, cb3);
+          ptx::tma_load_5d(sB, &tmB, full, k0, n0, c2, c3, c4);
         } else {
 #pragma unroll
           for (int blk = 0; blk < BN / C::MNB; ++blk)
-            ptx::tma_load_4d(sB + blk * C::KE * 128, &tmB, full, n0 + blk * C::MNB, k0, cb2, cb3);
+            ptx::tma_load_5d(sB + blk * C::KE * 128, &tmB, full, n0 + blk * C::MNB, k0, c2, c3, c4);
         }
       }
     }
@@ -150,7 +156,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* t = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
     ptx::mbar_wait(bar_acc, 0);
     ptx::tc_fence_after();
-    const long long cbase = (long long)b_lo * p.sc_lo + (long long)b_hi * p.sc_hi;
+    const long long cbase = (long long)b0 * p.sc[0] + (long long)b1 * p.sc[1] + (long long)b2 * p.sc[2];
+    const long long rbase = (long long)b0 * p.sr[0] + (long long)b1 * p.sr[1] + (long long)b2 * p.sr[2];
+    const float drop_inv = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     float* Cf = reinterpret_cast<float*>(p.C);
     __nv_bfloat16* Ch = reinterpret_cast<__nv_bfloat16*>(p.C);
 #pragma unroll 1
@@ -170,6 +178,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = m0 + q * 32 + r;
         if (row < p.M && col_ok) {
           const long long off = cbase + (long long)row * p.ldc + col;
+          const long long roff = rbase + (long long)row * p.ldr + col;
+          float keep = 1.f;
+          if (p.drop_p > 0.f) {
+            const unsigned long long e = ((unsigned long long)blockIdx.z * p.M + row) * p.N + col;
+            keep = hash_uniform(p.drop_seed, e) >= p.drop_p ? drop_inv : 0.f;
+          }
           float x = t[r * 33 + lane] * p.alpha + bias_v;
           if (p.c_bf16) {
             if (p.preact) reinterpret_cast<__nv_bfloat16*>(p.preact)[off] = __float2bfloat16_rn(x);
@@ -180,7 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               x *= (p.mul_mode == DL_MUL_GELU_GRAD) ? gelu_erf_grad(a)
                    : (p.mul_mode == DL_MUL_RELU_MASK) ? (a > 0.f ? 1.f : 0.f) : a;
             }
-            if (p.res) x += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[off]);
+            x *= keep;
+            if (p.res) x += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[roff]);
             Ch[off] = __float2bfloat16_rn(x);
           } else {
             if (p.preact) reinterpret_cast<float*>(p.preact)[off] = x;
@@ -191,7 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               x *= (p.mul_mode == DL_MUL_GELU_GRAD) ? gelu_erf_grad(a)
                    : (p.mul_mode == DL_MUL_RELU_MASK) ? (a > 0.f ? 1.f : 0.f) : a;
             }
-            if (p.res) x += reinterpret_cast<const float*>(p.res)[off];
+            x *= keep;
+            if (p.res) x += reinterpret_cast<const float*>(p.res)[roff];
             Cf[off] = x;
           }
         }
@@ -223,35 +239,38 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// One operand: `mn` rows/cols of the logical MN extent, K the contraction extent.
+// One operand: `mn` = logical MN extent, K = contraction extent, stored row-major with leading
+// dimension ld, either [mn, K] (K-major) or [K, mn] (MN-major); nb/s = batch extents / strides.
 int make_operand_map(CUtensorMap* m, const void* ptr, bool f32, bool mn_major, long long mn,
-                     long long K, long long ld, long long nb_lo, long long s_lo, long long nb_hi,
-                     long long s_hi, int tile_mn, const char* name) {
+                     long long K, long long ld, const int64_t* nb, const int64_t* s, int tile_mn,
+                     const char* name) {
   const int es = f32 ? 4 : 2;
   const int KE = 128 / es;
   DL_REQUIRE(((uintptr_t)ptr & 15) == 0, "dl_gemm: %s base pointer must be 16-byte aligned", name);
   DL_REQUIRE((ld * es) % 16 == 0, "dl_gemm: %s row stride (%lld elements) must be a multiple of 16 bytes", name, ld);
-  DL_REQUIRE((s_lo * es) % 16 == 0 && (s_hi * es) % 16 == 0, "dl_gemm: %s batch strides must be multiples of 16 bytes", name);
   const long long inner = mn_major ? mn : K, outer = mn_major ? K : mn;
   DL_REQUIRE(ld >= inner, "dl_gemm: %s leading dimension %lld < row length %lld", name, ld, inner);
-  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(s_lo ? nb_lo : 1),
-                        (cuuint64_t)(s_hi ? nb_hi : 1)};
-  const long long d_lo = s_lo ? s_lo : outer * ld;
-  const long long d_hi = s_hi ? s_hi : d_lo * (long long)dims[2];
-  cuuint64_t strides[3] = {(cuuint64_t)(ld * es), (cuuint64_t)(d_lo * es), (cuuint64_t)(d_hi * es)};
-  cuuint32_t box[4] = {(cuuint32_t)(mn_major ? 128 / es : KE), (cuuint32_t)(mn_major ? KE : tile_mn), 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint64_t dims[5] = {(cuuint64_t)inner, (cuuint64_t)outer, 1, 1, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)(ld * es), 0, 0, 0};
+  const long long dummy = outer * ld;   // stride for broadcast (extent-1) dims: any legal value
+  for (int i = 0; i < 3; ++i) {
+    DL_REQUIRE(s[i] >= 0 && (s[i] * es) % 16 == 0, "dl_gemm: %s batch stride %d must be a non-negative multiple of 16 bytes", name, i);
+    dims[2 + i] = (cuuint64_t)(s[i] ? nb[i] : 1);
+    strides[1 + i] = (cuuint64_t)((s[i] ? s[i] : dummy) * es);
+  }
+  cuuint32_t box[5] = {(cuuint32_t)(mn_major ? 128 / es : KE), (cuuint32_t)(mn_major ? KE : tile_mn), 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn fn = encode_fn();
   DL_REQUIRE(fn != nullptr, "dl_gemm: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   (f32 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error(-2, "dl_gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu ld %lld)",
+    return set_error(-2, "dl_gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu,%llu ld %lld)",
                      name, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
-                     (unsigned long long)dims[2], (unsigned long long)dims[3], ld);
+                     (unsigned long long)dims[2], (unsigned long long)dims[3],
+                     (unsigned long long)dims[4], ld);
   return 0;
 }
 
@@ -288,11 +307,12 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   DL_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), "dl_gemm: extent too large");
   DL_REQUIRE(a->dtype_ab == DL_F32 || a->dtype_ab == DL_BF16, "dl_gemm: dtype_ab must be DL_F32 or DL_BF16");
   DL_REQUIRE(a->dtype_c == DL_F32 || a->dtype_c == DL_BF16, "dl_gemm: dtype_c must be DL_F32 or DL_BF16");
-  DL_REQUIRE(a->batch_lo >= 1 && a->batch_hi >= 1, "dl_gemm: batch counts must be >= 1");
-  const long long batch = a->batch_lo * a->batch_hi;
+  DL_REQUIRE(a->batch[0] >= 1 && a->batch[1] >= 1 && a->batch[2] >= 1, "dl_gemm: batch extents must be >= 1");
+  const long long batch = a->batch[0] * a->batch[1] * a->batch[2];
   DL_REQUIRE(batch <= 65535, "dl_gemm: batch %lld exceeds 65535", batch);
   DL_REQUIRE(a->ldc >= a->N, "dl_gemm: ldc < N");
   DL_REQUIRE(a->mul_mode == DL_MUL_NONE || a->mul_aux != nullptr, "dl_gemm: mul_mode set without mul_aux");
+  DL_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "dl_gemm: drop_p must be in [0, 1)");
   DL_REQUIRE(a->act >= 0 && a->act <= 2 && a->mul_mode >= 0 && a->mul_mode <= 3, "dl_gemm: bad act / mul_mode");
   if (a->M == 0 || a->N == 0) return 0;
 
@@ -306,20 +326,24 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   const bool f32 = a->dtype_ab == DL_F32;
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, a->A, f32, a->trans_a != 0, a->M, a->K, a->lda, a->batch_lo,
-                            a->sa_lo, a->batch_hi, a->sa_hi, BM, "A");
+  int rc = make_operand_map(&tmA, a->A, f32, a->trans_a != 0, a->M, a->K, a->lda, a->batch, a->sa, BM, "A");
   if (rc) return rc;
-  rc = make_operand_map(&tmB, a->B, f32, a->trans_b != 0, a->N, a->K, a->ldb, a->batch_lo, a->sb_lo,
-                        a->batch_hi, a->sb_hi, bn, "B");
+  rc = make_operand_map(&tmB, a->B, f32, a->trans_b != 0, a->N, a->K, a->ldb, a->batch, a->sb, bn, "B");
   if (rc) return rc;
 
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.preact = a->preact_out; p.aux = a->mul_aux; p.res = a->residual;
-  p.ldc = a->ldc; p.sc_lo = a->sc_lo; p.sc_hi = a->sc_hi;
+  p.ldc = a->ldc;
+  p.ldr = a->ldr != 0 ? a->ldr : a->ldc;
+  for (int i = 0; i < 3; ++i) {
+    p.sc[i] = a->sc[i];
+    p.sr[i] = a->ldr != 0 ? a->sr[i] : a->sc[i];
+    p.a_on[i] = a->sa[i] != 0;
+    p.b_on[i] = a->sb[i] != 0;
+  }
+  p.drop_seed = a->drop_seed; p.drop_p = a->drop_p;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
-  p.batch_lo = (int)a->batch_lo;
-  p.a_lo_on = a->sa_lo != 0; p.a_hi_on = a->sa_hi != 0;
-  p.b_lo_on = a->sb_lo != 0; p.b_hi_on = a->sb_hi != 0;
+  p.nb0 = (int)a->batch[0]; p.nb1 = (int)a->batch[1];
   p.a_mn = a->trans_a != 0; p.b_mn = a->trans_b != 0;
   p.c_bf16 = a->dtype_c == DL_BF16;
   p.act = a->act; p.mul_mode = a->mul_mode; p.alpha = a->alpha;

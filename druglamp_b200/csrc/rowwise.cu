@@ -1,0 +1,474 @@
+// HBM-bound row kernels of the fusion path: LayerNorm fwd/bwd, row softmax fwd/bwd, column sums
+// (bias gradients), dropout, dtype casts and the positional-embedding add.  One warp owns one
+// row; loads are 8/16-byte vectors where the row length allows; statistics are fp32 and
+// reduced with warp shuffles.  Column reductions finish with one fp32 atomic per block.
+#include "../../include/druglamp_sm100.h"
+#include "common.cuh"
+
+namespace dl {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__host__ int row_grid(long long rows) {
+  long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  long long cap = (long long)sm_count() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ------------------------------------------------------------------ LayerNorm
+// VEC = cols / 128 float4 chunks per lane (cols is a multiple of 128, <= 1024)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, long long rows, float eps) {
+  constexpr int C = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      v[j] = ld4<T>(x + r * C + (j * 32 + lane) * 4);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c0 = (j * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c0);
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g.x + b.x;
+      o.y = (v[j].y - mean) * rstd * g.y + b.y;
+      o.z = (v[j].z - mean) * rstd * g.z + b.z;
+      o.w = (v[j].w - mean) * rstd * g.w + b.w;
+      st4<T>(y + r * C + c0, o);
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, T* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
+  constexpr int C = VEC * 128;
+  __shared__ float red[kWarpsPerBlock][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + w;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  float4 ag[VEC], ab[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float4 xh[VEC], dg[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c0 = (j * 32 + lane) * 4;
+      const float4 xv = ld4<T>(x + r * C + c0);
+      const float4 dv = ld4<T>(dy + r * C + c0);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+      xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                          (xv.w - mean) * rstd);
+      dg[j] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+      s1 += dg[j].x + dg[j].y + dg[j].z + dg[j].w;
+      s2 += dg[j].x * xh[j].x + dg[j].y * xh[j].y + dg[j].z * xh[j].z + dg[j].w * xh[j].w;
+      ag[j].x += dv.x * xh[j].x; ag[j].y += dv.y * xh[j].y;
+      ag[j].z += dv.z * xh[j].z; ag[j].w += dv.w * xh[j].w;
+      ab[j].x += dv.x; ab[j].y += dv.y; ab[j].z += dv.z; ab[j].w += dv.w;
+    }
+    const float c1 = warp_sum(s1) * (1.f / C), c2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c0 = (j * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (dg[j].x - c1 - xh[j].x * c2);
+      o.y = rstd * (dg[j].y - c1 - xh[j].y * c2);
+      o.z = rstd * (dg[j].z - c1 - xh[j].z * c2);
+      o.w = rstd * (dg[j].w - c1 - xh[j].w * c2);
+      st4<T>(dx + r * C + c0, o);
+    }
+  }
+  // block-reduce the per-warp column partials, then one atomic per column per block
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const float4 a = pass == 0 ? ag[j] : ab[j];
+      __syncthreads();
+      red[w][lane * 4 + 0] = a.x; red[w][lane * 4 + 1] = a.y;
+      red[w][lane * 4 + 2] = a.z; red[w][lane * 4 + 3] = a.w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) t += red[ww][threadIdx.x];
+        // threadIdx.x = l*4 + e  ->  column (j*32 + l)*4 + e = j*128 + threadIdx.x
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + j * 128 + threadIdx.x, t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ row softmax
+// cols <= 32 * kMaxPerLane; scalar coalesced accesses (lane stride 1)
+constexpr int kMaxPerLane = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_fwd_kernel(const T* __restrict__ s, T* __restrict__ p, long long rows, int cols,
+                   long long ld) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int n = (cols + 31) / 32;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float v[kMaxPerLane];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+      if (j < n) {
+        const int c = j * 32 + lane;
+        v[j] = c < cols ? ldf<T>(s, r * ld + c) : -INFINITY;
+        m = fmaxf(m, v[j]);
+      }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+      if (j < n) {
+        v[j] = __expf(v[j] - m);
+        sum += v[j];
+      }
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+      if (j < n) {
+        const int c = j * 32 + lane;
+        if (c < cols) stf<T>(p, r * ld + c, v[j] * inv);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
+                   long long rows, int cols, long long ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int n = (cols + 31) / 32;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float pv[kMaxPerLane], dv[kMaxPerLane];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+      if (j < n) {
+        const int c = j * 32 + lane;
+        pv[j] = c < cols ? ldf<T>(p, r * ld + c) : 0.f;
+        dv[j] = c < cols ? ldf<T>(dp, r * ld + c) : 0.f;
+        dot += pv[j] * dv[j];
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+      if (j < n) {
+        const int c = j * 32 + lane;
+        if (c < cols) stf<T>(ds, r * ld + c, scale * pv[j] * (dv[j] - dot));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ column sums
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols,
+              long long ld, long long rows_per_block) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += ldf<T>(x, r * ld + c);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ------------------------------------------------------------------ dropout / cast / add
+
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p,
+                               unsigned long long seed) {
+  const float inv = 1.f / (1.f - p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float keep = hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    stf<T>(y, i, ldf<T>(x, i) * keep);
+  }
+}
+
+// g = dy * act'(pre) * dropout_mask  (backward of the GEMM epilogue's act + dropout)
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre,
+                               T* __restrict__ g, long long n, int act, float p,
+                               unsigned long long seed) {
+  const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = ldf<T>(dy, i);
+    if (act == DL_ACT_GELU) v *= gelu_erf_grad(ldf<T>(pre, i));
+    else if (act == DL_ACT_RELU) v = ldf<T>(pre, i) > 0.f ? v : 0.f;
+    if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    stf<T>(g, i, v);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    st4<TO>(y + i * 4, ld4<TI>(x + i * 4));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    stf<TO>(y, i, ldf<TI>(x, i));
+  }
+}
+
+// y[b, i] = (x[b, i] + pe[i]) * dropout
+template <typename T>
+__global__ void add_pe_kernel(const T* __restrict__ x, const float* __restrict__ pe,
+                              T* __restrict__ y, long long n, long long period, float p,
+                              unsigned long long seed) {
+  const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = ldf<T>(x, i) + pe[i % period];
+    if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    stf<T>(y, i, v);
+  }
+}
+
+int ew_grid(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+template <typename T>
+int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* y, float* mean,
+                    float* rstd, long long rows, int cols, float eps, cudaStream_t st) {
+  const int grid = row_grid(rows), th = kWarpsPerBlock * 32;
+  const T* xx = (const T*)x;
+  T* yy = (T*)y;
+  switch (cols / 128) {
+    case 1: layernorm_fwd_kernel<T, 1><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 2: layernorm_fwd_kernel<T, 2><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 4: layernorm_fwd_kernel<T, 4><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 8: layernorm_fwd_kernel<T, 8><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
+    default: return set_error(-1, "dl_layernorm_fwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
+  }
+  DL_LAUNCH_CHECK("layernorm_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+template <typename T>
+int ln_bwd_dispatch(const void* dy, const void* x, const float* g, const float* mean,
+                    const float* rstd, void* dx, float* dg, float* db, long long rows, int cols,
+                    cudaStream_t st) {
+  int grid = row_grid(rows);
+  if (grid > sm_count() * 2) grid = sm_count() * 2;   // fewer blocks -> fewer atomics
+  const int th = kWarpsPerBlock * 32;
+  const T *dyy = (const T*)dy, *xx = (const T*)x;
+  T* dxx = (T*)dx;
+  switch (cols / 128) {
+    case 1: layernorm_bwd_kernel<T, 1><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 2: layernorm_bwd_kernel<T, 2><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 4: layernorm_bwd_kernel<T, 4><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 8: layernorm_bwd_kernel<T, 8><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    default: return set_error(-1, "dl_layernorm_bwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
+  }
+  DL_LAUNCH_CHECK("layernorm_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+}  // namespace dl
+
+using namespace dl;
+
+extern "C" int dl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                float* mean, float* rstd, int64_t rows, int32_t cols, float eps,
+                                int32_t dtype, void* stream) {
+  DL_REQUIRE(x && gamma && beta && y, "dl_layernorm_fwd: null pointer");
+  DL_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "dl_layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DL_BF16 ? ln_fwd_dispatch<__nv_bfloat16>(x, gamma, beta, y, mean, rstd, rows, cols, eps, st)
+                          : ln_fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, cols, eps, st);
+}
+
+extern "C" int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma,
+                                const float* mean, const float* rstd, void* dx, float* dgamma,
+                                float* dbeta, int64_t rows, int32_t cols, int32_t dtype,
+                                void* stream) {
+  DL_REQUIRE(dy && x && gamma && mean && rstd && dx, "dl_layernorm_bwd: null pointer");
+  DL_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "dl_layernorm_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dgamma) DL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
+  if (dbeta) DL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
+  if (rows == 0) return 0;
+  return dtype == DL_BF16 ? ln_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st)
+                          : ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
+}
+
+extern "C" int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols, int64_t ld,
+                              int32_t dtype, void* stream) {
+  DL_REQUIRE(s && p, "dl_softmax_fwd: null pointer");
+  DL_REQUIRE(cols > 0 && cols <= 32 * kMaxPerLane && ld >= cols, "dl_softmax_fwd: cols must be in [1, %d]", 32 * kMaxPerLane);
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = row_grid(rows), th = kWarpsPerBlock * 32;
+  if (dtype == DL_BF16)
+    softmax_fwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, cols, ld);
+  else
+    softmax_fwd_kernel<float><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, cols, ld);
+  DL_LAUNCH_CHECK("softmax_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t rows, int32_t cols,
+                              int64_t ld, float scale, int32_t dtype, void* stream) {
+  DL_REQUIRE(p && dp && ds, "dl_softmax_bwd: null pointer");
+  DL_REQUIRE(cols > 0 && cols <= 32 * kMaxPerLane && ld >= cols, "dl_softmax_bwd: cols must be in [1, %d]", 32 * kMaxPerLane);
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = row_grid(rows), th = kWarpsPerBlock * 32;
+  if (dtype == DL_BF16)
+    softmax_bwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, cols, ld, scale);
+  else
+    softmax_bwd_kernel<float><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, cols, ld, scale);
+  DL_LAUNCH_CHECK("softmax_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld,
+                         int32_t dtype, void* stream) {
+  DL_REQUIRE(x && out && cols > 0 && ld >= cols, "dl_colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (rows <= 0) return 0;
+  const int xb = ceil_div(cols, 32);
+  long long yb = (long long)sm_count() * 4 / xb;
+  if (yb < 1) yb = 1;
+  if (yb > (rows + 63) / 64) yb = (rows + 63) / 64;
+  const long long rpb = (rows + yb - 1) / yb;
+  dim3 grid(xb, (unsigned)yb), block(32, 8);
+  if (dtype == DL_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+  else
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, out, rows, cols, ld, rpb);
+  DL_LAUNCH_CHECK("colsum_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int32_t dtype,
+                          void* stream) {
+  DL_REQUIRE(x && y && p >= 0.f && p < 1.f, "dl_dropout: bad arguments");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(n, 256);
+  if (dtype == DL_BF16)
+    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
+  else
+    dropout_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n, p, seed);
+  DL_LAUNCH_CHECK("dropout_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
+                          uint64_t seed, int32_t dtype, void* stream) {
+  DL_REQUIRE(dy && g && (act == DL_ACT_NONE || pre) && p >= 0.f && p < 1.f, "dl_act_bwd: bad arguments");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(n, 256);
+  if (dtype == DL_BF16)
+    act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed);
+  else
+    act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)pre, (float*)g, n, act, p, seed);
+  DL_LAUNCH_CHECK("act_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n,
+                       void* stream) {
+  DL_REQUIRE(x && y, "dl_cast: null pointer");
+  DL_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "dl_cast: pointers must be 16-byte aligned");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid((n + 3) / 4, 256);
+  if (dtype_in == DL_F32 && dtype_out == DL_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else if (dtype_in == DL_BF16 && dtype_out == DL_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+  else if (dtype_in == DL_F32 && dtype_out == DL_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+  else
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+  DL_LAUNCH_CHECK("cast_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period,
+                         float p, uint64_t seed, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && pe && y && period > 0 && p >= 0.f && p < 1.f, "dl_add_pe: bad arguments");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(n, 256);
+  if (dtype == DL_BF16)
+    add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed);
+  else
+    add_pe_kernel<float><<<grid, 256, 0, st>>>((const float*)x, pe, (float*)y, n, period, p, seed);
+  DL_LAUNCH_CHECK("add_pe_kernel");
+  count_launch();
+  return 0;
+}

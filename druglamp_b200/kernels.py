@@ -1,0 +1,278 @@
+"""Thin, autograd-free Python wrappers over the C ABI.
+
+Every function takes CUDA tensors (2-D operands may be row/column *views* of larger buffers: only
+``stride(-1) == 1`` is required, the row stride becomes the leading dimension) and launches
+hand-written sm_100a kernels from ``libdruglamp_sm100.so`` on the current stream.  Nothing here
+falls back to PyTorch arithmetic.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, MUL_GELU_GRAD, MUL_NONE, MUL_RELU_MASK, MUL_VALUE  # noqa: F401
+
+_compute_dtype = torch.float32
+
+
+def set_compute_dtype(dtype: torch.dtype) -> None:
+    """fp32 (TF32 tensor cores, the reference's own matmul precision, main.py:43) or bf16."""
+    global _compute_dtype
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("compute dtype must be torch.float32 or torch.bfloat16")
+    _compute_dtype = dtype
+
+
+def compute_dtype() -> torch.dtype:
+    return _compute_dtype
+
+
+def _ld(t: torch.Tensor) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dtype conversion of a contiguous tensor with the dl_cast kernel."""
+    if x.dtype == dtype and out is None:
+        return x
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L.call("dl_cast", x.data_ptr(), L.dt(x), out.data_ptr(), L.dt(out), x.numel())
+    return out
+
+
+def to_compute(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous tensor in the compute dtype."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return cast(x, _compute_dtype)
+
+
+# ----------------------------------------------------------------------------- GEMM flavours
+def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, ta: bool = False,
+       tb: bool = False, bias=None, act: int = ACT_NONE, pre: Optional[torch.Tensor] = None,
+       mul_aux=None, mul_mode: int = MUL_NONE, res: Optional[torch.Tensor] = None,
+       drop: Tuple[float, int] = (0.0, 0), alpha: float = 1.0, out_dtype=None,
+       tile_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * op(a) @ op(b)).
+
+    ta=False: a is [M,K];  ta=True: a is stored [K,M].
+    tb=False: b is [N,K] (nn.Linear weight layout);  tb=True: b is stored [K,N].
+    """
+    M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"contraction mismatch: {tuple(a.shape)} ta={ta} vs {tuple(b.shape)} tb={tb}")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
+    ldr = 0
+    if res is not None and res.data_ptr() != out.data_ptr():
+        ldr = _ld(res)
+    L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldc=_ld(out), trans_a=ta, trans_b=tb,
+           alpha=alpha, bias=bias, act=act, preact_out=pre, mul_aux=mul_aux, mul_mode=mul_mode,
+           residual=res, ldr=ldr, drop_p=drop[0], drop_seed=drop[1], tile_n=tile_n)
+    return out
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    L.call("dl_colsum", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ld(x), L.dt(x))
+    return out
+
+
+def act_bwd(dy: torch.Tensor, pre: Optional[torch.Tensor], act: int, drop=(0.0, 0)) -> torch.Tensor:
+    """dy * act'(pre) * dropout_mask on contiguous tensors."""
+    if act == ACT_NONE and drop[0] == 0.0:
+        return dy
+    g = torch.empty_like(dy)
+    L.call("dl_act_bwd", dy.data_ptr(), None if pre is None else pre.data_ptr(), g.data_ptr(),
+           dy.numel(), act, drop[0], drop[1], L.dt(dy))
+    return g
+
+
+def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    if p == 0.0:
+        return x
+    y = torch.empty_like(x)
+    L.call("dl_dropout", x.data_ptr(), y.data_ptr(), x.numel(), p, seed, L.dt(x))
+    return y
+
+
+def add_pe(x: torch.Tensor, pe: torch.Tensor, p: float = 0.0, seed: int = 0) -> torch.Tensor:
+    y = torch.empty_like(x)
+    L.call("dl_add_pe", x.data_ptr(), pe.data_ptr(), y.data_ptr(), x.numel(), pe.numel(), p, seed, L.dt(x))
+    return y
+
+
+# ----------------------------------------------------------------------------- row kernels
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, save: bool = True):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    mean = rstd = None
+    if save:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+    L.call("dl_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+           L.ptr(mean), L.ptr(rstd), rows, cols, eps, L.dt(x))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = db = None
+    if need_param_grads:
+        dg = torch.empty(cols, dtype=torch.float32, device=x.device)
+        db = torch.empty_like(dg)
+    L.call("dl_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), dx.data_ptr(), L.ptr(dg), L.ptr(db), rows, cols, L.dt(x))
+    return dx, dg, db
+
+
+def softmax_fwd(s: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax over the last dim of a contiguous tensor (in place when out is None)."""
+    cols = s.shape[-1]
+    out = s if out is None else out
+    L.call("dl_softmax_fwd", s.data_ptr(), out.data_ptr(), s.numel() // cols, cols, cols, L.dt(s))
+    return out
+
+
+def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """in place on dp: dp <- scale * p * (dp - sum(p * dp))."""
+    cols = p.shape[-1]
+    L.call("dl_softmax_bwd", p.data_ptr(), dp.data_ptr(), dp.data_ptr(), p.numel() // cols, cols, cols,
+           scale, L.dt(p))
+    return dp
+
+
+# ----------------------------------------------------------------------------- GCN
+def spmm_norm(indptr, indices, norm_src, norm_dst, h: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(h)
+    L.call("dl_spmm_norm", indptr.data_ptr(), indices.data_ptr(), norm_src.data_ptr(),
+           norm_dst.data_ptr(), h.data_ptr(), out.data_ptr(), h.shape[0], h.shape[1], L.dt(h))
+    return out
+
+
+def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, eps: float,
+                  momentum: float, training: bool):
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(cols, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
+    L.call("dl_batchnorm_fwd", x.data_ptr(), L.ptr(gamma), L.ptr(beta), y.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt), ws.data_ptr(), rows, cols,
+           eps, momentum, int(training), L.dt(x))
+    return y, mean, rstd
+
+
+def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True):
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
+    dg = db = None
+    if need_param_grads:
+        dg = torch.empty(cols, dtype=torch.float32, device=x.device)
+        db = torch.empty_like(dg)
+    L.call("dl_batchnorm_bwd", dy.data_ptr(), x.data_ptr(), L.ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
+           dx.data_ptr(), L.ptr(dg), L.ptr(db), ws.data_ptr(), rows, cols, int(training), L.dt(x))
+    return dx, dg, db
+
+
+# ----------------------------------------------------------------------------- glue
+def fillbit_pool(x: torch.Tensor, S: int, want_bit=True, want_cat=False, want_pooled=True,
+                 pooled_dtype=None):
+    """x (B, S*L, C) fp32 -> (bit (B,S*L) | None, cat (B,S*L,C+1) | None, pooled (B,L,C+1) | None)."""
+    if x.dtype != torch.float32:
+        raise TypeError("fillbit_pool expects the fp32 embeddings the collate delivers")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    B, SL, C = x.shape
+    Lr = SL // S
+    bit = torch.empty((B, SL), dtype=torch.float32, device=x.device) if want_bit else None
+    cat = torch.empty((B, SL, C + 1), dtype=torch.float32, device=x.device) if want_cat else None
+    pooled = None
+    if want_pooled:
+        pooled = torch.empty((B, Lr, C + 1), dtype=pooled_dtype or _compute_dtype, device=x.device)
+    L.call("dl_fillbit_pool", x.data_ptr(), L.ptr(bit), L.ptr(cat), L.ptr(pooled),
+           L.dt(pooled) if pooled is not None else 0, B, S, Lr, C)
+    return bit, cat, pooled
+
+
+def site_pool_fwd(x: torch.Tensor, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (B, S*L, C) -> (B, L, C); `out` may be a column-slice view (row stride = ldy)."""
+    B, SL, C = x.shape
+    Lr = SL // S
+    if out is None:
+        out = torch.empty((B, Lr, C), dtype=x.dtype, device=x.device)
+    L.call("dl_site_pool_fwd", x.data_ptr(), out.data_ptr(), B, S, Lr, C, out.stride(1), L.dt(x))
+    return out
+
+
+def site_pool_bwd(dy: torch.Tensor, S: int) -> torch.Tensor:
+    B, Lr, C = dy.shape
+    dx = torch.empty((B, S * Lr, C), dtype=dy.dtype, device=dy.device)
+    L.call("dl_site_pool_bwd", dy.data_ptr(), dx.data_ptr(), B, S, Lr, C, dy.stride(1), L.dt(dy))
+    return dx
+
+
+def mhla_gate_ln_fwd(v: torch.Tensor, logits: torch.Tensor, gamma, beta, eps: float):
+    B, Lr, E = v.shape
+    H = logits.shape[-1]
+    y = torch.empty_like(v)
+    p = torch.empty((B, H, Lr), dtype=torch.float32, device=v.device)
+    mean = torch.empty(B * Lr, dtype=torch.float32, device=v.device)
+    rstd = torch.empty_like(mean)
+    L.call("dl_mhla_gate_ln_fwd", v.data_ptr(), logits.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           y.data_ptr(), p.data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, Lr, E, H, eps, L.dt(v))
+    return y, p, mean, rstd
+
+
+def mhla_gate_ln_bwd(dy, v, p, mean, rstd, gamma):
+    B, Lr, E = v.shape
+    H = p.shape[1]
+    dv = torch.empty_like(v)
+    dlogits = torch.empty((B, Lr, H), dtype=v.dtype, device=v.device)
+    dg = torch.empty(E, dtype=torch.float32, device=v.device)
+    db = torch.empty_like(dg)
+    L.call("dl_mhla_gate_ln_bwd", dy.data_ptr(), v.data_ptr(), p.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), gamma.data_ptr(), dv.data_ptr(), dlogits.data_ptr(), dg.data_ptr(),
+           db.data_ptr(), B, Lr, E, H, L.dt(v))
+    return dv, dlogits, dg, db
+
+
+def cm_triplet_fwd(cos: torch.Tensor, G: torch.Tensor, margin: float):
+    P, D = cos.shape
+    acc = torch.empty(2, dtype=torch.float64, device=cos.device)
+    loss = torch.empty((), dtype=torch.float32, device=cos.device)
+    L.call("dl_cm_triplet_fwd", cos.data_ptr(), G.data_ptr(), P, D, margin, acc.data_ptr(), loss.data_ptr())
+    return loss, acc
+
+
+def cm_triplet_bwd(cos, G, margin: float, acc, gout):
+    P, D = cos.shape
+    dcos = torch.empty_like(cos)
+    L.call("dl_cm_triplet_bwd", cos.data_ptr(), G.data_ptr(), P, D, margin, acc.data_ptr(),
+           gout.data_ptr(), dcos.data_ptr())
+    return dcos
+
+
+def bce_fwd(score: torch.Tensor, y: torch.Tensor):
+    n = score.numel()
+    prob = torch.empty(n, dtype=torch.float32, device=score.device)
+    loss = torch.empty((), dtype=torch.float32, device=score.device)
+    L.call("dl_bce_fwd", score.data_ptr(), y.data_ptr(), prob.data_ptr(), loss.data_ptr(), n)
+    return prob, loss
+
+
+def bce_bwd(prob, y, gout):
+    ds = torch.empty_like(prob)
+    L.call("dl_bce_bwd", prob.data_ptr(), y.data_ptr(), gout.data_ptr(), ds.data_ptr(), prob.numel())
+    return ds

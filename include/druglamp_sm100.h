@@ -46,14 +46,18 @@ int64_t dl_launch_count(void);
 /* ------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma, TMA-fed, accumulators in TMEM) with a fused epilogue.
  *
- *   C[b] = epilogue( alpha * op(A[b]) . op(B[b]) )          b = b_hi * batch_lo + b_lo
+ *   C[b] = epilogue( alpha * op(A[b]) . op(B[b]) )          b = (b0, b1, b2): three batch dims
  *     op(A) is M x K:  trans_a = 0 -> A stored [M, K] (K contiguous), 1 -> stored [K, M]
  *     op(B) is K x N:  trans_b = 0 -> B stored [N, K] (K contiguous, nn.Linear weight layout),
  *                      1 -> stored [K, N]
  *   epilogue(v):  v += bias[n];  if preact_out: preact_out = v;  v = act(v);
- *                 v *= f(mul_aux) (mul_mode);  v += residual;  C = v
+ *                 v *= f(mul_aux) (mul_mode);  v = dropout(v);  v += residual;  C = v
+ *   dropout keeps element e = (b*M + m)*N + n iff hash(drop_seed, e) >= drop_p and scales by
+ *   1/(1-drop_p) (same mask as dl_dropout on a contiguous [batch*M, N] tensor).
+ *   residual has its own layout (ldr, sr[]; ldr = 0 means "same as C"); a batch stride
+ *   of 0 with ldr != 0 broadcasts it (positional embeddings).
  *   dtype_ab: DL_BF16 (kind::f16) or DL_F32 (kind::tf32); fp32 accumulation always.
- *   dtype_c applies to C, preact_out, mul_aux and residual (all share C's layout: ldc, sc_*).
+ *   dtype_c applies to C, preact_out, mul_aux and residual (all share C's layout: ldc, sc[]).
  *   bias is fp32.  lda/ldb/ldc and batch strides are in ELEMENTS; every row stride and batch
  *   stride of A and B must be a multiple of 16 bytes and the base pointers 16-byte aligned
  *   (TMA).  A batch stride of 0 broadcasts that operand.
@@ -75,8 +79,11 @@ typedef struct dl_gemm_args {
   const void* residual; /* or NULL; may alias C */
   int64_t M, N, K;
   int64_t lda, ldb, ldc;
-  int64_t batch_lo, batch_hi;
-  int64_t sa_lo, sa_hi, sb_lo, sb_hi, sc_lo, sc_hi;
+  int64_t batch[3];     /* batch extents, fastest first; b = (b2*batch[1] + b1)*batch[0] + b0 */
+  int64_t sa[3], sb[3], sc[3]; /* batch strides (elements) of A, B, C */
+  int64_t ldr, sr[3];   /* residual layout; ldr = 0 -> same as C */
+  uint64_t drop_seed;
+  float drop_p;
   float alpha;
   int32_t dtype_ab, dtype_c;
   int32_t trans_a, trans_b;
@@ -85,6 +92,116 @@ typedef struct dl_gemm_args {
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound; one warp per row, 128-bit vector loads, warp-shuffle reductions).
+ * `dtype` is the activation dtype (x, y, dy, dx); statistics and parameters are fp32.
+ */
+
+/* nn.LayerNorm over the last dim.  cols in {128,256,512,1024}.  mean/rstd: [rows] (saved for bwd;
+ * may be NULL).  Replaces PMMA pre-norms and encoder_norm (model/PMMA/block.py:23-27,
+ * model/PMMA/encoder.py:31,55; eps 1e-6) and v/x_gca_norm (model/basic_model.py:115,118). */
+int dl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                     float* rstd, int64_t rows, int32_t cols, float eps, int32_t dtype,
+                     void* stream);
+/* dgamma/dbeta ([cols] fp32, overwritten; may be NULL). */
+int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                     const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                     int32_t cols, int32_t dtype, void* stream);
+
+/* softmax over the last dim of a [rows, cols<=1024] matrix with row stride ld; in-place allowed.
+ * Replaces F.softmax in PGCA (model/PGCA/guided_cross_attention_model.py:308) and
+ * Attention.softmax (model/PMMA/attention.py:42,60,71,112). */
+int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols, int64_t ld, int32_t dtype,
+                   void* stream);
+/* ds = scale * p * (dp - sum(p*dp)); in-place on dp allowed. */
+int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t rows, int32_t cols, int64_t ld,
+                   float scale, int32_t dtype, void* stream);
+
+/* out[c] = sum_r x[r, c]  (bias gradients); out is fp32 [cols], overwritten. */
+int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld, int32_t dtype,
+              void* stream);
+
+/* y = x * keep/(1-p), keep(i) = hash(seed, i) >= p (nn.Dropout of PMMA, model/PMMA/mlp.py:47,49,
+ * model/PMMA/embed.py:42,52; the mask is recomputed from the seed in backward). */
+int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int32_t dtype,
+               void* stream);
+/* g = dy * act'(pre) * dropout_mask(seed): backward of the dl_gemm epilogue's act + dropout. */
+int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
+               uint64_t seed, int32_t dtype, void* stream);
+int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
+/* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
+int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
+              uint64_t seed, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Molecular GCN (model/basic_model.py:545-638 GraphConv norm='both'; :411-436 GCNLayer).
+ */
+
+/* out[i,:] = norm_dst[i] * sum_{e in indptr[i]..indptr[i+1]} norm_src[indices[e]] * h[indices[e],:]
+ * CSR by destination = DGL update_all(copy_u, sum) with both degree norms folded in
+ * (model/basic_model.py:596-603,612-618,623-630).  Backward = same call on the transposed CSR
+ * with the norms swapped.  feats must be 128. */
+int dl_spmm_norm(const int32_t* indptr, const int32_t* indices, const float* norm_src,
+                 const float* norm_dst, const void* h, void* out, int64_t n_rows, int32_t feats,
+                 int32_t dtype, void* stream);
+
+/* nn.BatchNorm1d over [rows, cols] (model/basic_model.py:401,434 bn_layer; also
+ * cross_modality.py:168).  training!=0: batch statistics, running buffers updated with
+ * `momentum` (unbiased variance) and *num_batches_tracked += 1 when given; training==0: running
+ * statistics.  mean/rstd: [cols] outputs saved for backward.  workspace: 2*cols doubles. */
+int dl_batchnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                     float* rstd, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, double* workspace, int64_t rows, int32_t cols,
+                     float eps, float momentum, int32_t training, int32_t dtype, void* stream);
+int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                     const float* rstd, void* dx, float* dgamma, float* dbeta, double* workspace,
+                     int64_t rows, int32_t cols, int32_t training, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model glue.
+ */
+
+/* x: (B, S*L, C) fp32.  bit_out (B, S*L) = float(x.sum(-1) == 0)            [may be NULL]
+ *                       cat_out (B, S*L, C+1) = cat(x, bit) fp32           [may be NULL]
+ *                       pooled  (B, L, C+1) = cat(x, bit).view(B,S,L,C+1).mean(1)  [may be NULL]
+ * One pass over x (model/DrugLAMP.py:11-19,39-40).  S = 1 gives the plain fill-bit concat. */
+int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, void* pooled,
+                    int32_t pooled_dtype, int64_t B, int32_t S, int32_t L, int32_t C, void* stream);
+
+/* y[b, j, :] = mean_s x[b, s*L + j, :]; y rows have stride ldy (model/DrugLAMP.py:35-37). */
+int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, int32_t C,
+                     int64_t ldy, int32_t dtype, void* stream);
+int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L, int32_t C,
+                     int64_t ldy, int32_t dtype, void* stream);
+
+/* y = LayerNorm(v + gate(v)), gate = MultiHeadLinearAttention's softmax-over-sequence gating
+ * through its .view(B*H, L, E/H) reinterpretation (model/PMMA/encoder.py:132-140) applied to
+ * logits = lin2(act(lin1(v))) of shape (B, L, H); residual and LayerNorm from
+ * model/DrugLAMP.py:63-71.  p_out (B,H,L), mean/rstd (B*L) are saved for backward. */
+int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const float* gamma, const float* beta,
+                        void* y, float* p_out, float* mean, float* rstd, int64_t B, int32_t L,
+                        int32_t E, int32_t H, float eps, int32_t dtype, void* stream);
+/* dv = gradient through the gating/residual path only (add the lin1/lin2 path to it). */
+int dl_mhla_gate_ln_bwd(const void* dy, const void* v, const float* p, const float* mean,
+                        const float* rstd, const float* gamma, void* dv, void* dlogits,
+                        float* dgamma, float* dbeta, int64_t B, int32_t L, int32_t E, int32_t H,
+                        int32_t dtype, void* stream);
+
+/* CrossModality triplet loss on cos = P_lat . D_lat^T (unit rows) and labels G in {0,1}
+ * (model/cross_modality.py:15-47 with utils.py:571-574 distance).  acc: 2 doubles workspace
+ * (hinge sum, term count) kept for backward; loss: 1 float. */
+int dl_cm_triplet_fwd(const float* cos, const int8_t* G, int64_t P, int64_t D, float margin,
+                      double* acc, float* loss, void* stream);
+int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, int64_t D, float margin,
+                      const double* acc, const float* gout, float* dcos, void* stream);
+
+/* binary_cross_entropy: prob = sigmoid(score); loss = BCELoss(prob, y) mean
+ * (model/basic_model.py:17-22). */
+int dl_bce_fwd(const float* score, const float* y, float* prob, float* loss, int64_t n,
+               void* stream);
+int dl_bce_bwd(const float* prob, const float* y, const float* gout, float* dscore, int64_t n,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ def run_case(M, N, K, dtype, trans_a, trans_b, tile_n=0, integer=True, batch=(1,
     aux_t = _mk((bhi, blo, M, ldc), out_dtype, False, gen) if mul_mode else None
     pre_t = torch.zeros_like(Cc) if preact else None
     _lib.gemm(A, B, Cc, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, trans_a=trans_a, trans_b=trans_b,
-              batch_lo=blo, batch_hi=bhi, sa=(A.stride(1), A.stride(0)), sb=(B.stride(1), B.stride(0)),
+              batch=(blo, bhi), sa=(A.stride(1), A.stride(0)), sb=(B.stride(1), B.stride(0)),
               sc=(Cc.stride(1), Cc.stride(0)), alpha=alpha, bias=bias_t, act=act, preact_out=pre_t,
               mul_aux=aux_t, mul_mode=mul_mode, residual=res_t, tile_n=tile_n)
     torch.cuda.synchronize()
@@ -102,6 +102,39 @@ def test_random_numerics_and_epilogue(dtype, tol):
         assert err <= tol * scale, (kw, err, scale)
         if pre_err is not None:
             assert pre_err <= tol * scale, (kw, pre_err, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_three_batch_dims_with_broadcast_and_dropout(dtype):
+    """(head, query-set, pair) batching as the paired attention uses it: B broadcast over the
+    middle dim, C written into column halves of a wider buffer; dropout mask == dl_dropout's."""
+    from druglamp_b200 import _lib
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    H, S2, Bn, L, d = 4, 2, 3, 128, 64
+    Q = _mk((S2, Bn, L, H * d), dtype, True, gen)           # (set, pair, L, H*d)
+    Kt = _mk((Bn, L, H * d), dtype, True, gen)               # (pair, L, H*d)
+    out = torch.zeros(Bn, H, S2, L, L, device="cuda", dtype=torch.float32)
+    _lib.gemm(Q, Kt, out, M=L, N=L, K=d, lda=H * d, ldb=H * d, ldc=L, batch=(H, S2, Bn),
+              sa=(d, Bn * L * H * d, L * H * d), sb=(d, 0, L * H * d),
+              sc=(S2 * L * L, L * L, H * S2 * L * L))
+    torch.cuda.synchronize()
+    q = Q.double().view(S2, Bn, L, H, d).permute(1, 3, 0, 2, 4)      # (pair, H, set, L, d)
+    k = Kt.double().view(Bn, L, H, d).permute(0, 2, 1, 3)[:, :, None]  # (pair, H, 1, L, d)
+    ref = q @ k.transpose(-1, -2)
+    assert (out.double() - ref).abs().max().item() == 0.0
+    # dropout in the epilogue equals the standalone kernel on the contiguous result
+    x = _mk((256, 128), dtype, True, gen)
+    w = _mk((128, 128), dtype, True, gen)
+    y0 = torch.zeros(256, 128, device="cuda", dtype=torch.float32)
+    y1 = torch.zeros_like(y0)
+    _lib.gemm(x, w, y0, M=256, N=128, K=128, lda=128, ldb=128, ldc=128)
+    _lib.gemm(x, w, y1, M=256, N=128, K=128, lda=128, ldb=128, ldc=128, drop_p=0.25, drop_seed=77)
+    y2 = torch.empty_like(y0)
+    _lib.call("dl_dropout", y0.data_ptr(), y2.data_ptr(), y0.numel(), 0.25, 77, _lib.dt(y0))
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    frac = (y1 == 0).float().mean().item()
+    assert 0.15 < frac < 0.40
 
 
 def test_long_k_pipeline_wraps():

@@ -1,0 +1,234 @@
+"""GPU: each non-GEMM kernel of libdruglamp_sm100.so against a plain PyTorch fp32/fp64 reference of
+the same op (these are the floating-point row kernels; index/mask outputs are checked bit-exactly)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)]
+
+
+def _close(a, b, tol, what=""):
+    a, b = a.double(), b.double()
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"{what}: err {err:.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("cols", [128, 256, 512])
+def test_layernorm_fwd_bwd(dtype, tol, cols):
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(0)
+    rows = 1000
+    x = (torch.randn(rows, cols, device="cuda") * 2 + 0.5).to(dtype)
+    g = torch.randn(cols, device="cuda")
+    b = torch.randn(cols, device="cuda")
+    dy = torch.randn(rows, cols, device="cuda").to(dtype)
+    y, mean, rstd = K.layernorm_fwd(x, g, b, 1e-6)
+    dx, dg, db = K.layernorm_bwd(dy, x, g, mean, rstd)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (cols,), gr, br, 1e-6)
+    yr.backward(dy.double())
+    _close(y, yr, tol, "y")
+    _close(dx, xr.grad, tol, "dx")
+    _close(dg, gr.grad, max(tol, 1e-4), "dgamma")
+    _close(db, br.grad, max(tol, 1e-4), "dbeta")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("cols", [256, 290, 512])
+def test_softmax_fwd_bwd(dtype, tol, cols):
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(1)
+    s = (torch.randn(77, 3, cols, device="cuda") * 3).to(dtype)
+    dp = torch.randn(77, 3, cols, device="cuda").to(dtype)
+    p = K.softmax_fwd(s.clone())
+    sr = s.double().requires_grad_(True)
+    pr = F.softmax(sr, dim=-1)
+    _close(p, pr, tol, "p")
+    ds = K.softmax_bwd(p, dp.clone(), 0.5)
+    (gr,) = torch.autograd.grad(pr, sr, dp.double())
+    _close(ds, 0.5 * gr, max(tol, 1e-4) * 2, "ds")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_colsum_actbwd_dropout_cast_addpe(dtype, tol):
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(2)
+    x = torch.randn(3000, 264, device="cuda").to(dtype)
+    _close(K.colsum(x), x.double().sum(0), 1e-4, "colsum")
+    _close(K.colsum(x[:, 8:136]), x.double()[:, 8:136].sum(0), 1e-4, "colsum view")
+    pre = torch.randn_like(x)
+    a = pre.double().requires_grad_(True)
+    (gg,) = torch.autograd.grad(F.gelu(a).sum(), a)
+    _close(K.act_bwd(x, pre, K.ACT_GELU), x.double() * gg, tol, "gelu bwd")
+    _close(K.act_bwd(x, pre, K.ACT_RELU), x.double() * (pre.double() > 0), tol, "relu bwd")
+    d1 = K.dropout(x, 0.1, 1234)
+    d2 = K.act_bwd(x, None, K.ACT_NONE, (0.1, 1234))
+    assert torch.equal(d1, d2)
+    keep = (d1 != 0) | (x == 0)
+    assert 0.86 < keep.float().mean().item() < 0.94
+    _close(d1[keep], (x.double() / 0.9)[keep], tol, "dropout scale")
+    y = K.cast(x, torch.float32)
+    assert torch.equal(y, x.float())
+    z = K.cast(y, torch.bfloat16)
+    assert torch.equal(z, y.to(torch.bfloat16))
+    odd = torch.randn(1003, device="cuda")
+    assert torch.equal(K.cast(odd, torch.bfloat16), odd.to(torch.bfloat16))
+    pe = torch.randn(50, 264, device="cuda")
+    xb = x.view(60, 50, 264)
+    _close(K.add_pe(xb, pe), xb.double() + pe.double(), tol, "add_pe")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_spmm_norm_matches_index_add(dtype, tol):
+    from druglamp_b200 import kernels as K
+    from druglamp_b200.synth import make_batch
+    b = make_batch(3, seed=5)
+    g = b.graph.to("cuda")
+    torch.manual_seed(3)
+    h = torch.randn(g.num_nodes(), 128, device="cuda").to(dtype)
+    out = K.spmm_norm(g.indptr, g.indices, g.norm_src, g.norm_dst, h)
+    hd = h.double() * g.norm_src.double()[:, None]
+    ref = torch.zeros_like(hd).index_add_(0, g.dst, hd[g.src]) * g.norm_dst.double()[:, None]
+    _close(out, ref, tol, "spmm")
+    # backward operator = transposed CSR with swapped norms
+    outT = K.spmm_norm(g.indptr_t, g.indices_t, g.norm_dst, g.norm_src, h)
+    hd = h.double() * g.norm_dst.double()[:, None]
+    refT = torch.zeros_like(hd).index_add_(0, g.src, hd[g.dst]) * g.norm_src.double()[:, None]
+    _close(outT, refT, tol, "spmm^T")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_fwd_bwd(dtype, tol, training):
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(4)
+    rows, cols = 5000, 128
+    x = (torch.randn(rows, cols, device="cuda") * 1.5 + 0.3).to(dtype)
+    dy = torch.randn(rows, cols, device="cuda").to(dtype)
+    bn = torch.nn.BatchNorm1d(cols).cuda().double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+        bn.running_mean.uniform_(-0.2, 0.2)
+        bn.running_var.uniform_(0.8, 1.2)
+    bn.train(training)
+    g, b = bn.weight.detach().float(), bn.bias.detach().float()
+    rm, rv = bn.running_mean.detach().float().clone(), bn.running_var.detach().float().clone()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    y, mean, rstd = K.batchnorm_fwd(x, g, b, rm, rv, nbt, 1e-5, 0.1, training)
+    dx, dg, db = K.batchnorm_bwd(dy, x, g, mean, rstd, training)
+    xr = x.double().requires_grad_(True)
+    yr = bn(xr)
+    yr.backward(dy.double())
+    _close(y, yr, tol, "y")
+    _close(dx, xr.grad, tol, "dx")
+    _close(dg, bn.weight.grad, max(tol, 1e-4), "dgamma")
+    _close(db, bn.bias.grad, max(tol, 1e-4), "dbeta")
+    if training:
+        _close(rm, bn.running_mean, 1e-4, "running_mean")
+        _close(rv, bn.running_var, 1e-4, "running_var")
+        assert int(nbt) == 1
+
+
+def test_fillbit_pool_bit_exact_and_site_pool():
+    from druglamp_b200 import kernels as K
+    from druglamp_b200.synth import make_batch
+    b = make_batch(3, seed=11)
+    xp = b.xp.cuda()
+    bit, cat, pooled = K.fillbit_pool(xp, 9, want_cat=True, pooled_dtype=torch.float32)
+    ref_bit = (xp.sum(-1) == 0).float()
+    assert torch.equal(bit, ref_bit)                           # bit-exact padding mask
+    ref_cat = torch.cat((xp, ref_bit.unsqueeze(-1)), -1)
+    assert torch.equal(cat, ref_cat)
+    ref_pool = ref_cat.view(-1, 9, 256, 641).mean(1)
+    _close(pooled, ref_pool, 1e-6, "pooled")
+    xd = b.xd.cuda()
+    bit_d, cat_d, _ = K.fillbit_pool(xd, 1, want_cat=True, want_pooled=False)
+    assert torch.equal(bit_d, (xd.sum(-1) == 0).float())
+    assert torch.equal(cat_d, torch.cat((xd, bit_d.unsqueeze(-1)), -1))
+    for dtype, tol in DTYPES:
+        v = torch.randn(3, 2304, 128, device="cuda").to(dtype)
+        buf = torch.zeros(3, 256, 256, device="cuda", dtype=dtype)
+        K.site_pool_fwd(v, 9, out=buf[:, :, :128])
+        _close(buf[:, :, :128], v.double().view(3, 9, 256, 128).mean(1), tol, "site pool")
+        assert (buf[:, :, 128:] == 0).all()
+        dy = torch.randn(3, 256, 128, device="cuda").to(dtype)
+        dx = K.site_pool_bwd(dy, 9)
+        _close(dx, (dy.double() / 9)[:, None].expand(3, 9, 256, 128).reshape(3, 2304, 128), tol, "site pool bwd")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_mhla_gate_ln_fwd_bwd(dtype, tol):
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(6)
+    B, Lr, E, H = 3, 256, 256, 8
+    v = torch.randn(B, Lr, E, device="cuda").to(dtype)
+    logits = (torch.randn(B, Lr, H, device="cuda") * 2).to(dtype)
+    g = torch.rand(E, device="cuda") + 0.5
+    bt = torch.randn(E, device="cuda")
+    dy = torch.randn(B, Lr, E, device="cuda").to(dtype)
+    y, p, mean, rstd = K.mhla_gate_ln_fwd(v, logits, g, bt, 1e-5)
+    dv, dlog, dg, db = K.mhla_gate_ln_bwd(dy, v, p, mean, rstd, g)
+    vr = v.double().requires_grad_(True)
+    lr_ = logits.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), bt.double().requires_grad_(True)
+    a = F.softmax(lr_, dim=1).transpose(1, 2).contiguous()              # reference encoder.py:132-140
+    gated = (a.view(B * H, Lr, 1) * vr.contiguous().view(B * H, Lr, E // H)).view(B, Lr, E)
+    yr = F.layer_norm(gated + vr, (E,), gr, br, 1e-5)
+    yr.backward(dy.double())
+    _close(y, yr, tol, "y")
+    _close(p, a, 1e-5 if dtype == torch.float32 else tol, "p")
+    # dv here is only the direct (gate/residual) path == full grad w.r.t. v with logits held fixed
+    _close(dv, vr.grad, tol, "dv")
+    _close(dlog, lr_.grad, max(tol, 1e-4) * 2, "dlogits")
+    _close(dg, gr.grad, max(tol, 1e-4), "dgamma")
+    _close(db, br.grad, max(tol, 1e-4), "dbeta")
+
+
+def test_cm_triplet_and_bce():
+    from druglamp_b200 import kernels as K
+    from oracle import restatement as R
+    torch.manual_seed(7)
+    P, D = 37, 53
+    pl = F.normalize(torch.randn(P, 256, dtype=torch.float64), dim=-1)
+    dl = F.normalize(torch.randn(D, 256, dtype=torch.float64), dim=-1)
+    G = (torch.rand(P, D) < 0.15).long()
+    G[3] = 0                                   # a protein without positives
+    G[5] = 1                                   # a protein without negatives
+    cos = (pl @ dl.t()).requires_grad_(True)
+    for margin in (0.5, 0.0187):
+        # oracle on the same cosines (dense form pinned against the reference in test_oracle_golden)
+        S = torch.sigmoid(cos)
+        total, n = 0.0, 0
+        for i in range(P):
+            pi, ni = (G[i] == 1).nonzero().flatten(), (G[i] == 0).nonzero().flatten()
+            if len(pi) and len(ni):
+                total = total + F.relu(S[i, ni][None] - S[i, pi][:, None] + margin).sum(); n += len(pi) * len(ni)
+            elif len(ni):
+                total = total + F.relu(S[i, ni] - torch.sigmoid(torch.tensor(1.0, dtype=torch.float64)) + margin).sum(); n += len(ni)
+        ref = total / max(n, 1)
+        (gref,) = torch.autograd.grad(ref, cos)
+        c32 = cos.detach().float().cuda()
+        loss, acc = K.cm_triplet_fwd(c32, G.to(torch.int8).cuda(), margin)
+        assert int(acc[1].item()) == n
+        assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+        gout = torch.full((), 2.0, device="cuda")
+        dcos = K.cm_triplet_bwd(c32, G.to(torch.int8).cuda(), margin, acc, gout)
+        _close(dcos.cpu(), 2.0 * gref, 1e-4, "dcos")
+    assert abs(R.cm_triplet_dense(pl.float(), dl.float(), G, 0.5).item() - float(K.cm_triplet_fwd(
+        (pl @ dl.t()).float().cuda(), G.to(torch.int8).cuda(), 0.5)[0])) < 1e-5
+    score = torch.randn(64, 1, device="cuda") * 3
+    y = (torch.rand(64, device="cuda") < 0.45).float()
+    prob, loss = K.bce_fwd(score, y)
+    sr = score.clone().requires_grad_(True)
+    n_ref, l_ref = R.binary_cross_entropy(sr, y)
+    l_ref.backward()
+    _close(prob, n_ref, 1e-6, "prob")
+    assert abs(loss.item() - l_ref.item()) < 1e-5
+    ds = K.bce_bwd(prob, y, torch.ones((), device="cuda"))
+    _close(ds, sr.grad.flatten(), 1e-5, "dscore")
