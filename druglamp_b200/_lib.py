@@ -18,6 +18,10 @@ DL_F32, DL_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 MUL_NONE, MUL_GELU_GRAD, MUL_RELU_MASK, MUL_VALUE = 0, 1, 2, 3
 
+# fp32 operands: True = 3xTF32 split (fp32-grade, the parity mode), False = plain TF32 (the
+# precision the reference itself selects on GPUs via set_float32_matmul_precision, main.py:43)
+FP32_PRECISE = True
+
 _lib = None
 _I64x3 = C.c_int64 * 3
 
@@ -34,7 +38,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float),
         ("dtype_ab", C.c_int32), ("dtype_c", C.c_int32),
         ("trans_a", C.c_int32), ("trans_b", C.c_int32),
-        ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32),
+        ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
     ]
 
 
@@ -49,7 +53,11 @@ SIGNATURES = {
     "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _P],
     "dl_dropout": [_P, _P, _I64, _F, _U64, _I32, _P],
     "dl_act_bwd": [_P, _P, _P, _I64, _I32, _F, _U64, _I32, _P],
+    "dl_act_fwd": [_P, _P, _I64, _I32, _I32, _P],
+    "dl_l2norm_fwd": [_P, _P, _P, _I64, _I32, _F, _I32, _P],
+    "dl_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_cast": [_P, _I32, _P, _I32, _I64, _P],
+    "dl_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _P],
     "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _I32, _P],
     "dl_spmm_norm": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _I32, _P],
@@ -61,6 +69,8 @@ SIGNATURES = {
     "dl_mhla_gate_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_cm_triplet_fwd": [_P, _P, _I64, _I64, _F, _P, _P, _P],
     "dl_cm_triplet_bwd": [_P, _P, _I64, _I64, _F, _P, _P, _P, _P],
+    "dl_cross_entropy_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _I32, _P],
+    "dl_cross_entropy_bwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _P, _P, _I32, _P],
     "dl_bce_fwd": [_P, _P, _P, _P, _I64, _P],
     "dl_bce_bwd": [_P, _P, _P, _P, _I64, _P],
 }
@@ -134,7 +144,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          preact_out: Optional[torch.Tensor] = None, mul_aux: Optional[torch.Tensor] = None,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
-         sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0) -> None:
+         sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
+         precise: Optional[bool] = None) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -147,5 +158,5 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     a = GemmArgs(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(preact_out), ptr(mul_aux), ptr(residual),
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
-                 mul_mode, tile_n)
+                 mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise))
     check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")

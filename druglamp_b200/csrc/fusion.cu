@@ -115,6 +115,7 @@ mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
                         float* __restrict__ rstd_out, int L, int H, float eps) {
   constexpr int E = VEC * 128;
   extern __shared__ float sp[];                 // [H][L]
+  const bool plain = gamma == nullptr;
   const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int hd = E / H;
   // phase 1: column softmax, warp per head
@@ -146,11 +147,13 @@ mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
       const int e0 = (j * 32 + lane) * 4;
       const long long f = (long long)l * E + e0;
       const int hh = (int)(f / ((long long)L * hd)), ll = (int)((f % ((long long)L * hd)) / hd);
-      const float g = 1.f + sp[hh * L + ll];
+      const float g = plain ? sp[hh * L + ll] : 1.f + sp[hh * L + ll];
       const float4 x = ld4<T>(v + rbase + e0);
       u[j] = make_float4(x.x * g, x.y * g, x.z * g, x.w * g);
       s += u[j].x + u[j].y + u[j].z + u[j].w;
+      if (plain) st4<T>(y + rbase + e0, u[j]);
     }
+    if (plain) continue;            // gamma == NULL: gating only (MultiHeadLinearAttention.forward)
     const float mean = warp_sum(s) * (1.f / E);
     float q = 0.f;
 #pragma unroll
@@ -197,9 +200,11 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
 #pragma unroll
   for (int j = 0; j < VEC; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int lanes_per_chunk = hd / 4;           // lanes sharing one (hh, ll) gate
+  const bool plain = gamma == nullptr;          // gating only: no residual, no LayerNorm
   for (int l = w; l < L; l += 8) {
     const size_t rbase = ((size_t)b * L + l) * E;
-    const float mean = mean_in[(size_t)b * L + l], rstd = rstd_in[(size_t)b * L + l];
+    const float mean = plain ? 0.f : mean_in[(size_t)b * L + l];
+    const float rstd = plain ? 1.f : rstd_in[(size_t)b * L + l];
     float4 xv[VEC], xh[VEC], dg[VEC];
     float gate[VEC];
     int gidx[VEC];
@@ -210,10 +215,10 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
       const long long f = (long long)l * E + e0;
       const int hh = (int)(f / ((long long)L * hd)), ll = (int)((f % ((long long)L * hd)) / hd);
       gidx[j] = hh * L + ll;
-      gate[j] = 1.f + sp[gidx[j]];
+      gate[j] = plain ? sp[gidx[j]] : 1.f + sp[gidx[j]];
       xv[j] = ld4<T>(v + rbase + e0);
       const float4 d = ld4<T>(dy + rbase + e0);
-      const float4 g = *reinterpret_cast<const float4*>(gamma + e0);
+      const float4 g = plain ? make_float4(1.f, 1.f, 1.f, 1.f) : *reinterpret_cast<const float4*>(gamma + e0);
       xh[j] = make_float4((xv[j].x * gate[j] - mean) * rstd, (xv[j].y * gate[j] - mean) * rstd,
                           (xv[j].z * gate[j] - mean) * rstd, (xv[j].w * gate[j] - mean) * rstd);
       dg[j] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -222,7 +227,8 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
       ag[j].x += d.x * xh[j].x; ag[j].y += d.y * xh[j].y; ag[j].z += d.z * xh[j].z; ag[j].w += d.w * xh[j].w;
       ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
     }
-    const float c1 = warp_sum(s1) * (1.f / E), c2 = warp_sum(s2) * (1.f / E);
+    const float c1 = plain ? 0.f : warp_sum(s1) * (1.f / E);
+    const float c2 = plain ? 0.f : warp_sum(s2) * (1.f / E);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int e0 = (j * 32 + lane) * 4;
@@ -343,6 +349,62 @@ __global__ void cm_finalize_kernel(const double* __restrict__ acc, float* __rest
   loss[0] = (float)(acc[0] / cnt);
 }
 
+// ------------------------------------------------------------------ cross entropy (MLM heads)
+// logit[r, c] = x[r*ld + c] + (extra ? extra[r] * wextra[c] : 0);  rows with label == ignore are
+// skipped.  One warp per row, classes strided over lanes (C = 27 for the MLM heads).
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+cross_entropy_kernel(const T* __restrict__ x, const long long* __restrict__ labels,
+                     const float* __restrict__ extra, const float* __restrict__ wextra,
+                     long long rows, int C, long long ld, long long ignore_index,
+                     double* __restrict__ acc, const float* __restrict__ gout, T* __restrict__ dx,
+                     float* __restrict__ dextra_dot) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const long long lab = labels[r];
+  const bool skip = lab == ignore_index;
+  if (skip) {
+    if (BWD) {
+      for (int c = lane; c < C; c += 32) stf<T>(dx, r * ld + c, 0.f);
+      if (dextra_dot && lane == 0) dextra_dot[r] = 0.f;
+    }
+    return;
+  }
+  const float ex = extra ? extra[r] : 0.f;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, ldf<T>(x, r * ld + c) + (extra ? ex * wextra[c] : 0.f));
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __expf(ldf<T>(x, r * ld + c) + (extra ? ex * wextra[c] : 0.f) - m);
+  s = warp_sum(s);
+  if (!BWD) {
+    if (lane == 0) {
+      const float xl = ldf<T>(x, r * ld + lab) + (extra ? ex * wextra[lab] : 0.f);
+      atomicAdd(acc, (double)(m + __logf(s) - xl));
+      atomicAdd(acc + 1, 1.0);
+    }
+  } else {
+    const float coef = gout[0] / (float)acc[1];
+    const float inv = 1.f / s;
+    float dot = 0.f;   // sum_c dlogit[c] * wextra[c]  -> gradient w.r.t. extra[r]
+    for (int c = lane; c < C; c += 32) {
+      const float p = __expf(ldf<T>(x, r * ld + c) + (extra ? ex * wextra[c] : 0.f) - m) * inv;
+      const float d = coef * (p - (c == lab ? 1.f : 0.f));
+      stf<T>(dx, r * ld + c, d);
+      if (extra) dot += d * wextra[c];
+    }
+    if (dextra_dot) {
+      dot = warp_sum(dot);
+      if (lane == 0) dextra_dot[r] = dot;
+    }
+  }
+}
+
+__global__ void ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss) {
+  loss[0] = (float)(acc[0] / acc[1]);
+}
+
 // ------------------------------------------------------------------ BCE
 __global__ void bce_fwd_kernel(const float* __restrict__ score, const float* __restrict__ y,
                                float* __restrict__ prob, float* __restrict__ loss, int n) {
@@ -432,7 +494,8 @@ extern "C" int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const floa
                                    const float* beta, void* y, float* p_out, float* mean,
                                    float* rstd, int64_t B, int32_t L, int32_t E, int32_t H,
                                    float eps, int32_t dtype, void* stream) {
-  DL_REQUIRE(v && logits && gamma && beta && y && p_out && mean && rstd, "dl_mhla_gate_ln_fwd: null pointer");
+  DL_REQUIRE(v && logits && y && p_out, "dl_mhla_gate_ln_fwd: null pointer");
+  DL_REQUIRE(gamma == nullptr || (beta && mean && rstd), "dl_mhla_gate_ln_fwd: LayerNorm mode needs beta, mean, rstd");
   DL_REQUIRE(E % 128 == 0 && E <= 512 && H >= 1 && E % H == 0 && (E / H) % 4 == 0 && 32 % ((E / H) / 4) == 0,
              "dl_mhla_gate_ln_fwd: unsupported E=%d H=%d", E, H);
   DL_REQUIRE((long long)H * L * 4 <= 160 * 1024, "dl_mhla_gate_ln_fwd: H*L too large for shared memory");
@@ -462,7 +525,8 @@ extern "C" int dl_mhla_gate_ln_bwd(const void* dy, const void* v, const float* p
                                    const float* rstd, const float* gamma, void* dv, void* dlogits,
                                    float* dgamma, float* dbeta, int64_t B, int32_t L, int32_t E,
                                    int32_t H, int32_t dtype, void* stream) {
-  DL_REQUIRE(dy && v && p && mean && rstd && gamma && dv && dlogits, "dl_mhla_gate_ln_bwd: null pointer");
+  DL_REQUIRE(dy && v && p && dv && dlogits, "dl_mhla_gate_ln_bwd: null pointer");
+  DL_REQUIRE(gamma == nullptr || (mean && rstd), "dl_mhla_gate_ln_bwd: LayerNorm mode needs mean, rstd");
   DL_REQUIRE(E % 128 == 0 && E <= 512 && H >= 1 && E % H == 0 && (E / H) % 4 == 0 && 32 % ((E / H) / 4) == 0,
              "dl_mhla_gate_ln_bwd: unsupported E=%d H=%d", E, H);
   cudaStream_t st = (cudaStream_t)stream;
@@ -523,6 +587,48 @@ extern "C" int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, i
     DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cm_triplet_kernel<true><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, const_cast<double*>(acc), gout, dcos);
   DL_LAUNCH_CHECK("cm_triplet_kernel(bwd)");
+  count_launch();
+  return 0;
+}
+
+// acc: 2 doubles (loss sum, number of non-ignored rows), zeroed here; loss: 1 float (mean)
+extern "C" int dl_cross_entropy_fwd(const void* x, const int64_t* labels, const float* extra,
+                                    const float* wextra, int64_t rows, int32_t C, int64_t ld,
+                                    int64_t ignore_index, double* acc, float* loss, int32_t dtype,
+                                    void* stream) {
+  DL_REQUIRE(x && labels && acc && loss && C >= 1 && ld >= C, "dl_cross_entropy_fwd: bad arguments");
+  DL_REQUIRE((extra == nullptr) == (wextra == nullptr), "dl_cross_entropy_fwd: extra and wextra go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  DL_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  if (rows > 0) {
+    const int grid = ceil_div(rows, 8);
+    if (dtype == DL_BF16)
+      cross_entropy_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
+    else
+      cross_entropy_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
+    DL_LAUNCH_CHECK("cross_entropy_kernel");
+    count_launch();
+  }
+  ce_finalize_kernel<<<1, 1, 0, st>>>(acc, loss);
+  DL_LAUNCH_CHECK("ce_finalize_kernel");
+  count_launch();
+  return 0;
+}
+
+// dx: same layout as x; dextra: [rows] fp32 or NULL (gradient w.r.t. extra)
+extern "C" int dl_cross_entropy_bwd(const void* x, const int64_t* labels, const float* extra,
+                                    const float* wextra, int64_t rows, int32_t C, int64_t ld,
+                                    int64_t ignore_index, const double* acc, const float* gout,
+                                    void* dx, float* dextra, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && labels && acc && gout && dx && C >= 1 && ld >= C, "dl_cross_entropy_bwd: bad arguments");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(rows, 8);
+  if (dtype == DL_BF16)
+    cross_entropy_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (__nv_bfloat16*)dx, dextra);
+  else
+    cross_entropy_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (float*)dx, dextra);
+  DL_LAUNCH_CHECK("cross_entropy_kernel(bwd)");
   count_launch();
   return 0;
 }

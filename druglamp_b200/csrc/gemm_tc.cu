@@ -44,7 +44,12 @@ struct GemmParams {
   uint32_t idesc;
 };
 
-template <int BN, bool TF32>
+// SPLIT (fp32 operands only): "3xTF32".  kind::tf32 reads just the top 19 bits of each fp32
+// operand, which costs ~1e-3 relative accuracy.  In SPLIT mode the four otherwise idle epilogue
+// warps rewrite every landed stage in place as hi = x & 0xffffe000 and lo = x - hi (exact), and
+// the issuer runs three MMAs per K step (hi*hi + lo*hi + hi*lo): fp32-grade products on the
+// tensor cores.  The conversion is elementwise, so it is independent of the swizzled layout.
+template <int BN, bool TF32, bool SPLIT = false>
 struct Cfg {
   static constexpr int ELEM = TF32 ? 4 : 2;
   static constexpr int KE = 128 / ELEM;   // K elements per K-block
@@ -52,19 +57,22 @@ struct Cfg {
   static constexpr int MNB = 128 / ELEM;  // MN elements per 128-byte block (MN-major operands)
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;             // what TMA delivers per stage
+  static constexpr int STAGE_BYTES = SPLIT ? 2 * LOAD_BYTES : LOAD_BYTES;
+  static constexpr int STAGES = SPLIT ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4))
+                                      : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
   static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
   static_assert(EPI_BYTES <= STAGES * STAGE_BYTES, "epilogue staging aliases the stage ring");
 };
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, bool SPLIT>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-  using C = Cfg<BN, TF32>;
+  using C = Cfg<BN, TF32, SPLIT>;
+  static_assert(!SPLIT || TF32, "SPLIT applies to fp32 operands");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -73,7 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_full = ptx::smem_u32(bars);                    // [STAGES]
   const uint32_t bar_empty = bar_full + 8 * C::STAGES;              // [STAGES]
   const uint32_t bar_acc = bar_empty + 8 * C::STAGES;               // accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+  const uint32_t bar_conv = bar_acc + 8;                            // [STAGES] hi/lo split done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -88,6 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
       ptx::mbar_init(bar_empty + 8 * s, 1);
+      ptx::mbar_init(bar_conv + 8 * s, 128);
     }
     ptx::mbar_init(bar_acc, 1);
     ptx::fence_barrier_init();
@@ -108,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / C::STAGES) & 1;
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const uint32_t full = bar_full + 8 * s;
-        ptx::mbar_arrive_expect_tx(full, C::STAGE_BYTES);
+        ptx::mbar_arrive_expect_tx(full, C::LOAD_BYTES);
         const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
         const int k0 = kb * C::KE;
         if (!p.a_mn) {
@@ -133,7 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
-        ptx::mbar_wait(bar_full + 8 * s, ph);
+        ptx::mbar_wait((SPLIT ? bar_conv : bar_full) + 8 * s, ph);
         ptx::tc_fence_after();
         const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
 #pragma unroll
@@ -145,6 +155,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bd = p.b_mn ? ptx::make_smem_desc(sB + k * C::UK * 128, C::KE * 128, kMnSbo, kMnType)
                                      : ptx::make_smem_desc(sB + k * 32, 16, 1024);
           ptx::mma_ss<TF32>(tmem, ad, bd, p.idesc, (uint32_t)((kb | k) != 0));
+          if constexpr (SPLIT) {
+            // descriptors address 16-byte units: the lo copies sit LOAD_BYTES above the hi ones
+            constexpr uint64_t kLo = (uint64_t)(C::LOAD_BYTES >> 4);
+            ptx::mma_ss<TF32>(tmem, ad + kLo, bd, p.idesc, 1u);
+            ptx::mma_ss<TF32>(tmem, ad, bd + kLo, p.idesc, 1u);
+          }
         }
         ptx::mma_commit(bar_empty + 8 * s);   // frees the stage once these MMAs have read it
       }
@@ -154,6 +170,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // -------------------------------------------------------------- epilogue (warps 2..5)
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     float* t = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+    if constexpr (SPLIT) {
+      const int tid = threadIdx.x - 64;           // 0..127
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        ptx::mbar_wait(bar_full + 8 * s, ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + s * C::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + s * C::STAGE_BYTES + C::LOAD_BYTES);
+#pragma unroll 4
+        for (int i = tid; i < C::LOAD_BYTES / 16; i += 128) {
+          const uint4 u = hi[i];
+          const uint4 h = make_uint4(u.x & 0xffffe000u, u.y & 0xffffe000u, u.z & 0xffffe000u,
+                                     u.w & 0xffffe000u);
+          lo[i] = make_float4(__uint_as_float(u.x) - __uint_as_float(h.x),
+                              __uint_as_float(u.y) - __uint_as_float(h.y),
+                              __uint_as_float(u.z) - __uint_as_float(h.z),
+                              __uint_as_float(u.w) - __uint_as_float(h.w));
+          hi[i] = h;
+        }
+        ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the MMA
+        ptx::mbar_arrive(bar_conv + 8 * s);
+      }
+    }
     ptx::mbar_wait(bar_acc, 0);
     ptx::tc_fence_after();
     const long long cbase = (long long)b0 * p.sc[0] + (long long)b1 * p.sc[1] + (long long)b2 * p.sc[2];
@@ -274,21 +313,21 @@ int make_operand_map(CUtensorMap* m, const void* ptr, bool f32, bool mn_major, l
   return 0;
 }
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, bool SPLIT = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long long batch,
            cudaStream_t stream) {
-  using C = Cfg<BN, TF32>;
+  using C = Cfg<BN, TF32, SPLIT>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, SPLIT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   });
   if (attr_err != cudaSuccess)
     return set_error((int)attr_err, "dl_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   p.idesc = ptx::make_idesc(TF32, p.a_mn != 0, p.b_mn != 0, BM, BN);
   dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), (unsigned)batch);
-  gemm_tc_kernel<BN, TF32><<<grid, kGemmThreads, C::SMEM, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, TF32, SPLIT><<<grid, kGemmThreads, C::SMEM, stream>>>(tmA, tmB, p);
   DL_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
@@ -348,6 +387,11 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   p.c_bf16 = a->dtype_c == DL_BF16;
   p.act = a->act; p.mul_mode = a->mul_mode; p.alpha = a->alpha;
   p.idesc = 0;
+  if (f32 && a->precise) {
+    if (bn == 64) return launch<64, true, true>(tmA, tmB, p, batch, stream);
+    if (bn == 128) return launch<128, true, true>(tmA, tmB, p, batch, stream);
+    return launch<256, true, true>(tmA, tmB, p, batch, stream);
+  }
   if (f32) {
     if (bn == 64) return launch<64, true>(tmA, tmB, p, batch, stream);
     if (bn == 128) return launch<128, true>(tmA, tmB, p, batch, stream);

@@ -238,6 +238,47 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
   }
 }
 
+template <typename T>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = ldf<T>(x, i);
+    stf<T>(y, i, act == DL_ACT_GELU ? gelu_erf(v) : (act == DL_ACT_RELU ? fmaxf(v, 0.f) : v));
+  }
+}
+
+// F.normalize(x, dim=-1): y = x / max(||x||_2, eps); one warp per row, any cols
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ norm_out,
+                  long long rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float v = ldf<T>(x, r * cols + c); s += v * v; }
+  const float nrm = fmaxf(sqrtf(warp_sum(s)), eps);
+  const float inv = 1.f / nrm;
+  for (int c = lane; c < cols; c += 32) stf<T>(y, r * cols + c, ldf<T>(x, r * cols + c) * inv);
+  if (lane == 0 && norm_out) norm_out[r] = nrm;
+}
+
+// dx = (dy - y * <dy, y>) / ||x||
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float* __restrict__ norm,
+                  T* __restrict__ dx, long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot += ldf<T>(dy, r * cols + c) * ldf<T>(y, r * cols + c);
+  dot = warp_sum(dot);
+  const float inv = 1.f / norm[r];
+  for (int c = lane; c < cols; c += 32)
+    stf<T>(dx, r * cols + c, (ldf<T>(dy, r * cols + c) - ldf<T>(y, r * cols + c) * dot) * inv);
+}
+
 // g = dy * act'(pre) * dropout_mask  (backward of the GEMM epilogue's act + dropout)
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre,
@@ -251,6 +292,32 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
     else if (act == DL_ACT_RELU) v = ldf<T>(pre, i) > 0.f ? v : 0.f;
     if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
     stf<T>(g, i, v);
+  }
+}
+
+// AdamW over one flat fp32 buffer (torch.optim.AdamW semantics: decoupled weight decay, bias
+// correction from the device-side step counter) that also refreshes the bf16 shadow the GEMMs read.
+__global__ void adamw_tick_kernel(long long* step) { *step += 1; }
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                             float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ shadow, long long n,
+                             const long long* __restrict__ step, float lr, float b1, float b2,
+                             float eps, float wd, float grad_scale) {
+  const float t = (float)(*step);
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
   }
 }
 
@@ -423,6 +490,50 @@ extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t s
   return 0;
 }
 
+extern "C" int dl_act_fwd(const void* x, void* y, int64_t n, int32_t act, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && y && act >= 0 && act <= 2, "dl_act_fwd: bad arguments");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(n, 256);
+  if (dtype == DL_BF16)
+    act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, act);
+  else
+    act_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n, act);
+  DL_LAUNCH_CHECK("act_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_l2norm_fwd(const void* x, void* y, float* norm, int64_t rows, int32_t cols,
+                             float eps, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && y && norm && cols > 0, "dl_l2norm_fwd: bad arguments");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(rows, kWarpsPerBlock), th = kWarpsPerBlock * 32;
+  if (dtype == DL_BF16)
+    l2norm_fwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, norm, rows, cols, eps);
+  else
+    l2norm_fwd_kernel<float><<<grid, th, 0, st>>>((const float*)x, (float*)y, norm, rows, cols, eps);
+  DL_LAUNCH_CHECK("l2norm_fwd_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, void* dx,
+                             int64_t rows, int32_t cols, int32_t dtype, void* stream) {
+  DL_REQUIRE(dy && y && norm && dx && cols > 0, "dl_l2norm_bwd: bad arguments");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(rows, kWarpsPerBlock), th = kWarpsPerBlock * 32;
+  if (dtype == DL_BF16)
+    l2norm_bwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, norm, (__nv_bfloat16*)dx, rows, cols);
+  else
+    l2norm_bwd_kernel<float><<<grid, th, 0, st>>>((const float*)dy, (const float*)y, norm, (float*)dx, rows, cols);
+  DL_LAUNCH_CHECK("l2norm_bwd_kernel");
+  count_launch();
+  return 0;
+}
+
 extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
                           uint64_t seed, int32_t dtype, void* stream) {
   DL_REQUIRE(dy && g && (act == DL_ACT_NONE || pre) && p >= 0.f && p < 1.f, "dl_act_bwd: bad arguments");
@@ -435,6 +546,23 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
     act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)pre, (float*)g, n, act, p, seed);
   DL_LAUNCH_CHECK("act_bwd_kernel");
   count_launch();
+  return 0;
+}
+
+extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, float grad_scale,
+                             void* stream) {
+  DL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "dl_adamw_step: null pointer");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  adamw_tick_kernel<<<1, 1, 0, st>>>((long long*)step);
+  DL_LAUNCH_CHECK("adamw_tick_kernel");
+  adamw_kernel<<<ew_grid(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq,
+                                                (__nv_bfloat16*)shadow_bf16, n, (const long long*)step,
+                                                lr, beta1, beta2, eps, weight_decay, grad_scale);
+  DL_LAUNCH_CHECK("adamw_kernel");
+  count_launch(2);
   return 0;
 }
 

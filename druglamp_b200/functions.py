@@ -1,0 +1,648 @@
+"""torch.autograd.Function wrappers: forward AND backward of every op are hand-written sm_100a
+kernels (``kernels.py`` -> C ABI).  PyTorch only does the autograd bookkeeping.
+
+Activations flow in the compute dtype (``kernels.compute_dtype()``: fp32 -> TF32 tensor cores,
+bf16 -> bf16 tensor cores); parameters stay fp32 masters with compute-dtype shadows
+(``params.shadow``); parameter gradients are produced in fp32.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+from . import kernels as K
+from .params import shadow
+
+_seed_counter = itertools.count(0x5EED)
+
+
+def next_seed() -> int:
+    """A fresh dropout seed; masks are regenerated from it in backward."""
+    return (next(_seed_counter) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
+def _back(g: Optional[torch.Tensor], like_dtype: torch.dtype, shape=None):
+    if g is None:
+        return None
+    if g.dtype != like_dtype:
+        g = K.cast(g, like_dtype)
+    return g if shape is None else g.reshape(shape)
+
+
+# ================================================================================ Linear
+def _align() -> int:
+    """TMA needs 16-byte row strides: 8 bf16 or 4 fp32 elements."""
+    return 8 if K.compute_dtype() == torch.bfloat16 else 4
+
+
+def _pad_cols(t: torch.Tensor, n: int) -> torch.Tensor:
+    return t if t.shape[-1] == n else torch.nn.functional.pad(t, (0, n - t.shape[-1]))
+
+
+class LinearFn(Function):
+    """y = dropout(act(x W^T + b)) + residual   (one GEMM, everything else in its epilogue).
+    w is [out, in] (nn.Linear) or, with w_kn=True, [in, out] (GraphConv's layout).  Feature
+    widths that are not a multiple of the TMA alignment (75, 385, 641, 1) are zero-padded."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual, drop_p, seed, w_kn):
+        xs = x.shape
+        Kd = xs[-1]
+        N = w.shape[1] if w_kn else w.shape[0]
+        al = _align()
+        Kp, Np = -(-Kd // al) * al, -(-N // al) * al
+        x2 = _pad_cols(K.to_compute(x).view(-1, Kd), Kp)
+        wc = shadow(w)
+        if Kp != Kd or Np != N:
+            pad = (0, Np - N, 0, Kp - Kd) if w_kn else (0, Kp - Kd, 0, Np - N)
+            wc = torch.nn.functional.pad(wc, pad)
+        bias = None if b is None else _pad_cols(b.detach(), Np)
+        out = torch.empty((x2.shape[0], Np), dtype=x2.dtype, device=x2.device)
+        need_grad = any(ctx.needs_input_grad)
+        pre = torch.empty_like(out) if (act != K.ACT_NONE and need_grad) else None
+        r2 = _pad_cols(K.to_compute(residual).view(-1, N), Np) if residual is not None else None
+        K.mm(x2, wc, out, tb=w_kn, bias=bias, act=act, pre=pre, res=r2, drop=(drop_p, seed))
+        ctx.save_for_backward(x2, wc, pre)
+        ctx.meta = (act, drop_p, seed, xs, x.dtype, None if residual is None else residual.dtype,
+                    b is not None, w_kn, Kd, N)
+        y = out if Np == N else out[:, :N]
+        return y.reshape(*xs[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, wc, pre = ctx.saved_tensors
+        act, drop_p, seed, xs, xdt, rdt, has_b, w_kn, Kd, N = ctx.meta
+        Kp = x2.shape[1]
+        Np = wc.shape[1] if w_kn else wc.shape[0]
+        gy2 = K.to_compute(gy).view(-1, N)
+        g = K.act_bwd(_pad_cols(gy2, Np), pre, act, (drop_p, seed))
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = K.mm(g, wc, tb=not w_kn)
+            dx = _back(dx if Kp == Kd else dx[:, :Kd], xdt, xs)
+        if ctx.needs_input_grad[1]:
+            if w_kn:
+                dw = K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)
+                dw = dw if (Kp == Kd and Np == N) else dw[:Kd, :N]
+            else:
+                dw = K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)
+                dw = dw if (Kp == Kd and Np == N) else dw[:N, :Kd]
+        if has_b and ctx.needs_input_grad[2]:
+            db = K.colsum(g)[:N]
+        if rdt is not None and ctx.needs_input_grad[4]:
+            dres = _back(gy2, rdt, gy.shape)
+        return dx, dw, db, None, dres, None, None, None
+
+
+def linear(x, w, b=None, act=K.ACT_NONE, residual=None, drop_p=0.0, seed=0):
+    return LinearFn.apply(x, w, b, act, residual, drop_p, seed, False)
+
+
+# ================================================================================ FFN
+class FFNFn(Function):
+    """y = dropout(fc2(dropout(gelu(fc1(x))))) + residual  (PMMA Mlp, model/PMMA/mlp.py:44-50,
+    with the block's residual add, model/PMMA/block.py:45-47, fused into fc2's epilogue).
+    Backward fuses gelu' and the first dropout mask into the dX GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, p, seed1, seed2):
+        xs = x.shape
+        x2 = K.to_compute(x).view(-1, xs[-1])
+        w1c, w2c = shadow(w1), shadow(w2)
+        M, Dh = x2.shape[0], w1.shape[0]
+        pre1 = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
+        hd = torch.empty_like(pre1)
+        K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1))
+        r2 = K.to_compute(residual).view(-1, w2.shape[0]) if residual is not None else None
+        y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
+        ctx.save_for_backward(x2, w1, w2, pre1, hd)
+        ctx.meta = (p, seed1, seed2, xs, x.dtype, None if residual is None else residual.dtype)
+        return y.view(*xs[:-1], w2.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, w1, w2, pre1, hd = ctx.saved_tensors
+        p, seed1, seed2, xs, xdt, rdt = ctx.meta
+        gy2 = K.to_compute(gy).view(-1, w2.shape[0])
+        g2 = K.act_bwd(gy2, None, K.ACT_NONE, (p, seed2))
+        dw2 = K.mm(g2, hd, ta=True, tb=True, out_dtype=torch.float32)
+        db2 = K.colsum(g2)
+        dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD, drop=(p, seed1))
+        dw1 = K.mm(dpre1, x2, ta=True, tb=True, out_dtype=torch.float32)
+        db1 = K.colsum(dpre1)
+        dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs) if ctx.needs_input_grad[0] else None
+        dres = _back(gy2, rdt, gy.shape) if rdt is not None else None
+        return dx, dw1, db1, dw2, db2, dres, None, None, None
+
+
+def ffn(x, w1, b1, w2, b2, residual=None, p=0.0):
+    s1, s2 = (next_seed(), next_seed()) if p > 0 else (0, 0)
+    return FFNFn.apply(x, w1, b1, w2, b2, residual, p, s1, s2)
+
+
+# ================================================================================ LayerNorm
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xc = K.to_compute(x)
+        y, mean, rstd = K.layernorm_fwd(xc, gamma.detach(), beta.detach(), eps)
+        ctx.save_for_backward(xc, gamma, mean, rstd)
+        ctx.xdt = x.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xc, gamma, mean, rstd = ctx.saved_tensors
+        dx, dg, db = K.layernorm_bwd(K.to_compute(gy), xc, gamma.detach(), mean, rstd)
+        return _back(dx, ctx.xdt), dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+# ================================================================================ attention core
+def _attn_fwd(q, k, v, H, scale, keep_raw):
+    """q (S2,B,Lq,HD) contiguous; k, v (B,Lk,HD) with unit inner stride (row stride free).
+    Returns O (B,Lq,S2*HD), P (B,H,S2,Lq,Lk) and raw scaled logits (or None)."""
+    S2, B, Lq, HD = q.shape
+    Lk = k.shape[1]
+    d = HD // H
+    S = torch.empty((B, H, S2, Lq, Lk), dtype=q.dtype, device=q.device)
+    s_lay = (S2 * Lq * Lk, Lq * Lk, H * S2 * Lq * Lk)
+    L.gemm(q, k, S, M=Lq, N=Lk, K=d, lda=HD, ldb=k.stride(1), ldc=Lk, batch=(H, S2, B),
+           sa=(d, q.stride(0) if S2 > 1 else 0, q.stride(1)), sb=(d, 0, k.stride(0)), sc=s_lay,
+           alpha=scale)
+    raw = None
+    if keep_raw:
+        raw = S
+        P = K.softmax_fwd(S, out=torch.empty_like(S))
+    else:
+        P = K.softmax_fwd(S)
+    O = torch.empty((B, Lq, S2 * HD), dtype=q.dtype, device=q.device)
+    L.gemm(P, v, O, M=Lq, N=d, K=Lk, lda=Lk, ldb=v.stride(1), ldc=S2 * HD, trans_b=True,
+           batch=(H, S2, B), sa=s_lay, sb=(d, 0, v.stride(0)), sc=(d, HD, Lq * S2 * HD))
+    return O, P, raw
+
+
+def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None):
+    """Gradients of _attn_fwd.  d*_out may be preallocated (strided) destinations."""
+    S2, B, Lq, HD = q.shape
+    Lk = k.shape[1]
+    d = HD // H
+    s_lay = (S2 * Lq * Lk, Lq * Lk, H * S2 * Lq * Lk)
+    dV = dv_out if dv_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+    dK = dk_out if dk_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+    dQ = dq_out if dq_out is not None else torch.empty_like(q)
+    # dV = sum_set P_set^T dO_set
+    for s in range(S2):
+        Ps, dOs = P[:, :, s], dO[:, :, s * HD:(s + 1) * HD]
+        L.gemm(Ps, dOs, dV, M=Lk, N=d, K=Lq, lda=Lk, ldb=S2 * HD, ldc=dV.stride(1), trans_a=True,
+               trans_b=True, batch=(H, B), sa=(s_lay[0], s_lay[2]), sb=(d, Lq * S2 * HD),
+               sc=(d, dV.stride(0)), residual=dV if s > 0 else None)
+    # dP = dO V^T, then dS = scale * P * (dP - rowsum(P dP)) in place
+    dP = torch.empty_like(P)
+    L.gemm(dO, v, dP, M=Lq, N=Lk, K=d, lda=S2 * HD, ldb=v.stride(1), ldc=Lk, batch=(H, S2, B),
+           sa=(d, HD, Lq * S2 * HD), sb=(d, 0, v.stride(0)), sc=s_lay)
+    dS = K.softmax_bwd(P, dP, scale)
+    # dQ = dS K
+    L.gemm(dS, k, dQ, M=Lq, N=d, K=Lk, lda=Lk, ldb=k.stride(1), ldc=dQ.stride(2), trans_b=True,
+           batch=(H, S2, B), sa=s_lay, sb=(d, 0, k.stride(0)),
+           sc=(d, dQ.stride(0) if S2 > 1 else 0, dQ.stride(1)))
+    # dK = sum_set dS_set^T Q_set
+    for s in range(S2):
+        dSs, qs = dS[:, :, s], q[s]
+        L.gemm(dSs, qs, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=HD, ldc=dK.stride(1), trans_a=True,
+               trans_b=True, batch=(H, B), sa=(s_lay[0], s_lay[2]), sb=(d, qs.stride(0)),
+               sc=(d, dK.stride(0)), residual=dK if s > 0 else None)
+    return dQ, dK, dV
+
+
+class AttentionFn(Function):
+    """softmax(q k^T * scale) v for `S2` stacked query sets sharing one K/V (the PMMA paired
+    attention, model/PMMA/attention.py:44-88, and plain MHSA :109-122 with S2 = 1).
+    q (S2,B,L,H*d) -> O (B,L,S2*H*d): set s fills columns [s*H*d, (s+1)*H*d)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H, scale):
+        qc, kc, vc = K.to_compute(q), K.to_compute(k), K.to_compute(v)
+        O, P, _ = _attn_fwd(qc, kc, vc, H, scale, False)
+        ctx.save_for_backward(qc, kc, vc, P)
+        ctx.meta = (H, scale, q.dtype, k.dtype, v.dtype)
+        return O
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gO):
+        qc, kc, vc, P = ctx.saved_tensors
+        H, scale, qdt, kdt, vdt = ctx.meta
+        dQ, dK, dV = _attn_bwd(K.to_compute(gO), qc, kc, vc, P, H, scale)
+        return _back(dQ, qdt), _back(dK, kdt), _back(dV, vdt), None, None
+
+
+def attention(q, k, v, H, scale):
+    return AttentionFn.apply(q, k, v, H, scale)
+
+
+class PairedQFn(Function):
+    """Q[0] = x0 W0^T + b0, Q[1] = x1 W1^T + b1 written into one (2,B,L,D) buffer so the paired
+    attention can address both query sets with a batch stride (no torch.stack copy)."""
+
+    @staticmethod
+    def forward(ctx, x0, w0, b0, x1, w1, b1):
+        a0, a1 = K.to_compute(x0), K.to_compute(x1)
+        Bn, Lr, D = a0.shape
+        N = w0.shape[0]
+        Q = torch.empty((2, Bn, Lr, N), dtype=a0.dtype, device=a0.device)
+        K.mm(a0.view(-1, D), shadow(w0), Q[0].view(-1, N), bias=b0)
+        K.mm(a1.view(-1, D), shadow(w1), Q[1].view(-1, N), bias=b1)
+        ctx.save_for_backward(a0, w0, a1, w1)
+        ctx.dts = (x0.dtype, x1.dtype)
+        return Q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gQ):
+        a0, w0, a1, w1 = ctx.saved_tensors
+        g = K.to_compute(gQ)
+        N, D = w0.shape
+        g0, g1 = g[0].view(-1, N), g[1].view(-1, N)
+        dx0 = _back(K.mm(g0, shadow(w0), tb=True), ctx.dts[0], a0.shape)
+        dx1 = _back(K.mm(g1, shadow(w1), tb=True), ctx.dts[1], a1.shape)
+        dw0 = K.mm(g0, a0.view(-1, D), ta=True, tb=True, out_dtype=torch.float32)
+        dw1 = K.mm(g1, a1.view(-1, D), ta=True, tb=True, out_dtype=torch.float32)
+        return dx0, dw0, K.colsum(g0), dx1, dw1, K.colsum(g1)
+
+
+class FcCatFn(Function):
+    """y = cat(A_first, A_second) W^T + b where the input holds the two halves as columns
+    [0,D) and [D,2D).  swap=True means the buffer holds (A_second, A_first): the weight's column
+    halves are addressed crosswise instead of copying (model/PMMA/attention.py:81)."""
+
+    @staticmethod
+    def forward(ctx, o, w, b, swap):
+        oc = K.to_compute(o)
+        D2 = oc.shape[-1]
+        D = D2 // 2
+        o2 = oc.view(-1, D2)
+        wc = shadow(w)
+        N = w.shape[0]
+        if not swap:
+            y = K.mm(o2, wc, bias=b)
+        else:
+            y = K.mm(o2[:, :D], wc[:, D:], bias=b)
+            K.mm(o2[:, D:], wc[:, :D], y, res=y)
+        ctx.save_for_backward(o2, w)
+        ctx.meta = (swap, o.dtype, o.shape)
+        return y.view(*o.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        o2, w = ctx.saved_tensors
+        swap, odt, oshape = ctx.meta
+        N, D2 = w.shape
+        D = D2 // 2
+        g = K.to_compute(gy).view(-1, N)
+        wc = shadow(w)
+        if not swap:
+            do = K.mm(g, wc, tb=True)
+            dw = K.mm(g, o2, ta=True, tb=True, out_dtype=torch.float32)
+        else:
+            do = torch.empty_like(o2)
+            K.mm(g, wc[:, D:], do[:, :D], tb=True)
+            K.mm(g, wc[:, :D], do[:, D:], tb=True)
+            dw = torch.empty((N, D2), dtype=torch.float32, device=g.device)
+            K.mm(g, o2[:, :D], dw[:, D:], ta=True, tb=True)
+            K.mm(g, o2[:, D:], dw[:, :D], ta=True, tb=True)
+        return _back(do, odt, oshape), dw, K.colsum(g), None
+
+
+# ================================================================================ PGCA
+class PGCAFn(Function):
+    """GuidedCrossAttention forward/backward (model/PGCA/guided_cross_attention_model.py:124-329,
+    the enc-dec in-proj branch :138-162): in-proj GEMMs, scaled q k^T with the RAW logits kept
+    (:307,:319-320), softmax, p v, out-proj.  Inputs are sequence-first (L,N,E) like the
+    reference; the torch.equal host sync of :138 does not exist here."""
+
+    @staticmethod
+    def forward(ctx, query, key, value, in_w, in_b, out_w, out_b, H):
+        Lq, Bn, E = query.shape
+        Sk = key.shape[0]
+        shared = (key.data_ptr() == value.data_ptr() and key.stride() == value.stride()
+                  and key.shape == value.shape)
+        qb = K.to_compute(query.transpose(0, 1))                      # (B, L, E)
+        kb = K.to_compute(key.transpose(0, 1))                        # (B, S, E)
+        vb = kb if shared else K.to_compute(value.transpose(0, 1))
+        wi = shadow(in_w)
+        ib = in_b.detach()
+        Qp = K.mm(qb.view(-1, E), wi[:E], bias=ib[:E]).view(1, Bn, Lq, E)
+        KV = torch.empty((Bn, Sk, 2 * E), dtype=qb.dtype, device=qb.device)
+        if shared:
+            K.mm(kb.view(-1, E), wi[E:], KV.view(-1, 2 * E), bias=ib[E:])
+        else:
+            K.mm(kb.view(-1, E), wi[E:2 * E], KV.view(-1, 2 * E)[:, :E], bias=ib[E:2 * E])
+            K.mm(vb.view(-1, E), wi[2 * E:], KV.view(-1, 2 * E)[:, E:], bias=ib[2 * E:])
+        Kp, Vp = KV[:, :, :E], KV[:, :, E:]
+        scale = float(E // H) ** -0.5
+        O, P, raw = _attn_fwd(Qp, Kp, Vp, H, scale, True)
+        out = K.mm(O.view(-1, E), shadow(out_w), bias=out_b.detach()).view(Bn, Lq, E)
+        ctx.save_for_backward(qb, kb, vb, in_w, out_w, Qp, KV, P, O)
+        ctx.meta = (H, scale, shared, query.dtype, key.dtype, value.dtype)
+        raw = raw.view(Bn, H, Lq, Sk)
+        ctx.mark_non_differentiable(raw)
+        return out.transpose(0, 1), raw
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, _graw):
+        qb, kb, vb, in_w, out_w, Qp, KV, P, O = ctx.saved_tensors
+        H, scale, shared, qdt, kdt, vdt = ctx.meta
+        Bn, Lq, E = qb.shape
+        Sk = kb.shape[1]
+        g = K.to_compute(gout.transpose(0, 1)).view(-1, E)             # (B*L, E)
+        d_out_w = K.mm(g, O.view(-1, E), ta=True, tb=True, out_dtype=torch.float32)
+        d_out_b = K.colsum(g)
+        dO = K.mm(g, shadow(out_w), tb=True).view(Bn, Lq, E)
+        dKV = torch.empty_like(KV)
+        dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, H, scale,
+                              dk_out=dKV[:, :, :E], dv_out=dKV[:, :, E:])
+        wi = shadow(in_w)
+        dq2, dkv2 = dQp.view(-1, E), dKV.view(-1, 2 * E)
+        d_in_w = torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
+        d_in_b = torch.empty(3 * E, dtype=torch.float32, device=g.device)
+        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True)
+        K.colsum(dq2, d_in_b[:E])
+        K.colsum(dkv2, d_in_b[E:])
+        dquery = _back(K.mm(dq2, wi[:E], tb=True).view(Bn, Lq, E), qdt).transpose(0, 1)
+        if shared:
+            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True)
+            dkey = _back(K.mm(dkv2, wi[E:], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
+            dvalue = None
+        else:
+            K.mm(dkv2[:, :E], kb.view(-1, E), d_in_w[E:2 * E], ta=True, tb=True)
+            K.mm(dkv2[:, E:], vb.view(-1, E), d_in_w[2 * E:], ta=True, tb=True)
+            dkey = _back(K.mm(dkv2[:, :E], wi[E:2 * E], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
+            dvalue = _back(K.mm(dkv2[:, E:], wi[2 * E:], tb=True).view(Bn, Sk, E), vdt).transpose(0, 1)
+        return dquery, dkey, dvalue, d_in_w, d_in_b, d_out_w, d_out_b, None
+
+
+# ================================================================================ MHLA
+class MHLAFn(Function):
+    """MultiHeadLinearAttention (model/PMMA/encoder.py:127-140): logits = lin2(gelu(lin1(v))),
+    softmax over the sequence, gating through the reinterpreting view.  With gamma/beta the
+    residual add and LayerNorm of model/DrugLAMP.py:63-71 are fused in: y = LN(v + gate(v))."""
+
+    @staticmethod
+    def forward(ctx, v, w1, b1, w2, b2, gamma, beta, eps):
+        vc = K.to_compute(v)
+        Bn, Lr, E = vc.shape
+        v2 = vc.view(-1, E)
+        D, Hh = w1.shape[0], w2.shape[0]
+        pre1 = torch.empty((v2.shape[0], D), dtype=vc.dtype, device=vc.device)
+        h = torch.empty_like(pre1)
+        K.mm(v2, shadow(w1), h, bias=b1, act=K.ACT_GELU, pre=pre1)
+        logits = K.mm(h, shadow(w2), bias=b2).view(Bn, Lr, Hh)
+        g_ = None if gamma is None else gamma.detach()
+        b_ = None if beta is None else beta.detach()
+        y, p, mean, rstd = K.mhla_gate_ln_fwd(vc, logits, g_, b_, eps)
+        ctx.save_for_backward(vc, w1, w2, pre1, h, p, mean, rstd, gamma)
+        ctx.vdt = v.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        vc, w1, w2, pre1, h, p, mean, rstd, gamma = ctx.saved_tensors
+        Bn, Lr, E = vc.shape
+        Hh = w2.shape[0]
+        g_ = None if gamma is None else gamma.detach()
+        dv_direct, dlogits, dg, db = K.mhla_gate_ln_bwd(K.to_compute(gy), vc, p, mean, rstd, g_)
+        dl2 = dlogits.view(-1, Hh)
+        dw2 = K.mm(dl2, h, ta=True, tb=True, out_dtype=torch.float32)
+        db2 = K.colsum(dl2)
+        dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD)
+        dw1 = K.mm(dpre1, vc.view(-1, E), ta=True, tb=True, out_dtype=torch.float32)
+        db1 = K.colsum(dpre1)
+        dv = K.mm(dpre1, shadow(w1), tb=True, res=dv_direct.view(-1, E)).view(Bn, Lr, E)
+        return _back(dv, ctx.vdt), dw1, db1, dw2, db2, dg, db, None
+
+
+# ================================================================================ GCN pieces
+class SpmmFn(Function):
+    """Degree-normalised neighbourhood sum of GraphConv (model/basic_model.py:596-630)."""
+
+    @staticmethod
+    def forward(ctx, h, graph):
+        hc = K.to_compute(h)
+        ctx.graph = graph
+        ctx.hdt = h.dtype
+        return K.spmm_norm(graph.indptr, graph.indices, graph.norm_src, graph.norm_dst, hc)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        g = ctx.graph
+        dh = K.spmm_norm(g.indptr_t, g.indices_t, g.norm_dst, g.norm_src, K.to_compute(gy))
+        return _back(dh, ctx.hdt), None
+
+
+class BatchNormFn(Function):
+    """nn.BatchNorm1d over (rows, C) with the module's buffers updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training):
+        xc = K.to_compute(x)
+        x2 = xc.view(-1, xc.shape[-1])
+        g_ = None if gamma is None else gamma.detach()
+        b_ = None if beta is None else beta.detach()
+        y, mean, rstd = K.batchnorm_fwd(x2, g_, b_, running_mean, running_var, nbt, eps, momentum, training)
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.meta = (training, x.dtype, x.shape)
+        return y.view(xc.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        training, xdt, xshape = ctx.meta
+        g_ = None if gamma is None else gamma.detach()
+        dx, dg, db = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
+                                     need_param_grads=gamma is not None)
+        return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None
+
+
+def batch_norm(x, bn: torch.nn.BatchNorm1d):
+    """Apply an nn.BatchNorm1d module's parameters/buffers with the dl_batchnorm kernels."""
+    training = bn.training or bn.running_mean is None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked if training else None, bn.eps, momentum, training)
+
+
+# ================================================================================ glue
+class SitePoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, S):
+        xc = K.to_compute(x)
+        ctx.meta = (S, x.dtype)
+        return K.site_pool_fwd(xc, S)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        S, xdt = ctx.meta
+        return _back(K.site_pool_bwd(K.to_compute(gy), S), xdt), None
+
+
+class AddPEFn(Function):
+    """dropout(x + pe) (model/PMMA/embed.py:51-52)."""
+
+    @staticmethod
+    def forward(ctx, x, pe, p, seed):
+        xc = K.to_compute(x)
+        ctx.meta = (p, seed, x.dtype, pe.shape)
+        return K.add_pe(xc, pe.detach().contiguous(), p, seed)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        p, seed, xdt, pshape = ctx.meta
+        g = K.act_bwd(K.to_compute(gy), None, K.ACT_NONE, (p, seed))
+        n = 1
+        for s in pshape:
+            n *= s
+        dpe = K.colsum(g.view(-1, n)).view(pshape)
+        return _back(g, xdt), dpe, None, None
+
+
+class ActFn(Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        xc = K.to_compute(x)
+        ctx.save_for_backward(xc)
+        ctx.meta = (act, x.dtype)
+        return K.act_fwd(xc, act)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        act, xdt = ctx.meta
+        return _back(K.act_bwd(K.to_compute(gy), xc, act), xdt), None
+
+
+class L2NormFn(Function):
+    """l2norm = F.normalize(t, dim=-1) (utils.py:443-444)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = K.to_compute(x)
+        y, norm = K.l2norm_fwd(xc)
+        ctx.save_for_backward(y, norm)
+        ctx.xdt = x.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        y, norm = ctx.saved_tensors
+        return _back(K.l2norm_bwd(K.to_compute(gy), y, norm), ctx.xdt)
+
+
+class CMTripletFn(Function):
+    @staticmethod
+    def forward(ctx, cos, G, margin):
+        c32 = K.cast(cos.contiguous(), torch.float32)
+        loss, acc = K.cm_triplet_fwd(c32, G, margin)
+        ctx.save_for_backward(c32, G, acc)
+        ctx.meta = (margin, cos.dtype)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        c32, G, acc = ctx.saved_tensors
+        margin, cdt = ctx.meta
+        dcos = K.cm_triplet_bwd(c32, G, margin, acc, gl.contiguous().float())
+        return _back(dcos, cdt), None, None
+
+
+class BCEFn(Function):
+    @staticmethod
+    def forward(ctx, score, y):
+        s32 = K.cast(score.contiguous(), torch.float32).view(-1)
+        y32 = y.to(torch.float32).contiguous()
+        prob, loss = K.bce_fwd(s32, y32)
+        ctx.save_for_backward(prob, y32)
+        ctx.meta = (score.dtype, score.shape)
+        ctx.mark_non_differentiable(prob)
+        return prob, loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _gp, gl):
+        prob, y32 = ctx.saved_tensors
+        sdt, sshape = ctx.meta
+        ds = K.bce_bwd(prob, y32, gl.contiguous().float())
+        return _back(ds, sdt, sshape), None
+
+
+class CrossEntropyFn(Function):
+    """F.cross_entropy(logits (..., C), labels (...), ignore_index) with mean reduction."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        C = logits.shape[-1]
+        x = K.to_compute(logits).view(-1, C)
+        lab = labels.reshape(-1).to(torch.int64).contiguous()
+        loss, acc = K.cross_entropy_fwd(x, lab, C, ignore_index)
+        ctx.save_for_backward(x, lab, acc)
+        ctx.meta = (C, ignore_index, logits.dtype, logits.shape)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gl):
+        x, lab, acc = ctx.saved_tensors
+        C, ignore_index, ldt, lshape = ctx.meta
+        dx, _ = K.cross_entropy_bwd(x, lab, C, acc, gl.contiguous().float(), ignore_index)
+        return _back(dx, ldt, lshape), None, None
+
+
+class MatmulNTFn(Function):
+    """C = A B^T for row-major A (M,K), B (N,K) -- the CrossModality similarity matrix."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        M, N = a.shape[0], b.shape[0]
+        al = _align()
+        Mp, Np = -(-M // al) * al, -(-N // al) * al
+        pad = torch.nn.functional.pad
+        ac, bc = K.to_compute(a), K.to_compute(b)
+        if Mp != M:
+            ac = pad(ac, (0, 0, 0, Mp - M))
+        if Np != N:
+            bc = pad(bc, (0, 0, 0, Np - N))
+        ctx.save_for_backward(ac, bc)
+        ctx.meta = (a.dtype, b.dtype, M, N)
+        return K.mm(ac, bc, out_dtype=torch.float32)[:M, :N].contiguous()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gc):
+        ac, bc = ctx.saved_tensors
+        adt, bdt, M, N = ctx.meta
+        Mp, Np = ac.shape[0], bc.shape[0]
+        g = K.cast(torch.nn.functional.pad(gc, (0, Np - N, 0, Mp - M)).contiguous(), ac.dtype)
+        da = K.mm(g, bc, tb=True)[:M]           # (M,N) @ (N,K)
+        db = K.mm(g, ac, ta=True, tb=True)[:N]  # (N,M) @ (M,K)
+        return _back(da, adt), _back(db, bdt)

@@ -54,6 +54,8 @@ class BatchedMolGraph:
         self.out_deg = out_counts
         self.norm_dst = in_counts.clamp(min=1).to(torch.float32).pow(-0.5)
         self.norm_src = out_counts.clamp(min=1).to(torch.float32).pow(-0.5)
+        # evaluated once here so that GraphConv's guard costs no host sync per layer
+        self._zero_in = bool((in_counts == 0).any()) if self._n else False
 
     # ---- DGLGraph duck-typing -------------------------------------------------
     def num_nodes(self) -> int:
@@ -84,6 +86,7 @@ class BatchedMolGraph:
     def to(self, device, **kw) -> "BatchedMolGraph":
         g = object.__new__(BatchedMolGraph)
         g._n, g.batch_size = self._n, self.batch_size
+        g._zero_in = self._zero_in
         for k in ("src", "dst", "indptr", "indices", "indptr_t", "indices_t",
                   "in_deg", "out_deg", "norm_dst", "norm_src"):
             setattr(g, k, getattr(self, k).to(device, **kw))
@@ -102,6 +105,6 @@ class BatchedMolGraph:
 
     def check_no_zero_in_degree(self) -> None:
         """Mirror of the DGLError raised at ``basic_model.py:580-590``."""
-        if bool((self.in_deg == 0).any()):
+        if self._zero_in:
             raise Exception("There are 0-in-degree nodes in the graph, output for those nodes "
                             "will be invalid. Adding self-loop on the input graph will resolve the issue.")

@@ -97,6 +97,27 @@ def act_bwd(dy: torch.Tensor, pre: Optional[torch.Tensor], act: int, drop=(0.0, 
     return g
 
 
+def act_fwd(x: torch.Tensor, act: int) -> torch.Tensor:
+    y = torch.empty_like(x)
+    L.call("dl_act_fwd", x.data_ptr(), y.data_ptr(), x.numel(), act, L.dt(x))
+    return y
+
+
+def l2norm_fwd(x: torch.Tensor, eps: float = 1e-12):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    norm = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.call("dl_l2norm_fwd", x.data_ptr(), y.data_ptr(), norm.data_ptr(), rows, cols, eps, L.dt(x))
+    return y, norm
+
+
+def l2norm_bwd(dy, y, norm):
+    rows, cols = y.numel() // y.shape[-1], y.shape[-1]
+    dx = torch.empty_like(y)
+    L.call("dl_l2norm_bwd", dy.data_ptr(), y.data_ptr(), norm.data_ptr(), dx.data_ptr(), rows, cols, L.dt(y))
+    return dx
+
+
 def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     if p == 0.0:
         return x
@@ -224,14 +245,17 @@ def site_pool_bwd(dy: torch.Tensor, S: int) -> torch.Tensor:
 
 
 def mhla_gate_ln_fwd(v: torch.Tensor, logits: torch.Tensor, gamma, beta, eps: float):
+    """gamma=None -> gating only (no residual / LayerNorm)."""
     B, Lr, E = v.shape
     H = logits.shape[-1]
     y = torch.empty_like(v)
     p = torch.empty((B, H, Lr), dtype=torch.float32, device=v.device)
-    mean = torch.empty(B * Lr, dtype=torch.float32, device=v.device)
-    rstd = torch.empty_like(mean)
-    L.call("dl_mhla_gate_ln_fwd", v.data_ptr(), logits.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-           y.data_ptr(), p.data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, Lr, E, H, eps, L.dt(v))
+    mean = rstd = None
+    if gamma is not None:
+        mean = torch.empty(B * Lr, dtype=torch.float32, device=v.device)
+        rstd = torch.empty_like(mean)
+    L.call("dl_mhla_gate_ln_fwd", v.data_ptr(), logits.data_ptr(), L.ptr(gamma), L.ptr(beta),
+           y.data_ptr(), p.data_ptr(), L.ptr(mean), L.ptr(rstd), B, Lr, E, H, eps, L.dt(v))
     return y, p, mean, rstd
 
 
@@ -240,11 +264,13 @@ def mhla_gate_ln_bwd(dy, v, p, mean, rstd, gamma):
     H = p.shape[1]
     dv = torch.empty_like(v)
     dlogits = torch.empty((B, Lr, H), dtype=v.dtype, device=v.device)
-    dg = torch.empty(E, dtype=torch.float32, device=v.device)
-    db = torch.empty_like(dg)
-    L.call("dl_mhla_gate_ln_bwd", dy.data_ptr(), v.data_ptr(), p.data_ptr(), mean.data_ptr(),
-           rstd.data_ptr(), gamma.data_ptr(), dv.data_ptr(), dlogits.data_ptr(), dg.data_ptr(),
-           db.data_ptr(), B, Lr, E, H, L.dt(v))
+    dg = db = None
+    if gamma is not None:
+        dg = torch.empty(E, dtype=torch.float32, device=v.device)
+        db = torch.empty_like(dg)
+    L.call("dl_mhla_gate_ln_bwd", dy.data_ptr(), v.data_ptr(), p.data_ptr(), L.ptr(mean),
+           L.ptr(rstd), L.ptr(gamma), dv.data_ptr(), dlogits.data_ptr(), L.ptr(dg),
+           L.ptr(db), B, Lr, E, H, L.dt(v))
     return dv, dlogits, dg, db
 
 
@@ -262,6 +288,25 @@ def cm_triplet_bwd(cos, G, margin: float, acc, gout):
     L.call("dl_cm_triplet_bwd", cos.data_ptr(), G.data_ptr(), P, D, margin, acc.data_ptr(),
            gout.data_ptr(), dcos.data_ptr())
     return dcos
+
+
+def cross_entropy_fwd(x: torch.Tensor, labels: torch.Tensor, C: int, ignore_index: int = 0,
+                      extra=None, wextra=None):
+    """x: 2-D (rows, >=C) view; labels int64 (rows,).  Returns (mean loss, acc workspace)."""
+    acc = torch.empty(2, dtype=torch.float64, device=x.device)
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    L.call("dl_cross_entropy_fwd", x.data_ptr(), labels.data_ptr(), L.ptr(extra), L.ptr(wextra),
+           x.shape[0], C, _ld(x), ignore_index, acc.data_ptr(), loss.data_ptr(), L.dt(x))
+    return loss, acc
+
+
+def cross_entropy_bwd(x, labels, C, acc, gout, ignore_index: int = 0, extra=None, wextra=None):
+    dx = torch.zeros_like(x) if x.shape[1] != C else torch.empty_like(x)
+    dextra = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if extra is not None else None
+    L.call("dl_cross_entropy_bwd", x.data_ptr(), labels.data_ptr(), L.ptr(extra), L.ptr(wextra),
+           x.shape[0], C, _ld(x), ignore_index, acc.data_ptr(), gout.data_ptr(), dx.data_ptr(),
+           L.ptr(dextra), L.dt(x))
+    return dx, dextra
 
 
 def bce_fwd(score: torch.Tensor, y: torch.Tensor):

@@ -1,0 +1,133 @@
+"""Compute-dtype shadows of the fp32 master parameters.
+
+The reference keeps fp32 ``nn.Parameter``s (state_dict contract).  In bf16 mode
+the tensor-core GEMMs read bf16 copies.  Two mechanisms keep them fresh:
+
+* per-parameter cache keyed on ``(id, _version, data_ptr)`` -- works for any module used stand-alone;
+* :class:`FlatParams` -- re-homes every parameter of a model as a view of ONE flat fp32 buffer
+  (and its ``.grad`` as a view of one flat gradient buffer), so a single ``dl_cast`` launch
+  refreshes all shadows and a single NCCL all-reduce covers all gradients.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import kernels as K
+
+_CACHE: Dict[int, list] = {}
+_FLAT: Dict[int, "FlatParams"] = {}
+
+
+def shadow(p: torch.Tensor) -> torch.Tensor:
+    """`p` (fp32 parameter or a plain tensor) as a contiguous tensor in the compute dtype."""
+    cd = K.compute_dtype()
+    if p.dtype == cd:
+        return p.detach()
+    fp = _FLAT.get(id(p))
+    if fp is not None:
+        return fp.shadow_of(p)
+    if not isinstance(p, torch.nn.Parameter):      # temporaries (slices of parameters): no caching
+        return K.cast(p.detach().contiguous(), cd)
+    e = _CACHE.get(id(p))
+    if e is not None and e[0] == p._version and e[1] == p.data_ptr() and e[2].dtype == cd:
+        return e[2]
+    t = e[2] if (e is not None and e[2].dtype == cd and e[2].shape == p.shape) else \
+        torch.empty(p.shape, dtype=cd, device=p.device)
+    K.cast(p.detach(), cd, out=t)
+    _CACHE[id(p)] = [p._version, p.data_ptr(), t]
+    return t
+
+
+class FlatParams:
+    """All parameters of `module` as views of one flat fp32 buffer (+ flat grads, + bf16 shadow)."""
+
+    ALIGN = 64  # elements; keeps every view 256-byte aligned (TMA needs 16 B)
+
+    def __init__(self, module: torch.nn.Module):
+        params: List[torch.nn.Parameter] = []
+        seen = set()
+        for p in module.parameters():
+            if id(p) not in seen and p.dtype == torch.float32:
+                seen.add(id(p))
+                params.append(p)
+        if not params:
+            raise ValueError("module has no fp32 parameters")
+        dev = params[0].device
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.shadow16: Optional[torch.Tensor] = None
+        self._synced = -1
+        self._views16: Dict[int, torch.Tensor] = {}
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                _FLAT[id(p)] = self
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):          # re-attach if something reset .grad
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def sync(self, force: bool = False) -> None:
+        """Refresh the bf16 shadow with one kernel if any parameter changed since the last sync."""
+        if K.compute_dtype() != torch.bfloat16:
+            return
+        if self.shadow16 is None:
+            self.shadow16 = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
+            for p, o in zip(self.params, self.offsets):
+                self._views16[id(p)] = self.shadow16[o:o + p.numel()].view(p.shape)
+            force = True
+        # `p.data = view` keeps each parameter's own version counter, so sum them (in-place
+        # optimizer / load_state_dict updates bump them; raw-pointer updates by dl_* kernels
+        # that also write the shadow do not need a refresh)
+        ver = self.flat._version + sum(p._version for p in self.params)
+        if force or ver != self._synced:
+            K.cast(self.flat, torch.bfloat16, out=self.shadow16)
+            self._synced = ver
+
+    def mark_synced(self) -> None:
+        self._synced = self.flat._version + sum(p._version for p in self.params)
+
+    def shadow_of(self, p: torch.Tensor) -> torch.Tensor:
+        if K.compute_dtype() == torch.float32:
+            return p.detach()
+        self.sync()
+        return self._views16[id(p)]
+
+
+class FlatAdamW:
+    """AdamW (torch.optim.AdamW semantics) over a :class:`FlatParams` store: one kernel updates all
+    parameters, their Adam moments and the bf16 shadow.  CUDA-graph capturable (the step counter
+    lives on the device)."""
+
+    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=flat.flat.device)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.flat.zero_grad()
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        from . import _lib as L
+        f = self.flat
+        f.sync()
+        sh = f.shadow16.data_ptr() if (f.shadow16 is not None and K.compute_dtype() == torch.bfloat16) else None
+        L.call("dl_adamw_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+               self.exp_avg_sq.data_ptr(), sh, f.numel, self.step_count.data_ptr(), self.lr,
+               self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale)
+        f.mark_synced()       # raw-pointer update: versions unchanged, shadow already fresh

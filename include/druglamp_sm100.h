@@ -56,7 +56,9 @@ int64_t dl_launch_count(void);
  *   1/(1-drop_p) (same mask as dl_dropout on a contiguous [batch*M, N] tensor).
  *   residual has its own layout (ldr, sr[]; ldr = 0 means "same as C"); a batch stride
  *   of 0 with ldr != 0 broadcasts it (positional embeddings).
- *   dtype_ab: DL_BF16 (kind::f16) or DL_F32 (kind::tf32); fp32 accumulation always.
+ *   dtype_ab: DL_BF16 (kind::f16) or DL_F32 (kind::tf32); fp32 accumulation always.  With
+ *   precise = 1 fp32 operands are split in shared memory into hi + lo tf32 parts and three MMAs
+ *   per K step recover fp32-grade accuracy (what the fp32 parity mode uses).
  *   dtype_c applies to C, preact_out, mul_aux and residual (all share C's layout: ldc, sc[]).
  *   bias is fp32.  lda/ldb/ldc and batch strides are in ELEMENTS; every row stride and batch
  *   stride of A and B must be a multiple of 16 bytes and the base pointers 16-byte aligned
@@ -88,7 +90,8 @@ typedef struct dl_gemm_args {
   int32_t dtype_ab, dtype_c;
   int32_t trans_a, trans_b;
   int32_t act, mul_mode;
-  int32_t tile_n; /* 0 = auto, else 64 / 128 / 256 */
+  int32_t tile_n;  /* 0 = auto, else 64 / 128 / 256 */
+  int32_t precise; /* DL_F32 operands only: 1 = 3xTF32 split (fp32-grade products), 0 = plain TF32 */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
@@ -126,9 +129,23 @@ int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld,
  * model/PMMA/embed.py:42,52; the mask is recomputed from the seed in backward). */
 int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int32_t dtype,
                void* stream);
+/* y = act(x) elementwise (the ReLU inside Mean2Embed, model/cross_modality.py:166-171). */
+int dl_act_fwd(const void* x, void* y, int64_t n, int32_t act, int32_t dtype, void* stream);
+/* F.normalize(x, dim=-1) = l2norm (utils.py:443-444): y = x / max(||x||, eps); norm: [rows] fp32. */
+int dl_l2norm_fwd(const void* x, void* y, float* norm, int64_t rows, int32_t cols, float eps,
+                  int32_t dtype, void* stream);
+int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, void* dx, int64_t rows,
+                  int32_t cols, int32_t dtype, void* stream);
 /* g = dy * act'(pre) * dropout_mask(seed): backward of the dl_gemm epilogue's act + dropout. */
 int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
                uint64_t seed, int32_t dtype, void* stream);
+/* One AdamW step over a flat fp32 parameter buffer (torch.optim.AdamW semantics; the reference
+ * builds AdamW in main.py:158-160).  grad is multiplied by grad_scale first (1/world_size after a
+ * sum all-reduce); *step (device int64) is incremented; shadow_bf16 (optional) receives the
+ * updated parameters in bf16 for the tensor-core GEMMs. */
+int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, void* stream);
 int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
 /* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
 int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
@@ -178,7 +195,9 @@ int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L, 
 /* y = LayerNorm(v + gate(v)), gate = MultiHeadLinearAttention's softmax-over-sequence gating
  * through its .view(B*H, L, E/H) reinterpretation (model/PMMA/encoder.py:132-140) applied to
  * logits = lin2(act(lin1(v))) of shape (B, L, H); residual and LayerNorm from
- * model/DrugLAMP.py:63-71.  p_out (B,H,L), mean/rstd (B*L) are saved for backward. */
+ * model/DrugLAMP.py:63-71.  p_out (B,H,L), mean/rstd (B*L) are saved for backward.
+ * gamma == NULL selects the gating alone, y = gate(v) (MultiHeadLinearAttention.forward as the
+ * reference module returns it; beta/mean/rstd unused). */
 int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const float* gamma, const float* beta,
                         void* y, float* p_out, float* mean, float* rstd, int64_t B, int32_t L,
                         int32_t E, int32_t H, float eps, int32_t dtype, void* stream);
@@ -195,6 +214,18 @@ int dl_cm_triplet_fwd(const float* cos, const int8_t* G, int64_t P, int64_t D, f
                       double* acc, float* loss, void* stream);
 int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, int64_t D, float margin,
                       const double* acc, const float* gout, float* dcos, void* stream);
+
+/* F.cross_entropy(logits, labels, ignore_index) with mean reduction over the non-ignored rows --
+ * the two MLM heads of SSL.prot_mlm (model/self_supervised_learning.py:78-101).
+ * logit[r,c] = x[r*ld + c] + extra[r] * wextra[c] (extra/wextra optional: the fill-bit column of
+ * llm_to_logits applied without materialising cat(xp, bit)).  acc: 2 doubles workspace. */
+int dl_cross_entropy_fwd(const void* x, const int64_t* labels, const float* extra,
+                         const float* wextra, int64_t rows, int32_t C, int64_t ld,
+                         int64_t ignore_index, double* acc, float* loss, int32_t dtype, void* stream);
+int dl_cross_entropy_bwd(const void* x, const int64_t* labels, const float* extra,
+                         const float* wextra, int64_t rows, int32_t C, int64_t ld,
+                         int64_t ignore_index, const double* acc, const float* gout, void* dx,
+                         float* dextra, int32_t dtype, void* stream);
 
 /* binary_cross_entropy: prob = sigmoid(score); loss = BCELoss(prob, y) mean
  * (model/basic_model.py:17-22). */

@@ -8,7 +8,7 @@ from oracle import restatement as R
 from druglamp_b200.synth import make_batch
 from tests.util import load_golden, assert_digest_close
 
-CASES = ["druglamp2c2p_train_b4.npz", "druglamp_eval_b2.npz", "druglampwollm_train_b3.npz"]
+CASES = ["druglamp2c2p_train_b16.npz", "druglamp_eval_b2.npz", "druglampwollm_train_b12.npz"]
 
 
 def _state_for(fx, extra=()):
@@ -55,7 +55,7 @@ def test_restatement_matches_reference_fixture(case, model_shapes):
 
 
 def test_cm_losses_and_margin_schedule(model_shapes):
-    fx = load_golden("druglamp2c2p_train_b4.npz")
+    fx = load_golden("druglamp2c2p_train_b16.npz")
     sd, b, o, n, loss = oracle_run(fx, model_shapes)
     margins = [0.5] + [R.tanh_decay(0.5, 100, s) for s in (1, 2, 3)]
     assert np.allclose(margins, fx["cm_margins"], rtol=1e-12)

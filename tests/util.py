@@ -16,7 +16,7 @@ def digest(t: torch.Tensor) -> np.ndarray:
     """Same digest as tests/golden/make_golden.py: 64 evenly spaced samples + sum + abs-sum."""
     t = t.detach().double().flatten().cpu()
     n = t.numel()
-    idx = torch.linspace(0, n - 1, min(N_SAMPLES, n)).long()
+    idx = torch.linspace(0, n - 1, min(N_SAMPLES, n), dtype=torch.float64).long().clamp_(max=n - 1)
     out = torch.zeros(N_SAMPLES + 2, dtype=torch.float64)
     out[: idx.numel()] = t[idx]
     out[-2] = t.sum()
