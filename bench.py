@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""DrugLAMP hot-path benchmark: DTI pairs/sec, forward + backward (+ AdamW), on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: full DrugLAMP (GCN drug + CNN protein + LLM adaptors + PGCA +
+MHLA + PMMA + MLP head), BioSNAP-shaped synthetic pairs, batch 64 per GPU, bf16, train mode
+(PMMA dropout 0.1 live).  Data-parallel over pairs (weak scaling): every rank steps its own 64
+pairs, gradients are all-reduced once per step over NCCL.
+
+One JSON line on rank 0:
+  value     whole-job pairs/s with inputs resident in HBM (CUDA-graph replay, CUDA events, max over ranks)
+  e2e       same metric through the public API with HOST inputs: pinned H2D of every input + D2H of the loss
+  roofline  the dominant kernel (dl_gemm's tcgen05 kernel): algorithmic FLOPs / CUDA-event time of
+            every launch in one instrumented step, against the measured bf16 peak
+  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores (N=1 only)
+`--impl reference` times that CPU path as its own arm (same metric / config / unit).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "dti_pairs_per_sec_fwd_bwd"
+UNIT = "pairs/s"
+BATCH = 64
+FLOP_PER_PAIR_FWD_BWD = 24.61e9      # GEMM/bmm/conv 2MNK, dense padded shapes, fwd+bwd
+N_DISTINCT_BATCHES = 3
+
+
+def config(n_gpus):
+    return {"workload": "DrugLAMP full (BASELINE.json configs[1]): GCN+CNN+LLM adaptors+PGCA+MHLA+PMMA+MLP, "
+                        "BioSNAP-shaped synthetic pairs, train mode (dropout 0.1), fwd+BCE+bwd+AdamW",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "parallelism": f"dp{n_gpus}",
+            "protein_tokens": 2304, "drug_nodes": 512, "llm_dims": [640, 384],
+            "l2_policy": f"inputs larger than L2: {N_DISTINCT_BATCHES} distinct resident batches of ~440 MB rotate, "
+                         "each step reads one in full"}
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p.update(json.load(f))
+            p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------- CPU path
+def cpu_port_step_fn(batch_size, kind="DrugLAMP", seed=4321):
+    """The oracle port of the reference's CPU path: zero_grad -> forward -> BCE -> backward -> AdamW."""
+    from oracle import restatement as R
+    from druglamp_b200.synth import make_batch
+    with open(os.path.join(ROOT, "tests", "golden", "state_shapes.json")) as f:
+        shapes = {k: tuple(v) for k, v in json.load(f).items()}
+    sd = R.deterministic_state(shapes)
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    opt = torch.optim.AdamW(params, lr=1e-4)
+    b = make_batch(batch_size, seed=seed)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        o = R.druglamp_forward(sd, kind, b.graph.src, b.graph.dst, b.graph.ndata["h"], batch_size,
+                               b.vp, b.xd, b.xp, True)
+        _, loss = R.binary_cross_entropy(o["score"], b.y)
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+    return step
+
+
+def time_cpu(batch_size, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_port_step_fn(batch_size)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return batch_size / statistics.median(ts), sum(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = 8
+    warm = min(args.warmup, 1)
+    pps, total = time_cpu(bs, max(1, args.steps), warm)
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": 1000.0 * bs / pps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config(args.gpus),
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of {bs} pairs (zero_grad+fwd+BCE+bwd+AdamW), oracle port "
+                                       "of the reference modules, torch CPU fp32, all host threads"},
+            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import druglamp_b200 as D
+    from druglamp_b200 import _lib as L
+    from druglamp_b200.models import DrugLAMP
+    from druglamp_b200.synth import make_batch
+    from druglamp_b200.train import StaticBatch, TrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    D.set_compute_dtype(torch.bfloat16)
+    L.lib()
+
+    torch.manual_seed(1234)
+    model = DrugLAMP(384, 640).to(dev)
+    model.train()
+    model.flatten_parameters()
+    ts = TrainStep(model, world_size=world)
+    if world > 1:                      # replicas start from rank 0's weights
+        torch.distributed.broadcast(ts.flat.flat, 0)
+
+    batches = [StaticBatch(make_batch(BATCH, seed=1234 + rank * 100 + i), dev) for i in range(N_DISTINCT_BATCHES)]
+    hosts = [b.host_copy(pin=True) for b in batches]
+    h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+    for b in batches:
+        ts.capture(b)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, CUDA-graph replay ------------------------------------
+    for i in range(max(3, args.warmup)):
+        ts.replay(batches[i % len(batches)])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        ts.replay(batches[i % len(batches)])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_value = float(ts.loss.item())
+
+    # ---- e2e: host inputs -> pinned H2D -> step -> D2H of the loss, every step -----------------
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        batches[i % len(batches)].load_from(hosts[i % len(batches)])
+        ts.replay(batches[i % len(batches)]).item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        j = i % len(batches)
+        batches[j].load_from(hosts[j])
+        ts.replay(batches[j]).item()           # D2H read of the step's loss (4 bytes)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel: every dl_gemm launch of one eager step, CUDA events ---
+    roof = None
+    if rank == 0:
+        pk = peaks()
+
+        def local_step():                      # no collective: only rank 0 runs this pass
+            ts._fwd_bwd(batches[0])
+            ts._update()
+        local_step()
+        torch.cuda.synchronize()
+        L.PROFILE = []
+        local_step()
+        torch.cuda.synchronize()
+        prof, L.PROFILE = L.PROFILE, None
+        if os.environ.get("DL_BENCH_DUMP"):
+            agg = {}
+            for fl, a, b, shape in prof:
+                k = str(shape)
+                d = agg.setdefault(k, {"n": 0, "ms": 0.0, "flops": 0.0})
+                d["n"] += 1; d["ms"] += a.elapsed_time(b); d["flops"] += fl
+            rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+            os.makedirs(os.path.dirname(os.environ["DL_BENCH_DUMP"]) or ".", exist_ok=True)
+            with open(os.environ["DL_BENCH_DUMP"], "w") as f:
+                for k, d in rows:
+                    f.write(f"{d['ms']:9.3f} ms  n={d['n']:3d}  {d['flops'] / max(d['ms'], 1e-9) / 1e9:8.1f} TFLOP/s  (M,N,K,batch,ta,tb)={k}\n")
+        flops = sum(p[0] for p in prof)
+        gemm_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+        achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        step_ms = ms / args.steps
+        roof = {"kernel": "gemm_tc_kernel (dl_gemm: TMA + tcgen05.mma, bf16 in / fp32 TMEM accumulate)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained",
+                "launches_per_step": len(prof), "gemm_flops_per_step": flops,
+                "gemm_ms_per_step_eager_events": gemm_ms,
+                "share_of_graph_step": min(1.0, gemm_ms / step_ms) if step_ms > 0 else None,
+                "whole_step_tflops": FLOP_PER_PAIR_FWD_BWD * BATCH / (step_ms * 1e-3) / 1e12,
+                "whole_step_frac": FLOP_PER_PAIR_FWD_BWD * BATCH / (step_ms * 1e-3) / 1e12 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pps, _ = time_cpu(8, 3, 1)
+        cpu = {"value": pps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "3 timed steps of 8 pairs after 1 warm-up (zero_grad+fwd+BCE+bwd+AdamW), oracle port of "
+                         "the reference modules on torch CPU fp32 with all host threads"}
+
+    if rank == 0:
+        pairs = BATCH * world
+        line = {"metric": METRIC, "value": pairs * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config(world), "clocks": clocks,
+                "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "steps": e2e_steps},
+                "gpu_launches": ts.launches_per_step * args.steps, "gpu_launches_per_step": ts.launches_per_step,
+                "roofline": roof, "cpu_baseline": cpu, "loss": loss_value}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

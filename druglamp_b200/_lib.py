@@ -39,6 +39,7 @@ class GemmArgs(C.Structure):
         ("dtype_ab", C.c_int32), ("dtype_c", C.c_int32),
         ("trans_a", C.c_int32), ("trans_b", C.c_int32),
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
+        ("split_k", C.c_int32),
     ]
 
 
@@ -145,7 +146,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          preact_out: Optional[torch.Tensor] = None, mul_aux: Optional[torch.Tensor] = None,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
-         precise: Optional[bool] = None) -> None:
+         precise: Optional[bool] = None, split_k: int = 0) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -158,5 +159,16 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     a = GemmArgs(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(preact_out), ptr(mul_aux), ptr(residual),
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
-                 mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise))
+                 mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k)
+    if PROFILE is None:
+        check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
+    e1.record()
+    PROFILE.append((2.0 * M * N * K * b[0] * b[1] * b[2], e0, e1, (M, N, K, b, int(trans_a), int(trans_b))))
+
+
+# bench.py sets this to a list to time every dl_gemm launch with CUDA events on the launching stream
+PROFILE = None

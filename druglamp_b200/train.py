@@ -1,0 +1,123 @@
+"""A CUDA-graph-captured data-parallel training step over the sm_100a hot path.
+
+One step = zero the flat gradient buffer -> model forward -> ``binary_cross_entropy`` -> backward
+-> (data-parallel: one NCCL sum all-reduce of the flat gradient buffer) -> fused AdamW over the
+flat parameter buffer (which also refreshes the bf16 shadows).  Everything on the device side is a
+hand-written kernel launch (plus cuDNN for the adjacent ProteinCNN); capturing it in a CUDA graph
+removes the Python/launch overhead that otherwise dominates at batch 64.
+
+The reference does this through Lightning's manual optimisation with up to three backward passes
+and three all-reduces per step (``trainer.py:179-231``); this class is the B200-side
+equivalent of the classification step only and is what ``bench.py`` times.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+from .graph import BatchedMolGraph
+from .modules import binary_cross_entropy
+from .params import FlatAdamW
+
+
+class StaticBatch:
+    """Device-resident input buffers with fixed addresses (what a captured graph reads)."""
+
+    def __init__(self, batch, device):
+        self.graph: BatchedMolGraph = batch.graph.to(device)
+        self.h = self.graph.ndata["h"]
+        self.vp = batch.vp.to(device)
+        self.xd = batch.xd.to(device)
+        self.xp = batch.xp.to(device)
+        self.y = batch.y.to(device).float()
+        self.n_pairs = int(batch.y.shape[0])
+
+    def tensors(self) -> List[torch.Tensor]:
+        g = self.graph
+        return [self.h, self.vp, self.xd, self.xp, self.y, g.indptr, g.indices, g.indptr_t,
+                g.indices_t, g.norm_src, g.norm_dst]
+
+    def host_copy(self, pin=True) -> List[torch.Tensor]:
+        out = []
+        for t in self.tensors():
+            c = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=pin)
+            c.copy_(t)
+            out.append(c)
+        return out
+
+    def load_from(self, host: List[torch.Tensor]) -> int:
+        """Asynchronous H2D refresh of every input buffer; returns the bytes copied."""
+        n = 0
+        for dst, src in zip(self.tensors(), host):
+            dst.copy_(src, non_blocking=True)
+            n += src.numel() * src.element_size()
+        return n
+
+    def model_inputs(self):
+        self.graph.ndata["h"] = self.h            # MolecularGCN pops it every forward
+        return self.graph, self.vp, self.xd, self.xp
+
+
+class TrainStep:
+    def __init__(self, model, lr=1e-4, weight_decay=1e-2, world_size=1, process_group=None):
+        self.model = model
+        self.flat = model._flat or model.flatten_parameters()
+        self.opt = FlatAdamW(self.flat, lr=lr, weight_decay=weight_decay)
+        self.world_size = world_size
+        self.pg = process_group
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.flat.flat.device)
+        self._graphs = {}
+        self._pool = None
+        self.launches_per_step = 0
+
+    # ---- pieces ---------------------------------------------------------------------------------
+    def _fwd_bwd(self, sb: StaticBatch) -> None:
+        self.flat.zero_grad()
+        out = self.model(*sb.model_inputs())
+        _, loss = binary_cross_entropy(out[4], sb.y)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _reduce(self) -> None:
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+
+    def _update(self) -> None:
+        self.opt.step(grad_scale=1.0 / self.world_size)
+
+    def eager(self, sb: StaticBatch) -> torch.Tensor:
+        self._fwd_bwd(sb)
+        self._reduce()
+        self._update()
+        return self.loss
+
+    # ---- CUDA graphs ------------------------------------------------------------------------------
+    def capture(self, sb: StaticBatch, warmup: int = 2) -> None:
+        """Capture fwd+bwd and the optimizer update for this batch's buffers (the NCCL all-reduce
+        between them stays a stream-ordered eager call)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.eager(sb)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(g1, pool=self._pool):
+            self._fwd_bwd(sb)
+        if self._pool is None:
+            self._pool = g1.pool()
+        with torch.cuda.graph(g2, pool=self._pool):
+            self._update()
+        self.launches_per_step = L.launch_count() - n0
+        self._graphs[id(sb)] = (g1, g2)
+
+    def replay(self, sb: StaticBatch) -> torch.Tensor:
+        g1, g2 = self._graphs[id(sb)]
+        g1.replay()
+        self._reduce()
+        g2.replay()
+        return self.loss

@@ -92,6 +92,8 @@ typedef struct dl_gemm_args {
   int32_t act, mul_mode;
   int32_t tile_n;  /* 0 = auto, else 64 / 128 / 256 */
   int32_t precise; /* DL_F32 operands only: 1 = 3xTF32 split (fp32-grade products), 0 = plain TF32 */
+  int32_t split_k; /* 0 = auto, 1 = off, n > 1 = n K-slices accumulated atomically into a zeroed fp32 C
+                      (plain outputs only: no bias / activation / residual / batching) */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);

@@ -21,7 +21,8 @@ def _mk(shape, dtype, integer, gen):
 
 
 def run_case(M, N, K, dtype, trans_a, trans_b, tile_n=0, integer=True, batch=(1, 1), out_dtype=None,
-             bias=False, act=0, residual=False, preact=False, mul_mode=0, alpha=1.0, pad=0, seed=0):
+             bias=False, act=0, residual=False, preact=False, mul_mode=0, alpha=1.0, pad=0, seed=0,
+             split_k=0):
     from druglamp_b200 import _lib
     gen = torch.Generator(device="cuda").manual_seed(seed)
     blo, bhi = batch
@@ -39,7 +40,7 @@ def run_case(M, N, K, dtype, trans_a, trans_b, tile_n=0, integer=True, batch=(1,
     _lib.gemm(A, B, Cc, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, trans_a=trans_a, trans_b=trans_b,
               batch=(blo, bhi), sa=(A.stride(1), A.stride(0)), sb=(B.stride(1), B.stride(0)),
               sc=(Cc.stride(1), Cc.stride(0)), alpha=alpha, bias=bias_t, act=act, preact_out=pre_t,
-              mul_aux=aux_t, mul_mode=mul_mode, residual=res_t, tile_n=tile_n)
+              mul_aux=aux_t, mul_mode=mul_mode, residual=res_t, tile_n=tile_n, split_k=split_k)
     torch.cuda.synchronize()
     Ad = A.double()[..., :M] .transpose(-1, -2) if trans_a else A.double()[..., :K]
     Bd = B.double()[..., :N] if trans_b else B.double()[..., :K].transpose(-1, -2)
@@ -135,6 +136,20 @@ def test_three_batch_dims_with_broadcast_and_dropout(dtype):
     assert torch.equal(y1, y2)
     frac = (y1 == 0).float().mean().item()
     assert 0.15 < frac < 0.40
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_split_k_and_odd_output_widths(dtype):
+    # weight-gradient shape: few tiles, long K -> split-K with atomic accumulation (auto and explicit)
+    for sk in (0, 1, 7):
+        err, scale, _ = run_case(256, 192, 8192, dtype, True, True, out_dtype=torch.float32, split_k=sk)
+        assert err == 0.0, (sk, err, scale)
+    # odd N / odd ldc: the paired stores fall back to scalar accesses
+    for out_dtype in (torch.float32, dtype):
+        err, scale, _ = run_case(200, 27, 128, dtype, False, False, out_dtype=out_dtype, bias=True, residual=True)
+        assert err <= (0.0 if out_dtype == torch.float32 else 4e-3 * scale), (out_dtype, err, scale)
+        err, scale, _ = run_case(136, 77, 64, dtype, True, False, out_dtype=out_dtype)
+        assert err <= (0.0 if out_dtype == torch.float32 else 4e-3 * scale), (out_dtype, err, scale)
 
 
 def test_long_k_pipeline_wraps():
