@@ -203,6 +203,95 @@ softmax_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restr
   }
 }
 
+// Vectorised variants for cols == NCH * 256 (256 and 512 are the attention widths): each lane owns
+// NCH runs of 8 consecutive elements = 16-byte loads/stores for bf16, 2 x 16 bytes for fp32.
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&x)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&x)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    x[2 * k] = f.x; x[2 * k + 1] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&x)[8]);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&x)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(x[0], x[1], x[2], x[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(x[4], x[5], x[6], x[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&x)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_fwd_vec_kernel(const T* __restrict__ s, T* __restrict__ p, long long rows, long long ld) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float v[NCH][8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      ld8<T>(s + r * ld + c * 256 + lane * 8, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, v[c][j]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[c][j] = __expf(v[c][j] - m); sum += v[c][j]; }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] *= inv;
+      st8<T>(p + r * ld + c * 256 + lane * 8, v[c]);
+    }
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_bwd_vec_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
+                       long long rows, long long ld, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float pv[NCH][8], dv[NCH][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      ld8<T>(p + r * ld + c * 256 + lane * 8, pv[c]);
+      ld8<T>(dp + r * ld + c * 256 + lane * 8, dv[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += pv[c][j] * dv[c][j];
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[c][j] = scale * pv[c][j] * (dv[c][j] - dot);
+      st8<T>(ds + r * ld + c * 256 + lane * 8, dv[c]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ column sums
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -429,7 +518,16 @@ extern "C" int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(rows), th = kWarpsPerBlock * 32;
-  if (dtype == DL_BF16)
+  const bool al = ((uintptr_t)s & 15) == 0 && ((uintptr_t)p & 15) == 0 && ld % 8 == 0;
+  if (al && (cols == 256 || cols == 512)) {
+    if (dtype == DL_BF16) {
+      if (cols == 256) softmax_fwd_vec_kernel<__nv_bfloat16, 1><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
+      else softmax_fwd_vec_kernel<__nv_bfloat16, 2><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
+    } else {
+      if (cols == 256) softmax_fwd_vec_kernel<float, 1><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, ld);
+      else softmax_fwd_vec_kernel<float, 2><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, ld);
+    }
+  } else if (dtype == DL_BF16)
     softmax_fwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, cols, ld);
   else
     softmax_fwd_kernel<float><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, cols, ld);
@@ -445,7 +543,16 @@ extern "C" int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t r
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(rows), th = kWarpsPerBlock * 32;
-  if (dtype == DL_BF16)
+  const bool al = ((uintptr_t)p & 15) == 0 && ((uintptr_t)dp & 15) == 0 && ((uintptr_t)ds & 15) == 0 && ld % 8 == 0;
+  if (al && (cols == 256 || cols == 512)) {
+    if (dtype == DL_BF16) {
+      if (cols == 256) softmax_bwd_vec_kernel<__nv_bfloat16, 1><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
+      else softmax_bwd_vec_kernel<__nv_bfloat16, 2><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
+    } else {
+      if (cols == 256) softmax_bwd_vec_kernel<float, 1><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
+      else softmax_bwd_vec_kernel<float, 2><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
+    }
+  } else if (dtype == DL_BF16)
     softmax_bwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, cols, ld, scale);
   else
     softmax_bwd_kernel<float><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, cols, ld, scale);

@@ -495,14 +495,18 @@ class CrossModality(nn.Module):
                          torch.tensor(list(did2t.values()), dtype=torch.int64), G)
 
     @staticmethod
-    def _embed(seq, m2e):
-        x = Fn.SitePoolFn.apply(seq, seq.shape[1]).view(seq.shape[0], seq.shape[2])    # mean over L
+    def _pool(seq):
+        return Fn.SitePoolFn.apply(seq, seq.shape[1]).view(seq.shape[0], seq.shape[2])    # mean over L
+
+    @staticmethod
+    def _embed(x, m2e):
         x = Fn.batch_norm(x, m2e[0])
         x = Fn.ActFn.apply(x, K.ACT_RELU)
         return Fn.linear(x, m2e[2].weight, m2e[2].bias)
 
-    def latents(self, prot, aug_prot, drug, aug_drug, targets: CMTargets):
-        """Unit-norm protein / drug latents of the unique in-batch entities."""
+    def latents_from_pooled(self, prot, aug_prot, drug, aug_drug, targets: CMTargets):
+        """Unit-norm latents of the unique entities from the per-pair sequence means (B, hidden).
+        Selecting the unique rows after the mean equals the reference's select-then-mean."""
         prot, aug_prot = prot[targets.p_idx], aug_prot[targets.p_idx]
         drug, aug_drug = drug[targets.d_idx], aug_drug[targets.d_idx]
         pe = torch.cat([self._embed(prot, self.prot2latent), self._embed(aug_prot, self.aug_prot2latent)], -1)
@@ -510,6 +514,11 @@ class CrossModality(nn.Module):
         pl = Fn.L2NormFn.apply(Fn.linear(pe, self.to_prot_latent.weight))
         dl = Fn.L2NormFn.apply(Fn.linear(de, self.to_drug_latent.weight))
         return pl, dl
+
+    def latents(self, prot, aug_prot, drug, aug_drug, targets: CMTargets):
+        """Unit-norm protein / drug latents of the unique in-batch entities."""
+        return self.latents_from_pooled(self._pool(prot), self._pool(aug_prot), self._pool(drug),
+                                        self._pool(aug_drug), targets)
 
     def loss_from_latents(self, pl, dl, G):
         cos = Fn.MatmulNTFn.apply(pl, dl)

