@@ -39,7 +39,8 @@ class GemmArgs(C.Structure):
         ("dtype_ab", C.c_int32), ("dtype_c", C.c_int32),
         ("trans_a", C.c_int32), ("trans_b", C.c_int32),
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
-        ("split_k", C.c_int32),
+        ("split_k", C.c_int32), ("conv_taps", C.c_int32), ("conv_left", C.c_int32),
+        ("kred", C.c_int32), ("kred_shift", C.c_int32),
     ]
 
 
@@ -64,6 +65,7 @@ SIGNATURES = {
     "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _I32, _P],
     "dl_batchnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_fillbit_pool": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P],
+    "dl_transpose": [_P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_site_pool_fwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
     "dl_site_pool_bwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
     "dl_mhla_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
@@ -146,7 +148,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          preact_out: Optional[torch.Tensor] = None, mul_aux: Optional[torch.Tensor] = None,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
-         precise: Optional[bool] = None, split_k: int = 0) -> None:
+         precise: Optional[bool] = None, split_k: int = 0, conv_taps: int = 0, conv_left: int = 0,
+         kred: bool = False, kred_shift: int = 0) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -159,7 +162,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     a = GemmArgs(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(preact_out), ptr(mul_aux), ptr(residual),
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
-                 mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k)
+                 mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k,
+                 conv_taps, conv_left, int(kred), kred_shift)
     if PROFILE is None:
         check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
         return

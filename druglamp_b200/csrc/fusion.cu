@@ -349,6 +349,28 @@ __global__ void cm_finalize_kernel(const double* __restrict__ acc, float* __rest
   loss[0] = (float)(acc[0] / cnt);
 }
 
+// ------------------------------------------------------------------ batched 2-D transpose
+// y[b, c, r] = x[b, r, c]; 32x32 tiles through padded shared memory, coalesced both ways.
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * R * Cc;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    if (r < R && c < Cc) tile[ty + i][tx] = ldf<T>(x, base + (size_t)r * Cc + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (r < R && c < Cc) stf<T>(y, base + (size_t)c * R + r, tile[tx][ty + i]);
+  }
+}
+
 // ------------------------------------------------------------------ cross entropy (MLM heads)
 // logit[r, c] = x[r*ld + c] + (extra ? extra[r] * wextra[c] : 0);  rows with label == ignore are
 // skipped.  One warp per row, classes strided over lanes (C = 27 for the MLM heads).
@@ -587,6 +609,22 @@ extern "C" int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, i
     DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cm_triplet_kernel<true><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, const_cast<double*>(acc), gout, dcos);
   DL_LAUNCH_CHECK("cm_triplet_kernel(bwd)");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_t Cc, int32_t dtype,
+                            void* stream) {
+  DL_REQUIRE(x && y && R >= 1 && Cc >= 1 && B >= 0 && B <= 65535, "dl_transpose: bad arguments");
+  if (B == 0) return 0;
+  dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), (unsigned)B);
+  DL_REQUIRE(grid.y <= 65535, "dl_transpose: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, R, Cc);
+  else
+    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, R, Cc);
+  DL_LAUNCH_CHECK("transpose_kernel");
   count_launch();
   return 0;
 }

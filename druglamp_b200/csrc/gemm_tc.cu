@@ -52,6 +52,8 @@ struct GemmParams {
   int c_bf16;
   int act, mul_mode;
   int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work
+  int conv_cin, conv_left;      // implicit-GEMM conv1d on A (0 = off): channels per tap, left padding
+  int kred_kpb, kred_shift;     // K-reduction over batch[2] (0 = off): K-blocks per batch, B row shift
   float alpha;
   uint32_t idesc;
 };
@@ -303,19 +305,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_arrive_expect_tx(full, C::LOAD_BYTES);
           const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
           const int k0 = (T.kb_begin + kb) * C::KE;
+          int ka = k0, kbb = k0, a_row = T.m0, a4r = a4, c4r = c4;
+          if (p.conv_cin) {
+            // implicit-GEMM conv1d: K-block -> (tap, channel block); the A tile is the same rows
+            // shifted by the tap, out-of-range rows are zero-filled by TMA ('same' padding)
+            const int tap = k0 / p.conv_cin;
+            ka = k0 - tap * p.conv_cin;
+            a_row = T.m0 + tap - p.conv_left;
+          }
+          if (p.kred_kpb) {
+            // K runs over (reduction batch, rows): conv weight gradient; batch dim 0 is the tap and
+            // shifts the rows of B
+            const int kbi = T.kb_begin + kb;
+            const int rb = kbi / p.kred_kpb;
+            ka = (kbi - rb * p.kred_kpb) * C::KE;
+            kbb = ka + T.b0 + p.kred_shift;
+            a4r = c4r = rb;
+          }
           if (!p.a_mn) {
-            ptx::tma_load_5d(sA, &tmA, full, k0, T.m0, a2, a3, a4);
+            ptx::tma_load_5d(sA, &tmA, full, ka, a_row, a2, a3, a4r);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BM / C::MNB; ++blk)
-              ptx::tma_load_5d(sA + blk * C::KE * 128, &tmA, full, T.m0 + blk * C::MNB, k0, a2, a3, a4);
+              ptx::tma_load_5d(sA + blk * C::KE * 128, &tmA, full, T.m0 + blk * C::MNB, ka, a2, a3, a4r);
           }
           if (!p.b_mn) {
-            ptx::tma_load_5d(sB, &tmB, full, k0, T.n0, c2, c3, c4);
+            ptx::tma_load_5d(sB, &tmB, full, kbb, T.n0, c2, c3, c4r);
           } else {
 #pragma unroll
             for (int blk = 0; blk < BN / C::MNB; ++blk)
-              ptx::tma_load_5d(sB + blk * C::KE * 128, &tmB, full, T.n0 + blk * C::MNB, k0, c2, c3, c4);
+              ptx::tma_load_5d(sB + blk * C::KE * 128, &tmB, full, T.n0 + blk * C::MNB, kbb, c2, c3, c4r);
           }
         }
       }
@@ -502,7 +521,25 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   DL_REQUIRE(a->dtype_ab == DL_F32 || a->dtype_ab == DL_BF16, "dl_gemm: dtype_ab must be DL_F32 or DL_BF16");
   DL_REQUIRE(a->dtype_c == DL_F32 || a->dtype_c == DL_BF16, "dl_gemm: dtype_c must be DL_F32 or DL_BF16");
   DL_REQUIRE(a->batch[0] >= 1 && a->batch[1] >= 1 && a->batch[2] >= 1, "dl_gemm: batch extents must be >= 1");
-  const long long batch = a->batch[0] * a->batch[1] * a->batch[2];
+  const int KE_ = a->dtype_ab == DL_F32 ? 32 : 64;
+  // conv modes (implicit-GEMM conv1d; see the header)
+  const bool conv = a->conv_taps > 0, kred = a->kred != 0;
+  int conv_cin = 0, kred_kpb = 0;
+  if (conv) {
+    DL_REQUIRE(!a->trans_a && !kred, "dl_gemm: conv_taps needs a K-major A");
+    DL_REQUIRE(a->K % a->conv_taps == 0 && (a->K / a->conv_taps) % KE_ == 0,
+               "dl_gemm: conv needs K = taps * channels with channels a multiple of %d", KE_);
+    conv_cin = (int)(a->K / a->conv_taps);
+  }
+  if (kred) {
+    DL_REQUIRE(a->trans_a && a->trans_b, "dl_gemm: kred needs both operands MN-major");
+    DL_REQUIRE(a->sa[2] > 0 && a->sb[2] > 0, "dl_gemm: kred needs batch[2] strides for A and B");
+    kred_kpb = ceil_div(a->K, KE_);
+  }
+  // with kred, batch[2] is a reduction dimension: it does not multiply the output tiles
+  const long long batch = a->batch[0] * a->batch[1] * (kred ? 1 : a->batch[2]);
+  const long long k_total = kred ? (long long)a->batch[2] * kred_kpb * KE_ : a->K;
+  DL_REQUIRE(k_total < (1ll << 31), "dl_gemm: reduction extent too large");
   DL_REQUIRE(batch < (1ll << 24), "dl_gemm: batch %lld too large", batch);
   DL_REQUIRE(a->ldc >= a->N, "dl_gemm: ldc < N");
   DL_REQUIRE(a->mul_mode == DL_MUL_NONE || a->mul_aux != nullptr, "dl_gemm: mul_mode set without mul_aux");
@@ -528,11 +565,15 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   // into a zero-initialised C.
   int splits = 1;
   const long long tiles = (long long)ceil_div(a->N, bn) * ceil_div(a->M, BM) * batch;
-  const int nkb = ceil_div(a->K, f32 ? 32 : 64);
+  const int nkb = ceil_div(k_total, KE_);
+  // batched outputs can be split too when C is one dense [batch, M, N] block (a single memset)
+  const bool dense_c = batch == 1 || (a->ldc == a->N && a->sc[0] == a->M * a->N &&
+                                      (a->batch[1] == 1 || a->sc[1] == a->M * a->N * a->batch[0]) &&
+                                      (kred || a->batch[2] == 1 || a->sc[2] == a->M * a->N * a->batch[0] * a->batch[1]));
   const bool plain = a->dtype_c == DL_F32 && !a->bias && !a->preact_out && !a->mul_aux && !a->residual &&
-                     a->act == DL_ACT_NONE && a->drop_p == 0.f && batch == 1;
+                     a->act == DL_ACT_NONE && a->drop_p == 0.f && dense_c;
   if (a->split_k > 1) {
-    DL_REQUIRE(plain, "dl_gemm: split_k needs a plain fp32 output without epilogue operands or batching");
+    DL_REQUIRE(plain, "dl_gemm: split_k needs a plain fp32 output (no epilogue operands; batched C must be dense)");
     splits = a->split_k;
   } else if (a->split_k == 0 && plain && tiles * 2 <= sms && nkb >= 16) {
     splits = (int)((sms + tiles - 1) / tiles);
@@ -540,11 +581,15 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   }
   if (splits > nkb) splits = nkb;
   if (splits < 1) splits = 1;
-  if (splits > 1)
-    DL_CUDA(cudaMemset2DAsync(a->C, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, stream));
+  if (splits > 1) {
+    if (batch == 1)
+      DL_CUDA(cudaMemset2DAsync(a->C, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, stream));
+    else
+      DL_CUDA(cudaMemsetAsync(a->C, 0, (size_t)(a->M * a->N * batch) * 4, stream));
+  }
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, a->A, f32, a->trans_a != 0, a->M, a->K, a->lda, a->batch, a->sa, BM, "A");
+  int rc = make_operand_map(&tmA, a->A, f32, a->trans_a != 0, a->M, conv ? conv_cin : a->K, a->lda, a->batch, a->sa, BM, "A");
   if (rc) return rc;
   rc = make_operand_map(&tmB, a->B, f32, a->trans_b != 0, a->N, a->K, a->ldb, a->batch, a->sb, bn, "B");
   if (rc) return rc;
@@ -560,8 +605,11 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
     p.b_on[i] = a->sb[i] != 0;
   }
   p.drop_seed = a->drop_seed; p.drop_p = a->drop_p;
-  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)k_total;
   p.nb0 = (int)a->batch[0]; p.nb1 = (int)a->batch[1];
+  p.conv_cin = conv_cin; p.conv_left = a->conv_left;
+  p.kred_kpb = kred_kpb; p.kred_shift = a->kred_shift;
+  if (kred) { p.a_on[2] = p.b_on[2] = 1; }
   p.splits = splits;
   p.a_mn = a->trans_a != 0; p.b_mn = a->trans_b != 0;
   p.c_bf16 = a->dtype_c == DL_BF16;

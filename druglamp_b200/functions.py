@@ -524,6 +524,62 @@ class AddPEFn(Function):
         return _back(g, xdt), dpe, None, None
 
 
+class Conv1dSameFn(Function):
+    """nn.Conv1d(padding='same') + optional ReLU on channels-last activations, as an implicit GEMM
+    on dl_gemm (TMA row-shifted A tiles, out-of-range rows zero-filled): the three convolutions of
+    ProteinCNN (model/basic_model.py:163-178).  x (B, L, Cin) -> (B, L, Cout); w is the module's
+    (Cout, Cin, k) parameter.  PyTorch's 'same' puts the extra pad of an even kernel on the right."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        xc = K.to_compute(x)
+        Cout, Cin, k = w.shape
+        left = (k - 1) // 2
+        wc = shadow(w)
+        w_taps = wc.permute(0, 2, 1).reshape(Cout, k * Cin).contiguous()
+        out = torch.empty(xc.shape[:2] + (Cout,), dtype=xc.dtype, device=xc.device)
+        K.conv1d_same(xc, w_taps, out, taps=k, left=left, bias=None if b is None else b.detach(),
+                      act=K.ACT_RELU if relu else K.ACT_NONE)
+        ctx.save_for_backward(xc, w, out if relu else None)
+        ctx.meta = (relu, left, x.dtype, b is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xc, w, out = ctx.saved_tensors
+        relu, left, xdt, has_b = ctx.meta
+        Cout, Cin, k = w.shape
+        g = K.to_compute(gy)
+        if relu:
+            g = K.act_bwd(g, out, K.ACT_RELU)          # mask from the post-ReLU output (y > 0 <=> pre > 0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wd = shadow(w).flip(2).permute(1, 2, 0).reshape(Cin, k * Cout).contiguous()
+            dx = torch.empty_like(xc)
+            K.conv1d_same(g, wd, dx, taps=k, left=k - 1 - left)
+            dx = _back(dx, xdt)
+        if ctx.needs_input_grad[1]:
+            dw = K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0).contiguous()
+        if has_b and ctx.needs_input_grad[2]:
+            db = K.colsum(g.view(-1, Cout))
+        return dx, dw, db, None
+
+
+class TransposeFn(Function):
+    """(B, R, C) -> (B, C, R) contiguous."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.xdt = x.dtype
+        return K.transpose_last2(K.to_compute(x))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        return _back(K.transpose_last2(K.to_compute(gy)), ctx.xdt)
+
+
 class ActFn(Function):
     @staticmethod
     def forward(ctx, x, act):

@@ -227,6 +227,37 @@ def fillbit_pool(x: torch.Tensor, S: int, want_bit=True, want_cat=False, want_po
     return bit, cat, pooled
 
 
+def transpose_last2(x: torch.Tensor) -> torch.Tensor:
+    """(B, R, C) -> (B, C, R), contiguous."""
+    B, R, Cc = x.shape
+    y = torch.empty((B, Cc, R), dtype=x.dtype, device=x.device)
+    L.call("dl_transpose", x.data_ptr(), y.data_ptr(), B, R, Cc, L.dt(x))
+    return y
+
+
+def conv1d_same(x: torch.Tensor, w_taps: torch.Tensor, out: torch.Tensor, *, taps: int, left: int,
+                bias=None, act: int = ACT_NONE) -> torch.Tensor:
+    """Channels-last 'same' conv1d as an implicit GEMM.  x (B, L, Cin), w_taps (Cout, taps*Cin) with
+    w_taps[co, t*Cin + ci] = weight of tap t; out (B, L, Cout)."""
+    B, Ls, Cin = x.shape
+    Cout = w_taps.shape[0]
+    L.gemm(x, w_taps, out, M=Ls, N=Cout, K=taps * Cin, lda=Cin, ldb=taps * Cin, ldc=Cout,
+           batch=(1, 1, B), sa=(0, 0, Ls * Cin), sb=(0, 0, 0), sc=(0, 0, Ls * Cout), bias=bias, act=act,
+           conv_taps=taps, conv_left=left)
+    return out
+
+
+def conv1d_same_wgrad(g: torch.Tensor, x: torch.Tensor, taps: int, left: int) -> torch.Tensor:
+    """dW[t, co, ci] = sum_{b,l} g[b, l, co] * x[b, l + t - left, ci]  (fp32, (taps, Cout, Cin))."""
+    B, Ls, Cout = g.shape
+    Cin = x.shape[2]
+    dw = torch.empty((taps, Cout, Cin), dtype=torch.float32, device=g.device)
+    L.gemm(g, x, dw, M=Cout, N=Cin, K=Ls, lda=Cout, ldb=Cin, ldc=Cin, trans_a=True, trans_b=True,
+           batch=(taps, 1, B), sa=(0, 0, Ls * Cout), sb=(0, 0, Ls * Cin), sc=(Cout * Cin, 0, 0),
+           kred=True, kred_shift=-left)
+    return dw
+
+
 def site_pool_fwd(x: torch.Tensor, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (B, S*L, C) -> (B, L, C); `out` may be a column-slice view (row stride = ldy)."""
     B, SL, C = x.shape

@@ -553,16 +553,18 @@ class ProteinCNN(nn.Module):
             setattr(self, f"bn{i + 1}", nn.BatchNorm1d(in_ch[i + 1]))
 
     def forward(self, v, fill_mask):
-        bf16 = K.compute_dtype() == torch.bfloat16
-        from . import _lib
-        # fp32 parity mode: keep cuDNN off TF32 like the 3xTF32 GEMMs; bf16 mode: autocast
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=bf16 or not _lib.FP32_PRECISE), \
-                torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16 and v.is_cuda):
-            v = self.embedding(v.long())
-            v = torch.cat((v, fill_mask.unsqueeze(-1).to(v.dtype)), dim=-1).transpose(2, 1)
-            for i in (1, 2, 3):
-                v = getattr(self, f"bn{i}")(F.relu(getattr(self, f"conv{i}")(v)))
-        return v.reshape(v.size(0), v.size(2), -1)
+        """Channels-last throughout: each Conv1d('same')+ReLU is one implicit-GEMM dl_gemm launch,
+        each BatchNorm1d runs on the (B*L, C) rows with the dl_batchnorm kernels; the result is
+        transposed once into the reference's (B, C, L) buffer and reinterpreted like its
+        ``.view(B, L, C)`` (App. A4)."""
+        x = self.embedding(v.long())                                        # (B, L, 127) gather
+        x = torch.cat((x, fill_mask.unsqueeze(-1).to(x.dtype)), dim=-1)      # (B, L, 128)
+        for i in (1, 2, 3):
+            conv, bn = getattr(self, f"conv{i}"), getattr(self, f"bn{i}")
+            x = Fn.Conv1dSameFn.apply(x, conv.weight, conv.bias, True)
+            x = Fn.batch_norm(x, bn)
+        y = Fn.TransposeFn.apply(x)                                         # (B, C, L) like the reference
+        return y.view(y.size(0), y.size(2), -1)
 
 
 class FeedForwardLayer(nn.Module):

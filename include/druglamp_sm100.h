@@ -93,7 +93,15 @@ typedef struct dl_gemm_args {
   int32_t tile_n;  /* 0 = auto, else 64 / 128 / 256 */
   int32_t precise; /* DL_F32 operands only: 1 = 3xTF32 split (fp32-grade products), 0 = plain TF32 */
   int32_t split_k; /* 0 = auto, 1 = off, n > 1 = n K-slices accumulated atomically into a zeroed fp32 C
-                      (plain outputs only: no bias / activation / residual / batching) */
+                      (plain outputs only: no bias / activation / residual; batched C must be dense) */
+  /* Implicit-GEMM conv1d ('same' padding, channels-last activations [batch, L, C]) -- ProteinCNN
+   * (model/basic_model.py:155-180).  conv_taps = k > 0: A is the K-major activation [L, cin] per
+   * batch, K = k * cin enumerates (tap, channel) and the A tile of tap t is rows m + t - conv_left,
+   * rows outside [0, L) read as zero; B = weights [cout, k * cin].  kred = 1 (weight gradient): both
+   * operands MN-major, K = L rows per batch[2] entry, batch[2] is REDUCED over, batch[0] is the
+   * tap and shifts B's rows by b0 + kred_shift (zero outside [0, L)); C is [taps, M, N]. */
+  int32_t conv_taps, conv_left;
+  int32_t kred, kred_shift;
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
@@ -193,6 +201,11 @@ int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, in
                      int64_t ldy, int32_t dtype, void* stream);
 int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L, int32_t C,
                      int64_t ldy, int32_t dtype, void* stream);
+
+/* y[b, c, r] = x[b, r, c]: the channels-last ProteinCNN output laid out as the reference's
+ * (B, C, L) buffer, which the reference then reinterprets with .view(B, L, C)
+ * (model/basic_model.py:179). */
+int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_t C, int32_t dtype, void* stream);
 
 /* y = LayerNorm(v + gate(v)), gate = MultiHeadLinearAttention's softmax-over-sequence gating
  * through its .view(B*H, L, E/H) reinterpretation (model/PMMA/encoder.py:132-140) applied to

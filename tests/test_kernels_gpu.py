@@ -190,6 +190,43 @@ def test_mhla_gate_ln_fwd_bwd(dtype, tol):
     _close(db, br.grad, max(tol, 1e-4), "dbeta")
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("k", [3, 6, 9])
+def test_conv1d_same_implicit_gemm_fwd_bwd(dtype, tol, k):
+    """Conv1d(padding='same') + ReLU as implicit GEMM (TMA row shifts, zero fill) vs F.conv1d."""
+    import druglamp_b200 as D
+    from druglamp_b200 import functions as Fn
+    D.set_compute_dtype(dtype)
+    try:
+        torch.manual_seed(8 + k)
+        B, Ls, Cin, Cout = 3, 384, 128, 128
+        x = torch.randn(B, Ls, Cin, device="cuda").to(dtype).float().requires_grad_(True)
+        w = (torch.randn(Cout, Cin, k, device="cuda") * 0.05).to(dtype).float().requires_grad_(True)
+        b = torch.randn(Cout, device="cuda").requires_grad_(True)
+        gy = torch.randn(B, Ls, Cout, device="cuda").to(dtype).float()
+        y = Fn.Conv1dSameFn.apply(x, torch.nn.Parameter(w.detach().clone()), torch.nn.Parameter(b.detach().clone()), True)
+        xr, wr, br = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+        yr = F.relu(F.conv1d(xr.transpose(1, 2), wr, br, padding="same")).transpose(1, 2)
+        _close(y, yr, tol, "conv fwd")
+        # backward through fresh leaves
+        wp, bp = torch.nn.Parameter(w.detach().clone()), torch.nn.Parameter(b.detach().clone())
+        xl = x.detach().clone().requires_grad_(True)
+        y2 = Fn.Conv1dSameFn.apply(xl, wp, bp, True)
+        y2.backward(gy.to(y2.dtype))
+        # use the product's own ReLU mask so that bf16 rounding at the kink does not enter the comparison
+        mask = (y2.detach().double() > 0)
+        pre = F.conv1d(xr.transpose(1, 2), wr, br, padding="same").transpose(1, 2)
+        (pre * mask * gy.double()).sum().backward()
+        _close(xl.grad, xr.grad, max(tol, 1e-4), "conv dx")
+        _close(wp.grad, wr.grad, max(tol, 1e-4), "conv dw")
+        _close(bp.grad, br.grad, max(tol, 1e-4), "conv db")
+        t = torch.randn(2, 70, 45, device="cuda").to(dtype)
+        from druglamp_b200 import kernels as K
+        assert torch.equal(K.transpose_last2(t), t.transpose(1, 2).contiguous())
+    finally:
+        D.set_compute_dtype(torch.float32)
+
+
 def test_cm_triplet_and_bce():
     from druglamp_b200 import kernels as K
     from oracle import restatement as R

@@ -62,12 +62,13 @@ def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
     report = []
     # Train-mode BatchNorm over a small batch amplifies bf16 rounding noise: PyTorch's own bf16
     # autocast moves the UNMODIFIED reference's logits by `bf16_autocast_score_dev` (0.2-0.7 of
-    # max|logit| on these fixtures, recorded by make_golden.py).  There the logits are bounded by
-    # that inherent figure, the loss and the pre-BN tensors by the 2e-2 bar; the eval-mode
-    # fixture (running statistics) carries the strict 2e-2 logit bar and the gradient check.
+    # max|logit| and its loss by 2.5-3.4e-2 on these fixtures (recorded by make_golden.py).  There the
+    # logits and the loss are bounded by 1.5x those inherent figures (and never tighter than the
+    # 2e-2 bar); the eval-mode fixture (running statistics) carries the strict 2e-2 logit / loss
+    # bar and the gradient check.
     noisy = dtype == torch.bfloat16 and bool(int(fx["meta_training"]))
     stol = max(tol, 1.5 * float(fx["bf16_autocast_score_dev"])) if noisy else tol
-    ltol = tol
+    ltol = max(tol, 1.5 * float(fx["bf16_autocast_loss_dev"])) if noisy else tol
     if noisy:
         # intermediates (three stacked train-mode BatchNorms in the GCN, 92 % identical rows) sit at
         # ~5e-2 in bf16 and move a little from run to run (atomic reduction order): diagnostic bound
