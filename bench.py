@@ -290,13 +290,29 @@ def run_gpu(args):
         if os.environ.get("DL_BENCH_DUMP"):
             agg = {}
             for r in prof:
-                d = agg.setdefault(str(r["shape"]), {"n": 0, "flops": 0.0})
+                d = agg.setdefault(str(r["shape"]), {"n": 0, "flops": 0.0, "rec": r})
                 d["n"] += 1; d["flops"] += r["flops"]
+            for d in agg.values():                 # time each distinct shape alone (10 launches per graph)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    for _ in range(10):
+                        L.replay_gemm(d["rec"])
+                g1.replay()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(3):
+                    g1.replay()
+                a1.record()
+                torch.cuda.synchronize()
+                d["us"] = a0.elapsed_time(a1) * 1000 / 30
+                del g1
             os.makedirs(os.path.dirname(os.environ["DL_BENCH_DUMP"]) or ".", exist_ok=True)
             with open(os.environ["DL_BENCH_DUMP"], "w") as f:
                 f.write(f"# {len(prof)} dl_gemm launches per step, {flops / 1e9:.1f} GFLOP, {gemm_ms:.3f} ms back-to-back\n")
-                for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["flops"]):
-                    f.write(f"n={d['n']:3d}  {d['flops'] / 1e9:9.2f} GFLOP  (M,N,K,batch,ta,tb)={k}\n")
+                f.write("# total_us  n  us/launch  TFLOP/s  (M,N,K,batch,ta,tb)\n")
+                for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["n"] * kv[1]["us"]):
+                    f.write(f"{d['n'] * d['us']:9.1f}  n={d['n']:3d}  {d['us']:8.1f}  {d['flops'] / d['n'] / d['us'] / 1e6:7.1f}  {k}\n")
         del gg
         achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]

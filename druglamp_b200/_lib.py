@@ -40,7 +40,7 @@ class GemmArgs(C.Structure):
         ("trans_a", C.c_int32), ("trans_b", C.c_int32),
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
         ("split_k", C.c_int32), ("conv_taps", C.c_int32), ("conv_left", C.c_int32),
-        ("kred", C.c_int32), ("kred_shift", C.c_int32),
+        ("kred", C.c_int32), ("kred_shift", C.c_int32), ("accumulate", C.c_int32),
     ]
 
 
@@ -52,7 +52,7 @@ SIGNATURES = {
     "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],
     "dl_softmax_bwd": [_P, _P, _P, _I64, _I32, _I64, _F, _I32, _P],
-    "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _P],
+    "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _I32, _P],
     "dl_dropout": [_P, _P, _I64, _F, _U64, _I32, _P],
     "dl_act_bwd": [_P, _P, _P, _I64, _I32, _F, _U64, _I32, _P],
     "dl_act_fwd": [_P, _P, _I64, _I32, _I32, _P],
@@ -149,7 +149,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
          precise: Optional[bool] = None, split_k: int = 0, conv_taps: int = 0, conv_left: int = 0,
-         kred: bool = False, kred_shift: int = 0) -> None:
+         kred: bool = False, kred_shift: int = 0, accumulate: bool = False) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -163,7 +163,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
                  mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k,
-                 conv_taps, conv_left, int(kred), kred_shift)
+                 conv_taps, conv_left, int(kred), kred_shift, int(accumulate))
     if PROFILE is None:
         check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
         return

@@ -557,6 +557,15 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
     bn = 64;
     if (a->N > 128 && mt * ceil_div(a->N, 256) * batch >= sms) bn = 256;
     else if (a->N > 64 && mt * ceil_div(a->N, 128) * batch >= sms) bn = 128;
+    // weight-gradient shapes get their parallelism from split-K.  Atomic traffic grows with
+    // splits x tile area, so narrow tiles stay (measured: 256x256x16384 21 us at BN=64 vs 44 us at
+    // BN=256); only a single 128-wide N (the conv weight gradients) takes the 128 tile.
+    const bool split_candidate = a->dtype_c == DL_F32 && !a->bias && !a->preact_out && !a->mul_aux &&
+                                 !a->residual && a->act == DL_ACT_NONE && a->split_k != 1 &&
+                                 ceil_div(k_total, KE_) >= 16;
+    if (bn == 64 && split_candidate && a->N > 64 && a->N <= 128 &&
+        (long long)ceil_div(k_total, KE_) * mt * batch / sms >= 32)
+      bn = 128;
   }
   DL_REQUIRE(bn == 64 || bn == 128 || bn == 256, "dl_gemm: tile_n must be 0, 64, 128 or 256");
 
@@ -581,7 +590,10 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   }
   if (splits > nkb) splits = nkb;
   if (splits < 1) splits = 1;
-  if (splits > 1) {
+  if (a->accumulate) {
+    DL_REQUIRE(plain, "dl_gemm: accumulate needs a plain fp32 output (no epilogue operands)");
+  }
+  if (splits > 1 && !a->accumulate) {
     if (batch == 1)
       DL_CUDA(cudaMemset2DAsync(a->C, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, stream));
     else
@@ -610,6 +622,11 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   p.conv_cin = conv_cin; p.conv_left = a->conv_left;
   p.kred_kpb = kred_kpb; p.kred_shift = a->kred_shift;
   if (kred) { p.a_on[2] = p.b_on[2] = 1; }
+  if (a->accumulate && splits == 1) {     // C += result through the residual path (same layout)
+    p.res = a->C;
+    p.ldr = a->ldc;
+    for (int i = 0; i < 3; ++i) p.sr[i] = a->sc[i];
+  }
   p.splits = splits;
   p.a_mn = a->trans_a != 0; p.b_mn = a->trans_b != 0;
   p.c_bf16 = a->dtype_c == DL_BF16;

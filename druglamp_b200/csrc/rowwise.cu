@@ -562,10 +562,10 @@ extern "C" int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t r
 }
 
 extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld,
-                         int32_t dtype, void* stream) {
+                         int32_t accumulate, int32_t dtype, void* stream) {
   DL_REQUIRE(x && out && cols > 0 && ld >= cols, "dl_colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (!accumulate) DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
   if (rows <= 0) return 0;
   const int xb = ceil_div(cols, 32);
   long long yb = (long long)sm_count() * 4 / xb;

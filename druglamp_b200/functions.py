@@ -16,7 +16,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 from . import kernels as K
-from .params import shadow
+from .params import flat_grad_of, shadow
 
 _seed_counter = itertools.count(0x5EED)
 
@@ -32,6 +32,34 @@ def _back(g: Optional[torch.Tensor], like_dtype: torch.dtype, shape=None):
     if g.dtype != like_dtype:
         g = K.cast(g, like_dtype)
     return g if shape is None else g.reshape(shape)
+
+
+def _grad_target(p):
+    """The fp32 gradient buffer of a parameter that lives in a FlatParams store (None otherwise).
+    Weight / bias gradients are then accumulated straight into it by the producing kernel
+    (dl_gemm accumulate / dl_colsum accumulate) and the Function returns None for that input, which
+    saves a temporary, a memset and an `at::add` launch per parameter."""
+    if p is None or not torch.is_tensor(p):
+        return None
+    g = flat_grad_of(p)
+    return g if (g is not None and g.is_contiguous()) else None
+
+
+def _wgrad(p, a, b):
+    """dW = a^T b (both stored [rows, features]); into p.grad when possible."""
+    tgt = _grad_target(p)
+    if tgt is not None and tgt.dim() == 2:
+        K.mm(a, b, tgt, ta=True, tb=True, accumulate=True)
+        return None
+    return K.mm(a, b, ta=True, tb=True, out_dtype=torch.float32)
+
+
+def _bgrad(p, g):
+    tgt = _grad_target(p)
+    if tgt is not None:
+        K.colsum(g, tgt, accumulate=True)
+        return None
+    return K.colsum(g)
 
 
 # ================================================================================ Linear
@@ -68,6 +96,7 @@ class LinearFn(Function):
         r2 = _pad_cols(K.to_compute(residual).view(-1, N), Np) if residual is not None else None
         K.mm(x2, wc, out, tb=w_kn, bias=bias, act=act, pre=pre, res=r2, drop=(drop_p, seed))
         ctx.save_for_backward(x2, wc, pre)
+        ctx.params = (w, b)
         ctx.meta = (act, drop_p, seed, xs, x.dtype, None if residual is None else residual.dtype,
                     b is not None, w_kn, Kd, N)
         y = out if Np == N else out[:, :N]
@@ -86,15 +115,15 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dx = K.mm(g, wc, tb=not w_kn)
             dx = _back(dx if Kp == Kd else dx[:, :Kd], xdt, xs)
+        wp, bp = ctx.params
+        exact = Kp == Kd and Np == N
         if ctx.needs_input_grad[1]:
             if w_kn:
-                dw = K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)
-                dw = dw if (Kp == Kd and Np == N) else dw[:Kd, :N]
+                dw = _wgrad(wp, x2, g) if exact else K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)[:Kd, :N]
             else:
-                dw = K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)
-                dw = dw if (Kp == Kd and Np == N) else dw[:N, :Kd]
+                dw = _wgrad(wp, g, x2) if exact else K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)[:N, :Kd]
         if has_b and ctx.needs_input_grad[2]:
-            db = K.colsum(g)[:N]
+            db = _bgrad(bp, g) if exact else K.colsum(g)[:N]
         if rdt is not None and ctx.needs_input_grad[4]:
             dres = _back(gy2, rdt, gy.shape)
         return dx, dw, db, None, dres, None, None, None
@@ -122,6 +151,7 @@ class FFNFn(Function):
         r2 = K.to_compute(residual).view(-1, w2.shape[0]) if residual is not None else None
         y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
         ctx.save_for_backward(x2, w1, w2, pre1, hd)
+        ctx.biases = (b1, b2)
         ctx.meta = (p, seed1, seed2, xs, x.dtype, None if residual is None else residual.dtype)
         return y.view(*xs[:-1], w2.shape[0])
 
@@ -132,11 +162,12 @@ class FFNFn(Function):
         p, seed1, seed2, xs, xdt, rdt = ctx.meta
         gy2 = K.to_compute(gy).view(-1, w2.shape[0])
         g2 = K.act_bwd(gy2, None, K.ACT_NONE, (p, seed2))
-        dw2 = K.mm(g2, hd, ta=True, tb=True, out_dtype=torch.float32)
-        db2 = K.colsum(g2)
+        b1p, b2p = ctx.biases
+        dw2 = _wgrad(w2, g2, hd)
+        db2 = _bgrad(b2p, g2)
         dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD, drop=(p, seed1))
-        dw1 = K.mm(dpre1, x2, ta=True, tb=True, out_dtype=torch.float32)
-        db1 = K.colsum(dpre1)
+        dw1 = _wgrad(w1, dpre1, x2)
+        db1 = _bgrad(b1p, dpre1)
         dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs) if ctx.needs_input_grad[0] else None
         dres = _back(gy2, rdt, gy.shape) if rdt is not None else None
         return dx, dw1, db1, dw2, db2, dres, None, None, None
@@ -265,6 +296,7 @@ class PairedQFn(Function):
         K.mm(a0.view(-1, D), shadow(w0), Q[0].view(-1, N), bias=b0)
         K.mm(a1.view(-1, D), shadow(w1), Q[1].view(-1, N), bias=b1)
         ctx.save_for_backward(a0, w0, a1, w1)
+        ctx.biases = (b0, b1)
         ctx.dts = (x0.dtype, x1.dtype)
         return Q
 
@@ -277,9 +309,10 @@ class PairedQFn(Function):
         g0, g1 = g[0].view(-1, N), g[1].view(-1, N)
         dx0 = _back(K.mm(g0, shadow(w0), tb=True), ctx.dts[0], a0.shape)
         dx1 = _back(K.mm(g1, shadow(w1), tb=True), ctx.dts[1], a1.shape)
-        dw0 = K.mm(g0, a0.view(-1, D), ta=True, tb=True, out_dtype=torch.float32)
-        dw1 = K.mm(g1, a1.view(-1, D), ta=True, tb=True, out_dtype=torch.float32)
-        return dx0, dw0, K.colsum(g0), dx1, dw1, K.colsum(g1)
+        b0, b1 = ctx.biases
+        dw0 = _wgrad(w0, g0, a0.view(-1, D))
+        dw1 = _wgrad(w1, g1, a1.view(-1, D))
+        return dx0, dw0, _bgrad(b0, g0), dx1, dw1, _bgrad(b1, g1)
 
 
 class FcCatFn(Function):
@@ -301,6 +334,7 @@ class FcCatFn(Function):
             y = K.mm(o2[:, :D], wc[:, D:], bias=b)
             K.mm(o2[:, D:], wc[:, :D], y, res=y)
         ctx.save_for_backward(o2, w)
+        ctx.bias = b
         ctx.meta = (swap, o.dtype, o.shape)
         return y.view(*o.shape[:-1], N)
 
@@ -315,7 +349,7 @@ class FcCatFn(Function):
         wc = shadow(w)
         if not swap:
             do = K.mm(g, wc, tb=True)
-            dw = K.mm(g, o2, ta=True, tb=True, out_dtype=torch.float32)
+            dw = _wgrad(w, g, o2)
         else:
             do = torch.empty_like(o2)
             K.mm(g, wc[:, D:], do[:, :D], tb=True)
@@ -323,7 +357,7 @@ class FcCatFn(Function):
             dw = torch.empty((N, D2), dtype=torch.float32, device=g.device)
             K.mm(g, o2[:, :D], dw[:, D:], ta=True, tb=True)
             K.mm(g, o2[:, D:], dw[:, :D], ta=True, tb=True)
-        return _back(do, odt, oshape), dw, K.colsum(g), None
+        return _back(do, odt, oshape), dw, _bgrad(ctx.bias, g), None
 
 
 # ================================================================================ PGCA
@@ -415,6 +449,7 @@ class MHLAFn(Function):
         b_ = None if beta is None else beta.detach()
         y, p, mean, rstd = K.mhla_gate_ln_fwd(vc, logits, g_, b_, eps)
         ctx.save_for_backward(vc, w1, w2, pre1, h, p, mean, rstd, gamma)
+        ctx.biases = (b1, b2)
         ctx.vdt = v.dtype
         return y
 
@@ -427,11 +462,12 @@ class MHLAFn(Function):
         g_ = None if gamma is None else gamma.detach()
         dv_direct, dlogits, dg, db = K.mhla_gate_ln_bwd(K.to_compute(gy), vc, p, mean, rstd, g_)
         dl2 = dlogits.view(-1, Hh)
-        dw2 = K.mm(dl2, h, ta=True, tb=True, out_dtype=torch.float32)
-        db2 = K.colsum(dl2)
+        b1, b2 = ctx.biases
+        dw2 = _wgrad(w2, dl2, h)
+        db2 = _bgrad(b2, dl2)
         dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD)
-        dw1 = K.mm(dpre1, vc.view(-1, E), ta=True, tb=True, out_dtype=torch.float32)
-        db1 = K.colsum(dpre1)
+        dw1 = _wgrad(w1, dpre1, vc.view(-1, E))
+        db1 = _bgrad(b1, dpre1)
         dv = K.mm(dpre1, shadow(w1), tb=True, res=dv_direct.view(-1, E)).view(Bn, Lr, E)
         return _back(dv, ctx.vdt), dw1, db1, dw2, db2, dg, db, None
 

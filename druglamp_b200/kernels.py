@@ -59,7 +59,7 @@ def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, 
        tb: bool = False, bias=None, act: int = ACT_NONE, pre: Optional[torch.Tensor] = None,
        mul_aux=None, mul_mode: int = MUL_NONE, res: Optional[torch.Tensor] = None,
        drop: Tuple[float, int] = (0.0, 0), alpha: float = 1.0, out_dtype=None,
-       tile_n: int = 0) -> torch.Tensor:
+       tile_n: int = 0, accumulate: bool = False) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * op(a) @ op(b)).
 
     ta=False: a is [M,K];  ta=True: a is stored [K,M].
@@ -76,14 +76,14 @@ def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, 
         ldr = _ld(res)
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldc=_ld(out), trans_a=ta, trans_b=tb,
            alpha=alpha, bias=bias, act=act, preact_out=pre, mul_aux=mul_aux, mul_mode=mul_mode,
-           residual=res, ldr=ldr, drop_p=drop[0], drop_seed=drop[1], tile_n=tile_n)
+           residual=res, ldr=ldr, drop_p=drop[0], drop_seed=drop[1], tile_n=tile_n, accumulate=accumulate)
     return out
 
 
-def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     if out is None:
         out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
-    L.call("dl_colsum", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ld(x), L.dt(x))
+    L.call("dl_colsum", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ld(x), int(accumulate), L.dt(x))
     return out
 
 

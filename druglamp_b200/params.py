@@ -10,14 +10,34 @@ the tensor-core GEMMs read bf16 copies.  Two mechanisms keep them fresh:
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import torch
+from torch.utils.weak import WeakIdKeyDictionary
 
 from . import kernels as K
 
-_CACHE: Dict[int, list] = {}
-_FLAT: Dict[int, "FlatParams"] = {}
+# All registries hold the parameters weakly: entries die with the model, and a new parameter that
+# happens to reuse a Python id or a device address can never hit a stale entry.
+# (WeakIdKeyDictionary: identity-keyed -- tensors overload ==, so the stdlib weak dict cannot hold them)
+_CACHE = WeakIdKeyDictionary()      # Parameter -> [version, ptr, shadow]
+_FLAT = WeakIdKeyDictionary()       # Parameter -> weakref to its FlatParams store
+_BY_PTR: Dict[int, "weakref.ref"] = {}                              # data_ptr of a flat view -> Parameter
+
+
+def flat_grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """The flat-buffer gradient view of the parameter `t` refers to (None when `t` is not a whole
+    parameter of a FlatParams store).  Used to accumulate weight gradients in place."""
+    r = _BY_PTR.get(t.data_ptr()) if t.dtype == torch.float32 else None
+    p = r() if r is not None else None
+    if p is None:
+        if r is not None:
+            _BY_PTR.pop(t.data_ptr(), None)
+        return None
+    if p.data_ptr() != t.data_ptr() or p.shape != t.shape or p.grad is None or p.grad.dtype != torch.float32:
+        return None
+    return p.grad
 
 
 def shadow(p: torch.Tensor) -> torch.Tensor:
@@ -25,18 +45,19 @@ def shadow(p: torch.Tensor) -> torch.Tensor:
     cd = K.compute_dtype()
     if p.dtype == cd:
         return p.detach()
-    fp = _FLAT.get(id(p))
-    if fp is not None:
-        return fp.shadow_of(p)
     if not isinstance(p, torch.nn.Parameter):      # temporaries (slices of parameters): no caching
         return K.cast(p.detach().contiguous(), cd)
-    e = _CACHE.get(id(p))
+    r = _FLAT.get(p)
+    fp = r() if r is not None else None
+    if fp is not None:
+        return fp.shadow_of(p)
+    e = _CACHE.get(p)
     if e is not None and e[0] == p._version and e[1] == p.data_ptr() and e[2].dtype == cd:
         return e[2]
     t = e[2] if (e is not None and e[2].dtype == cd and e[2].shape == p.shape) else \
         torch.empty(p.shape, dtype=cd, device=p.device)
     K.cast(p.detach(), cd, out=t)
-    _CACHE[id(p)] = [p._version, p.data_ptr(), t]
+    _CACHE[p] = [p._version, p.data_ptr(), t]
     return t
 
 
@@ -73,7 +94,8 @@ class FlatParams:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
-                _FLAT[id(p)] = self
+                _FLAT[p] = weakref.ref(self)
+                _BY_PTR[p.data_ptr()] = weakref.ref(p)
 
     def zero_grad(self) -> None:
         self.grad.zero_()

@@ -132,8 +132,11 @@ class SSL(nn.Module):
     # ---------------------------------------------------------------- protein branch
     def prot_mlm(self, seq, extractor, xp, fill_bit, mode, mask_ignore_token_ids=(0,), mask_prob=0.15,
                  replace_prob=0.9, pad_token_id=0, mask_token_id=26):
-        labels, masked_seq, pos = sample_mlm_mask(seq, mask_prob, replace_prob, mask_ignore_token_ids,
-                                                  mask_token_id)
+        if getattr(self, "_mask_override", None) is not None:      # tests: a mask sampled elsewhere
+            labels, masked_seq, pos = (t.to(seq.device) for t in self._mask_override)
+        else:
+            labels, masked_seq, pos = sample_mlm_mask(seq, mask_prob, replace_prob, mask_ignore_token_ids,
+                                                      mask_token_id)
         B, M = pos.shape
         valid = pos >= 0
         posc = pos.clamp(min=0)

@@ -102,6 +102,8 @@ typedef struct dl_gemm_args {
    * tap and shifts B's rows by b0 + kred_shift (zero outside [0, L)); C is [taps, M, N]. */
   int32_t conv_taps, conv_left;
   int32_t kred, kred_shift;
+  int32_t accumulate; /* 1: C += result (plain fp32 outputs only) -- weight gradients land directly in
+                         the flat gradient buffer instead of a temporary plus an add kernel */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
@@ -131,9 +133,10 @@ int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols, int64_t l
 int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t rows, int32_t cols, int64_t ld,
                    float scale, int32_t dtype, void* stream);
 
-/* out[c] = sum_r x[r, c]  (bias gradients); out is fp32 [cols], overwritten. */
-int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld, int32_t dtype,
-              void* stream);
+/* out[c] (+)= sum_r x[r, c]  (bias gradients); out is fp32 [cols]: overwritten, or accumulated
+ * into when accumulate != 0 (gradients written straight into the flat gradient buffer). */
+int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld, int32_t accumulate,
+              int32_t dtype, void* stream);
 
 /* y = x * keep/(1-p), keep(i) = hash(seed, i) >= p (nn.Dropout of PMMA, model/PMMA/mlp.py:47,49,
  * model/PMMA/embed.py:42,52; the mask is recomputed from the seed in backward). */

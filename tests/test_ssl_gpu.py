@@ -1,0 +1,79 @@
+"""GPU: the self-supervised heads (H13) against the fixture generated from the unmodified reference
+(tests/golden/make_golden.py::run_ssl): protein MLM through the shared ProteinCNN + LLM-logit head and
+drug SimSiam, losses and every SSL parameter gradient.  The MLM mask is sampled on the CPU with the
+fixture's torch seed (the sampler itself is pinned bit-exactly in test_abi_and_host_cpu.py), so both
+sides mask the same positions."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, digest, N_SAMPLES
+
+pytestmark = pytest.mark.gpu
+
+
+def _digest_err(actual, gold, floor=0.0):
+    a = digest(actual.float())
+    k = min(N_SAMPLES, actual.numel())
+    scale = max(np.abs(gold[:k]).max(), gold[-1] / max(actual.numel(), 1), floor, 1e-30)
+    return float(np.abs(a[:k] - gold[:k]).max() / scale)
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-3, 2e-2), (torch.bfloat16, 3e-2, None)])
+def test_ssl_losses_and_grads_match_reference_fixture(dtype, tol, gtol):
+    import druglamp_b200 as D
+    from druglamp_b200 import models
+    from druglamp_b200.ssl import sample_mlm_mask
+    from druglamp_b200.synth import make_batch
+    from oracle import restatement as R
+    fx = load_golden("druglamp_train_b8_ssl.npz")
+    B, seed = int(fx["meta_B"]), int(fx["meta_seed"])
+    D.set_compute_dtype(dtype)
+    try:
+        m = models.DrugLAMP(384, 640).cuda()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        m.train(True)
+        b = make_batch(B, seed=seed)
+        bc = b.to("cuda")
+
+        def det_load():
+            shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+            m.load_state_dict(R.deterministic_state(shapes), strict=True)
+
+        det_load()
+        from druglamp_b200.modules import binary_cross_entropy
+        outs = m(*bc.model_inputs())
+        ssl = outs[2]
+        # the fixture was recorded after the classification backward of the same model without a
+        # zero_grad in between (make_golden.run_model -> run_ssl), so the shared ProteinCNN's
+        # gradients are the sum of both losses: follow the same sequence
+        binary_cross_entropy(outs[4], bc.y)[1].backward()
+        inp = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in ssl.items()}
+        m.ssl_model(**inp)                      # materialises the lazy SimSiam projectors (App. A13)
+        assert any(".projector." in k for k in m.state_dict())
+        det_load()                              # like the fixture: deterministic weights incl. projectors
+        torch.manual_seed(12)
+        m.ssl_model._mask_override = sample_mlm_mask(b.vp)          # CPU sampler, fixture's seed
+        assert np.array_equal(m.ssl_model._mask_override[0].numpy().astype(np.int8), fx["ssl_labels"])
+        out = m.ssl_model(**inp)
+        prot, drug = float(out["prot_ssl"]), float(out["drug_ssl"])
+        assert abs(prot - float(fx["ssl_prot"])) <= tol * abs(float(fx["ssl_prot"])), (prot, float(fx["ssl_prot"]))
+        assert abs(drug - float(fx["ssl_drug"])) <= tol * abs(float(fx["ssl_drug"])), (drug, float(fx["ssl_drug"]))
+        (out["prot_ssl"] + out["drug_ssl"]).backward()
+        if gtol is not None:
+            params = dict(m.ssl_model.named_parameters())
+            gmax = max(np.abs(fx[k][:64]).max() for k in fx if k.startswith("ssl_grad/"))
+            errs = []
+            for k in fx:
+                if k.startswith("ssl_grad/"):
+                    g = params[k[len("ssl_grad/"):]].grad
+                    assert g is not None, k
+                    errs.append((_digest_err(g, fx[k], floor=1e-3 * gmax), k, float(np.abs(fx[k][:64]).max()),
+                                 float(g.abs().max())))
+            errs.sort(reverse=True)
+            print("gmax %.3e; " % gmax + "; ".join(f"{k[9:]} err={e:.2e} gold={s:.2e} mine={mn:.2e}" for e, k, s, mn in errs[:10]))
+            assert errs[0][0] <= gtol, errs[0]
+    finally:
+        D.set_compute_dtype(torch.float32)
