@@ -188,6 +188,18 @@ def run_gpu(args):
     batches = [StaticBatch(make_batch(BATCH, seed=1234 + rank * 100 + i), dev) for i in range(N_DISTINCT_BATCHES)]
     hosts = [b.host_copy(pin=True) for b in batches]
     h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+    if args.ncu_step:
+        # profiling aid (never a bench value): one eager step between cudaProfilerStart/Stop so that
+        #   ncu --profile-from-start off ... python bench.py --ncu-step
+        # sees exactly the kernels of one step (forward, backward on the autograd thread, optimizer)
+        for _ in range(2):
+            ts._fwd_bwd(batches[0]); ts._update()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ts._fwd_bwd(batches[0]); ts._update()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     for b in batches:
         ts.capture(b)
 
@@ -357,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="run one eager step in an NVTX range and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2,12 +2,12 @@
 // memory and a fused epilogue.
 //
 // One CTA per SM loops over 128 x BN output tiles (optionally K-slices of tiles: split-K).
-// Warp roles (320 threads):
+// Warp roles (576 threads):
 //   warp 0      TMA producer: fills a ring of kStages {A tile, B tile} buffers (SWIZZLE_128B),
 //               running ahead across tiles
 //   warp 1      allocates 2*BN TMEM columns, issues tcgen05.mma (one thread) into accumulator
 //               buffer (tile & 1), commits to mbarriers
-//   warps 2..9  epilogue (two warps per TMEM lane quadrant, half the columns each): tcgen05.ld
+//   warps 2..17 epilogue (four warps per TMEM lane quadrant, a quarter of the columns each): tcgen05.ld
 //               16 columns of the thread's row at a time, apply bias / activation / auxiliary
 //               multiply / dropout / residual in registers and store whole 32-byte sectors with
 //               16-byte vector stores (or atomically accumulate, split-K).  The epilogue of tile i
@@ -29,7 +29,8 @@ void count_launch(int n = 1);
 namespace {
 
 constexpr int BM = 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                 // four warps per TMEM lane quadrant
+constexpr int kColSplit = kEpiWarps / 4;      // column slices per tile
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 struct GemmParams {
@@ -169,7 +170,7 @@ __device__ __forceinline__ float apply_mul(float x, float a, int mode) {
               : mode == DL_MUL_RELU_MASK ? (a > 0.f ? 1.f : 0.f) : a);
 }
 
-// One warp's 32-row x (BN/2)-column slice of a tile, straight from tensor memory to global memory:
+// One warp's 32-row x (BN/4)-column slice of a tile, straight from tensor memory to global memory:
 // thread = row (the tcgen05.ld 32x32b layout), 16 columns per step = one or two 16-byte stores per
 // thread.  Every 32-byte sector a thread touches is written (or read) in full.
 template <typename TC, int BN>
@@ -193,7 +194,7 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, uint32_t tme
   const long long crow = cbase + (long long)row * p.ldc;
   const long long rrow = rbase + (long long)row * p.ldr;
 #pragma unroll 1
-  for (int c0 = col_begin; c0 < col_begin + BN / 2; c0 += 16) {
+  for (int c0 = col_begin; c0 < col_begin + BN / kColSplit; c0 += 16) {
     const int col = n0 + c0;
     if (col >= p.N) break;                           // warp-uniform
     uint32_t v[16];
@@ -380,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // -------------------------------------------------------------- epilogue (warps 2..9)
     const int we = warp - 2;
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = we >> 2;                     // which half of the tile's columns
+    const int half = we >> 2;                     // which column slice of the tile
     uint32_t it = 0, ti = 0;
     for (int tl = blockIdx.x; tl < p.total_tiles; tl += gridDim.x, ++ti) {
       const Tile T = decode_tile<BN, C::KE>(p, tl);
@@ -415,9 +416,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tmem_q = tmem + ab * BN + ((uint32_t)(q * 32) << 16);
       if (p.dbg == 2) {
       } else if (p.c_bf16)
-        epilogue_slice<__nv_bfloat16, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / 2), cbase, rbase, T.zb);
+        epilogue_slice<__nv_bfloat16, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / kColSplit), cbase, rbase, T.zb);
       else
-        epilogue_slice<float, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / 2), cbase, rbase, T.zb);
+        epilogue_slice<float, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / kColSplit), cbase, rbase, T.zb);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * ab);
