@@ -77,6 +77,34 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// one 16-byte access <-> 4 (fp32) or 8 (bf16) floats
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+__device__ __forceinline__ void ldv(const float* p, float (&x)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    x[2 * i] = f.x; x[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void stv(float* p, const float (&x)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const float (&x)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ------------------------------------------------------------------ math
 // erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 rounding level) with one
 // ex2 and one fast reciprocal: ~12 instructions instead of erff's ~40 -- the GELU epilogues of the

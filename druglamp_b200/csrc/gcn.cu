@@ -148,12 +148,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
   }
 }
 
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma, int acc,
                                      float* __restrict__ dbeta, int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) {
-    if (dbeta) dbeta[c] = (float)sums[c];
-    if (dgamma) dgamma[c] = (float)sums[cols + c];
+    if (dbeta) dbeta[c] = (acc ? dbeta[c] : 0.f) + (float)sums[c];
+    if (dgamma) dgamma[c] = (acc ? dgamma[c] : 0.f) + (float)sums[cols + c];
   }
 }
 
@@ -165,6 +165,226 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean,
     mean[c] = running_mean[c];
     rstd[c] = rsqrtf(running_var[c] + eps);
   }
+}
+
+// ---------------------------------------------------------------- vectorised BatchNorm passes
+// Column-slice layout shared by the three kernels below: `tpr` threads cover one row slice with
+// 16-byte accesses (thread = V fixed columns, so the per-column constants live in registers),
+// 256 / tpr rows per pass, blockIdx.y strides over row blocks.  Needs cols % V == 0.
+struct ColSlice {
+  int tpr, xb;
+  unsigned yb;
+  long long rpb;
+};
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+bn_colstats_vec_kernel(const T* __restrict__ a, const T* __restrict__ x, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, double* __restrict__ sums, long long rows,
+                       int cols, long long rows_per_block, int tpr) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[2][256][V + 1];
+  const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
+  const int c = (blockIdx.x * tpr + vcol) * V;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s1[V], s2[V], mu[V], rs[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; rs[j] = 0.f; }
+  if (c < cols) {
+    if (BWD) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { mu[j] = mean[c + j]; rs[j] = rstd[c + j]; }
+    }
+    long long r = r0 + rsub;
+    for (; r + rpp < r1; r += 2 * rpp) {             // two rows (four 16-byte loads) in flight
+      float av[2][V], xv[2][V];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ldv(a + (r + u * rpp) * cols + c, av[u]);
+        if (BWD) ldv(x + (r + u * rpp) * cols + c, xv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float bv = BWD ? (xv[u][j] - mu[j]) * rs[j] : av[u][j];
+          s1[j] += av[u][j];
+          s2[j] = fmaf(av[u][j], bv, s2[j]);
+        }
+    }
+    for (; r < r1; r += rpp) {
+      float av[V], xv[V];
+      ldv(a + r * cols + c, av);
+      if (BWD) ldv(x + r * cols + c, xv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float bv = BWD ? (xv[j] - mu[j]) * rs[j] : av[j];
+        s1[j] += av[j];
+        s2[j] = fmaf(av[j], bv, s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) { red[0][threadIdx.x][j] = s1[j]; red[1][threadIdx.x][j] = s2[j]; }
+  __syncthreads();
+  // per-thread fp32 partials cover at most a few dozen rows; everything above that is fp64
+  for (int o = threadIdx.x; o < tpr * V; o += 256) {
+    const int vc = o / V, j = o % V;
+    const int col = (blockIdx.x * tpr + vc) * V + j;
+    if (col < cols) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int i = 0; i < rpp; ++i) { t1 += red[0][i * tpr + vc][j]; t2 += red[1][i * tpr + vc][j]; }
+      atomicAdd(sums + col, t1);
+      atomicAdd(sums + cols + col, t2);
+    }
+  }
+}
+
+// y = (x - mean) * rstd * gamma + beta.  FINALIZE: mean / rstd come from the fp64 column sums
+// (biased variance); the first row block also stores them for the backward pass and updates the
+// running statistics (momentum, unbiased variance) and num_batches_tracked.
+template <typename T, bool FINALIZE>
+__global__ void __launch_bounds__(256)
+bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, float* __restrict__ mean,
+                    float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ running_mean,
+                    float* __restrict__ running_var, long long* __restrict__ nbt, T* __restrict__ y,
+                    long long rows, int cols, long long rows_per_block, int tpr, float eps,
+                    float momentum) {
+  constexpr int V = Vec16<T>::N;
+  const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
+  const int c = (blockIdx.x * tpr + vcol) * V;
+  if (FINALIZE && nbt && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *nbt += 1;
+  if (c >= cols) return;
+  float sc[V], sh[V], mu_[V];
+  const bool writer = blockIdx.y == 0 && rsub == 0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float mu, rs;
+    if (FINALIZE) {
+      const double m = sums[c + j] / (double)rows;
+      double var = sums[cols + c + j] / (double)rows - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = (float)m;
+      rs = (float)(1.0 / sqrt(var + (double)eps));
+      if (writer) {
+        mean[c + j] = mu;
+        rstd[c + j] = rs;
+        if (running_mean) {
+          const double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+          running_mean[c + j] = (1.f - momentum) * running_mean[c + j] + momentum * mu;
+          running_var[c + j] = (1.f - momentum) * running_var[c + j] + momentum * (float)unb;
+        }
+      }
+    } else {
+      mu = mean[c + j];
+      rs = rstd[c + j];
+    }
+    sc[j] = rs * (gamma ? gamma[c + j] : 1.f);
+    sh[j] = beta ? beta[c + j] : 0.f;
+    mu_[j] = mu;
+  }
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  long long r = r0 + rsub;
+  for (; r + 3 * rpp < r1; r += 4 * rpp) {
+    float v[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ldv(x + (r + u * rpp) * cols + c, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[u][j] = fmaf(v[u][j] - mu_[j], sc[j], sh[j]);
+      stv(y + (r + u * rpp) * cols + c, v[u]);
+    }
+  }
+  for (; r < r1; r += rpp) {
+    float v[V];
+    ldv(x + r * cols + c, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaf(v[j] - mu_[j], sc[j], sh[j]);
+    stv(y + r * cols + c, v);
+  }
+}
+
+// training: dx = gamma*rstd * (dy - sum_dy/N - xhat * sum_dyxhat/N); eval: dx = gamma*rstd*dy.
+// The first row block also writes dbeta = sum dy, dgamma = sum dy*xhat.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, long long rows, int cols, long long rows_per_block,
+                        int tpr, int training, int acc) {
+  constexpr int V = Vec16<T>::N;
+  const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
+  const int c = (blockIdx.x * tpr + vcol) * V;
+  if (c >= cols) return;
+  // dx = k0 * (dy - m1 - (x - mu) * k1) with per-column constants
+  float k0[V], k1[V], m1[V], mu_[V];
+  const bool writer = blockIdx.y == 0 && rsub == 0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float g = gamma ? gamma[c + j] : 1.f, rs = rstd[c + j], mu = mean[c + j];
+    const double sdy = sums[c + j], sdyx = sums[cols + c + j];
+    if (writer) {
+      if (dbeta) dbeta[c + j] = (acc ? dbeta[c + j] : 0.f) + (float)sdy;
+      if (dgamma) dgamma[c + j] = (acc ? dgamma[c + j] : 0.f) + (float)sdyx;
+    }
+    k0[j] = g * rs;
+    mu_[j] = mu;
+    m1[j] = training ? (float)(sdy / (double)rows) : 0.f;
+    k1[j] = training ? rs * (float)(sdyx / (double)rows) : 0.f;
+  }
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  long long r = r0 + rsub;
+  for (; r + rpp < r1; r += 2 * rpp) {
+    float d[2][V], xv[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ldv(dy + (r + u * rpp) * cols + c, d[u]);
+      ldv(x + (r + u * rpp) * cols + c, xv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) d[u][j] = k0[j] * (d[u][j] - m1[j] - (xv[u][j] - mu_[j]) * k1[j]);
+      stv(dx + (r + u * rpp) * cols + c, d[u]);
+    }
+  }
+  for (; r < r1; r += rpp) {
+    float d[V], xv[V];
+    ldv(dy + r * cols + c, d);
+    ldv(x + r * cols + c, xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) d[j] = k0[j] * (d[j] - m1[j] - (xv[j] - mu_[j]) * k1[j]);
+    stv(dx + r * cols + c, d);
+  }
+}
+
+// geometry for the vectorised passes; false when the shape / alignment does not qualify
+bool col_slice(const void* p0, const void* p1, const void* p2, long long rows, int cols, int vec,
+               int max_rows_per_thread, ColSlice* g) {
+  if (cols % vec != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2)) & 15)
+    return false;
+  int tpr = 1;
+  while (tpr < 256 && tpr * vec < cols) tpr <<= 1;
+  g->tpr = tpr;
+  g->xb = ceil_div(cols, tpr * vec);
+  const int rpp = 256 / tpr;
+  long long yb = (long long)sm_count() * 2 / g->xb;
+  const long long need = (rows + (long long)max_rows_per_thread * rpp - 1) / ((long long)max_rows_per_thread * rpp);
+  if (yb < need) yb = need;
+  const long long maxy = (rows + 2 * rpp - 1) / (2 * rpp);
+  if (yb > maxy) yb = maxy;
+  if (yb < 1) yb = 1;
+  if (yb > 65535) return false;
+  g->yb = (unsigned)yb;
+  g->rpb = (rows + yb - 1) / yb;
+  return true;
 }
 
 void stats_grid(long long rows, int cols, dim3* grid, long long* rpb) {
@@ -216,6 +436,34 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
   DL_REQUIRE(x && y && mean && rstd, "dl_batchnorm_fwd: null pointer");
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_fwd: cols must be a positive multiple of 4 and rows >= 1");
   cudaStream_t st = (cudaStream_t)stream;
+  ColSlice g;
+  const int vec = dtype == DL_BF16 ? 8 : 4;
+  if (col_slice(x, y, nullptr, rows, cols, vec, 32, &g)) {
+    const dim3 grid(g.xb, g.yb);
+    if (training) {
+      DL_REQUIRE(workspace != nullptr, "dl_batchnorm_fwd: workspace required in training mode");
+      DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
+      if (dtype == DL_BF16) {
+        bn_colstats_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
+        bn_apply_vec_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+      } else {
+        bn_colstats_vec_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
+        bn_apply_vec_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+      }
+      DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_apply_vec_kernel");
+      count_launch(2);
+    } else {
+      DL_REQUIRE(running_mean && running_var, "dl_batchnorm_fwd: eval mode needs running statistics");
+      bn_eval_stats_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(running_mean, running_var, mean, rstd, cols, eps);
+      if (dtype == DL_BF16)
+        bn_apply_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+      else
+        bn_apply_vec_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+      DL_LAUNCH_CHECK("bn_eval_stats_kernel / bn_apply_vec_kernel");
+      count_launch(2);
+    }
+    return 0;
+  }
   if (training) {
     DL_REQUIRE(workspace != nullptr, "dl_batchnorm_fwd: workspace required in training mode");
     DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
@@ -248,11 +496,25 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
 extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma,
                                 const float* mean, const float* rstd, void* dx, float* dgamma,
                                 float* dbeta, double* workspace, int64_t rows, int32_t cols,
-                                int32_t training, int32_t dtype, void* stream) {
+                                int32_t training, int32_t accumulate, int32_t dtype, void* stream) {
   DL_REQUIRE(dy && x && mean && rstd && dx && workspace, "dl_batchnorm_bwd: null pointer");
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
+  ColSlice g;
+  if (col_slice(dy, x, dx, rows, cols, dtype == DL_BF16 ? 8 : 4, 32, &g)) {
+    const dim3 vgrid(g.xb, g.yb);
+    if (dtype == DL_BF16) {
+      bn_colstats_vec_kernel<__nv_bfloat16, true><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
+      bn_bwd_apply_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+    } else {
+      bn_colstats_vec_kernel<float, true><<<vgrid, 256, 0, st>>>((const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
+      bn_bwd_apply_vec_kernel<float><<<vgrid, 256, 0, st>>>((const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+    }
+    DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_bwd_apply_vec_kernel");
+    count_launch(2);
+    return 0;
+  }
   dim3 grid; long long rpb;
   stats_grid(rows, cols, &grid, &rpb);
   if (dtype == DL_BF16)
@@ -261,7 +523,7 @@ extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamm
     bn_colstats_kernel<float, true><<<grid, dim3(32, 8), 0, st>>>((const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, rpb);
   DL_LAUNCH_CHECK("bn_colstats_kernel(bwd)");
   if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, dgamma, dbeta, cols);
+    bn_param_grad_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, dgamma, accumulate, dbeta, cols);
     DL_LAUNCH_CHECK("bn_param_grad_kernel");
     count_launch();
   }

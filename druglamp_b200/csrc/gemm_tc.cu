@@ -241,9 +241,17 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, uint32_t tme
     }
     if (p.dbg == 1 && x[0] != 12345.678f) continue;
     if (atomic) {
+      float* dst = reinterpret_cast<float*>(p.C) + off;
+      if (full && al_c) {                            // 4 x 16-byte vector reductions (REDG.F32x4)
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) atomicAdd(reinterpret_cast<float*>(p.C) + off + j, x[j]);
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                       :: "l"(dst + j), "f"(x[j]), "f"(x[j + 1]), "f"(x[j + 2]), "f"(x[j + 3]) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) atomicAdd(dst + j, x[j]);
+      }
     } else {
       store16<TC>(Cp + off, x, full && al_c, nvalid);
     }
@@ -555,18 +563,30 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
     // widest tile that still gives every SM a tile (wider tiles halve the operand re-reads and
     // measured 1.1 PFLOP/s at 128x256 vs 0.74 at 128x128 on 8192^3)
     const long long mt = ceil_div(a->M, BM);
-    bn = 64;
-    if (a->N > 128 && mt * ceil_div(a->N, 256) * batch >= sms) bn = 256;
-    else if (a->N > 64 && mt * ceil_div(a->N, 128) * batch >= sms) bn = 128;
-    // weight-gradient shapes get their parallelism from split-K.  Atomic traffic grows with
-    // splits x tile area, so narrow tiles stay (measured: 256x256x16384 21 us at BN=64 vs 44 us at
-    // BN=256); only a single 128-wide N (the conv weight gradients) takes the 128 tile.
+    auto tiles_at = [&](int w) { return mt * ceil_div(a->N, w) * batch; };
+    const int widest = a->N > 128 ? 256 : a->N > 64 ? 128 : 64;
+    // weight-gradient shapes get their parallelism from split-K: the widest tile that still leaves
+    // four output tiles (wider tiles re-read less of the long-K operands from L2; the split slices
+    // land with 16-byte vector reductions).  Measured on B200, K = 16384: 512x512 40.7 us at BN=64,
+    // 24.6 at 256; 256x256 16.7 / 12.1 (128) / 14.1; 128x256 best at 64.
     const bool split_candidate = a->dtype_c == DL_F32 && !a->bias && !a->preact_out && !a->mul_aux &&
-                                 !a->residual && a->act == DL_ACT_NONE && a->split_k != 1 &&
-                                 ceil_div(k_total, KE_) >= 16;
-    if (bn == 64 && split_candidate && a->N > 64 && a->N <= 128 &&
-        (long long)ceil_div(k_total, KE_) * mt * batch / sms >= 32)
-      bn = 128;
+                                 !a->residual && a->act == DL_ACT_NONE && a->drop_p == 0.f &&
+                                 a->split_k != 1 && ceil_div(k_total, KE_) >= 16;
+    bn = 0;
+    if (split_candidate) {
+      int w = widest;
+      while (w > 64 && tiles_at(w) < 4) w >>= 1;
+      if (tiles_at(w) * 2 <= sms) bn = w;
+    }
+    if (bn == 0) {
+      // otherwise minimise waves x per-tile operand traffic (a 128 x w tile loads 128 + w rows per
+      // k-block): wide tiles unless they leave most SMs idle.  8192^3: 1.11 PFLOP/s at 256, 0.73 at 128.
+      long long best = -1;
+      for (int w = widest; w >= 64; w >>= 1) {
+        const long long cost = ceil_div(tiles_at(w), (long long)sms) * (BM + w);
+        if (best < 0 || cost < best) { best = cost; bn = w; }
+      }
+    }
   }
   DL_REQUIRE(bn == 64 || bn == 128 || bn == 256, "dl_gemm: tile_n must be 0, 64, 128 or 256");
 

@@ -314,6 +314,54 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, 
   }
 }
 
+// Vectorised variant (cols and ld multiples of the 16-byte vector, 16-byte aligned base): `tpr`
+// threads cover one row slice with 16-byte loads, 256 / tpr rows per pass, four passes in flight.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols,
+                  long long ld, long long rows_per_block, int tpr) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float red[256][V + 1];
+  const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
+  const int c = (blockIdx.x * tpr + vcol) * V;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  if (c < cols) {
+    long long r = r0 + rsub;
+    for (; r + 3 * rpp < r1; r += 4 * rpp) {
+      float v[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ldv(x + (r + u * rpp) * ld + c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += v[u][j];
+    }
+    for (; r < r1; r += rpp) {
+      float v[V];
+      ldv(x + r * ld + c, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  // thread t finishes column (t % tpr) * V + (t / tpr) when that sub-index is a vector lane
+  for (int o = threadIdx.x; o < tpr * V; o += 256) {
+    const int vc = o / V, j = o % V;
+    const int col = (blockIdx.x * tpr + vc) * V + j;
+    if (col < cols) {
+      float t = 0.f;
+      for (int i = 0; i < rpp; ++i) t += red[i * tpr + vc][j];
+      atomicAdd(out + col, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dropout / cast / add
 
 template <typename T>
@@ -499,13 +547,13 @@ extern "C" int dl_layernorm_fwd(const void* x, const float* gamma, const float* 
 
 extern "C" int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma,
                                 const float* mean, const float* rstd, void* dx, float* dgamma,
-                                float* dbeta, int64_t rows, int32_t cols, int32_t dtype,
-                                void* stream) {
+                                float* dbeta, int64_t rows, int32_t cols, int32_t accumulate,
+                                int32_t dtype, void* stream) {
   DL_REQUIRE(dy && x && gamma && mean && rstd && dx, "dl_layernorm_bwd: null pointer");
   DL_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "dl_layernorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dgamma) DL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
-  if (dbeta) DL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
+  if (dgamma && !accumulate) DL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
+  if (dbeta && !accumulate) DL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
   if (rows == 0) return 0;
   return dtype == DL_BF16 ? ln_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st)
                           : ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
@@ -567,6 +615,24 @@ extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, 
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) DL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
   if (rows <= 0) return 0;
+  const int vec = dtype == DL_BF16 ? 8 : 4;
+  if (cols % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    int tpr = 1;
+    while (tpr < 256 && tpr * vec < cols) tpr <<= 1;
+    const int xb = ceil_div(cols, tpr * vec), rpp = 256 / tpr;
+    long long yb = (long long)sm_count() * 2 / xb;
+    if (yb < 1) yb = 1;
+    if (yb > (rows + 4 * rpp - 1) / (4 * rpp)) yb = (rows + 4 * rpp - 1) / (4 * rpp);
+    const long long rpb = (rows + yb - 1) / yb;
+    dim3 grid(xb, (unsigned)yb);
+    if (dtype == DL_BF16)
+      colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb, tpr);
+    else
+      colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, rows, cols, ld, rpb, tpr);
+    DL_LAUNCH_CHECK("colsum_vec_kernel");
+    count_launch();
+    return 0;
+  }
   const int xb = ceil_div(cols, 32);
   long long yb = (long long)sm_count() * 4 / xb;
   if (yb < 1) yb = 1;

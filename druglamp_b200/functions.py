@@ -184,14 +184,18 @@ class LayerNormFn(Function):
     def forward(ctx, x, gamma, beta, eps):
         xc = K.to_compute(x)
         y, mean, rstd = K.layernorm_fwd(xc, gamma.detach(), beta.detach(), eps)
-        ctx.save_for_backward(xc, gamma, mean, rstd)
+        ctx.save_for_backward(xc, gamma, beta, mean, rstd)
         ctx.xdt = x.dtype
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        xc, gamma, mean, rstd = ctx.saved_tensors
+        xc, gamma, beta, mean, rstd = ctx.saved_tensors
+        tg, tb = _grad_target(gamma), _grad_target(beta)
+        if tg is not None and tb is not None:       # straight into the flat gradient buffer
+            dx, _, _ = K.layernorm_bwd(K.to_compute(gy), xc, gamma.detach(), mean, rstd, acc_into=(tg, tb))
+            return _back(dx, ctx.xdt), None, None, None
         dx, dg, db = K.layernorm_bwd(K.to_compute(gy), xc, gamma.detach(), mean, rstd)
         return _back(dx, ctx.xdt), dg, db, None
 
@@ -389,7 +393,7 @@ class PGCAFn(Function):
         scale = float(E // H) ** -0.5
         O, P, raw = _attn_fwd(Qp, Kp, Vp, H, scale, True)
         out = K.mm(O.view(-1, E), shadow(out_w), bias=out_b.detach()).view(Bn, Lq, E)
-        ctx.save_for_backward(qb, kb, vb, in_w, out_w, Qp, KV, P, O)
+        ctx.save_for_backward(qb, kb, vb, in_w, out_w, Qp, KV, P, O, in_b, out_b)
         ctx.meta = (H, scale, shared, query.dtype, key.dtype, value.dtype)
         raw = raw.view(Bn, H, Lq, Sk)
         ctx.mark_non_differentiable(raw)
@@ -398,34 +402,39 @@ class PGCAFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gout, _graw):
-        qb, kb, vb, in_w, out_w, Qp, KV, P, O = ctx.saved_tensors
+        qb, kb, vb, in_w, out_w, Qp, KV, P, O, in_b, out_b = ctx.saved_tensors
         H, scale, shared, qdt, kdt, vdt = ctx.meta
         Bn, Lq, E = qb.shape
         Sk = kb.shape[1]
         g = K.to_compute(gout.transpose(0, 1)).view(-1, E)             # (B*L, E)
-        d_out_w = K.mm(g, O.view(-1, E), ta=True, tb=True, out_dtype=torch.float32)
-        d_out_b = K.colsum(g)
+        d_out_w = _wgrad(out_w, g, O.view(-1, E))
+        d_out_b = _bgrad(out_b, g)
         dO = K.mm(g, shadow(out_w), tb=True).view(Bn, Lq, E)
         dKV = torch.empty_like(KV)
         dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, H, scale,
                               dk_out=dKV[:, :, :E], dv_out=dKV[:, :, E:])
         wi = shadow(in_w)
         dq2, dkv2 = dQp.view(-1, E), dKV.view(-1, 2 * E)
-        d_in_w = torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
-        d_in_b = torch.empty(3 * E, dtype=torch.float32, device=g.device)
-        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True)
-        K.colsum(dq2, d_in_b[:E])
-        K.colsum(dkv2, d_in_b[E:])
+        # the packed in-proj gradients go straight into the flat gradient buffer when there is one
+        tw, tb_ = _grad_target(in_w), _grad_target(in_b)
+        acc = tw is not None and tb_ is not None
+        d_in_w = tw if acc else torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
+        d_in_b = tb_ if acc else torch.empty(3 * E, dtype=torch.float32, device=g.device)
+        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True, accumulate=acc)
+        K.colsum(dq2, d_in_b[:E], accumulate=acc)
+        K.colsum(dkv2, d_in_b[E:], accumulate=acc)
         dquery = _back(K.mm(dq2, wi[:E], tb=True).view(Bn, Lq, E), qdt).transpose(0, 1)
         if shared:
-            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True)
+            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True, accumulate=acc)
             dkey = _back(K.mm(dkv2, wi[E:], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
             dvalue = None
         else:
-            K.mm(dkv2[:, :E], kb.view(-1, E), d_in_w[E:2 * E], ta=True, tb=True)
-            K.mm(dkv2[:, E:], vb.view(-1, E), d_in_w[2 * E:], ta=True, tb=True)
+            K.mm(dkv2[:, :E], kb.view(-1, E), d_in_w[E:2 * E], ta=True, tb=True, accumulate=acc)
+            K.mm(dkv2[:, E:], vb.view(-1, E), d_in_w[2 * E:], ta=True, tb=True, accumulate=acc)
             dkey = _back(K.mm(dkv2[:, :E], wi[E:2 * E], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
             dvalue = _back(K.mm(dkv2[:, E:], wi[2 * E:], tb=True).view(Bn, Sk, E), vdt).transpose(0, 1)
+        if acc:
+            d_in_w = d_in_b = None
         return dquery, dkey, dvalue, d_in_w, d_in_b, d_out_w, d_out_b, None
 
 
@@ -501,16 +510,21 @@ class BatchNormFn(Function):
         g_ = None if gamma is None else gamma.detach()
         b_ = None if beta is None else beta.detach()
         y, mean, rstd = K.batchnorm_fwd(x2, g_, b_, running_mean, running_var, nbt, eps, momentum, training)
-        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.save_for_backward(x2, gamma, beta, mean, rstd)
         ctx.meta = (training, x.dtype, x.shape)
         return y.view(xc.shape)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x2, gamma, mean, rstd = ctx.saved_tensors
+        x2, gamma, beta, mean, rstd = ctx.saved_tensors
         training, xdt, xshape = ctx.meta
         g_ = None if gamma is None else gamma.detach()
+        tg, tb = _grad_target(gamma), _grad_target(beta)
+        if tg is not None and tb is not None:       # straight into the flat gradient buffer
+            dx, _, _ = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
+                                       acc_into=(tg, tb))
+            return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None
         dx, dg, db = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
                                      need_param_grads=gamma is not None)
         return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None
@@ -576,14 +590,14 @@ class Conv1dSameFn(Function):
         out = torch.empty(xc.shape[:2] + (Cout,), dtype=xc.dtype, device=xc.device)
         K.conv1d_same(xc, w_taps, out, taps=k, left=left, bias=None if b is None else b.detach(),
                       act=K.ACT_RELU if relu else K.ACT_NONE)
-        ctx.save_for_backward(xc, w, out if relu else None)
+        ctx.save_for_backward(xc, w, out if relu else None, b)
         ctx.meta = (relu, left, x.dtype, b is not None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        xc, w, out = ctx.saved_tensors
+        xc, w, out, b = ctx.saved_tensors
         relu, left, xdt, has_b = ctx.meta
         Cout, Cin, k = w.shape
         g = K.to_compute(gy)
@@ -598,7 +612,7 @@ class Conv1dSameFn(Function):
         if ctx.needs_input_grad[1]:
             dw = K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0).contiguous()
         if has_b and ctx.needs_input_grad[2]:
-            db = K.colsum(g.view(-1, Cout))
+            db = _bgrad(b, g.view(-1, Cout))
         return dx, dw, db, None
 
 

@@ -145,15 +145,18 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, save: bool = True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True):
+def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True, acc_into=None):
+    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to."""
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     dx = torch.empty_like(x)
     dg = db = None
-    if need_param_grads:
+    if acc_into is not None:
+        dg, db = acc_into
+    elif need_param_grads:
         dg = torch.empty(cols, dtype=torch.float32, device=x.device)
         db = torch.empty_like(dg)
     L.call("dl_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-           rstd.data_ptr(), dx.data_ptr(), L.ptr(dg), L.ptr(db), rows, cols, L.dt(x))
+           rstd.data_ptr(), dx.data_ptr(), L.ptr(dg), L.ptr(db), rows, cols, int(acc_into is not None), L.dt(x))
     return dx, dg, db
 
 
@@ -194,16 +197,20 @@ def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, 
     return y, mean, rstd
 
 
-def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True):
+def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True, acc_into=None):
+    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to."""
     rows, cols = x.shape
     dx = torch.empty_like(x)
     ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
     dg = db = None
-    if need_param_grads:
+    if acc_into is not None:
+        dg, db = acc_into
+    elif need_param_grads:
         dg = torch.empty(cols, dtype=torch.float32, device=x.device)
         db = torch.empty_like(dg)
     L.call("dl_batchnorm_bwd", dy.data_ptr(), x.data_ptr(), L.ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
-           dx.data_ptr(), L.ptr(dg), L.ptr(db), ws.data_ptr(), rows, cols, int(training), L.dt(x))
+           dx.data_ptr(), L.ptr(dg), L.ptr(db), ws.data_ptr(), rows, cols, int(training),
+           int(acc_into is not None), L.dt(x))
     return dx, dg, db
 
 

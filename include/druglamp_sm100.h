@@ -119,10 +119,11 @@ int dl_gemm(const dl_gemm_args* args, void* stream);
 int dl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                      float* rstd, int64_t rows, int32_t cols, float eps, int32_t dtype,
                      void* stream);
-/* dgamma/dbeta ([cols] fp32, overwritten; may be NULL). */
+/* dgamma/dbeta ([cols] fp32; may be NULL): overwritten, or added to when accumulate != 0 (the
+ * parameter's .grad buffer itself, torch's AccumulateGrad semantics without the extra add). */
 int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                      const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows,
-                     int32_t cols, int32_t dtype, void* stream);
+                     int32_t cols, int32_t accumulate, int32_t dtype, void* stream);
 
 /* softmax over the last dim of a [rows, cols<=1024] matrix with row stride ld; in-place allowed.
  * Replaces F.softmax in PGCA (model/PGCA/guided_cross_attention_model.py:308) and
@@ -186,7 +187,8 @@ int dl_batchnorm_fwd(const void* x, const float* gamma, const float* beta, void*
                      float eps, float momentum, int32_t training, int32_t dtype, void* stream);
 int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                      const float* rstd, void* dx, float* dgamma, float* dbeta, double* workspace,
-                     int64_t rows, int32_t cols, int32_t training, int32_t dtype, void* stream);
+                     int64_t rows, int32_t cols, int32_t training, int32_t accumulate,
+                     int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Model glue.

@@ -25,6 +25,11 @@ SHAPES = [
     (1024, 256, 16384, (1, 1, 1), 1, 1),
     (512, 2048, 16384, (1, 1, 1), 1, 1),
     (128, 128, 32768, (1, 1, 1), 1, 1),
+    (512, 512, 16384, (1, 1, 1), 1, 1),
+    (256, 1024, 16384, (1, 1, 1), 1, 1),
+    (128, 128, 16384, (1, 1, 1), 1, 1),
+    (128, 256, 32768, (1, 1, 1), 1, 1),
+    (256, 648, 16384, (1, 1, 1), 1, 1),
     (256, 256, 64, (4, 2, 64), 0, 0),
     (256, 64, 256, (4, 2, 64), 0, 1),
     (256, 512, 128, (1, 1, 64), 0, 0),
