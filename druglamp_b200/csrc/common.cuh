@@ -78,7 +78,7 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
 }
 
 // one 16-byte access <-> 4 (fp32) or 8 (bf16) floats
-template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T> struct VecWidth { static constexpr int N = 16 / sizeof(T); };
 __device__ __forceinline__ void ldv(const float* p, float (&x)[4]) {
   const float4 v = *reinterpret_cast<const float4*>(p);
   x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
@@ -126,6 +126,37 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+// GELU for bf16 activations: the tanh form on the hardware tanh (1 MUFU + 5 FMA-pipe instructions
+// instead of 2 MUFU + ~16).  |gelu_tanh - gelu_erf| <= 4.8e-4 and |d/dx difference| <= 8.7e-4 over
+// all x -- a fraction of the bf16 rounding step (3.9e-3 relative) the result is stored with.  fp32
+// activations keep the erf form above.  T selects by storage type so forward and backward agree.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> __device__ __forceinline__ float gelu_fwd(float x) {
+  if constexpr (sizeof(T) == 2) {
+    const float u = x * x;
+    const float t = tanh_approx(x * fmaf(u, 0.044715f * 0.7978845608f, 0.7978845608f));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+  } else {
+    return gelu_erf(x);
+  }
+}
+template <typename T> __device__ __forceinline__ float gelu_grad(float x) {
+  if constexpr (sizeof(T) == 2) {
+    const float u = x * x;
+    const float t = tanh_approx(x * fmaf(u, 0.044715f * 0.7978845608f, 0.7978845608f));
+    const float dz = fmaf(u, 3.0f * 0.044715f * 0.7978845608f, 0.7978845608f);
+    const float a = 0.5f * x * fmaf(-t, t, 1.0f);
+    return fmaf(a, dz, fmaf(0.5f, t, 0.5f));
+  } else {
+    return gelu_erf_grad(x);
+  }
 }
 
 // counter-based uniform in [0,1): splitmix64 of (seed, element index).  Dropout masks are a pure

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256)
 bn_colstats_vec_kernel(const T* __restrict__ a, const T* __restrict__ x, const float* __restrict__ mean,
                        const float* __restrict__ rstd, double* __restrict__ sums, long long rows,
                        int cols, long long rows_per_block, int tpr) {
-  constexpr int V = Vec16<T>::N;
+  constexpr int V = VecWidth<T>::N;
   __shared__ float red[2][256][V + 1];
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
   const int c = (blockIdx.x * tpr + vcol) * V;
@@ -252,7 +252,7 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
                     float* __restrict__ running_var, long long* __restrict__ nbt, T* __restrict__ y,
                     long long rows, int cols, long long rows_per_block, int tpr, float eps,
                     float momentum) {
-  constexpr int V = Vec16<T>::N;
+  constexpr int V = VecWidth<T>::N;
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
   const int c = (blockIdx.x * tpr + vcol) * V;
   if (FINALIZE && nbt && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *nbt += 1;
@@ -317,7 +317,7 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
                         const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, long long rows, int cols, long long rows_per_block,
                         int tpr, int training, int acc) {
-  constexpr int V = Vec16<T>::N;
+  constexpr int V = VecWidth<T>::N;
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
   const int c = (blockIdx.x * tpr + vcol) * V;
   if (c >= cols) return;

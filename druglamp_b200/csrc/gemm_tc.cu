@@ -33,7 +33,22 @@ constexpr int kEpiWarps = 16;                 // four warps per TMEM lane quadra
 constexpr int kColSplit = kEpiWarps / 4;      // column slices per tile
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
+// n / d for n < 2^31 with a multiply-high and a shift (every role decodes a tile index per tile;
+// hardware integer division costs ~100 dependent cycles each)
+struct FastDiv {
+  uint32_t mul, shr, d;
+  void init(uint32_t dv) {
+    d = dv;
+    shr = 0;
+    while ((1u << shr) < dv) ++shr;
+    mul = (uint32_t)(((1ull << 32) * ((1ull << shr) - dv)) / dv + 1);
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, mul) + n) >> shr; }
+};
+
 struct GemmParams {
+  FastDiv fd_perz, fd_nt, fd_splits, fd_nb0, fd_nb1, fd_conv, fd_kred;
+  int nkb_all;                  // K-blocks of the whole reduction
   void* C;
   const float* bias;
   void* preact;
@@ -92,19 +107,23 @@ struct Tile {
 template <int BN, int KE>
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
   Tile T;
-  const int per_z = p.mt * p.nt;
-  const int z = t / per_z, r = t - z * per_z;
-  const int mi = r / p.nt, ni = r - mi * p.nt;
-  T.m0 = mi * BM;
-  T.n0 = ni * BN;
-  T.zb = (unsigned)(z / p.splits);
-  const int ks = z - (int)T.zb * p.splits;
-  T.b0 = T.zb % p.nb0;
-  T.b1 = (T.zb / p.nb0) % p.nb1;
-  T.b2 = T.zb / (p.nb0 * p.nb1);
-  const int nkb_all = (p.K + KE - 1) / KE;
-  T.kb_begin = (int)((long long)nkb_all * ks / p.splits);
-  T.nkb = (int)((long long)nkb_all * (ks + 1) / p.splits) - T.kb_begin;
+  const uint32_t z = p.fd_perz.div((uint32_t)t), r = (uint32_t)t - z * p.fd_perz.d;
+  const uint32_t mi = p.fd_nt.div(r), ni = r - mi * p.fd_nt.d;
+  T.m0 = (int)mi * BM;
+  T.n0 = (int)ni * BN;
+  T.zb = p.fd_splits.div(z);
+  const uint32_t ks = z - T.zb * p.fd_splits.d;
+  const uint32_t q0 = p.fd_nb0.div(T.zb);
+  T.b0 = (int)(T.zb - q0 * p.fd_nb0.d);
+  T.b2 = (int)p.fd_nb1.div(q0);
+  T.b1 = (int)(q0 - (uint32_t)T.b2 * p.fd_nb1.d);
+  if (p.splits == 1) {
+    T.kb_begin = 0;
+    T.nkb = p.nkb_all;
+  } else {                       // host guarantees nkb_all * splits < 2^31
+    T.kb_begin = (int)p.fd_splits.div((uint32_t)p.nkb_all * ks);
+    T.nkb = (int)p.fd_splits.div((uint32_t)p.nkb_all * (ks + 1)) - T.kb_begin;
+  }
   return T;
 }
 
@@ -124,125 +143,162 @@ template <> struct Vec16<float> {
       reinterpret_cast<float4*>(p)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
   }
 };
+// 16 bf16 = one 32-byte sector.  `wide` (32-byte aligned address): a single 256-bit access
+// (LDG/STG.256, sm_100+) instead of two 128-bit ones -- thread = row, so every access is its own
+// sector and the L1 processes one sector access per cycle: half the accesses, half the time.
 template <> struct Vec16<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&x)[16]) {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&x)[16], bool wide) {
+    uint32_t w[8];
+    if (wide) {
+      asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                   : "l"(p));
+    } else {
+      const uint4 u0 = reinterpret_cast<const uint4*>(p)[0], u1 = reinterpret_cast<const uint4*>(p)[1];
+      w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w;
+      w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
+    }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const uint4 u = reinterpret_cast<const uint4*>(p)[i];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-        x[8 * i + 2 * k] = f.x; x[8 * i + 2 * k + 1] = f.y;
-      }
+    for (int k = 0; k < 8; ++k) {          // bf16 -> fp32 is a 16-bit shift
+      x[2 * k] = __uint_as_float(w[k] << 16);
+      x[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
     }
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&x)[16]) {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&x)[16], bool wide) {
+    uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(x[8 * i + 2 * k], x[8 * i + 2 * k + 1]);
-        w[k] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      reinterpret_cast<uint4*>(p)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    if (wide) {
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+    } else {
+      reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
 };
 
+// vec: 16-byte vector access is legal; wide: 32-byte access is legal (bf16 only)
 template <typename TC>
-__device__ __forceinline__ void load16(const TC* p, float (&x)[16], bool vec, int nvalid) {
-  if (vec) { Vec16<TC>::load(p, x); return; }
+__device__ __forceinline__ void load16(const TC* p, float (&x)[16], bool vec, int nvalid, bool wide = false) {
+  if (vec) {
+    if constexpr (sizeof(TC) == 2) Vec16<TC>::load(p, x, wide);
+    else Vec16<TC>::load(p, x);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 16; ++j) x[j] = j < nvalid ? Cvt<TC>::to_f(p[j]) : 0.f;
 }
 template <typename TC>
-__device__ __forceinline__ void store16(TC* p, const float (&x)[16], bool vec, int nvalid) {
-  if (vec) { Vec16<TC>::store(p, x); return; }
+__device__ __forceinline__ void store16(TC* p, const float (&x)[16], bool vec, int nvalid, bool wide = false) {
+  if (vec) {
+    if constexpr (sizeof(TC) == 2) Vec16<TC>::store(p, x, wide);
+    else Vec16<TC>::store(p, x);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 16; ++j)
     if (j < nvalid) p[j] = Cvt<TC>::from_f(x[j]);
 }
 
+template <typename TC>
 __device__ __forceinline__ float apply_mul(float x, float a, int mode) {
-  return x * (mode == DL_MUL_GELU_GRAD ? gelu_erf_grad(a)
+  return x * (mode == DL_MUL_GELU_GRAD ? gelu_grad<TC>(a)
               : mode == DL_MUL_RELU_MASK ? (a > 0.f ? 1.f : 0.f) : a);
 }
 
-// One warp's 32-row x (BN/4)-column slice of a tile, straight from tensor memory to global memory:
-// thread = row (the tcgen05.ld 32x32b layout), 16 columns per step = one or two 16-byte stores per
-// thread.  Every 32-byte sector a thread touches is written (or read) in full.
-template <typename TC, int BN>
-__device__ __forceinline__ void epilogue_slice(const GemmParams& p, uint32_t tmem_q, int lane,
-                                               int row0, int n0, int col_begin, long long cbase,
-                                               long long rbase, unsigned zidx) {
-  const int row = row0 + lane;
-  const bool row_ok = row < p.M;
-  TC* Cp = reinterpret_cast<TC*>(p.C);
-  TC* Pre = reinterpret_cast<TC*>(p.preact);
-  const TC* Aux = reinterpret_cast<const TC*>(p.aux);
-  const TC* Res = reinterpret_cast<const TC*>(p.res);
-  const bool atomic = p.splits > 1;
-  const float drop_inv = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  // 16-byte vector accesses need 16-byte aligned rows (tile columns are multiples of 16 elements)
+// Launch-invariant epilogue facts, evaluated once per epilogue warp (not per tile).
+struct EpiFlags {
+  bool vec_c, vec_r, vec_p, vec_b;   // 16-byte vector access legal: C / residual / preact+aux / bias
+  bool wide_c, wide_r, wide_p;       // one 32-byte access per 16 bf16 legal
+  bool atomic, simple;
+  float drop_inv;
+};
+
+template <typename TC>
+__device__ __forceinline__ EpiFlags make_epi_flags(const GemmParams& p) {
+  EpiFlags f;
   constexpr long long kEl = 16 / sizeof(TC);
-  const bool al_c = (p.ldc % kEl) == 0 && (cbase % kEl) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
-  const bool al_r = (p.ldr % kEl) == 0 && (rbase % kEl) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
-  const bool al_p = al_c && (reinterpret_cast<uintptr_t>(p.preact) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0;
-  const long long crow = cbase + (long long)row * p.ldc;
-  const long long rrow = rbase + (long long)row * p.ldr;
-#pragma unroll 1
-  for (int c0 = col_begin; c0 < col_begin + BN / kColSplit; c0 += 16) {
-    const int col = n0 + c0;
-    if (col >= p.N) break;                           // warp-uniform
-    uint32_t v[16];
-    ptx::tmem_ld_32x16(tmem_q + (uint32_t)c0, v);    // warp-collective: before any divergence
-    ptx::tmem_ld_wait();
-    if (!row_ok) continue;
-    const int nvalid = min(16, p.N - col);
-    const bool full = nvalid == 16;
-    float x[16];
+  auto strides_ok = [](long long ld, const long long* s, long long el) {
+    return (ld % el) == 0 && (s[0] % el) == 0 && (s[1] % el) == 0 && (s[2] % el) == 0;
+  };
+  auto addr_ok = [](const void* q, uintptr_t bytes) { return (reinterpret_cast<uintptr_t>(q) & (bytes - 1)) == 0; };
+  f.vec_c = strides_ok(p.ldc, p.sc, kEl) && addr_ok(p.C, 16);
+  f.vec_r = strides_ok(p.ldr, p.sr, kEl) && addr_ok(p.res, 16);
+  f.vec_p = f.vec_c && addr_ok(p.preact, 16) && addr_ok(p.aux, 16);
+  f.vec_b = addr_ok(p.bias, 16);
+  const bool w = sizeof(TC) == 2;
+  f.wide_c = w && strides_ok(p.ldc, p.sc, 16) && addr_ok(p.C, 32);
+  f.wide_r = w && strides_ok(p.ldr, p.sr, 16) && addr_ok(p.res, 32);
+  f.wide_p = f.wide_c && addr_ok(p.preact, 32) && addr_ok(p.aux, 32);
+  f.atomic = p.splits > 1;
+  f.simple = !p.bias && !p.preact && !p.aux && !p.res && p.act == DL_ACT_NONE &&
+             p.mul_mode == DL_MUL_NONE && p.drop_p == 0.f && !f.atomic && p.dbg == 0;
+  f.drop_inv = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  return f;
+}
+
+// 16 accumulator columns of one row -> global memory, with the fused element-wise work.
+template <typename TC, bool SIMPLE>
+__device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f, const uint32_t* v,
+                                         int row, int col, long long crow, long long rrow,
+                                         unsigned zidx) {
+  TC* Cp = reinterpret_cast<TC*>(p.C);
+  const int nvalid = min(16, p.N - col);
+  const bool full = nvalid == 16;
+  const long long off = crow + col;
+  float x[16];
+  if constexpr (SIMPLE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+    store16<TC>(Cp + off, x, full && f.vec_c, nvalid, f.wide_c);
+    return;
+  } else {
+    TC* Pre = reinterpret_cast<TC*>(p.preact);
+    const TC* Aux = reinterpret_cast<const TC*>(p.aux);
+    const TC* Res = reinterpret_cast<const TC*>(p.res);
     if (p.bias) {
       float b[16];
-      load16<float>(p.bias + col, b, full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0), nvalid);
+      load16<float>(p.bias + col, b, full && f.vec_b, nvalid);
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha + b[j];
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
     }
-    const long long off = crow + col;
-    if (Pre) store16<TC>(Pre + off, x, full && al_p, nvalid);
+    if (Pre) store16<TC>(Pre + off, x, full && f.vec_p, nvalid, f.wide_p);
     if (p.act == DL_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = gelu_erf(x[j]);
+      for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
     } else if (p.act == DL_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
     }
     if (p.mul_mode != DL_MUL_NONE) {
       float m[16];
-      load16<TC>(Aux + off, m, full && al_p, nvalid);
+      load16<TC>(Aux + off, m, full && f.vec_p, nvalid, f.wide_p);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = apply_mul(x[j], m[j], p.mul_mode);
+      for (int j = 0; j < 16; ++j) x[j] = apply_mul<TC>(x[j], m[j], p.mul_mode);
     }
     if (p.drop_p > 0.f) {
       const unsigned long long e = ((unsigned long long)zidx * p.M + row) * p.N + col;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] *= hash_uniform(p.drop_seed, e + j) >= p.drop_p ? drop_inv : 0.f;
+      for (int j = 0; j < 16; ++j) x[j] *= hash_uniform(p.drop_seed, e + j) >= p.drop_p ? f.drop_inv : 0.f;
     }
     if (Res) {
       float r[16];
-      load16<TC>(Res + rrow + col, r, full && al_r, nvalid);
+      load16<TC>(Res + rrow + col, r, full && f.vec_r, nvalid, f.wide_r);
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] += r[j];
     }
-    if (p.dbg == 1 && x[0] != 12345.678f) continue;
-    if (atomic) {
+    if (p.dbg == 1 && x[0] != 12345.678f) return;
+    if (f.atomic) {
       float* dst = reinterpret_cast<float*>(p.C) + off;
-      if (full && al_c) {                            // 4 x 16-byte vector reductions (REDG.F32x4)
+      if (full && f.vec_c) {                           // 4 x 16-byte vector reductions (REDG.F32x4)
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -253,7 +309,36 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, uint32_t tme
           if (j < nvalid) atomicAdd(dst + j, x[j]);
       }
     } else {
-      store16<TC>(Cp + off, x, full && al_c, nvalid);
+      store16<TC>(Cp + off, x, full && f.vec_c, nvalid, f.wide_c);
+    }
+  }
+}
+
+// One warp's 32-row x (BN/4)-column slice of a tile, straight from tensor memory to global memory:
+// thread = row (the tcgen05.ld 32x32b layout).  Every 32-byte sector a thread touches is written
+// (or read) in full.  Plain stores (SIMPLE) pull 32 columns per tensor-memory round trip.
+template <typename TC, int BN, bool SIMPLE>
+__device__ __forceinline__ void epilogue_slice(const GemmParams& p, const EpiFlags& f, uint32_t tmem_q,
+                                               int lane, int row0, int n0, int col_begin,
+                                               long long cbase, long long rbase, unsigned zidx) {
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  const long long crow = cbase + (long long)row * p.ldc;
+  const long long rrow = rbase + (long long)row * p.ldr;
+  constexpr int W = BN / kColSplit;
+  constexpr int STEP = (SIMPLE && W >= 32) ? 32 : 16;
+#pragma unroll 1
+  for (int c0 = col_begin; c0 < col_begin + W; c0 += STEP) {
+    const int col = n0 + c0;
+    if (col >= p.N) break;                           // warp-uniform
+    uint32_t v[STEP];
+    if constexpr (STEP == 32) ptx::tmem_ld_32x32(tmem_q + (uint32_t)c0, v);   // warp-collective:
+    else ptx::tmem_ld_32x16(tmem_q + (uint32_t)c0, v);                        // before any divergence
+    ptx::tmem_ld_wait();
+    if (!row_ok) continue;
+    finish16<TC, SIMPLE>(p, f, v, row, col, crow, rrow, zidx);
+    if constexpr (STEP == 32) {
+      if (col + 16 < p.N) finish16<TC, SIMPLE>(p, f, v + 16, row, col + 16, crow, rrow, zidx);
     }
   }
 }
@@ -318,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.conv_cin) {
             // implicit-GEMM conv1d: K-block -> (tap, channel block); the A tile is the same rows
             // shifted by the tap, out-of-range rows are zero-filled by TMA ('same' padding)
-            const int tap = k0 / p.conv_cin;
+            const int tap = (int)p.fd_conv.div((uint32_t)k0);
             ka = k0 - tap * p.conv_cin;
             a_row = T.m0 + tap - p.conv_left;
           }
@@ -326,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // K runs over (reduction batch, rows): conv weight gradient; batch dim 0 is the tap and
             // shifts the rows of B
             const int kbi = T.kb_begin + kb;
-            const int rb = kbi / p.kred_kpb;
+            const int rb = (int)p.fd_kred.div((uint32_t)kbi);
             ka = (kbi - rb * p.kred_kpb) * C::KE;
             kbb = ka + T.b0 + p.kred_shift;
             a4r = c4r = rb;
@@ -390,6 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int we = warp - 2;
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = we >> 2;                     // which column slice of the tile
+    const EpiFlags ef = p.c_bf16 ? make_epi_flags<__nv_bfloat16>(p) : make_epi_flags<float>(p);
     uint32_t it = 0, ti = 0;
     for (int tl = blockIdx.x; tl < p.total_tiles; tl += gridDim.x, ++ti) {
       const Tile T = decode_tile<BN, C::KE>(p, tl);
@@ -422,11 +508,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long cbase = (long long)T.b0 * p.sc[0] + (long long)T.b1 * p.sc[1] + (long long)T.b2 * p.sc[2];
       const long long rbase = (long long)T.b0 * p.sr[0] + (long long)T.b1 * p.sr[1] + (long long)T.b2 * p.sr[2];
       const uint32_t tmem_q = tmem + ab * BN + ((uint32_t)(q * 32) << 16);
+      const int row0 = T.m0 + q * 32, cb = half * (BN / kColSplit);
       if (p.dbg == 2) {
-      } else if (p.c_bf16)
-        epilogue_slice<__nv_bfloat16, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / kColSplit), cbase, rbase, T.zb);
-      else
-        epilogue_slice<float, BN>(p, tmem_q, lane, T.m0 + q * 32, T.n0, half * (BN / kColSplit), cbase, rbase, T.zb);
+      } else if (p.c_bf16) {
+        if (ef.simple) epilogue_slice<__nv_bfloat16, BN, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+        else epilogue_slice<__nv_bfloat16, BN, false>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+      } else {
+        if (ef.simple) epilogue_slice<float, BN, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+        else epilogue_slice<float, BN, false>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * ab);
@@ -508,6 +598,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long l
   p.nt = ceil_div(p.N, BN);
   const long long total = (long long)p.mt * p.nt * batch * p.splits;
   DL_REQUIRE(total < (1ll << 31), "dl_gemm: too many tiles");
+  p.nkb_all = ceil_div(p.K, C::KE);
+  DL_REQUIRE((long long)p.nkb_all * p.splits < (1ll << 31), "dl_gemm: K x split_k too large");
+  p.fd_perz.init((uint32_t)(p.mt * p.nt));
+  p.fd_nt.init((uint32_t)p.nt);
+  p.fd_splits.init((uint32_t)p.splits);
+  p.fd_nb0.init((uint32_t)p.nb0);
+  p.fd_nb1.init((uint32_t)p.nb1);
+  p.fd_conv.init((uint32_t)(p.conv_cin > 0 ? p.conv_cin : 1));
+  p.fd_kred.init((uint32_t)(p.kred_kpb > 0 ? p.kred_kpb : 1));
   p.total_tiles = (int)total;
   const int grid = (int)(total < sm_count() ? total : sm_count());
   gemm_tc_kernel<BN, TF32, SPLIT><<<grid, kGemmThreads, C::SMEM, stream>>>(tmA, tmB, p);

@@ -380,7 +380,7 @@ __global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float v = ldf<T>(x, i);
-    stf<T>(y, i, act == DL_ACT_GELU ? gelu_erf(v) : (act == DL_ACT_RELU ? fmaxf(v, 0.f) : v));
+    stf<T>(y, i, act == DL_ACT_GELU ? gelu_fwd<T>(v) : (act == DL_ACT_RELU ? fmaxf(v, 0.f) : v));
   }
 }
 
@@ -425,7 +425,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = ldf<T>(dy, i);
-    if (act == DL_ACT_GELU) v *= gelu_erf_grad(ldf<T>(pre, i));
+    if (act == DL_ACT_GELU) v *= gelu_grad<T>(ldf<T>(pre, i));
     else if (act == DL_ACT_RELU) v = ldf<T>(pre, i) > 0.f ? v : 0.f;
     if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
     stf<T>(g, i, v);
