@@ -15,57 +15,62 @@ void count_launch(int n = 1);
 namespace {
 
 // ------------------------------------------------------------------ fill bit + concat + site mean
-// x: (B, S*L, C) fp32.  grid (L, B), 256 threads, each thread owns float4 chunks tid, tid+256.
+// x: (B, S*L, C) fp32.  One block per pooled row (grid (L, B)); its 8 warps take the S site rows
+// round-robin, so all of them are in flight at once.  A warp sums its row with shuffles (the fill
+// bit is "row sums to exactly 0", utils.py / DrugLAMP.py:20-24), adds the row into its own shared
+// accumulator (lane-owned columns, plain read-modify-write) and, for the concat output, bounces
+// the row through shared memory so the (C+1)-strided rows are written with consecutive lanes on
+// consecutive floats.  pooled rows have leading dimension ldp >= C+1; columns C+1..ldp-1 are zero
+// (TMA-aligned rows for the GEMM that consumes them).
 template <typename TO>
 __global__ void __launch_bounds__(256)
 fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
-                    float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C) {
-  __shared__ float red[32];
-  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int nchunk = C >> 2;
-  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-  float bit_acc = 0.f;
-  for (int s = 0; s < S; ++s) {
+                    float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C, int ldp) {
+  extern __shared__ float fb_smem[];
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nchunk = C >> 2, stride = C + 4;
+  float* part = fb_smem + w * stride;                 // this warp's column sums (+ bit count at [C])
+  float* rowbuf = fb_smem + 8 * stride + w * stride;  // concat staging (only touched when cat_out)
+  for (int c = lane; c < stride; c += 32) part[c] = 0.f;
+  __syncwarp();
+  float bits = 0.f;
+  for (int s = w; s < S; s += 8) {
     const size_t t = (size_t)b * S * L + (size_t)s * L + j;
     const float* row = x + t * C;
-    float4 v[2];
-    float part = 0.f;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int ch = tid + k * 256;
-      v[k] = ch < nchunk ? *reinterpret_cast<const float4*>(row + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      part += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-      acc[k].x += v[k].x; acc[k].y += v[k].y; acc[k].z += v[k].z; acc[k].w += v[k].w;
+    float psum = 0.f;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(row + ch * 4);
+      psum += (v.x + v.y) + (v.z + v.w);
+      float4* a = reinterpret_cast<float4*>(part + ch * 4);
+      float4 q = *a;
+      q.x += v.x; q.y += v.y; q.z += v.z; q.w += v.w;
+      *a = q;
+      if (cat_out) *reinterpret_cast<float4*>(rowbuf + ch * 4) = v;
     }
-    const float total = block_sum(part, red);
-    const float bit = total == 0.f ? 1.f : 0.f;
-    bit_acc += bit;
-    if (tid == 0 && bit_out) bit_out[t] = bit;
+    const float bit = warp_sum(psum) == 0.f ? 1.f : 0.f;
+    bits += bit;
+    if (lane == 0 && bit_out) bit_out[t] = bit;
     if (cat_out) {
+      __syncwarp();
       float* crow = cat_out + t * (C + 1);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int ch = tid + k * 256;
-        if (ch < nchunk) {
-          crow[ch * 4 + 0] = v[k].x; crow[ch * 4 + 1] = v[k].y;
-          crow[ch * 4 + 2] = v[k].z; crow[ch * 4 + 3] = v[k].w;
-        }
-      }
-      if (tid == 0) crow[C] = bit;
+      for (int c = lane; c < C; c += 32) crow[c] = rowbuf[c];
+      if (lane == 0) crow[C] = bit;
+      __syncwarp();
     }
   }
+  if (lane == 0) part[C] = bits;
+  __syncthreads();
   if (pooled) {
     const float inv = 1.f / (float)S;
-    TO* prow = pooled + ((size_t)b * L + j) * (C + 1);
+    TO* prow = pooled + ((size_t)b * L + j) * ldp;
+    for (int c = tid; c < ldp; c += 256) {
+      float t = 0.f;
+      if (c <= C) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int ch = tid + k * 256;
-      if (ch < nchunk) {
-        stf<TO>(prow, ch * 4 + 0, acc[k].x * inv); stf<TO>(prow, ch * 4 + 1, acc[k].y * inv);
-        stf<TO>(prow, ch * 4 + 2, acc[k].z * inv); stf<TO>(prow, ch * 4 + 3, acc[k].w * inv);
+        for (int ww = 0; ww < 8; ++ww) t += fb_smem[ww * stride + c];
       }
+      stf<TO>(prow, c, t * inv);
     }
-    if (tid == 0) stf<TO>(prow, C, bit_acc * inv);
   }
 }
 
@@ -451,6 +456,88 @@ __global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- ProteinCNN input
+// out[r, 0:127] = table[tok[r], :], out[r, 127] = fill[r]   (embedding gather + concat + cast in
+// one pass; model/basic_model.py:171-173).  The 27 x 127 fp32 table sits in shared memory; one
+// warp writes one 128-wide row per step, lane = 4 consecutive columns.
+constexpr int kEmbW = 128;          // embedding_dim: 127 table columns + the fill bit
+constexpr int kEmbMaxVocab = 32;
+
+template <typename TokT> __device__ __forceinline__ int tok_index(const TokT* t, long long i) { return (int)t[i]; }
+
+template <typename T, typename TokT>
+__global__ void __launch_bounds__(256)
+embed_fill_fwd_kernel(const TokT* __restrict__ tok, const float* __restrict__ fill,
+                      const float* __restrict__ table, T* __restrict__ out, long long rows, int vocab) {
+  __shared__ float tab[kEmbMaxVocab * (kEmbW - 1) + 4];
+  for (int i = threadIdx.x; i < vocab * (kEmbW - 1); i += 256) tab[i] = table[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 8;
+  for (long long r = w0; r < rows; r += nw) {
+    int v = tok_index(tok, r);
+    v = v < 0 ? 0 : (v >= vocab ? vocab - 1 : v);
+    const float* src = tab + v * (kEmbW - 1) + lane * 4;
+    float4 o;
+    o.x = src[0]; o.y = src[1]; o.z = src[2];
+    o.w = lane == 31 ? fill[r] : src[3];
+    st4<T>(out + r * kEmbW + lane * 4, o);
+  }
+}
+
+// dtable[v, c] += sum over rows with token v of g[r, c], c < 127 (the fill-bit column has no
+// parameter).  Every warp owns a private 27 x 128 fp32 table in shared memory and adds its rows
+// with plain vector read-modify-writes (lane = 4 fixed columns, so no two lanes share an address);
+// the block then folds its 8 tables and issues one atomic per table entry.
+template <typename T, typename TokT>
+__global__ void __launch_bounds__(256)
+embed_fill_bwd_kernel(const TokT* __restrict__ tok, const T* __restrict__ g, float* __restrict__ dtable,
+                      long long rows, int vocab, int padding_idx) {
+  extern __shared__ float acc[];                     // [8 warps][vocab][128]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int per_warp = vocab * kEmbW;
+  for (int i = threadIdx.x; i < 8 * per_warp; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  float* mine = acc + w * per_warp + lane * 4;
+  const long long w0 = (long long)blockIdx.x * 8 + w, nw = (long long)gridDim.x * 8;
+  long long r = w0;
+  for (; r + 3 * nw < rows; r += 4 * nw) {           // four rows of loads in flight
+    float4 gv[4];
+    int v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gv[u] = ld4<T>(g + (r + u * nw) * kEmbW + lane * 4);
+      v[u] = tok_index(tok, r + u * nw);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v[u] < 0 || v[u] >= vocab) continue;
+      float4* a = reinterpret_cast<float4*>(mine + v[u] * kEmbW);
+      float4 t = *a;
+      t.x += gv[u].x; t.y += gv[u].y; t.z += gv[u].z; t.w += gv[u].w;
+      *a = t;
+    }
+  }
+  for (; r < rows; r += nw) {
+    const float4 gv = ld4<T>(g + r * kEmbW + lane * 4);
+    const int v = tok_index(tok, r);
+    if (v < 0 || v >= vocab) continue;
+    float4* a = reinterpret_cast<float4*>(mine + v * kEmbW);
+    float4 t = *a;
+    t.x += gv.x; t.y += gv.y; t.z += gv.z; t.w += gv.w;
+    *a = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < per_warp; i += 256) {
+    const int v = i / kEmbW, c = i % kEmbW;
+    if (c == kEmbW - 1 || v == padding_idx) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += acc[ww * per_warp + i];
+    if (t != 0.f) atomicAdd(dtable + v * (kEmbW - 1) + c, t);
+  }
+}
+
 int ew_grid(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)sm_count() * 16;
@@ -464,22 +551,94 @@ using namespace dl;
 
 extern "C" int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, void* pooled,
                                int32_t pooled_dtype, int64_t B, int32_t S, int32_t L, int32_t C,
-                               void* stream) {
+                               int32_t ld_pooled, void* stream) {
   DL_REQUIRE(x != nullptr, "dl_fillbit_pool: null input");
   DL_REQUIRE(B >= 0 && S >= 1 && L >= 1 && C >= 4 && C % 4 == 0 && C <= 2048,
              "dl_fillbit_pool: need C %% 4 == 0 and C <= 2048 (got B=%lld S=%d L=%d C=%d)", (long long)B, S, L, C);
   DL_REQUIRE(((uintptr_t)x & 15) == 0, "dl_fillbit_pool: x must be 16-byte aligned");
   DL_REQUIRE(B <= 65535, "dl_fillbit_pool: B too large");
+  if (ld_pooled == 0) ld_pooled = C + 1;
+  DL_REQUIRE(ld_pooled >= C + 1, "dl_fillbit_pool: ld_pooled %d < C + 1", ld_pooled);
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(L, (unsigned)B);
+  const int smem = 16 * (C + 4) * (int)sizeof(float);
+  static int configured[2] = {48 * 1024, 48 * 1024};
+  const int which = pooled_dtype == DL_BF16 ? 0 : 1;
+  if (smem > configured[which]) {
+    DL_CUDA(which == 0 ? cudaFuncSetAttribute(fillbit_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                       : cudaFuncSetAttribute(fillbit_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[which] = smem;
+  }
   if (pooled_dtype == DL_BF16)
-    fillbit_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C);
+    fillbit_pool_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C, ld_pooled);
   else
-    fillbit_pool_kernel<float><<<grid, 256, 0, st>>>(x, bit_out, cat_out, (float*)pooled, S, L, C);
+    fillbit_pool_kernel<float><<<grid, 256, smem, st>>>(x, bit_out, cat_out, (float*)pooled, S, L, C, ld_pooled);
   DL_LAUNCH_CHECK("fillbit_pool_kernel");
   count_launch();
   return 0;
+}
+
+namespace {
+template <typename T, typename TokT>
+int embed_fwd_launch(const void* tok, const float* fill, const float* table, void* out, long long rows,
+                     int vocab, cudaStream_t st) {
+  long long blocks = (rows + 63) / 64;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  embed_fill_fwd_kernel<T, TokT><<<(int)blocks, 256, 0, st>>>((const TokT*)tok, fill, table, (T*)out, rows, vocab);
+  DL_LAUNCH_CHECK("embed_fill_fwd_kernel");
+  count_launch();
+  return 0;
+}
+template <typename T, typename TokT>
+int embed_bwd_launch(const void* tok, const void* g, float* dtable, long long rows, int vocab,
+                     int padding_idx, cudaStream_t st) {
+  const int smem = 8 * vocab * kEmbW * (int)sizeof(float);
+  static int configured = 0;       // the attribute is per kernel instantiation
+  if (configured < smem) {
+    DL_CUDA(cudaFuncSetAttribute(embed_fill_bwd_kernel<T, TokT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  long long blocks = (rows + 255) / 256;
+  if (blocks > sm_count()) blocks = sm_count();
+  embed_fill_bwd_kernel<T, TokT><<<(int)blocks, 256, smem, st>>>((const TokT*)tok, (const T*)g, dtable, rows, vocab, padding_idx);
+  DL_LAUNCH_CHECK("embed_fill_bwd_kernel");
+  count_launch();
+  return 0;
+}
+}  // namespace
+
+extern "C" int dl_embed_fill_fwd(const void* tokens, int32_t tok_dtype, const float* fill,
+                                 const float* table, void* out, int64_t rows, int32_t vocab,
+                                 int32_t width, int32_t dtype, void* stream) {
+  DL_REQUIRE(tokens && fill && table && out, "dl_embed_fill_fwd: null pointer");
+  DL_REQUIRE(width == kEmbW, "dl_embed_fill_fwd: width must be 128 (127 embedding columns + fill bit), got %d", width);
+  DL_REQUIRE(vocab >= 1 && vocab <= kEmbMaxVocab, "dl_embed_fill_fwd: vocab must be in [1, %d]", kEmbMaxVocab);
+  DL_REQUIRE(tok_dtype == DL_TOK_I64 || tok_dtype == DL_TOK_F64, "dl_embed_fill_fwd: tok_dtype must be DL_TOK_I64 or DL_TOK_F64");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    return tok_dtype == DL_TOK_I64 ? embed_fwd_launch<__nv_bfloat16, long long>(tokens, fill, table, out, rows, vocab, st)
+                                   : embed_fwd_launch<__nv_bfloat16, double>(tokens, fill, table, out, rows, vocab, st);
+  return tok_dtype == DL_TOK_I64 ? embed_fwd_launch<float, long long>(tokens, fill, table, out, rows, vocab, st)
+                                 : embed_fwd_launch<float, double>(tokens, fill, table, out, rows, vocab, st);
+}
+
+extern "C" int dl_embed_fill_bwd(const void* tokens, int32_t tok_dtype, const void* g, float* dtable,
+                                 int64_t rows, int32_t vocab, int32_t width, int32_t padding_idx,
+                                 int32_t dtype, void* stream) {
+  DL_REQUIRE(tokens && g && dtable, "dl_embed_fill_bwd: null pointer");
+  DL_REQUIRE(width == kEmbW, "dl_embed_fill_bwd: width must be 128, got %d", width);
+  DL_REQUIRE(vocab >= 1 && vocab <= kEmbMaxVocab, "dl_embed_fill_bwd: vocab must be in [1, %d]", kEmbMaxVocab);
+  DL_REQUIRE(tok_dtype == DL_TOK_I64 || tok_dtype == DL_TOK_F64, "dl_embed_fill_bwd: tok_dtype must be DL_TOK_I64 or DL_TOK_F64");
+  if (rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    return tok_dtype == DL_TOK_I64 ? embed_bwd_launch<__nv_bfloat16, long long>(tokens, g, dtable, rows, vocab, padding_idx, st)
+                                   : embed_bwd_launch<__nv_bfloat16, double>(tokens, g, dtable, rows, vocab, padding_idx, st);
+  return tok_dtype == DL_TOK_I64 ? embed_bwd_launch<float, long long>(tokens, g, dtable, rows, vocab, padding_idx, st)
+                                 : embed_bwd_launch<float, double>(tokens, g, dtable, rows, vocab, padding_idx, st);
 }
 
 extern "C" int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, int32_t C,

@@ -78,59 +78,70 @@ class LinearFn(Function):
     widths that are not a multiple of the TMA alignment (75, 385, 641, 1) are zero-padded."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, residual, drop_p, seed, w_kn):
+    def forward(ctx, x, w, b, act, residual, drop_p, seed, w_kn, keep_pad=False):
+        """x may already carry the alignment padding of the weight's input width (zero columns, e.g.
+        the 648-wide fill-bit concat for a 641-input layer): it is then used as is.  keep_pad
+        returns the output with its alignment padding (zero columns) instead of slicing it off, so
+        a chain of odd-width layers runs without padding or compaction copies."""
         xs = x.shape
         Kd = xs[-1]
+        Kw = w.shape[0] if w_kn else w.shape[1]
         N = w.shape[1] if w_kn else w.shape[0]
         al = _align()
-        Kp, Np = -(-Kd // al) * al, -(-N // al) * al
+        Kp, Np = -(-Kw // al) * al, -(-N // al) * al
+        if Kd != Kw and Kd != Kp:
+            raise ValueError(f"input width {Kd} matches neither the weight's {Kw} nor its padded {Kp}")
         x2 = _pad_cols(K.to_compute(x).view(-1, Kd), Kp)
         wc = shadow(w)
-        if Kp != Kd or Np != N:
-            pad = (0, Np - N, 0, Kp - Kd) if w_kn else (0, Kp - Kd, 0, Np - N)
+        if Kp != Kw or Np != N:
+            pad = (0, Np - N, 0, Kp - Kw) if w_kn else (0, Kp - Kw, 0, Np - N)
             wc = torch.nn.functional.pad(wc, pad)
         bias = None if b is None else _pad_cols(b.detach(), Np)
         out = torch.empty((x2.shape[0], Np), dtype=x2.dtype, device=x2.device)
         need_grad = any(ctx.needs_input_grad)
         pre = torch.empty_like(out) if (act != K.ACT_NONE and need_grad) else None
-        r2 = _pad_cols(K.to_compute(residual).view(-1, N), Np) if residual is not None else None
+        r2 = None
+        if residual is not None:
+            r2 = _pad_cols(K.to_compute(residual).view(-1, residual.shape[-1]), Np)
         K.mm(x2, wc, out, tb=w_kn, bias=bias, act=act, pre=pre, res=r2, drop=(drop_p, seed))
         ctx.save_for_backward(x2, wc, pre)
         ctx.params = (w, b)
+        No = Np if keep_pad else N
         ctx.meta = (act, drop_p, seed, xs, x.dtype, None if residual is None else residual.dtype,
-                    b is not None, w_kn, Kd, N)
-        y = out if Np == N else out[:, :N]
-        return y.reshape(*xs[:-1], N)
+                    b is not None, w_kn, Kd, Kw, N, No, None if residual is None else residual.shape)
+        y = out if Np == No else out[:, :N]
+        return y.reshape(*xs[:-1], No)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x2, wc, pre = ctx.saved_tensors
-        act, drop_p, seed, xs, xdt, rdt, has_b, w_kn, Kd, N = ctx.meta
+        act, drop_p, seed, xs, xdt, rdt, has_b, w_kn, Kd, Kw, N, No, rshape = ctx.meta
         Kp = x2.shape[1]
         Np = wc.shape[1] if w_kn else wc.shape[0]
-        gy2 = K.to_compute(gy).view(-1, N)
+        gy2 = K.to_compute(gy).view(-1, No)
         g = K.act_bwd(_pad_cols(gy2, Np), pre, act, (drop_p, seed))
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = K.mm(g, wc, tb=not w_kn)
             dx = _back(dx if Kp == Kd else dx[:, :Kd], xdt, xs)
         wp, bp = ctx.params
-        exact = Kp == Kd and Np == N
+        exact = Kp == Kw and Np == N
         if ctx.needs_input_grad[1]:
             if w_kn:
-                dw = _wgrad(wp, x2, g) if exact else K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)[:Kd, :N]
+                dw = _wgrad(wp, x2, g) if exact else K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)[:Kw, :N]
             else:
-                dw = _wgrad(wp, g, x2) if exact else K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)[:N, :Kd]
+                dw = _wgrad(wp, g, x2) if exact else K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)[:N, :Kw]
         if has_b and ctx.needs_input_grad[2]:
             db = _bgrad(bp, g) if exact else K.colsum(g)[:N]
         if rdt is not None and ctx.needs_input_grad[4]:
-            dres = _back(gy2, rdt, gy.shape)
-        return dx, dw, db, None, dres, None, None, None
+            gr = gy2 if rshape[-1] == No else gy2[:, :rshape[-1]]
+            dres = _back(gr, rdt, rshape)
+        return dx, dw, db, None, dres, None, None, None, None
 
 
-def linear(x, w, b=None, act=K.ACT_NONE, residual=None, drop_p=0.0, seed=0):
-    return LinearFn.apply(x, w, b, act, residual, drop_p, seed, False)
+def linear(x, w, b=None, act=K.ACT_NONE, residual=None, drop_p=0.0, seed=0, keep_pad=False):
+    return LinearFn.apply(x, w, b, act, residual, drop_p, seed, False, keep_pad)
 
 
 # ================================================================================ FFN
@@ -572,6 +583,34 @@ class AddPEFn(Function):
             n *= s
         dpe = K.colsum(g.view(-1, n)).view(pshape)
         return _back(g, xdt), dpe, None, None
+
+
+class EmbedFillFn(Function):
+    """ProteinCNN's input: cat(embedding(tokens), fill_mask) in the compute dtype
+    (model/basic_model.py:171-173) as one gather kernel; the backward sums the gradient rows per
+    token in shared memory instead of nn.Embedding's sort-based dense backward."""
+
+    @staticmethod
+    def forward(ctx, tokens, fill, table, padding_idx):
+        tok = tokens if tokens.dtype in (torch.int64, torch.float64) else tokens.long()
+        tok = tok.contiguous()
+        out = K.embed_fill_fwd(tok, fill.float().contiguous(), table.detach().contiguous())
+        ctx.save_for_backward(tok, table)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        tok, table = ctx.saved_tensors
+        g = K.to_compute(gy)
+        tgt = _grad_target(table)
+        if tgt is not None:
+            K.embed_fill_bwd(tok, g, tgt, ctx.padding_idx)
+            return None, None, None, None
+        dt = torch.zeros(table.shape, dtype=torch.float32, device=g.device)
+        K.embed_fill_bwd(tok, g, dt, ctx.padding_idx)
+        return None, None, dt, None
 
 
 class Conv1dSameFn(Function):

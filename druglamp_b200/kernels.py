@@ -216,22 +216,48 @@ def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bo
 
 # ----------------------------------------------------------------------------- glue
 def fillbit_pool(x: torch.Tensor, S: int, want_bit=True, want_cat=False, want_pooled=True,
-                 pooled_dtype=None):
-    """x (B, S*L, C) fp32 -> (bit (B,S*L) | None, cat (B,S*L,C+1) | None, pooled (B,L,C+1) | None)."""
+                 pooled_dtype=None, pad_to: int = 1):
+    """x (B, S*L, C) fp32 -> (bit (B,S*L) | None, cat (B,S*L,C+1) | None, pooled (B,L,Cp) | None).
+    Cp = C+1 rounded up to a multiple of `pad_to`; the extra columns are zeros (a GEMM operand
+    with TMA-aligned rows; `linear` accepts the wider input as is)."""
     if x.dtype != torch.float32:
         raise TypeError("fillbit_pool expects the fp32 embeddings the collate delivers")
     if not x.is_contiguous():
         x = x.contiguous()
     B, SL, C = x.shape
     Lr = SL // S
+    Cp = -(-(C + 1) // pad_to) * pad_to
     bit = torch.empty((B, SL), dtype=torch.float32, device=x.device) if want_bit else None
     cat = torch.empty((B, SL, C + 1), dtype=torch.float32, device=x.device) if want_cat else None
     pooled = None
     if want_pooled:
-        pooled = torch.empty((B, Lr, C + 1), dtype=pooled_dtype or _compute_dtype, device=x.device)
+        pooled = torch.empty((B, Lr, Cp), dtype=pooled_dtype or _compute_dtype, device=x.device)
     L.call("dl_fillbit_pool", x.data_ptr(), L.ptr(bit), L.ptr(cat), L.ptr(pooled),
-           L.dt(pooled) if pooled is not None else 0, B, S, Lr, C)
+           L.dt(pooled) if pooled is not None else 0, B, S, Lr, C, Cp)
     return bit, cat, pooled
+
+
+def _tok_dtype(tokens: torch.Tensor) -> int:
+    if tokens.dtype == torch.int64:
+        return 0
+    if tokens.dtype == torch.float64:
+        return 1
+    raise TypeError(f"tokens must be int64 or float64 (got {tokens.dtype})")
+
+
+def embed_fill_fwd(tokens: torch.Tensor, fill: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """tokens (B, L) int64/float64, fill (B, L) fp32, table (V, 127) fp32 -> (B, L, 128) compute dtype."""
+    B, Ls = tokens.shape
+    out = torch.empty((B, Ls, table.shape[1] + 1), dtype=_compute_dtype, device=table.device)
+    L.call("dl_embed_fill_fwd", tokens.data_ptr(), _tok_dtype(tokens), fill.data_ptr(), table.data_ptr(),
+           out.data_ptr(), B * Ls, table.shape[0], table.shape[1] + 1, L.dt(out))
+    return out
+
+
+def embed_fill_bwd(tokens: torch.Tensor, g: torch.Tensor, dtable: torch.Tensor, padding_idx: int) -> None:
+    """dtable (V, 127) fp32 += per-token sums of g (B, L, 128)[..., :127]."""
+    L.call("dl_embed_fill_bwd", tokens.data_ptr(), _tok_dtype(tokens), g.data_ptr(), dtable.data_ptr(),
+           tokens.numel(), dtable.shape[0], g.shape[-1], padding_idx, L.dt(g))
 
 
 def transpose_last2(x: torch.Tensor) -> torch.Tensor:

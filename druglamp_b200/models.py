@@ -122,11 +122,14 @@ class DrugLAMPBase(nn.Module):
         return self.mlp_classifier(f)
 
     def _masks(self, xd, xp, need_xd=True):
-        bit_p, xp_cat, xp_pool = K.fillbit_pool(xp, self.site_len, want_cat=not self.lazy_ssl_concat)
-        bit_d = xd_cat = None
+        # the pooled / concatenated LLM features feed 641- and 385-input linears: they are written
+        # with zero columns up to the TMA alignment so no padding copy is needed downstream
+        al = Fn._align()
+        bit_p, xp_cat, xp_pool = K.fillbit_pool(xp, self.site_len, want_cat=not self.lazy_ssl_concat, pad_to=al)
+        bit_d = xd_cat = xd_lin = None
         if need_xd:
-            bit_d, xd_cat, _ = K.fillbit_pool(xd, 1, want_cat=True, want_pooled=False)
-        return bit_p, xp_cat, xp_pool, bit_d, xd_cat
+            bit_d, xd_cat, xd_lin = K.fillbit_pool(xd, 1, want_cat=True, want_pooled=True, pad_to=al)
+        return bit_p, xp_cat, xp_pool, bit_d, xd_cat, xd_lin
 
     def forward(self, vd, vp, xd, xp, mode="train"):
         raise NotImplementedError
@@ -139,10 +142,10 @@ class DrugLAMP(DrugLAMPBase):
         if self._flat is not None:
             self._flat.sync()
         vd = self.drug_extractor(vd)                                    # (B, 512, 128)
-        bit_p, xp_cat, xp_pool, _, xd_cat = self._masks(xd, xp)
+        bit_p, xp_cat, xp_pool, _, xd_cat, xd_lin = self._masks(xd, xp)
         ssl = {'vp': vp, 'xp': xp if xp_cat is None else xp_cat, 'fill_bit_p': bit_p, 'vd': vd, 'xd': xd_cat}
         vpf = self._protein_branch(vp, bit_p)
-        xpa, xda = self._llm_adaptors(xp_pool, xd_cat)
+        xpa, xda = self._llm_adaptors(xp_pool, xd_lin)
         mv, self.A_v_gca = self._guided(self.v_gca, self.v_mhla, self.v_gca_norm, vpf, vd)
         mx, self.A_x_gca = self._guided(self.x_gca, self.x_mhla, self.x_gca_norm, xpa, xda)
         f, self.attn, self.guide_attn = self.pmma(mx, mv)

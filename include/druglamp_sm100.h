@@ -30,7 +30,8 @@ extern "C" {
 #define DL_BF16 1
 
 #define DL_ACT_NONE 0
-#define DL_ACT_GELU 1 /* exact erf GELU (nn.GELU default) */
+#define DL_ACT_GELU 1 /* nn.GELU: erf form for fp32 activations; bf16 activations use
+                         the tanh form on the hardware tanh (|diff| <= 4.8e-4, a fraction of a bf16 ulp) */
 #define DL_ACT_RELU 2
 
 #define DL_MUL_NONE 0
@@ -197,9 +198,12 @@ int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma, const fl
 /* x: (B, S*L, C) fp32.  bit_out (B, S*L) = float(x.sum(-1) == 0)            [may be NULL]
  *                       cat_out (B, S*L, C+1) = cat(x, bit) fp32           [may be NULL]
  *                       pooled  (B, L, C+1) = cat(x, bit).view(B,S,L,C+1).mean(1)  [may be NULL]
- * One pass over x (model/DrugLAMP.py:11-19,39-40).  S = 1 gives the plain fill-bit concat. */
+ * One pass over x (model/DrugLAMP.py:11-19,39-40).  S = 1 gives the plain fill-bit concat.
+ * pooled rows have leading dimension ld_pooled (0 = C+1); columns C+1..ld_pooled-1 are written
+ * as zeros, so a 641- or 385-wide result can feed dl_gemm without a padding copy. */
 int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, void* pooled,
-                    int32_t pooled_dtype, int64_t B, int32_t S, int32_t L, int32_t C, void* stream);
+                    int32_t pooled_dtype, int64_t B, int32_t S, int32_t L, int32_t C,
+                    int32_t ld_pooled, void* stream);
 
 /* y[b, j, :] = mean_s x[b, s*L + j, :]; y rows have stride ldy (model/DrugLAMP.py:35-37). */
 int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, int32_t C,
@@ -211,6 +215,21 @@ int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L, 
  * (B, C, L) buffer, which the reference then reinterprets with .view(B, L, C)
  * (model/basic_model.py:179). */
 int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_t C, int32_t dtype, void* stream);
+
+/* ProteinCNN input (model/basic_model.py:171-173: nn.Embedding(27, 127, padding_idx=0), then
+ * torch.cat with the fill mask): out[r, 0:127] = table[tokens[r], :], out[r, 127] = fill[r], written
+ * in the compute dtype.  tokens: [rows] int64 (DL_TOK_I64) or the float64 the reference collate
+ * delivers (DL_TOK_F64, utils.py:403-407), clamped to [0, vocab).  width must be 128. */
+#define DL_TOK_I64 0
+#define DL_TOK_F64 1
+int dl_embed_fill_fwd(const void* tokens, int32_t tok_dtype, const float* fill, const float* table,
+                      void* out, int64_t rows, int32_t vocab, int32_t width, int32_t dtype,
+                      void* stream);
+/* dtable[v, c] += sum_{r: tokens[r] == v} g[r, c] for c < 127; the padding_idx row (pass -1 for
+ * none) receives nothing, like nn.Embedding's backward.  dtable: [vocab, 127] fp32, accumulated. */
+int dl_embed_fill_bwd(const void* tokens, int32_t tok_dtype, const void* g, float* dtable,
+                      int64_t rows, int32_t vocab, int32_t width, int32_t padding_idx, int32_t dtype,
+                      void* stream);
 
 /* y = LayerNorm(v + gate(v)), gate = MultiHeadLinearAttention's softmax-over-sequence gating
  * through its .view(B*H, L, E/H) reinterpretation (model/PMMA/encoder.py:132-140) applied to

@@ -269,3 +269,33 @@ def test_cm_triplet_and_bce():
     assert abs(loss.item() - l_ref.item()) < 1e-5
     ds = K.bce_bwd(prob, y, torch.ones((), device="cuda"))
     _close(ds, sr.grad.flatten(), 1e-5, "dscore")
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("tok_dtype", [torch.int64, torch.float64])
+def test_embed_fill_fwd_bwd_matches_embedding_cat(dtype, tol, tok_dtype):
+    """ProteinCNN input (basic_model.py:171-173): nn.Embedding(27, 127, padding_idx=0) + cat(fill)."""
+    import druglamp_b200 as D
+    from druglamp_b200 import functions as Fn
+    torch.manual_seed(3)
+    B, Ls = 5, 1200
+    emb = torch.nn.Embedding(27, 127, padding_idx=0).cuda()
+    tokens = torch.randint(0, 26, (B, Ls), device="cuda")
+    tokens[:, 900:] = 0                                             # padded tail
+    fill = (torch.rand(B, Ls, device="cuda") < 0.3).float()
+    gy = torch.randn(B, Ls, 128, device="cuda")
+    ref = torch.cat((emb(tokens), fill.unsqueeze(-1)), -1)
+    ref.backward(gy.to(dtype).float())
+    gref = emb.weight.grad.clone()
+    emb.weight.grad = None
+    D.set_compute_dtype(dtype)
+    try:
+        out = Fn.EmbedFillFn.apply(tokens.to(tok_dtype), fill, emb.weight, emb.padding_idx)
+        assert out.dtype == dtype and out.shape == (B, Ls, 128)
+        _close(out, ref.detach(), 4e-3 if dtype == torch.bfloat16 else 0.0, "embed+fill")
+        assert torch.equal(out[..., 127].float(), fill)
+        out.backward(gy.to(dtype))
+    finally:
+        D.set_compute_dtype(torch.float32)
+    assert emb.weight.grad[0].abs().max().item() == 0.0             # padding row gets no gradient
+    _close(emb.weight.grad, gref, 1e-5, "dtable")
