@@ -1,5 +1,6 @@
 // Library-wide plumbing of the C ABI: version, thread-local error message, launch counter.
 #include <atomic>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -29,6 +30,14 @@ int sm_count() {
     return v > 0 ? v : 148;
   }();
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DL_NO_PDL");
+    return !(e && atoi(e) != 0);
+  }();
+  return on;
 }
 
 }  // namespace dl

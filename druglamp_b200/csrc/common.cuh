@@ -37,6 +37,38 @@ int set_error(int code, const char* fmt, ...);
 
 int sm_count();   // cached multiProcessorCount of the current device
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute
+// and begins with pdl_trigger(); pdl_wait():  its blocks may be scheduled (and run their
+// prologue: barrier init, TMEM allocation, tensor-map prefetch, shared-memory zeroing) while the
+// previous kernel in the stream is still draining; pdl_wait() then blocks until that kernel has
+// completed and its writes are visible, so no global access ever overtakes a producer.  A step is
+// ~480 launches of 5-20 us each: this hides the launch latency between them.  DL_NO_PDL=1 turns
+// the attribute off (the device-side instructions are then no-ops).
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// DL_LAUNCH((kernel<T>), grid, block, smem, stream, args...): parenthesise templated kernel names
+#define DL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)dl::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
 // ------------------------------------------------------------------ dtype helpers
 enum : int { DT_F32 = 0, DT_BF16 = 1 };
 

@@ -26,6 +26,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256)
 fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
                     float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C, int ldp) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float fb_smem[];
   const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nchunk = C >> 2, stride = C + 4;
@@ -78,6 +80,8 @@ fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
 template <typename T>
 __global__ void site_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int S, long long LC4,
                                      long long n4, long long ldy4, long long C4) {
+  pdl_trigger();
+  pdl_wait();
   // y[b, j, c] = mean_s x[b, s*L + j, c];  index in float4 units; y row stride ldy (elements)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -96,6 +100,8 @@ __global__ void site_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
 template <typename T>
 __global__ void site_pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int S,
                                      long long LC4, long long n4, long long ldy4, long long C4) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / LC4, r = i % LC4;
@@ -118,6 +124,8 @@ mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         T* __restrict__ y, float* __restrict__ p_out, float* __restrict__ mean_out,
                         float* __restrict__ rstd_out, int L, int H, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int E = VEC * 128;
   extern __shared__ float sp[];                 // [H][L]
   const bool plain = gamma == nullptr;
@@ -192,6 +200,8 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
                         const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                         T* __restrict__ dv, T* __restrict__ dlogits, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int L, int H) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int E = VEC * 128;
   extern __shared__ float smem[];
   float* sp = smem;                 // [H][L] probabilities
@@ -286,6 +296,8 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 cm_triplet_kernel(const float* __restrict__ cos, const int8_t* __restrict__ G, int D, float margin,
                   double* __restrict__ acc, const float* __restrict__ gout, float* __restrict__ dcos) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sig = sm;                          // [D]
   int* pos = reinterpret_cast<int*>(sm + D);  // [D] compacted positive columns
@@ -350,6 +362,8 @@ cm_triplet_kernel(const float* __restrict__ cos, const int8_t* __restrict__ G, i
 }
 
 __global__ void cm_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss) {
+  pdl_trigger();
+  pdl_wait();
   const double cnt = acc[1] > 1.0 ? acc[1] : 1.0;
   loss[0] = (float)(acc[0] / cnt);
 }
@@ -359,6 +373,8 @@ __global__ void cm_finalize_kernel(const double* __restrict__ acc, float* __rest
 template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int R, int Cc) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * R * Cc;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -386,6 +402,8 @@ cross_entropy_kernel(const T* __restrict__ x, const long long* __restrict__ labe
                      long long rows, int C, long long ld, long long ignore_index,
                      double* __restrict__ acc, const float* __restrict__ gout, T* __restrict__ dx,
                      float* __restrict__ dextra_dot) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -429,12 +447,16 @@ cross_entropy_kernel(const T* __restrict__ x, const long long* __restrict__ labe
 }
 
 __global__ void ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss) {
+  pdl_trigger();
+  pdl_wait();
   loss[0] = (float)(acc[0] / acc[1]);
 }
 
 // ------------------------------------------------------------------ BCE
 __global__ void bce_fwd_kernel(const float* __restrict__ score, const float* __restrict__ y,
                                float* __restrict__ prob, float* __restrict__ loss, int n) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   float local = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -449,6 +471,8 @@ __global__ void bce_fwd_kernel(const float* __restrict__ score, const float* __r
 
 __global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y,
                                const float* __restrict__ gout, float* __restrict__ dscore, int n) {
+  pdl_trigger();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float pr = prob[i];
     const float dn = (pr - y[i]) / fmaxf((1.f - pr) * pr, 1e-12f);   // BCELoss backward
@@ -469,6 +493,8 @@ template <typename T, typename TokT>
 __global__ void __launch_bounds__(256)
 embed_fill_fwd_kernel(const TokT* __restrict__ tok, const float* __restrict__ fill,
                       const float* __restrict__ table, T* __restrict__ out, long long rows, int vocab) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tab[kEmbMaxVocab * (kEmbW - 1) + 4];
   for (int i = threadIdx.x; i < vocab * (kEmbW - 1); i += 256) tab[i] = table[i];
   __syncthreads();
@@ -493,6 +519,8 @@ template <typename T, typename TokT>
 __global__ void __launch_bounds__(256)
 embed_fill_bwd_kernel(const TokT* __restrict__ tok, const T* __restrict__ g, float* __restrict__ dtable,
                       long long rows, int vocab, int padding_idx) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float acc[];                     // [8 warps][vocab][128]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int per_warp = vocab * kEmbW;
@@ -571,9 +599,9 @@ extern "C" int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, v
     configured[which] = smem;
   }
   if (pooled_dtype == DL_BF16)
-    fillbit_pool_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C, ld_pooled);
+    DL_LAUNCH((fillbit_pool_kernel<__nv_bfloat16>), grid, 256, smem, st, x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C, ld_pooled);
   else
-    fillbit_pool_kernel<float><<<grid, 256, smem, st>>>(x, bit_out, cat_out, (float*)pooled, S, L, C, ld_pooled);
+    DL_LAUNCH((fillbit_pool_kernel<float>), grid, 256, smem, st, x, bit_out, cat_out, (float*)pooled, S, L, C, ld_pooled);
   DL_LAUNCH_CHECK("fillbit_pool_kernel");
   count_launch();
   return 0;
@@ -586,7 +614,7 @@ int embed_fwd_launch(const void* tok, const float* fill, const float* table, voi
   long long blocks = (rows + 63) / 64;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  embed_fill_fwd_kernel<T, TokT><<<(int)blocks, 256, 0, st>>>((const TokT*)tok, fill, table, (T*)out, rows, vocab);
+  DL_LAUNCH((embed_fill_fwd_kernel<T, TokT>), (int)blocks, 256, 0, st, (const TokT*)tok, fill, table, (T*)out, rows, vocab);
   DL_LAUNCH_CHECK("embed_fill_fwd_kernel");
   count_launch();
   return 0;
@@ -602,7 +630,7 @@ int embed_bwd_launch(const void* tok, const void* g, float* dtable, long long ro
   }
   long long blocks = (rows + 255) / 256;
   if (blocks > sm_count()) blocks = sm_count();
-  embed_fill_bwd_kernel<T, TokT><<<(int)blocks, 256, smem, st>>>((const TokT*)tok, (const T*)g, dtable, rows, vocab, padding_idx);
+  DL_LAUNCH((embed_fill_bwd_kernel<T, TokT>), (int)blocks, 256, smem, st, (const TokT*)tok, (const T*)g, dtable, rows, vocab, padding_idx);
   DL_LAUNCH_CHECK("embed_fill_bwd_kernel");
   count_launch();
   return 0;
@@ -648,9 +676,9 @@ extern "C" int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, in
   if (n4 <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DL_BF16)
-    site_pool_fwd_kernel<__nv_bfloat16><<<ew_grid(n4, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, S, LC4, n4, ldy / 4, C / 4);
+    DL_LAUNCH((site_pool_fwd_kernel<__nv_bfloat16>), ew_grid(n4, 256), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, S, LC4, n4, ldy / 4, C / 4);
   else
-    site_pool_fwd_kernel<float><<<ew_grid(n4, 256), 256, 0, st>>>((const float*)x, (float*)y, S, LC4, n4, ldy / 4, C / 4);
+    DL_LAUNCH((site_pool_fwd_kernel<float>), ew_grid(n4, 256), 256, 0, st, (const float*)x, (float*)y, S, LC4, n4, ldy / 4, C / 4);
   DL_LAUNCH_CHECK("site_pool_fwd_kernel");
   count_launch();
   return 0;
@@ -663,9 +691,9 @@ extern "C" int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, 
   if (n4 <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DL_BF16)
-    site_pool_bwd_kernel<__nv_bfloat16><<<ew_grid(n4, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, S, LC4, n4, ldy / 4, C / 4);
+    DL_LAUNCH((site_pool_bwd_kernel<__nv_bfloat16>), ew_grid(n4, 256), 256, 0, st, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, S, LC4, n4, ldy / 4, C / 4);
   else
-    site_pool_bwd_kernel<float><<<ew_grid(n4, 256), 256, 0, st>>>((const float*)dy, (float*)dx, S, LC4, n4, ldy / 4, C / 4);
+    DL_LAUNCH((site_pool_bwd_kernel<float>), ew_grid(n4, 256), 256, 0, st, (const float*)dy, (float*)dx, S, LC4, n4, ldy / 4, C / 4);
   DL_LAUNCH_CHECK("site_pool_bwd_kernel");
   count_launch();
   return 0;
@@ -687,7 +715,7 @@ extern "C" int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const floa
   do {                                                                                              \
     if (smem > 48 * 1024)                                                                           \
       DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_fwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mhla_gate_ln_fwd_kernel<TT, VV><<<(unsigned)B, 256, smem, st>>>((const TT*)v, (const TT*)logits, gamma, beta, (TT*)y, p_out, mean, rstd, L, H, eps); \
+    DL_LAUNCH((mhla_gate_ln_fwd_kernel<TT, VV>), (unsigned)B, 256, smem, st, (const TT*)v, (const TT*)logits, gamma, beta, (TT*)y, p_out, mean, rstd, L, H, eps); \
   } while (0)
   if (dtype == DL_BF16) {
     if (E == 128) DL_MHLA_FWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_FWD(__nv_bfloat16, 2);
@@ -720,7 +748,7 @@ extern "C" int dl_mhla_gate_ln_bwd(const void* dy, const void* v, const float* p
   do {                                                                                              \
     if (smem > 48 * 1024)                                                                           \
       DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_bwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    mhla_gate_ln_bwd_kernel<TT, VV><<<(unsigned)B, 256, smem, st>>>((const TT*)dy, (const TT*)v, p, mean, rstd, gamma, (TT*)dv, (TT*)dlogits, dgamma, dbeta, L, H); \
+    DL_LAUNCH((mhla_gate_ln_bwd_kernel<TT, VV>), (unsigned)B, 256, smem, st, (const TT*)dy, (const TT*)v, p, mean, rstd, gamma, (TT*)dv, (TT*)dlogits, dgamma, dbeta, L, H); \
   } while (0)
   if (dtype == DL_BF16) {
     if (E == 128) DL_MHLA_BWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_BWD(__nv_bfloat16, 2);
@@ -746,11 +774,11 @@ extern "C" int dl_cm_triplet_fwd(const float* cos, const int8_t* G, int64_t P, i
   if (P > 0) {
     if (smem > 48 * 1024)
       DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cm_triplet_kernel<false><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, acc, nullptr, nullptr);
+    DL_LAUNCH((cm_triplet_kernel<false>), (unsigned)P, 256, smem, st, cos, G, (int)D, margin, acc, nullptr, nullptr);
     DL_LAUNCH_CHECK("cm_triplet_kernel");
     count_launch();
   }
-  cm_finalize_kernel<<<1, 1, 0, st>>>(acc, loss);
+  DL_LAUNCH(cm_finalize_kernel, 1, 1, 0, st, acc, loss);
   DL_LAUNCH_CHECK("cm_finalize_kernel");
   count_launch();
   return 0;
@@ -766,7 +794,7 @@ extern "C" int dl_cm_triplet_bwd(const float* cos, const int8_t* G, int64_t P, i
   const size_t smem = (size_t)D * 8;
   if (smem > 48 * 1024)
     DL_CUDA(cudaFuncSetAttribute(cm_triplet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cm_triplet_kernel<true><<<(unsigned)P, 256, smem, st>>>(cos, G, (int)D, margin, const_cast<double*>(acc), gout, dcos);
+  DL_LAUNCH((cm_triplet_kernel<true>), (unsigned)P, 256, smem, st, cos, G, (int)D, margin, const_cast<double*>(acc), gout, dcos);
   DL_LAUNCH_CHECK("cm_triplet_kernel(bwd)");
   count_launch();
   return 0;
@@ -780,9 +808,9 @@ extern "C" int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_
   DL_REQUIRE(grid.y <= 65535, "dl_transpose: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DL_BF16)
-    transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, R, Cc);
+    DL_LAUNCH((transpose_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, R, Cc);
   else
-    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, R, Cc);
+    DL_LAUNCH((transpose_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, R, Cc);
   DL_LAUNCH_CHECK("transpose_kernel");
   count_launch();
   return 0;
@@ -800,13 +828,13 @@ extern "C" int dl_cross_entropy_fwd(const void* x, const int64_t* labels, const 
   if (rows > 0) {
     const int grid = ceil_div(rows, 8);
     if (dtype == DL_BF16)
-      cross_entropy_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
+      DL_LAUNCH((cross_entropy_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
     else
-      cross_entropy_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
+      DL_LAUNCH((cross_entropy_kernel<float, false>), grid, 256, 0, st, (const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, acc, nullptr, nullptr, nullptr);
     DL_LAUNCH_CHECK("cross_entropy_kernel");
     count_launch();
   }
-  ce_finalize_kernel<<<1, 1, 0, st>>>(acc, loss);
+  DL_LAUNCH(ce_finalize_kernel, 1, 1, 0, st, acc, loss);
   DL_LAUNCH_CHECK("ce_finalize_kernel");
   count_launch();
   return 0;
@@ -822,9 +850,9 @@ extern "C" int dl_cross_entropy_bwd(const void* x, const int64_t* labels, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(rows, 8);
   if (dtype == DL_BF16)
-    cross_entropy_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (__nv_bfloat16*)dx, dextra);
+    DL_LAUNCH((cross_entropy_kernel<__nv_bfloat16, true>), grid, 256, 0, st, (const __nv_bfloat16*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (__nv_bfloat16*)dx, dextra);
   else
-    cross_entropy_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (float*)dx, dextra);
+    DL_LAUNCH((cross_entropy_kernel<float, true>), grid, 256, 0, st, (const float*)x, (const long long*)labels, extra, wextra, rows, C, ld, ignore_index, const_cast<double*>(acc), gout, (float*)dx, dextra);
   DL_LAUNCH_CHECK("cross_entropy_kernel(bwd)");
   count_launch();
   return 0;
@@ -833,7 +861,7 @@ extern "C" int dl_cross_entropy_bwd(const void* x, const int64_t* labels, const 
 extern "C" int dl_bce_fwd(const float* score, const float* y, float* prob, float* loss, int64_t n,
                           void* stream) {
   DL_REQUIRE(score && y && prob && loss && n >= 1 && n < (1 << 30), "dl_bce_fwd: bad arguments");
-  bce_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(score, y, prob, loss, (int)n);
+  DL_LAUNCH(bce_fwd_kernel, 1, 256, 0, (cudaStream_t)stream, score, y, prob, loss, (int)n);
   DL_LAUNCH_CHECK("bce_fwd_kernel");
   count_launch();
   return 0;
@@ -842,7 +870,7 @@ extern "C" int dl_bce_fwd(const float* score, const float* y, float* prob, float
 extern "C" int dl_bce_bwd(const float* prob, const float* y, const float* gout, float* dscore,
                           int64_t n, void* stream) {
   DL_REQUIRE(prob && y && gout && dscore && n >= 1 && n < (1 << 30), "dl_bce_bwd: bad arguments");
-  bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(prob, y, gout, dscore, (int)n);
+  DL_LAUNCH(bce_bwd_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream, prob, y, gout, dscore, (int)n);
   DL_LAUNCH_CHECK("bce_bwd_kernel");
   count_launch();
   return 0;

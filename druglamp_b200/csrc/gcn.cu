@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256)
 spmm_norm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
                  const float* __restrict__ norm_src, const float* __restrict__ norm_dst,
                  const T* __restrict__ h, T* __restrict__ out, int n_rows) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -46,6 +48,8 @@ __global__ void __launch_bounds__(256)
 bn_colstats_kernel(const T* __restrict__ a, const T* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, double* __restrict__ sums, long long rows,
                    int cols, long long rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[2][8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -77,6 +81,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, float* __res
                                    float* __restrict__ rstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, long long* __restrict__ nbt,
                                    long long rows, int cols, float eps, float momentum) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) {
     const double mu = sums[c] / (double)rows;
@@ -99,6 +105,8 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, T* __restrict__ y, long long n4,
                                 int cols) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % cols);
@@ -124,6 +132,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
                                     const float* __restrict__ gamma, const double* __restrict__ sums,
                                     T* __restrict__ dx, long long n4, int cols, double inv_rows,
                                     int training) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % cols);
@@ -150,6 +160,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma, int acc,
                                      float* __restrict__ dbeta, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) {
     if (dbeta) dbeta[c] = (acc ? dbeta[c] : 0.f) + (float)sums[c];
@@ -160,6 +172,8 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __r
 __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean,
                                      const float* __restrict__ running_var, float* __restrict__ mean,
                                      float* __restrict__ rstd, int cols, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) {
     mean[c] = running_mean[c];
@@ -182,6 +196,8 @@ __global__ void __launch_bounds__(256)
 bn_colstats_vec_kernel(const T* __restrict__ a, const T* __restrict__ x, const float* __restrict__ mean,
                        const float* __restrict__ rstd, double* __restrict__ sums, long long rows,
                        int cols, long long rows_per_block, int tpr) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = VecWidth<T>::N;
   __shared__ float red[2][256][V + 1];
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
@@ -252,6 +268,8 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
                     float* __restrict__ running_var, long long* __restrict__ nbt, T* __restrict__ y,
                     long long rows, int cols, long long rows_per_block, int tpr, float eps,
                     float momentum) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = VecWidth<T>::N;
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
   const int c = (blockIdx.x * tpr + vcol) * V;
@@ -317,6 +335,8 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
                         const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, long long rows, int cols, long long rows_per_block,
                         int tpr, int training, int acc) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = VecWidth<T>::N;
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
   const int c = (blockIdx.x * tpr + vcol) * V;
@@ -418,9 +438,9 @@ extern "C" int dl_spmm_norm(const int32_t* indptr, const int32_t* indices, const
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(n_rows, 8);
   if (dtype == DL_BF16)
-    spmm_norm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(indptr, indices, norm_src, norm_dst, (const __nv_bfloat16*)h, (__nv_bfloat16*)out, (int)n_rows);
+    DL_LAUNCH((spmm_norm_kernel<__nv_bfloat16>), grid, 256, 0, st, indptr, indices, norm_src, norm_dst, (const __nv_bfloat16*)h, (__nv_bfloat16*)out, (int)n_rows);
   else
-    spmm_norm_kernel<float><<<grid, 256, 0, st>>>(indptr, indices, norm_src, norm_dst, (const float*)h, (float*)out, (int)n_rows);
+    DL_LAUNCH((spmm_norm_kernel<float>), grid, 256, 0, st, indptr, indices, norm_src, norm_dst, (const float*)h, (float*)out, (int)n_rows);
   DL_LAUNCH_CHECK("spmm_norm_kernel");
   count_launch();
   return 0;
@@ -444,21 +464,21 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
       DL_REQUIRE(workspace != nullptr, "dl_batchnorm_fwd: workspace required in training mode");
       DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
       if (dtype == DL_BF16) {
-        bn_colstats_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
-        bn_apply_vec_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
+        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, true>), grid, 256, 0, st, (const __nv_bfloat16*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
       } else {
-        bn_colstats_vec_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
-        bn_apply_vec_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_colstats_vec_kernel<float, false>), grid, 256, 0, st, (const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
+        DL_LAUNCH((bn_apply_vec_kernel<float, true>), grid, 256, 0, st, (const float*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
       }
       DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_apply_vec_kernel");
       count_launch(2);
     } else {
       DL_REQUIRE(running_mean && running_var, "dl_batchnorm_fwd: eval mode needs running statistics");
-      bn_eval_stats_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(running_mean, running_var, mean, rstd, cols, eps);
+      DL_LAUNCH(bn_eval_stats_kernel, ceil_div(cols, 128), 128, 0, st, running_mean, running_var, mean, rstd, cols, eps);
       if (dtype == DL_BF16)
-        bn_apply_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
       else
-        bn_apply_vec_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_apply_vec_kernel<float, false>), grid, 256, 0, st, (const float*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
       DL_LAUNCH_CHECK("bn_eval_stats_kernel / bn_apply_vec_kernel");
       count_launch(2);
     }
@@ -470,24 +490,24 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
     dim3 grid; long long rpb;
     stats_grid(rows, cols, &grid, &rpb);
     if (dtype == DL_BF16)
-      bn_colstats_kernel<__nv_bfloat16, false><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb);
+      DL_LAUNCH((bn_colstats_kernel<__nv_bfloat16, false>), grid, dim3(32, 8), 0, st, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb);
     else
-      bn_colstats_kernel<float, false><<<grid, dim3(32, 8), 0, st>>>((const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb);
+      DL_LAUNCH((bn_colstats_kernel<float, false>), grid, dim3(32, 8), 0, st, (const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb);
     DL_LAUNCH_CHECK("bn_colstats_kernel");
-    bn_finalize_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, mean, rstd, running_mean, running_var, (long long*)num_batches_tracked, rows, cols, eps, momentum);
+    DL_LAUNCH(bn_finalize_kernel, ceil_div(cols, 128), 128, 0, st, workspace, mean, rstd, running_mean, running_var, (long long*)num_batches_tracked, rows, cols, eps, momentum);
     DL_LAUNCH_CHECK("bn_finalize_kernel");
     count_launch(2);
   } else {
     DL_REQUIRE(running_mean && running_var, "dl_batchnorm_fwd: eval mode needs running statistics");
-    bn_eval_stats_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(running_mean, running_var, mean, rstd, cols, eps);
+    DL_LAUNCH(bn_eval_stats_kernel, ceil_div(cols, 128), 128, 0, st, running_mean, running_var, mean, rstd, cols, eps);
     DL_LAUNCH_CHECK("bn_eval_stats_kernel");
     count_launch();
   }
   const long long n4 = rows * cols / 4;
   if (dtype == DL_BF16)
-    bn_apply_kernel<__nv_bfloat16><<<ew_grid4(n4), 256, 0, st>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)y, n4, cols);
+    DL_LAUNCH((bn_apply_kernel<__nv_bfloat16>), ew_grid4(n4), 256, 0, st, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)y, n4, cols);
   else
-    bn_apply_kernel<float><<<ew_grid4(n4), 256, 0, st>>>((const float*)x, mean, rstd, gamma, beta, (float*)y, n4, cols);
+    DL_LAUNCH((bn_apply_kernel<float>), ew_grid4(n4), 256, 0, st, (const float*)x, mean, rstd, gamma, beta, (float*)y, n4, cols);
   DL_LAUNCH_CHECK("bn_apply_kernel");
   count_launch();
   return 0;
@@ -505,11 +525,11 @@ extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamm
   if (col_slice(dy, x, dx, rows, cols, dtype == DL_BF16 ? 8 : 4, 32, &g)) {
     const dim3 vgrid(g.xb, g.yb);
     if (dtype == DL_BF16) {
-      bn_colstats_vec_kernel<__nv_bfloat16, true><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      bn_bwd_apply_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+      DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, true>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
     } else {
-      bn_colstats_vec_kernel<float, true><<<vgrid, 256, 0, st>>>((const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      bn_bwd_apply_vec_kernel<float><<<vgrid, 256, 0, st>>>((const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+      DL_LAUNCH((bn_colstats_vec_kernel<float, true>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
     }
     DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_bwd_apply_vec_kernel");
     count_launch(2);
@@ -518,20 +538,20 @@ extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamm
   dim3 grid; long long rpb;
   stats_grid(rows, cols, &grid, &rpb);
   if (dtype == DL_BF16)
-    bn_colstats_kernel<__nv_bfloat16, true><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, rpb);
+    DL_LAUNCH((bn_colstats_kernel<__nv_bfloat16, true>), grid, dim3(32, 8), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, rpb);
   else
-    bn_colstats_kernel<float, true><<<grid, dim3(32, 8), 0, st>>>((const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, rpb);
+    DL_LAUNCH((bn_colstats_kernel<float, true>), grid, dim3(32, 8), 0, st, (const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, rpb);
   DL_LAUNCH_CHECK("bn_colstats_kernel(bwd)");
   if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, dgamma, accumulate, dbeta, cols);
+    DL_LAUNCH(bn_param_grad_kernel, ceil_div(cols, 128), 128, 0, st, workspace, dgamma, accumulate, dbeta, cols);
     DL_LAUNCH_CHECK("bn_param_grad_kernel");
     count_launch();
   }
   const long long n4 = rows * cols / 4;
   if (dtype == DL_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid4(n4), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, n4, cols, 1.0 / (double)rows, training);
+    DL_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16>), ew_grid4(n4), 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, n4, cols, 1.0 / (double)rows, training);
   else
-    bn_bwd_apply_kernel<float><<<ew_grid4(n4), 256, 0, st>>>((const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, n4, cols, 1.0 / (double)rows, training);
+    DL_LAUNCH((bn_bwd_apply_kernel<float>), ew_grid4(n4), 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, n4, cols, 1.0 / (double)rows, training);
   DL_LAUNCH_CHECK("bn_bwd_apply_kernel");
   count_launch(2);
   return 0;

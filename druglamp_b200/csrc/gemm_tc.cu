@@ -362,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -382,6 +383,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // everything above overlaps the tail of the previous kernel; nothing below (TMA loads, epilogue
+  // reads and writes) may start before that kernel's results are visible
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -609,7 +613,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long l
   p.fd_kred.init((uint32_t)(p.kred_kpb > 0 ? p.kred_kpb : 1));
   p.total_tiles = (int)total;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_tc_kernel<BN, TF32, SPLIT><<<grid, kGemmThreads, C::SMEM, stream>>>(tmA, tmB, p);
+  DL_LAUNCH((gemm_tc_kernel<BN, TF32, SPLIT>), grid, kGemmThreads, C::SMEM, stream, tmA, tmB, p);
   DL_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = VEC * 128;
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -69,6 +71,8 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, T* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = VEC * 128;
   __shared__ float red[kWarpsPerBlock][32 * 4 + 4];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -137,6 +141,8 @@ template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 softmax_fwd_kernel(const T* __restrict__ s, T* __restrict__ p, long long rows, int cols,
                    long long ld) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
@@ -176,6 +182,8 @@ template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 softmax_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
                    long long rows, int cols, long long ld, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
@@ -237,6 +245,8 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 template <typename T, int NCH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 softmax_fwd_vec_kernel(const T* __restrict__ s, T* __restrict__ p, long long rows, long long ld) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
@@ -269,6 +279,8 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 softmax_bwd_vec_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
                        long long rows, long long ld, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
@@ -297,6 +309,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols,
               long long ld, long long rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -320,6 +334,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols,
                   long long ld, long long rows_per_block, int tpr) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = 16 / sizeof(T);
   __shared__ float red[256][V + 1];
   const int vcol = threadIdx.x % tpr, rsub = threadIdx.x / tpr, rpp = 256 / tpr;
@@ -367,6 +383,8 @@ colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long ro
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p,
                                unsigned long long seed) {
+  pdl_trigger();
+  pdl_wait();
   const float inv = 1.f / (1.f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -377,6 +395,8 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
 
 template <typename T>
 __global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float v = ldf<T>(x, i);
@@ -389,6 +409,8 @@ template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ norm_out,
                   long long rows, int cols, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -405,6 +427,8 @@ template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float* __restrict__ norm,
                   T* __restrict__ dx, long long rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -421,6 +445,8 @@ template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre,
                                T* __restrict__ g, long long n, int act, float p,
                                unsigned long long seed) {
+  pdl_trigger();
+  pdl_wait();
   const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -434,13 +460,17 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
 
 // AdamW over one flat fp32 buffer (torch.optim.AdamW semantics: decoupled weight decay, bias
 // correction from the device-side step counter) that also refreshes the bf16 shadow the GEMMs read.
-__global__ void adamw_tick_kernel(long long* step) { *step += 1; }
+__global__ void adamw_tick_kernel(long long* step) {
+  pdl_trigger();
+  pdl_wait(); *step += 1; }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ shadow, long long n,
                              const long long* __restrict__ step, float lr, float b1, float b2,
                              float eps, float wd, float grad_scale) {
+  pdl_trigger();
+  pdl_wait();
   const float t = (float)(*step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -460,6 +490,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x)
@@ -475,6 +507,8 @@ template <typename T>
 __global__ void add_pe_kernel(const T* __restrict__ x, const float* __restrict__ pe,
                               T* __restrict__ y, long long n, long long period, float p,
                               unsigned long long seed) {
+  pdl_trigger();
+  pdl_wait();
   const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -497,10 +531,10 @@ int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* y, floa
   const T* xx = (const T*)x;
   T* yy = (T*)y;
   switch (cols / 128) {
-    case 1: layernorm_fwd_kernel<T, 1><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 2: layernorm_fwd_kernel<T, 2><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 4: layernorm_fwd_kernel<T, 4><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 8: layernorm_fwd_kernel<T, 8><<<grid, th, 0, st>>>(xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 1: DL_LAUNCH((layernorm_fwd_kernel<T, 1>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 2: DL_LAUNCH((layernorm_fwd_kernel<T, 2>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 4: DL_LAUNCH((layernorm_fwd_kernel<T, 4>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 8: DL_LAUNCH((layernorm_fwd_kernel<T, 8>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
     default: return set_error(-1, "dl_layernorm_fwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_fwd_kernel");
@@ -518,10 +552,10 @@ int ln_bwd_dispatch(const void* dy, const void* x, const float* g, const float* 
   const T *dyy = (const T*)dy, *xx = (const T*)x;
   T* dxx = (T*)dx;
   switch (cols / 128) {
-    case 1: layernorm_bwd_kernel<T, 1><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 2: layernorm_bwd_kernel<T, 2><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 4: layernorm_bwd_kernel<T, 4><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 8: layernorm_bwd_kernel<T, 8><<<grid, th, 0, st>>>(dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 1>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 2>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 4>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 8>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
     default: return set_error(-1, "dl_layernorm_bwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_bwd_kernel");
@@ -569,16 +603,16 @@ extern "C" int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols
   const bool al = ((uintptr_t)s & 15) == 0 && ((uintptr_t)p & 15) == 0 && ld % 8 == 0;
   if (al && (cols == 256 || cols == 512)) {
     if (dtype == DL_BF16) {
-      if (cols == 256) softmax_fwd_vec_kernel<__nv_bfloat16, 1><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
-      else softmax_fwd_vec_kernel<__nv_bfloat16, 2><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
+      if (cols == 256) DL_LAUNCH((softmax_fwd_vec_kernel<__nv_bfloat16, 1>), grid, th, 0, st, (const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
+      else DL_LAUNCH((softmax_fwd_vec_kernel<__nv_bfloat16, 2>), grid, th, 0, st, (const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, ld);
     } else {
-      if (cols == 256) softmax_fwd_vec_kernel<float, 1><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, ld);
-      else softmax_fwd_vec_kernel<float, 2><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, ld);
+      if (cols == 256) DL_LAUNCH((softmax_fwd_vec_kernel<float, 1>), grid, th, 0, st, (const float*)s, (float*)p, rows, ld);
+      else DL_LAUNCH((softmax_fwd_vec_kernel<float, 2>), grid, th, 0, st, (const float*)s, (float*)p, rows, ld);
     }
   } else if (dtype == DL_BF16)
-    softmax_fwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, cols, ld);
+    DL_LAUNCH((softmax_fwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, cols, ld);
   else
-    softmax_fwd_kernel<float><<<grid, th, 0, st>>>((const float*)s, (float*)p, rows, cols, ld);
+    DL_LAUNCH((softmax_fwd_kernel<float>), grid, th, 0, st, (const float*)s, (float*)p, rows, cols, ld);
   DL_LAUNCH_CHECK("softmax_fwd_kernel");
   count_launch();
   return 0;
@@ -594,16 +628,16 @@ extern "C" int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t r
   const bool al = ((uintptr_t)p & 15) == 0 && ((uintptr_t)dp & 15) == 0 && ((uintptr_t)ds & 15) == 0 && ld % 8 == 0;
   if (al && (cols == 256 || cols == 512)) {
     if (dtype == DL_BF16) {
-      if (cols == 256) softmax_bwd_vec_kernel<__nv_bfloat16, 1><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
-      else softmax_bwd_vec_kernel<__nv_bfloat16, 2><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
+      if (cols == 256) DL_LAUNCH((softmax_bwd_vec_kernel<__nv_bfloat16, 1>), grid, th, 0, st, (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
+      else DL_LAUNCH((softmax_bwd_vec_kernel<__nv_bfloat16, 2>), grid, th, 0, st, (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, ld, scale);
     } else {
-      if (cols == 256) softmax_bwd_vec_kernel<float, 1><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
-      else softmax_bwd_vec_kernel<float, 2><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
+      if (cols == 256) DL_LAUNCH((softmax_bwd_vec_kernel<float, 1>), grid, th, 0, st, (const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
+      else DL_LAUNCH((softmax_bwd_vec_kernel<float, 2>), grid, th, 0, st, (const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
     }
   } else if (dtype == DL_BF16)
-    softmax_bwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, cols, ld, scale);
+    DL_LAUNCH((softmax_bwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, cols, ld, scale);
   else
-    softmax_bwd_kernel<float><<<grid, th, 0, st>>>((const float*)p, (const float*)dp, (float*)ds, rows, cols, ld, scale);
+    DL_LAUNCH((softmax_bwd_kernel<float>), grid, th, 0, st, (const float*)p, (const float*)dp, (float*)ds, rows, cols, ld, scale);
   DL_LAUNCH_CHECK("softmax_bwd_kernel");
   count_launch();
   return 0;
@@ -626,9 +660,9 @@ extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, 
     const long long rpb = (rows + yb - 1) / yb;
     dim3 grid(xb, (unsigned)yb);
     if (dtype == DL_BF16)
-      colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb, tpr);
+      DL_LAUNCH((colsum_vec_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, out, rows, cols, ld, rpb, tpr);
     else
-      colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, rows, cols, ld, rpb, tpr);
+      DL_LAUNCH((colsum_vec_kernel<float>), grid, 256, 0, st, (const float*)x, out, rows, cols, ld, rpb, tpr);
     DL_LAUNCH_CHECK("colsum_vec_kernel");
     count_launch();
     return 0;
@@ -640,9 +674,9 @@ extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, 
   const long long rpb = (rows + yb - 1) / yb;
   dim3 grid(xb, (unsigned)yb), block(32, 8);
   if (dtype == DL_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+    DL_LAUNCH((colsum_kernel<__nv_bfloat16>), grid, block, 0, st, (const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
   else
-    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, out, rows, cols, ld, rpb);
+    DL_LAUNCH((colsum_kernel<float>), grid, block, 0, st, (const float*)x, out, rows, cols, ld, rpb);
   DL_LAUNCH_CHECK("colsum_kernel");
   count_launch();
   return 0;
@@ -655,9 +689,9 @@ extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t s
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
+    DL_LAUNCH((dropout_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
   else
-    dropout_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n, p, seed);
+    DL_LAUNCH((dropout_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, n, p, seed);
   DL_LAUNCH_CHECK("dropout_kernel");
   count_launch();
   return 0;
@@ -669,9 +703,9 @@ extern "C" int dl_act_fwd(const void* x, void* y, int64_t n, int32_t act, int32_
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, act);
+    DL_LAUNCH((act_fwd_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, act);
   else
-    act_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n, act);
+    DL_LAUNCH((act_fwd_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, n, act);
   DL_LAUNCH_CHECK("act_fwd_kernel");
   count_launch();
   return 0;
@@ -684,9 +718,9 @@ extern "C" int dl_l2norm_fwd(const void* x, void* y, float* norm, int64_t rows, 
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(rows, kWarpsPerBlock), th = kWarpsPerBlock * 32;
   if (dtype == DL_BF16)
-    l2norm_fwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, norm, rows, cols, eps);
+    DL_LAUNCH((l2norm_fwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, norm, rows, cols, eps);
   else
-    l2norm_fwd_kernel<float><<<grid, th, 0, st>>>((const float*)x, (float*)y, norm, rows, cols, eps);
+    DL_LAUNCH((l2norm_fwd_kernel<float>), grid, th, 0, st, (const float*)x, (float*)y, norm, rows, cols, eps);
   DL_LAUNCH_CHECK("l2norm_fwd_kernel");
   count_launch();
   return 0;
@@ -699,9 +733,9 @@ extern "C" int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, v
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(rows, kWarpsPerBlock), th = kWarpsPerBlock * 32;
   if (dtype == DL_BF16)
-    l2norm_bwd_kernel<__nv_bfloat16><<<grid, th, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, norm, (__nv_bfloat16*)dx, rows, cols);
+    DL_LAUNCH((l2norm_bwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, norm, (__nv_bfloat16*)dx, rows, cols);
   else
-    l2norm_bwd_kernel<float><<<grid, th, 0, st>>>((const float*)dy, (const float*)y, norm, (float*)dx, rows, cols);
+    DL_LAUNCH((l2norm_bwd_kernel<float>), grid, th, 0, st, (const float*)dy, (const float*)y, norm, (float*)dx, rows, cols);
   DL_LAUNCH_CHECK("l2norm_bwd_kernel");
   count_launch();
   return 0;
@@ -714,9 +748,9 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed);
+    DL_LAUNCH((act_bwd_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed);
   else
-    act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)pre, (float*)g, n, act, p, seed);
+    DL_LAUNCH((act_bwd_kernel<float>), grid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, n, act, p, seed);
   DL_LAUNCH_CHECK("act_bwd_kernel");
   count_launch();
   return 0;
@@ -729,9 +763,9 @@ extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, fl
   DL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "dl_adamw_step: null pointer");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  adamw_tick_kernel<<<1, 1, 0, st>>>((long long*)step);
+  DL_LAUNCH(adamw_tick_kernel, 1, 1, 0, st, (long long*)step);
   DL_LAUNCH_CHECK("adamw_tick_kernel");
-  adamw_kernel<<<ew_grid(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq,
+  DL_LAUNCH(adamw_kernel, ew_grid(n, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq,
                                                 (__nv_bfloat16*)shadow_bf16, n, (const long long*)step,
                                                 lr, beta1, beta2, eps, weight_decay, grad_scale);
   DL_LAUNCH_CHECK("adamw_kernel");
@@ -747,13 +781,13 @@ extern "C" int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_o
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid((n + 3) / 4, 256);
   if (dtype_in == DL_F32 && dtype_out == DL_BF16)
-    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n);
+    DL_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)y, n);
   else if (dtype_in == DL_BF16 && dtype_out == DL_F32)
-    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n);
+    DL_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid, 256, 0, st, (const __nv_bfloat16*)x, (float*)y, n);
   else if (dtype_in == DL_F32 && dtype_out == DL_F32)
-    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+    DL_LAUNCH((cast_kernel<float, float>), grid, 256, 0, st, (const float*)x, (float*)y, n);
   else
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+    DL_LAUNCH((cast_kernel<__nv_bfloat16, __nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
   DL_LAUNCH_CHECK("cast_kernel");
   count_launch();
   return 0;
@@ -766,9 +800,9 @@ extern "C" int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed);
+    DL_LAUNCH((add_pe_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed);
   else
-    add_pe_kernel<float><<<grid, 256, 0, st>>>((const float*)x, pe, (float*)y, n, period, p, seed);
+    DL_LAUNCH((add_pe_kernel<float>), grid, 256, 0, st, (const float*)x, pe, (float*)y, n, period, p, seed);
   DL_LAUNCH_CHECK("add_pe_kernel");
   count_launch();
   return 0;
