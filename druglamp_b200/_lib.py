@@ -41,6 +41,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
         ("split_k", C.c_int32), ("conv_taps", C.c_int32), ("conv_left", C.c_int32),
         ("kred", C.c_int32), ("kred_shift", C.c_int32), ("accumulate", C.c_int32),
+        ("colsum_a", C.c_void_p),
     ]
 
 
@@ -151,7 +152,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
          precise: Optional[bool] = None, split_k: int = 0, conv_taps: int = 0, conv_left: int = 0,
-         kred: bool = False, kred_shift: int = 0, accumulate: bool = False) -> None:
+         kred: bool = False, kred_shift: int = 0, accumulate: bool = False,
+         colsum_a: Optional[torch.Tensor] = None) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -165,14 +167,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
                  mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k,
-                 conv_taps, conv_left, int(kred), kred_shift, int(accumulate))
+                 conv_taps, conv_left, int(kred), kred_shift, int(accumulate), ptr(colsum_a))
     if PROFILE is None:
         check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
         return
     check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
     # keep the argument block and its buffers alive so the launch can be re-issued for timing
     PROFILE.append({"flops": 2.0 * M * N * K * b[0] * b[1] * b[2], "args": a,
-                    "keep": (A, B, out, bias, preact_out, mul_aux, residual),
+                    "keep": (A, B, out, bias, preact_out, mul_aux, residual, colsum_a),
                     "shape": (M, N, K, b, int(trans_a), int(trans_b))})
 
 

@@ -32,6 +32,10 @@ constexpr int BM = 128;
 constexpr int kEpiWarps = 16;                 // four warps per TMEM lane quadrant
 constexpr int kColSplit = kEpiWarps / 4;      // column slices per tile
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+// Weight-gradient GEMMs dW = dY^T X stream dY through shared memory as the MN-major A operand;
+// while the tensor core consumes a stage, the first four (otherwise idle) epilogue warps also sum
+// its columns: db[m] += sum_k A[k, m], the bias gradient, without a second pass over dY.
+constexpr int kColsumWarps = 4;
 
 // n / d for n < 2^31 with a multiply-high and a shift (every role decodes a tile index per tile;
 // hardware integer division costs ~100 dependent cycles each)
@@ -49,6 +53,7 @@ struct FastDiv {
 struct GemmParams {
   FastDiv fd_perz, fd_nt, fd_splits, fd_nb0, fd_nb1, fd_conv, fd_kred;
   int nkb_all;                  // K-blocks of the whole reduction
+  float* colsum_a;              // bias gradient fused into a weight-gradient GEMM (see kColsumWarps)
   void* C;
   const float* bias;
   void* preact;
@@ -369,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, p.colsum_a ? 1 + kColsumWarps : 1);
       ptx::mbar_init(bar_conv + 8 * s, 32 * kEpiWarps);
     }
     for (int i = 0; i < 2; ++i) {
@@ -504,6 +509,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           ptx::fence_proxy_async();               // generic-proxy writes -> visible to the MMA
           ptx::mbar_arrive(bar_conv + 8 * s);
+        }
+      }
+      if constexpr (!TF32) {
+        if (p.colsum_a != nullptr && we < kColsumWarps) {
+          // Column sums of the MN-major bf16 A tile (two blocks of [64 k-rows][64 mn = 128 B],
+          // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)).  Thread = (block,
+          // chunk, row class r & 7): its eight rows share the XOR, so its chunk never moves, and
+          // the eight threads of a quarter-warp read eight different chunk positions (no bank
+          // conflicts).  Only the first n-tile of every (m-tile, K-slice) adds to the result; the
+          // warps still take part in the stage hand-shake for the other tiles.
+          const int t = threadIdx.x - 64;
+          const int blk = t >> 6, ch = (t >> 3) & 7, rcls = t & 7;
+          const bool active = T.n0 == 0;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int kb = 0; kb < T.nkb; ++kb, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            ptx::mbar_wait(bar_full + 8 * s, ph);
+            if (active) {
+              const uint8_t* src = smem + s * C::STAGE_BYTES + blk * (C::KE * 128) + ((ch ^ rcls) << 4) + rcls * 128;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(src + i * 1024);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  acc[2 * k] += __uint_as_float(w[k] << 16);
+                  acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_empty + 8 * s);
+          }
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+              acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+              acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+            }
+            if (rcls == 0) {
+              const int m = T.m0 + blk * 64 + ch * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (m + j < p.M) atomicAdd(p.colsum_a + m + j, acc[j]);
+            }
+          }
         }
       }
       const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
@@ -752,6 +807,11 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
     for (int i = 0; i < 3; ++i) p.sr[i] = a->sc[i];
   }
   p.splits = splits;
+  p.colsum_a = a->colsum_a;
+  if (a->colsum_a) {
+    DL_REQUIRE(!f32 && a->trans_a && batch == 1 && !conv && !kred,
+               "dl_gemm: colsum_a needs bf16 operands, an MN-major A (trans_a = 1) and no batch / conv modes");
+  }
   p.a_mn = a->trans_a != 0; p.b_mn = a->trans_b != 0;
   p.c_bf16 = a->dtype_c == DL_BF16;
   p.act = a->act; p.mul_mode = a->mul_mode; p.alpha = a->alpha;

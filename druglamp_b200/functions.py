@@ -62,6 +62,17 @@ def _bgrad(p, g):
     return K.colsum(g)
 
 
+def _wbgrad(wp, bp, g, x):
+    """(dW, db) of y = x W^T + b given g = dL/dy.  With a flat gradient store and bf16 operands this
+    is ONE launch: the weight-gradient GEMM dW = g^T x also sums g's columns from the tiles it
+    streams through shared memory (dl_gemm colsum_a), which is the bias gradient."""
+    tw, tb = _grad_target(wp), _grad_target(bp)
+    if tw is not None and tw.dim() == 2 and tb is not None and g.dtype == torch.bfloat16:
+        K.mm(g, x, tw, ta=True, tb=True, accumulate=True, colsum_a=tb)
+        return None, None
+    return _wgrad(wp, g, x), (None if bp is None else _bgrad(bp, g))
+
+
 # ================================================================================ Linear
 def _align() -> int:
     """TMA needs 16-byte row strides: 8 bf16 or 4 fp32 elements."""
@@ -127,13 +138,16 @@ class LinearFn(Function):
             dx = _back(dx if Kp == Kd else dx[:, :Kd], xdt, xs)
         wp, bp = ctx.params
         exact = Kp == Kw and Np == N
-        if ctx.needs_input_grad[1]:
-            if w_kn:
-                dw = _wgrad(wp, x2, g) if exact else K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)[:Kw, :N]
-            else:
-                dw = _wgrad(wp, g, x2) if exact else K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)[:N, :Kw]
-        if has_b and ctx.needs_input_grad[2]:
-            db = _bgrad(bp, g) if exact else K.colsum(g)[:N]
+        if exact and not w_kn and has_b and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            dw, db = _wbgrad(wp, bp, g, x2)
+        else:
+            if ctx.needs_input_grad[1]:
+                if w_kn:
+                    dw = _wgrad(wp, x2, g) if exact else K.mm(x2, g, ta=True, tb=True, out_dtype=torch.float32)[:Kw, :N]
+                else:
+                    dw = _wgrad(wp, g, x2) if exact else K.mm(g, x2, ta=True, tb=True, out_dtype=torch.float32)[:N, :Kw]
+            if has_b and ctx.needs_input_grad[2]:
+                db = _bgrad(bp, g) if exact else K.colsum(g)[:N]
         if rdt is not None and ctx.needs_input_grad[4]:
             gr = gy2 if rshape[-1] == No else gy2[:, :rshape[-1]]
             dres = _back(gr, rdt, rshape)
@@ -174,11 +188,9 @@ class FFNFn(Function):
         gy2 = K.to_compute(gy).view(-1, w2.shape[0])
         g2 = K.act_bwd(gy2, None, K.ACT_NONE, (p, seed2))
         b1p, b2p = ctx.biases
-        dw2 = _wgrad(w2, g2, hd)
-        db2 = _bgrad(b2p, g2)
+        dw2, db2 = _wbgrad(w2, b2p, g2, hd)
         dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD, drop=(p, seed1))
-        dw1 = _wgrad(w1, dpre1, x2)
-        db1 = _bgrad(b1p, dpre1)
+        dw1, db1 = _wbgrad(w1, b1p, dpre1, x2)
         dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs) if ctx.needs_input_grad[0] else None
         dres = _back(gy2, rdt, gy.shape) if rdt is not None else None
         return dx, dw1, db1, dw2, db2, dres, None, None, None
@@ -325,9 +337,9 @@ class PairedQFn(Function):
         dx0 = _back(K.mm(g0, shadow(w0), tb=True), ctx.dts[0], a0.shape)
         dx1 = _back(K.mm(g1, shadow(w1), tb=True), ctx.dts[1], a1.shape)
         b0, b1 = ctx.biases
-        dw0 = _wgrad(w0, g0, a0.view(-1, D))
-        dw1 = _wgrad(w1, g1, a1.view(-1, D))
-        return dx0, dw0, _bgrad(b0, g0), dx1, dw1, _bgrad(b1, g1)
+        dw0, db0 = _wbgrad(w0, b0, g0, a0.view(-1, D))
+        dw1, db1 = _wbgrad(w1, b1, g1, a1.view(-1, D))
+        return dx0, dw0, db0, dx1, dw1, db1
 
 
 class FcCatFn(Function):
@@ -364,15 +376,23 @@ class FcCatFn(Function):
         wc = shadow(w)
         if not swap:
             do = K.mm(g, wc, tb=True)
-            dw = _wgrad(w, g, o2)
+            dw, db = _wbgrad(w, ctx.bias, g, o2)
         else:
             do = torch.empty_like(o2)
             K.mm(g, wc[:, D:], do[:, :D], tb=True)
             K.mm(g, wc[:, :D], do[:, D:], tb=True)
-            dw = torch.empty((N, D2), dtype=torch.float32, device=g.device)
-            K.mm(g, o2[:, :D], dw[:, D:], ta=True, tb=True)
-            K.mm(g, o2[:, D:], dw[:, :D], ta=True, tb=True)
-        return _back(do, odt, oshape), dw, _bgrad(ctx.bias, g), None
+            tw, tb_ = _grad_target(w), _grad_target(ctx.bias)
+            if tw is not None and tb_ is not None and g.dtype == torch.bfloat16:
+                # crosswise halves straight into the flat gradient; the first GEMM also sums g's columns
+                K.mm(g, o2[:, :D], tw[:, D:], ta=True, tb=True, accumulate=True, colsum_a=tb_)
+                K.mm(g, o2[:, D:], tw[:, :D], ta=True, tb=True, accumulate=True)
+                dw = db = None
+            else:
+                dw = torch.empty((N, D2), dtype=torch.float32, device=g.device)
+                K.mm(g, o2[:, :D], dw[:, D:], ta=True, tb=True)
+                K.mm(g, o2[:, D:], dw[:, :D], ta=True, tb=True)
+                db = _bgrad(ctx.bias, g)
+        return _back(do, odt, oshape), dw, db, None
 
 
 # ================================================================================ PGCA
@@ -418,8 +438,7 @@ class PGCAFn(Function):
         Bn, Lq, E = qb.shape
         Sk = kb.shape[1]
         g = K.to_compute(gout.transpose(0, 1)).view(-1, E)             # (B*L, E)
-        d_out_w = _wgrad(out_w, g, O.view(-1, E))
-        d_out_b = _bgrad(out_b, g)
+        d_out_w, d_out_b = _wbgrad(out_w, out_b, g, O.view(-1, E))
         dO = K.mm(g, shadow(out_w), tb=True).view(Bn, Lq, E)
         dKV = torch.empty_like(KV)
         dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, H, scale,
@@ -431,12 +450,17 @@ class PGCAFn(Function):
         acc = tw is not None and tb_ is not None
         d_in_w = tw if acc else torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
         d_in_b = tb_ if acc else torch.empty(3 * E, dtype=torch.float32, device=g.device)
-        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True, accumulate=acc)
-        K.colsum(dq2, d_in_b[:E], accumulate=acc)
-        K.colsum(dkv2, d_in_b[E:], accumulate=acc)
+        fuse = acc and dq2.dtype == torch.bfloat16      # bias gradients summed inside the dW GEMMs
+        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True, accumulate=acc,
+             colsum_a=d_in_b[:E] if fuse else None)
+        if not fuse:
+            K.colsum(dq2, d_in_b[:E], accumulate=acc)
+        if not (fuse and shared):
+            K.colsum(dkv2, d_in_b[E:], accumulate=acc)
         dquery = _back(K.mm(dq2, wi[:E], tb=True).view(Bn, Lq, E), qdt).transpose(0, 1)
         if shared:
-            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True, accumulate=acc)
+            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True, accumulate=acc,
+                 colsum_a=d_in_b[E:] if fuse else None)
             dkey = _back(K.mm(dkv2, wi[E:], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
             dvalue = None
         else:
@@ -483,11 +507,9 @@ class MHLAFn(Function):
         dv_direct, dlogits, dg, db = K.mhla_gate_ln_bwd(K.to_compute(gy), vc, p, mean, rstd, g_)
         dl2 = dlogits.view(-1, Hh)
         b1, b2 = ctx.biases
-        dw2 = _wgrad(w2, dl2, h)
-        db2 = _bgrad(b2, dl2)
+        dw2, db2 = _wbgrad(w2, b2, dl2, h)
         dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD)
-        dw1 = _wgrad(w1, dpre1, vc.view(-1, E))
-        db1 = _bgrad(b1, dpre1)
+        dw1, db1 = _wbgrad(w1, b1, dpre1, vc.view(-1, E))
         dv = K.mm(dpre1, shadow(w1), tb=True, res=dv_direct.view(-1, E)).view(Bn, Lr, E)
         return _back(dv, ctx.vdt), dw1, db1, dw2, db2, dg, db, None
 

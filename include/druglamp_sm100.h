@@ -105,6 +105,10 @@ typedef struct dl_gemm_args {
   int32_t kred, kred_shift;
   int32_t accumulate; /* 1: C += result (plain fp32 outputs only) -- weight gradients land directly in
                          the flat gradient buffer instead of a temporary plus an add kernel */
+  float* colsum_a;    /* or NULL.  bf16 operands, trans_a = 1, no batch: colsum_a[m] += sum_k A[k, m],
+                         computed from the A tiles while they sit in shared memory.  For a weight
+                         gradient dW = dY^T X (A = dY) this is the bias gradient, so nn.Linear's
+                         backward needs no separate pass over dY (fp32 [M], accumulated into). */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);

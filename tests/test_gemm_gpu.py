@@ -164,3 +164,24 @@ def test_argument_errors_are_reported():
     Cc = torch.zeros(16, 16, device="cuda")
     with pytest.raises(RuntimeError, match="multiple of 16 bytes"):
         _lib.gemm(A, B, Cc, M=16, N=16, K=75, lda=75, ldb=75, ldc=16)
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(256, 256, 4096, 0), (8, 1024, 2048, 0), (200, 648, 1000, 64),
+                                           (512, 512, 16384, 0), (128, 128, 192, 128)])
+def test_weight_gradient_with_fused_bias_gradient(M, N, K, tile_n):
+    """dW += dY^T X with colsum_a: the bias gradient sum_k dY[k, :] comes out of the same launch
+    (integer operands: both results are exact, also across split-K slices and several n-tiles)."""
+    from druglamp_b200 import _lib
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    dY = _mk((K, M), torch.bfloat16, True, gen)
+    X = _mk((K, N), torch.bfloat16, True, gen)
+    dW = torch.full((M, N), 2.0, device="cuda")
+    db = torch.full((M,), -1.0, device="cuda")
+    _lib.gemm(dY, X, dW, M=M, N=N, K=K, lda=M, ldb=N, ldc=N, trans_a=True, trans_b=True,
+              accumulate=True, colsum_a=db, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert torch.equal(dW.double(), 2.0 + dY.double().t() @ X.double())
+    assert torch.equal(db.double(), -1.0 + dY.double().sum(0))
+    with pytest.raises(RuntimeError, match="colsum_a"):
+        _lib.gemm(dY.float(), X.float(), dW, M=M, N=N, K=K, lda=M, ldb=N, ldc=N, trans_a=True,
+                  trans_b=True, accumulate=True, colsum_a=db)
