@@ -185,9 +185,13 @@ def run_gpu(args):
     if world > 1:                      # replicas start from rank 0's weights
         torch.distributed.broadcast(ts.flat.flat, 0)
 
-    batches = [StaticBatch(make_batch(BATCH, seed=1234 + rank * 100 + i), dev) for i in range(N_DISTINCT_BATCHES)]
+    raw = [make_batch(BATCH, seed=1234 + rank * 100 + i) for i in range(N_DISTINCT_BATCHES)]
+    batches = [StaticBatch(b, dev) for b in raw]
     hosts = [b.host_copy(pin=True) for b in batches]
     h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+    # packed wire format (druglamp_b200/collate.py): the embedding rows as the dataset yields them,
+    # before the reference collate tiles / pads them on the host
+    hosts_packed = [sb.host_copy_packed(b, pin=True) for sb, b in zip(batches, raw)]
     if args.ncu_step:
         # profiling aid (never a bench value): one eager step between cudaProfilerStart/Stop so that
         #   ncu --profile-from-start off ... python bench.py --ncu-step
@@ -236,37 +240,44 @@ def run_gpu(args):
     consumed = [torch.cuda.Event() for _ in range(nb)]
     main = torch.cuda.current_stream()
 
-    def enqueue_copy(i):
+    h2d_bytes = {"dense": 0, "packed": 0}
+
+    def enqueue_copy(i, fmt):
         j = i % nb
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[j])      # the step that last read these buffers is done
-            batches[j].load_from(hosts[j])
+            if fmt == "packed":                      # untiled rows over PCIe, tiled on the device
+                h2d_bytes[fmt] = batches[j].load_from_packed(hosts_packed[j])
+            else:                                    # the reference collate's dense tensors
+                h2d_bytes[fmt] = batches[j].load_from(hosts[j])
             copied[j].record(copy_stream)
 
-    def e2e_loop(n):
+    def e2e_loop(n, fmt):
         for j in range(nb):
             consumed[j].record(main)
-        enqueue_copy(0)
+        enqueue_copy(0, fmt)
         for i in range(n):
             j = i % nb
             main.wait_event(copied[j])
             out = ts.replay(batches[j])
             consumed[j].record(main)
             if i + 1 < n:
-                enqueue_copy(i + 1)
+                enqueue_copy(i + 1, fmt)
             out.item()                               # D2H read of the step's loss (4 bytes), every step
 
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_times = {}
+    for fmt in ("dense", "packed"):
+        e2e_loop(3, fmt)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(e2e_steps, fmt)
+        barrier()
+        e2e_times[fmt] = time.perf_counter() - t0
 
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_times["dense"], e2e_times["packed"]], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_s = float(t[0]), float(t[1])
+    ms, e2e_dense_s, e2e_s = float(t[0]), float(t[1]), float(t[2])
 
     # ---- roofline of the dominant kernel: every dl_gemm launch of one eager step, CUDA events ---
     roof = None
@@ -353,8 +364,17 @@ def run_gpu(args):
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": config(world), "clocks": clocks,
-                "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 4, "steps": e2e_steps},
+                # e2e: host buffers as the reference DATASET yields them (per-sample embedding rows,
+                # druglamp_b200.collate.pack_rows) -> pinned H2D -> device-side tail_pad / repeat_pad
+                # (dl_expand_rows, bit-identical to the reference collate's tensors) -> step -> loss D2H.
+                # e2e_dense: the same with the reference COLLATE's dense padded tensors crossing PCIe.
+                "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": UNIT,
+                        "h2d_bytes_per_step": h2d_bytes["packed"], "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "wire_format": "packed per-sample embedding rows, padded/tiled on the device"},
+                "e2e_dense": {"value": pairs * e2e_steps / e2e_dense_s, "unit": UNIT,
+                              "h2d_bytes_per_step": h2d_bytes["dense"], "d2h_bytes_per_step": 4,
+                              "steps": e2e_steps,
+                              "wire_format": "dense fp32 tensors of utils.multimodality_collate_func (PCIe-bound)"},
                 "gpu_launches": ts.launches_per_step * args.steps, "gpu_launches_per_step": ts.launches_per_step,
                 "roofline": roof, "cpu_baseline": cpu, "loss": loss_value}
         print(json.dumps(line), flush=True)

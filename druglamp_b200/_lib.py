@@ -68,6 +68,7 @@ SIGNATURES = {
     "dl_embed_fill_fwd": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_embed_fill_bwd": [_P, _I32, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_fillbit_pool": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _I32, _P],
+    "dl_expand_rows": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_transpose": [_P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_site_pool_fwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
     "dl_site_pool_bwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],

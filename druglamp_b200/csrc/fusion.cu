@@ -480,6 +480,34 @@ __global__ void bce_bwd_kernel(const float* __restrict__ prob, const float* __re
   }
 }
 
+// ---------------------------------------------------------------- packed collate -> dense
+// The reference's collate pads every sample's LLM embedding rows on the host (utils.py:304-324):
+// tail_pad copies the R_b rows once, repeat_pad tiles them floor(maxsize / R_b) times, the rest is
+// zeros.  Here the host ships the R_b rows only and this kernel writes the identical dense
+// (B, maxsize, C) tensor: out[b, r, :] = rows[off_b + r mod R_b] for r < reps_b * R_b, else 0.
+// One warp per output row, 16-byte vectors; the source rows are re-read from L2.
+__global__ void __launch_bounds__(256)
+expand_rows_kernel(const float* __restrict__ rows, const int* __restrict__ offsets,
+                   float* __restrict__ out, int B, int maxsize, int C4, int repeat) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * maxsize;
+  const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 8;
+  for (long long o = w0; o < total; o += nw) {
+    const int b = (int)(o / maxsize), r = (int)(o - (long long)b * maxsize);
+    const int off = offsets[b], R = offsets[b + 1] - off;
+    const int filled = R <= 0 ? 0 : (repeat ? (maxsize / R) * R : (R < maxsize ? R : maxsize));
+    float4* dst = reinterpret_cast<float4*>(out) + o * C4;
+    if (r < filled) {
+      const float4* src = reinterpret_cast<const float4*>(rows) + (long long)(off + r % R) * C4;
+      for (int c = lane; c < C4; c += 32) dst[c] = src[c];
+    } else {
+      for (int c = lane; c < C4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- ProteinCNN input
 // out[r, 0:127] = table[tok[r], :], out[r, 127] = fill[r]   (embedding gather + concat + cast in
 // one pass; model/basic_model.py:171-173).  The 27 x 127 fp32 table sits in shared memory; one
@@ -667,6 +695,22 @@ extern "C" int dl_embed_fill_bwd(const void* tokens, int32_t tok_dtype, const vo
                                    : embed_bwd_launch<__nv_bfloat16, double>(tokens, g, dtable, rows, vocab, padding_idx, st);
   return tok_dtype == DL_TOK_I64 ? embed_bwd_launch<float, long long>(tokens, g, dtable, rows, vocab, padding_idx, st)
                                  : embed_bwd_launch<float, double>(tokens, g, dtable, rows, vocab, padding_idx, st);
+}
+
+extern "C" int dl_expand_rows(const float* rows, const int32_t* offsets, float* out, int64_t B,
+                              int32_t maxsize, int32_t C, int32_t repeat, void* stream) {
+  DL_REQUIRE(rows && offsets && out, "dl_expand_rows: null pointer");
+  DL_REQUIRE(B >= 0 && maxsize >= 1 && C >= 4 && C % 4 == 0, "dl_expand_rows: need C %% 4 == 0 (got B=%lld maxsize=%d C=%d)", (long long)B, maxsize, C);
+  DL_REQUIRE((((uintptr_t)rows | (uintptr_t)out) & 15) == 0, "dl_expand_rows: rows and out must be 16-byte aligned");
+  DL_REQUIRE(B * (long long)maxsize < (1ll << 31), "dl_expand_rows: too many rows");
+  if (B == 0) return 0;
+  long long blocks = (B * (long long)maxsize + 7) / 8;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  DL_LAUNCH(expand_rows_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, rows, offsets, out, (int)B, maxsize, C / 4, repeat);
+  DL_LAUNCH_CHECK("expand_rows_kernel");
+  count_launch();
+  return 0;
 }
 
 extern "C" int dl_site_pool_fwd(const void* x, void* y, int64_t B, int32_t S, int32_t L, int32_t C,

@@ -239,6 +239,18 @@ def fillbit_pool(x: torch.Tensor, S: int, want_bit=True, want_cat=False, want_po
     return bit, cat, pooled
 
 
+def expand_rows(rows: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor, repeat: bool) -> torch.Tensor:
+    """Packed per-sample rows [sum R_b, C] + offsets [B+1] (int32) -> dense out (B, maxsize, C) fp32,
+    exactly as utils.tail_pad (repeat=False) / utils.repeat_pad (repeat=True) build it on the host."""
+    if rows.dtype != torch.float32 or out.dtype != torch.float32 or offsets.dtype != torch.int32:
+        raise TypeError("expand_rows: rows/out must be fp32 and offsets int32")
+    B, maxsize, C = out.shape
+    if offsets.numel() != B + 1 or rows.shape[-1] != C or not out.is_contiguous() or not rows.is_contiguous():
+        raise ValueError("expand_rows: inconsistent shapes")
+    L.call("dl_expand_rows", rows.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, maxsize, C, int(repeat))
+    return out
+
+
 def _tok_dtype(tokens: torch.Tensor) -> int:
     if tokens.dtype == torch.int64:
         return 0

@@ -45,6 +45,13 @@ class Batch:
         """(vd, vp, xd, xp) in the order ``Model.forward`` takes them (DrugLAMP.py:8)."""
         return self.graph, self.vp, self.xd, self.xp
 
+    def llm_blocks(self):
+        """The per-sample embedding rows BEFORE the collate pads them (``l['drug'].x`` /
+        ``l['prot'].x`` in ``utils.multimodality_collate_func``): (drug blocks, protein blocks)."""
+        d = [self.xd[b, :min(int(self.n_atoms[b]) + 2, self.xd.shape[1])] for b in range(self.xd.shape[0])]
+        p = [self.xp[b, :int(self.prot_len[b]) + 2] for b in range(self.xp.shape[0])]
+        return d, p
+
 
 def _molecule_edges(rng: np.random.Generator, n: int):
     """Random spanning tree + round(0.1 n) ring closures, both directions."""

@@ -3,8 +3,8 @@
 One step = zero the flat gradient buffer -> model forward -> ``binary_cross_entropy`` -> backward
 -> (data-parallel: one NCCL sum all-reduce of the flat gradient buffer) -> fused AdamW over the
 flat parameter buffer (which also refreshes the bf16 shadows).  Everything on the device side is a
-hand-written kernel launch (plus cuDNN for the adjacent ProteinCNN); capturing it in a CUDA graph
-removes the Python/launch overhead that otherwise dominates at batch 64.
+hand-written kernel launch (a few PyTorch tensor adds / copies remain as autograd glue); capturing it
+in a CUDA graph removes the Python/launch overhead that otherwise dominates at batch 64.
 
 The reference does this through Lightning's manual optimisation with up to three backward passes
 and three all-reduces per step (``trainer.py:179-231``); this class is the B200-side
@@ -33,6 +33,7 @@ class StaticBatch:
         self.xp = batch.xp.to(device)
         self.y = batch.y.to(device).float()
         self.n_pairs = int(batch.y.shape[0])
+        self._stage = {}                          # device staging of packed rows (load_from_packed)
 
     def tensors(self) -> List[torch.Tensor]:
         g = self.graph
@@ -53,6 +54,48 @@ class StaticBatch:
         for dst, src in zip(self.tensors(), host):
             dst.copy_(src, non_blocking=True)
             n += src.numel() * src.element_size()
+        return n
+
+    # ---- packed wire format (druglamp_b200.collate): untiled embedding rows over PCIe ---------
+    def _small(self) -> List[torch.Tensor]:
+        g = self.graph
+        return [self.h, self.vp, self.y, g.indptr, g.indices, g.indptr_t, g.indices_t, g.norm_src, g.norm_dst]
+
+    def host_copy_packed(self, batch, pin=True) -> dict:
+        """Host image of this batch with the LLM embeddings as packed rows (what the dataset yields
+        before ``utils.tail_pad`` / ``repeat_pad``) instead of the dense padded tensors."""
+        from .collate import pack_rows
+        small = []
+        for t in self._small():
+            c = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=pin)
+            c.copy_(t)
+            small.append(c)
+        d_blocks, p_blocks = batch.llm_blocks()
+        return {"small": small,
+                "xd": pack_rows(d_blocks, self.xd.shape[1], repeat=False, pin=pin),
+                "xp": pack_rows(p_blocks, self.xp.shape[1], repeat=True, pin=pin)}
+
+    def load_from_packed(self, host: dict) -> int:
+        """Asynchronous H2D of the packed image, then the device-side padding / tiling into the
+        dense input buffers (bit-identical to the reference collate's tensors); returns bytes copied."""
+        from . import kernels as K
+        n = 0
+        for dst, src in zip(self._small(), host["small"]):
+            dst.copy_(src, non_blocking=True)
+            n += src.numel() * src.element_size()
+        for key, dense in (("xd", self.xd), ("xp", self.xp)):
+            pk = host[key]
+            stage = self._stage.get(key)
+            if stage is None or stage[0].shape[0] < pk.rows.shape[0]:
+                cap = max(pk.rows.shape[0], 0 if stage is None else stage[0].shape[0])
+                stage = (torch.empty((cap, pk.rows.shape[1]), dtype=torch.float32, device=dense.device),
+                         torch.empty(pk.offsets.shape, dtype=torch.int32, device=dense.device))
+                self._stage[key] = stage
+            rows = stage[0][:pk.rows.shape[0]]
+            rows.copy_(pk.rows, non_blocking=True)
+            stage[1].copy_(pk.offsets, non_blocking=True)
+            K.expand_rows(rows, stage[1], dense, pk.repeat)
+            n += pk.nbytes()
         return n
 
     def model_inputs(self):

@@ -413,3 +413,23 @@ def alias_state(sd: SD) -> SD:
         if k.startswith("ssl_model.extractor."):
             sd[k] = sd["protein_extractor." + k[len("ssl_model.extractor."):]]
     return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# Collate padding (utils.py:304-324), the checker for druglamp_b200.collate / dl_expand_rows
+def tail_pad(blocks, maxsize: int):
+    """utils.py:304-312: each sample's rows once, zeros after."""
+    out = torch.zeros(len(blocks), maxsize, blocks[0].shape[-1])
+    for i, a in enumerate(blocks):
+        out[i, :a.shape[-2], :] = a
+    return out
+
+
+def repeat_pad(blocks, maxsize: int):
+    """utils.py:314-324: each sample's rows tiled floor(maxsize / rows) times, zeros after."""
+    out = torch.zeros(len(blocks), maxsize, blocks[0].shape[-1])
+    for i, a in enumerate(blocks):
+        n = a.shape[-2]
+        for j in range(maxsize // n):
+            out[i, j * n:(j + 1) * n, :] = a
+    return out

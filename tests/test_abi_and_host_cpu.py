@@ -168,3 +168,24 @@ def test_graph_carrier_csr_is_exact():
     assert int(g.in_deg.min()) >= 1
     real = make_batch(3, seed=9).n_atoms
     assert int(g.in_deg[0]) >= 3 and int(g.in_deg[int(real[0])]) == 1       # virtual node: one self loop
+
+
+def test_pack_rows_host_layout_and_errors():
+    """druglamp_b200.collate.pack_rows: back-to-back rows + int32 offsets; tail_pad overflow raises
+    like the reference's slice assignment does; the restated pads agree with the dense synthetic batch."""
+    import pytest
+    import torch
+    from druglamp_b200.collate import pack_rows
+    from druglamp_b200.synth import make_batch
+    from oracle import restatement as R
+    blocks = [torch.arange(6.0).view(3, 2), torch.arange(10.0, 14.0).view(2, 2)]
+    pk = pack_rows(blocks, 8, repeat=True, pin=False)
+    assert pk.offsets.tolist() == [0, 3, 5] and pk.offsets.dtype == torch.int32
+    assert torch.equal(pk.rows, torch.cat(blocks)) and pk.batch == 2 and pk.nbytes() == 5 * 2 * 4 + 3 * 4
+    with pytest.raises(ValueError):
+        pack_rows([torch.zeros(9, 2)], 8, repeat=False, pin=False)
+    with pytest.raises(ValueError):
+        pack_rows([torch.zeros(3, 2), torch.zeros(3, 4)], 8, repeat=True, pin=False)
+    b = make_batch(3, seed=5)
+    d, p = b.llm_blocks()
+    assert torch.equal(R.tail_pad(d, 512), b.xd) and torch.equal(R.repeat_pad(p, 2304), b.xp)

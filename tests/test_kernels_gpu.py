@@ -299,3 +299,27 @@ def test_embed_fill_fwd_bwd_matches_embedding_cat(dtype, tol, tok_dtype):
         D.set_compute_dtype(torch.float32)
     assert emb.weight.grad[0].abs().max().item() == 0.0             # padding row gets no gradient
     _close(emb.weight.grad, gref, 1e-5, "dtable")
+
+
+def test_packed_collate_expands_bit_exactly_like_the_reference_pads():
+    """dl_expand_rows against the restated utils.tail_pad / utils.repeat_pad (:304-324), ragged
+    blocks incl. one longer than half of maxsize (tiled once) and a single-row block; and the
+    whole packed input path against the dense synthetic batch."""
+    from druglamp_b200.collate import pack_rows
+    from druglamp_b200.synth import make_batch
+    from druglamp_b200.train import StaticBatch
+    from oracle import restatement as R
+    torch.manual_seed(1)
+    blocks = [torch.randn(n, 64) for n in (7, 1, 130, 255, 256, 33)]
+    for repeat, ref in ((False, R.tail_pad), (True, R.repeat_pad)):
+        pk = pack_rows(blocks, 256, repeat).to("cuda")
+        assert torch.equal(pk.dense().cpu(), ref(blocks, 256))
+    b = make_batch(6, seed=77)
+    sb = StaticBatch(b, torch.device("cuda"))
+    host = sb.host_copy_packed(b)
+    dense_bytes = sum(t.numel() * t.element_size() for t in sb.host_copy(pin=False))
+    sb.xp.fill_(-1.0); sb.xd.fill_(-1.0); sb.vp.zero_()
+    n = sb.load_from_packed(host)
+    torch.cuda.synchronize()
+    assert torch.equal(sb.xp.cpu(), b.xp) and torch.equal(sb.xd.cpu(), b.xd) and torch.equal(sb.vp.cpu(), b.vp)
+    assert n < dense_bytes / 2
