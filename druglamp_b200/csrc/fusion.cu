@@ -114,10 +114,13 @@ __global__ void site_pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ d
 }
 
 // ------------------------------------------------------------------ MHLA gate + residual + LN
-// One block (256 threads = 8 warps) per batch element.
 //   p[h, l]  = softmax over l of logits[b, l, h]
 //   u[b,l,e] = v[b,l,e] * (1 + p[hh, ll]),  f = l*E + e, hh = f / (L*hd), ll = (f % (L*hd)) / hd
 //   y        = LayerNorm_E(u) * gamma + beta
+// The reinterpreting view gives head hh exactly the rows [hh*L/H, (hh+1)*L/H) when H divides L, so
+// the work of one batch element splits into H independent blocks (grid (B, H)): block (b, hh)
+// needs only head hh's softmax and owns all of its gates, forward and backward.  Otherwise one
+// block per batch element (grid (B, 1)) handles every head.  256 threads = 8 warps per block.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
@@ -131,8 +134,11 @@ mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
   const bool plain = gamma == nullptr;
   const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int hd = E / H;
+  const bool sliced = gridDim.y > 1;
+  const int h_begin = sliced ? blockIdx.y : 0, h_end = sliced ? blockIdx.y + 1 : H;
+  const int l_begin = sliced ? blockIdx.y * (L / H) : 0, l_end = sliced ? l_begin + L / H : L;
   // phase 1: column softmax, warp per head
-  for (int h = w; h < H; h += 8) {
+  for (int h = h_begin + w; h < h_end; h += 8) {
     float m = -INFINITY;
     for (int l = lane; l < L; l += 32) m = fmaxf(m, ldf<T>(logits, ((size_t)b * L + l) * H + h));
     m = warp_max(m);
@@ -151,7 +157,7 @@ mhla_gate_ln_fwd_kernel(const T* __restrict__ v, const T* __restrict__ logits,
   }
   __syncthreads();
   // phase 2: gate + residual + LayerNorm, warp per row
-  for (int l = w; l < L; l += 8) {
+  for (int l = l_begin + w; l < l_end; l += 8) {
     const size_t rbase = ((size_t)b * L + l) * E;
     float4 u[VEC];
     float s = 0.f;
@@ -216,7 +222,10 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
   for (int j = 0; j < VEC; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int lanes_per_chunk = hd / 4;           // lanes sharing one (hh, ll) gate
   const bool plain = gamma == nullptr;          // gating only: no residual, no LayerNorm
-  for (int l = w; l < L; l += 8) {
+  const bool sliced = gridDim.y > 1;            // block (b, hh): the rows and the gates of head hh
+  const int h_begin = sliced ? blockIdx.y : 0, h_end = sliced ? blockIdx.y + 1 : H;
+  const int l_begin = sliced ? blockIdx.y * (L / H) : 0, l_end = sliced ? l_begin + L / H : L;
+  for (int l = l_begin + w; l < l_end; l += 8) {
     const size_t rbase = ((size_t)b * L + l) * E;
     const float mean = plain ? 0.f : mean_in[(size_t)b * L + l];
     const float rstd = plain ? 1.f : rstd_in[(size_t)b * L + l];
@@ -260,7 +269,7 @@ mhla_gate_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ v,
   }
   __syncthreads();
   // softmax-over-L backward, warp per head: dlogit[l,h] = p (dp - sum_l p dp)
-  for (int h = w; h < H; h += 8) {
+  for (int h = h_begin + w; h < h_end; h += 8) {
     float dot = 0.f;
     for (int l = lane; l < L; l += 32) dot += sp[h * L + l] * sdp[h * L + l];
     dot = warp_sum(dot);
@@ -759,7 +768,7 @@ extern "C" int dl_mhla_gate_ln_fwd(const void* v, const void* logits, const floa
   do {                                                                                              \
     if (smem > 48 * 1024)                                                                           \
       DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_fwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    DL_LAUNCH((mhla_gate_ln_fwd_kernel<TT, VV>), (unsigned)B, 256, smem, st, (const TT*)v, (const TT*)logits, gamma, beta, (TT*)y, p_out, mean, rstd, L, H, eps); \
+    DL_LAUNCH((mhla_gate_ln_fwd_kernel<TT, VV>), dim3((unsigned)B, L % H == 0 ? H : 1), 256, smem, st, (const TT*)v, (const TT*)logits, gamma, beta, (TT*)y, p_out, mean, rstd, L, H, eps); \
   } while (0)
   if (dtype == DL_BF16) {
     if (E == 128) DL_MHLA_FWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_FWD(__nv_bfloat16, 2);
@@ -792,7 +801,7 @@ extern "C" int dl_mhla_gate_ln_bwd(const void* dy, const void* v, const float* p
   do {                                                                                              \
     if (smem > 48 * 1024)                                                                           \
       DL_CUDA(cudaFuncSetAttribute(mhla_gate_ln_bwd_kernel<TT, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    DL_LAUNCH((mhla_gate_ln_bwd_kernel<TT, VV>), (unsigned)B, 256, smem, st, (const TT*)dy, (const TT*)v, p, mean, rstd, gamma, (TT*)dv, (TT*)dlogits, dgamma, dbeta, L, H); \
+    DL_LAUNCH((mhla_gate_ln_bwd_kernel<TT, VV>), dim3((unsigned)B, L % H == 0 ? H : 1), 256, smem, st, (const TT*)dy, (const TT*)v, p, mean, rstd, gamma, (TT*)dv, (TT*)dlogits, dgamma, dbeta, L, H); \
   } while (0)
   if (dtype == DL_BF16) {
     if (E == 128) DL_MHLA_BWD(__nv_bfloat16, 1); else if (E == 256) DL_MHLA_BWD(__nv_bfloat16, 2);

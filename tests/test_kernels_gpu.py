@@ -163,10 +163,11 @@ def test_fillbit_pool_bit_exact_and_site_pool():
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
-def test_mhla_gate_ln_fwd_bwd(dtype, tol):
+@pytest.mark.parametrize("shape", [(3, 256, 256, 8), (2, 100, 128, 8)])   # H | L: one block per head; else per pair
+def test_mhla_gate_ln_fwd_bwd(dtype, tol, shape):
     from druglamp_b200 import kernels as K
     torch.manual_seed(6)
-    B, Lr, E, H = 3, 256, 256, 8
+    B, Lr, E, H = shape
     v = torch.randn(B, Lr, E, device="cuda").to(dtype)
     logits = (torch.randn(B, Lr, H, device="cuda") * 2).to(dtype)
     g = torch.rand(E, device="cuda") + 0.5
