@@ -15,44 +15,56 @@ void count_launch(int n = 1);
 namespace {
 
 // ------------------------------------------------------------------ fill bit + concat + site mean
-// x: (B, S*L, C) fp32.  One block per pooled row (grid (L, B)); its 8 warps take the S site rows
-// round-robin, so all of them are in flight at once.  A warp sums its row with shuffles (the fill
-// bit is "row sums to exactly 0", utils.py / DrugLAMP.py:20-24), adds the row into its own shared
-// accumulator (lane-owned columns, plain read-modify-write) and, for the concat output, bounces
-// the row through shared memory so the (C+1)-strided rows are written with consecutive lanes on
-// consecutive floats.  pooled rows have leading dimension ldp >= C+1; columns C+1..ldp-1 are zero
-// (TMA-aligned rows for the GEMM that consumes them).
-template <typename TO>
+// x: (B, S*L, C) fp32.  One WARP per pooled row (b, j): it streams the row's S site rows (lane =
+// float4 chunks lane, lane+32, ...; NK chunks per lane, all of a site row's loads in flight at once),
+// sums each with shuffles (the fill bit is "row sums to exactly 0", DrugLAMP.py:11-19) and keeps the
+// running site mean in registers: no shared-memory reduction, no block barrier.  For the concat
+// output the row bounces through a per-warp shared-memory line so the (C+1)-strided rows are
+// written with consecutive lanes on consecutive floats.  pooled rows have leading dimension
+// ldp >= C+1; columns C+1..ldp-1 are zero (TMA-aligned rows for the GEMM that consumes them).
+template <typename TO, int NK>
 __global__ void __launch_bounds__(256)
 fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
-                    float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C, int ldp) {
+                    float* __restrict__ cat_out, TO* __restrict__ pooled, int S, int L, int C, int ldp,
+                    long long n_rows) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float fb_smem[];
-  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nchunk = C >> 2, stride = C + 4;
-  float* part = fb_smem + w * stride;                 // this warp's column sums (+ bit count at [C])
-  float* rowbuf = fb_smem + 8 * stride + w * stride;  // concat staging (only touched when cat_out)
-  for (int c = lane; c < stride; c += 32) part[c] = 0.f;
-  __syncwarp();
+  extern __shared__ float fb_smem[];                 // [8 warps][C] concat staging
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long pr = (long long)blockIdx.x * 8 + w;   // pooled row index b * L + j
+  if (pr >= n_rows) return;
+  const int b = (int)(pr / L), j = (int)(pr - (long long)b * L);
+  const int nchunk = C >> 2;
+  float* rowbuf = fb_smem + w * C;
+  float4 acc[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float bits = 0.f;
-  for (int s = w; s < S; s += 8) {
+#pragma unroll 2
+  for (int s = 0; s < S; ++s) {
     const size_t t = (size_t)b * S * L + (size_t)s * L + j;
     const float* row = x + t * C;
+    float4 v[NK];
     float psum = 0.f;
-    for (int ch = lane; ch < nchunk; ch += 32) {
-      const float4 v = *reinterpret_cast<const float4*>(row + ch * 4);
-      psum += (v.x + v.y) + (v.z + v.w);
-      float4* a = reinterpret_cast<float4*>(part + ch * 4);
-      float4 q = *a;
-      q.x += v.x; q.y += v.y; q.z += v.z; q.w += v.w;
-      *a = q;
-      if (cat_out) *reinterpret_cast<float4*>(rowbuf + ch * 4) = v;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int ch = lane + 32 * k;
+      v[k] = ch < nchunk ? *reinterpret_cast<const float4*>(row + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      psum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      acc[k].x += v[k].x; acc[k].y += v[k].y; acc[k].z += v[k].z; acc[k].w += v[k].w;
     }
     const float bit = warp_sum(psum) == 0.f ? 1.f : 0.f;
     bits += bit;
     if (lane == 0 && bit_out) bit_out[t] = bit;
     if (cat_out) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int ch = lane + 32 * k;
+        if (ch < nchunk) *reinterpret_cast<float4*>(rowbuf + ch * 4) = v[k];
+      }
       __syncwarp();
       float* crow = cat_out + t * (C + 1);
       for (int c = lane; c < C; c += 32) crow[c] = rowbuf[c];
@@ -60,19 +72,25 @@ fillbit_pool_kernel(const float* __restrict__ x, float* __restrict__ bit_out,
       __syncwarp();
     }
   }
-  if (lane == 0) part[C] = bits;
-  __syncthreads();
   if (pooled) {
     const float inv = 1.f / (float)S;
-    TO* prow = pooled + ((size_t)b * L + j) * ldp;
-    for (int c = tid; c < ldp; c += 256) {
-      float t = 0.f;
-      if (c <= C) {
+    TO* prow = pooled + (size_t)pr * ldp;
+    // ldp % 4 == 0 and 8-byte (bf16) / 16-byte (fp32) aligned rows: vector stores for the C columns
+    const bool vec = (ldp & 3) == 0;
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) t += fb_smem[ww * stride + c];
+    for (int k = 0; k < NK; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < nchunk) {
+        const float4 o = make_float4(acc[k].x * inv, acc[k].y * inv, acc[k].z * inv, acc[k].w * inv);
+        if (vec) {
+          st4<TO>(prow + ch * 4, o);
+        } else {
+          stf<TO>(prow, ch * 4 + 0, o.x); stf<TO>(prow, ch * 4 + 1, o.y);
+          stf<TO>(prow, ch * 4 + 2, o.z); stf<TO>(prow, ch * 4 + 3, o.w);
+        }
       }
-      stf<TO>(prow, c, t * inv);
     }
+    for (int c = C + lane; c < ldp; c += 32) stf<TO>(prow, c, c == C ? bits * inv : 0.f);
   }
 }
 
@@ -626,19 +644,24 @@ extern "C" int dl_fillbit_pool(const float* x, float* bit_out, float* cat_out, v
   DL_REQUIRE(ld_pooled >= C + 1, "dl_fillbit_pool: ld_pooled %d < C + 1", ld_pooled);
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(L, (unsigned)B);
-  const int smem = 16 * (C + 4) * (int)sizeof(float);
-  static int configured[2] = {48 * 1024, 48 * 1024};
-  const int which = pooled_dtype == DL_BF16 ? 0 : 1;
-  if (smem > configured[which]) {
-    DL_CUDA(which == 0 ? cudaFuncSetAttribute(fillbit_pool_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                       : cudaFuncSetAttribute(fillbit_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[which] = smem;
-  }
-  if (pooled_dtype == DL_BF16)
-    DL_LAUNCH((fillbit_pool_kernel<__nv_bfloat16>), grid, 256, smem, st, x, bit_out, cat_out, (__nv_bfloat16*)pooled, S, L, C, ld_pooled);
-  else
-    DL_LAUNCH((fillbit_pool_kernel<float>), grid, 256, smem, st, x, bit_out, cat_out, (float*)pooled, S, L, C, ld_pooled);
+  const long long n_rows = B * (long long)L;
+  const unsigned grid = (unsigned)((n_rows + 7) / 8);
+  const int smem = cat_out ? 8 * C * (int)sizeof(float) : 0;
+  const int nk = (C / 4 + 31) / 32;                 // float4 chunks per lane: 3 (C=384), 5 (640), <= 16
+#define DL_FILLBIT(TT, NKK)                                                                        \
+  do {                                                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      DL_CUDA(cudaFuncSetAttribute(fillbit_pool_kernel<TT, NKK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    DL_LAUNCH((fillbit_pool_kernel<TT, NKK>), grid, 256, smem, st, x, bit_out, cat_out, (TT*)pooled, S, L, C, ld_pooled, n_rows); \
+  } while (0)
+#define DL_FILLBIT_T(TT)                                                                           \
+  do {                                                                                             \
+    if (nk <= 3) DL_FILLBIT(TT, 3); else if (nk <= 5) DL_FILLBIT(TT, 5);                           \
+    else if (nk <= 8) DL_FILLBIT(TT, 8); else DL_FILLBIT(TT, 16);                                  \
+  } while (0)
+  if (pooled_dtype == DL_BF16) DL_FILLBIT_T(__nv_bfloat16); else DL_FILLBIT_T(float);
+#undef DL_FILLBIT_T
+#undef DL_FILLBIT
   DL_LAUNCH_CHECK("fillbit_pool_kernel");
   count_launch();
   return 0;
