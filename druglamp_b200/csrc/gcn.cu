@@ -328,13 +328,15 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
 
 // training: dx = gamma*rstd * (dy - sum_dy/N - xhat * sum_dyxhat/N); eval: dx = gamma*rstd*dy.
 // The first row block also writes dbeta = sum dy, dgamma = sum dy*xhat.
+// relu != 0: x is the output of a ReLU (ProteinCNN: conv -> ReLU -> BN); its backward mask
+// (x > 0) is applied to dx here instead of in a separate pass over the gradient.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                         const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, long long rows, int cols, long long rows_per_block,
-                        int tpr, int training, int acc) {
+                        int tpr, int training, int acc, int relu) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = VecWidth<T>::N;
@@ -370,7 +372,10 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) d[u][j] = k0[j] * (d[u][j] - m1[j] - (xv[u][j] - mu_[j]) * k1[j]);
+      for (int j = 0; j < V; ++j) {
+        const float t = k0[j] * (d[u][j] - m1[j] - (xv[u][j] - mu_[j]) * k1[j]);
+        d[u][j] = (relu && !(xv[u][j] > 0.f)) ? 0.f : t;
+      }
       stv(dx + (r + u * rpp) * cols + c, d[u]);
     }
   }
@@ -379,7 +384,10 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
     ldv(dy + r * cols + c, d);
     ldv(x + r * cols + c, xv);
 #pragma unroll
-    for (int j = 0; j < V; ++j) d[j] = k0[j] * (d[j] - m1[j] - (xv[j] - mu_[j]) * k1[j]);
+    for (int j = 0; j < V; ++j) {
+      const float t = k0[j] * (d[j] - m1[j] - (xv[j] - mu_[j]) * k1[j]);
+      d[j] = (relu && !(xv[j] > 0.f)) ? 0.f : t;
+    }
     stv(dx + r * cols + c, d);
   }
 }
@@ -516,7 +524,8 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
 extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma,
                                 const float* mean, const float* rstd, void* dx, float* dgamma,
                                 float* dbeta, double* workspace, int64_t rows, int32_t cols,
-                                int32_t training, int32_t accumulate, int32_t dtype, void* stream) {
+                                int32_t training, int32_t accumulate, int32_t relu_mask, int32_t dtype,
+                                void* stream) {
   DL_REQUIRE(dy && x && mean && rstd && dx && workspace, "dl_batchnorm_bwd: null pointer");
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -526,15 +535,16 @@ extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamm
     const dim3 vgrid(g.xb, g.yb);
     if (dtype == DL_BF16) {
       DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, true>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      DL_LAUNCH((bn_bwd_apply_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask);
     } else {
       DL_LAUNCH((bn_colstats_vec_kernel<float, true>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      DL_LAUNCH((bn_bwd_apply_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask);
     }
     DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_bwd_apply_vec_kernel");
     count_launch(2);
     return 0;
   }
+  DL_REQUIRE(!relu_mask, "dl_batchnorm_bwd: relu_mask needs cols %% (16 / element size) == 0 and 16-byte aligned tensors");
   dim3 grid; long long rpb;
   stats_grid(rows, cols, &grid, &rpb);
   if (dtype == DL_BF16)

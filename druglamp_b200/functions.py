@@ -537,38 +537,41 @@ class BatchNormFn(Function):
     """nn.BatchNorm1d over (rows, C) with the module's buffers updated in place."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, relu_input=False):
+        """relu_input: x is the output of a ReLU whose own backward is skipped (Conv1dSameFn with
+        mask_in_bwd=False); the mask (x > 0) is applied to dx inside the BatchNorm backward kernel."""
         xc = K.to_compute(x)
         x2 = xc.view(-1, xc.shape[-1])
         g_ = None if gamma is None else gamma.detach()
         b_ = None if beta is None else beta.detach()
         y, mean, rstd = K.batchnorm_fwd(x2, g_, b_, running_mean, running_var, nbt, eps, momentum, training)
         ctx.save_for_backward(x2, gamma, beta, mean, rstd)
-        ctx.meta = (training, x.dtype, x.shape)
+        ctx.meta = (training, x.dtype, x.shape, bool(relu_input))
         return y.view(xc.shape)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x2, gamma, beta, mean, rstd = ctx.saved_tensors
-        training, xdt, xshape = ctx.meta
+        training, xdt, xshape, relu = ctx.meta
         g_ = None if gamma is None else gamma.detach()
         tg, tb = _grad_target(gamma), _grad_target(beta)
         if tg is not None and tb is not None:       # straight into the flat gradient buffer
             dx, _, _ = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
-                                       acc_into=(tg, tb))
-            return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None
+                                       acc_into=(tg, tb), relu_mask=relu)
+            return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None, None
         dx, dg, db = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
-                                     need_param_grads=gamma is not None)
-        return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None
+                                     need_param_grads=gamma is not None, relu_mask=relu)
+        return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None, None
 
 
-def batch_norm(x, bn: torch.nn.BatchNorm1d):
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu_input: bool = False):
     """Apply an nn.BatchNorm1d module's parameters/buffers with the dl_batchnorm kernels."""
     training = bn.training or bn.running_mean is None
     momentum = 0.1 if bn.momentum is None else bn.momentum
     return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                             bn.num_batches_tracked if training else None, bn.eps, momentum, training)
+                             bn.num_batches_tracked if training else None, bn.eps, momentum, training,
+                             relu_input)
 
 
 # ================================================================================ glue
@@ -642,7 +645,9 @@ class Conv1dSameFn(Function):
     (Cout, Cin, k) parameter.  PyTorch's 'same' puts the extra pad of an even kernel on the right."""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu):
+    def forward(ctx, x, w, b, relu, mask_in_bwd=True):
+        """mask_in_bwd=False: the consumer (batch_norm(..., relu_input=True)) applies the ReLU mask
+        to the gradient it sends back, so this backward takes the gradient as is."""
         xc = K.to_compute(x)
         Cout, Cin, k = w.shape
         left = (k - 1) // 2
@@ -651,8 +656,8 @@ class Conv1dSameFn(Function):
         out = torch.empty(xc.shape[:2] + (Cout,), dtype=xc.dtype, device=xc.device)
         K.conv1d_same(xc, w_taps, out, taps=k, left=left, bias=None if b is None else b.detach(),
                       act=K.ACT_RELU if relu else K.ACT_NONE)
-        ctx.save_for_backward(xc, w, out if relu else None, b)
-        ctx.meta = (relu, left, x.dtype, b is not None)
+        ctx.save_for_backward(xc, w, out if (relu and mask_in_bwd) else None, b)
+        ctx.meta = (relu and mask_in_bwd, left, x.dtype, b is not None)
         return out
 
     @staticmethod
@@ -674,7 +679,7 @@ class Conv1dSameFn(Function):
             dw = K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0).contiguous()
         if has_b and ctx.needs_input_grad[2]:
             db = _bgrad(b, g.view(-1, Cout))
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class TransposeFn(Function):

@@ -199,8 +199,10 @@ def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, 
     return y, mean, rstd
 
 
-def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True, acc_into=None):
-    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to."""
+def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True, acc_into=None,
+                  relu_mask: bool = False):
+    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to.
+    relu_mask: x is a ReLU output; dx is additionally multiplied by (x > 0)."""
     rows, cols = x.shape
     dx = torch.empty_like(x)
     ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
@@ -212,7 +214,7 @@ def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bo
         db = torch.empty_like(dg)
     L.call("dl_batchnorm_bwd", dy.data_ptr(), x.data_ptr(), L.ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
            dx.data_ptr(), L.ptr(dg), L.ptr(db), ws.data_ptr(), rows, cols, int(training),
-           int(acc_into is not None), L.dt(x))
+           int(acc_into is not None), int(relu_mask), L.dt(x))
     return dx, dg, db
 
 

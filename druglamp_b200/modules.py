@@ -562,8 +562,9 @@ class ProteinCNN(nn.Module):
         x = Fn.EmbedFillFn.apply(v, fill_mask, emb.weight, emb.padding_idx)    # (B, L, 128): gather + fill bit
         for i in (1, 2, 3):
             conv, bn = getattr(self, f"conv{i}"), getattr(self, f"bn{i}")
-            x = Fn.Conv1dSameFn.apply(x, conv.weight, conv.bias, True)
-            x = Fn.batch_norm(x, bn)
+            # conv -> ReLU -> BN: the ReLU's backward mask rides on the BatchNorm backward kernel
+            x = Fn.Conv1dSameFn.apply(x, conv.weight, conv.bias, True, False)
+            x = Fn.batch_norm(x, bn, relu_input=True)
         y = Fn.TransposeFn.apply(x)                                         # (B, C, L) like the reference
         return y.view(y.size(0), y.size(2), -1)
 

@@ -190,10 +190,13 @@ int dl_batchnorm_fwd(const void* x, const float* gamma, const float* beta, void*
                      float* rstd, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, double* workspace, int64_t rows, int32_t cols,
                      float eps, float momentum, int32_t training, int32_t dtype, void* stream);
+/* accumulate != 0: dgamma/dbeta are added to (the parameters' .grad buffers).  relu_mask != 0: x is
+ * a ReLU output (ProteinCNN conv -> ReLU -> BN, model/basic_model.py:174-178) and dx is also
+ * multiplied by (x > 0), so the activation's backward needs no pass of its own. */
 int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                      const float* rstd, void* dx, float* dgamma, float* dbeta, double* workspace,
                      int64_t rows, int32_t cols, int32_t training, int32_t accumulate,
-                     int32_t dtype, void* stream);
+                     int32_t relu_mask, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Model glue.

@@ -133,6 +133,9 @@ def test_batchnorm_fwd_bwd(dtype, tol, training):
         _close(rm, bn.running_mean, 1e-4, "running_mean")
         _close(rv, bn.running_var, 1e-4, "running_var")
         assert int(nbt) == 1
+    # relu_mask: the same dx with the ReLU mask of the BatchNorm input folded in
+    dxm, _, _ = K.batchnorm_bwd(dy, x, g, mean, rstd, training, relu_mask=True)
+    assert torch.equal(dxm, torch.where(x > 0, dx, torch.zeros_like(dx)))
 
 
 def test_fillbit_pool_bit_exact_and_site_pool():
@@ -205,14 +208,14 @@ def test_conv1d_same_implicit_gemm_fwd_bwd(dtype, tol, k):
         w = (torch.randn(Cout, Cin, k, device="cuda") * 0.05).to(dtype).float().requires_grad_(True)
         b = torch.randn(Cout, device="cuda").requires_grad_(True)
         gy = torch.randn(B, Ls, Cout, device="cuda").to(dtype).float()
-        y = Fn.Conv1dSameFn.apply(x, torch.nn.Parameter(w.detach().clone()), torch.nn.Parameter(b.detach().clone()), True)
+        y = Fn.Conv1dSameFn.apply(x, torch.nn.Parameter(w.detach().clone()), torch.nn.Parameter(b.detach().clone()), True, True)
         xr, wr, br = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
         yr = F.relu(F.conv1d(xr.transpose(1, 2), wr, br, padding="same")).transpose(1, 2)
         _close(y, yr, tol, "conv fwd")
         # backward through fresh leaves
         wp, bp = torch.nn.Parameter(w.detach().clone()), torch.nn.Parameter(b.detach().clone())
         xl = x.detach().clone().requires_grad_(True)
-        y2 = Fn.Conv1dSameFn.apply(xl, wp, bp, True)
+        y2 = Fn.Conv1dSameFn.apply(xl, wp, bp, True, True)
         y2.backward(gy.to(y2.dtype))
         # use the product's own ReLU mask so that bf16 rounding at the kink does not enter the comparison
         mask = (y2.detach().double() > 0)
