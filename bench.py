@@ -340,9 +340,16 @@ def run_gpu(args):
         achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
         step_ms = ms / args.steps
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):              # committed ncu measurement (never taken inside a bench run)
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         roof = {"kernel": "gemm_tc_kernel (dl_gemm: TMA + tcgen05.mma, bf16 in / fp32 TMEM accumulate)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean)",
+                "traffic_source": traffic_src, "peak_source": pk["source"] + " bf16_tflops_sustained",
                 "launches_per_step": len(prof), "flops_per_launch_avg": flops / max(len(prof), 1),
                 "gemm_flops_per_step": flops, "avg_launch_us": 1000.0 * gemm_ms / max(len(prof), 1),
                 "gemm_ms_per_step": gemm_ms,
