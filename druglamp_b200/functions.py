@@ -16,7 +16,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 from . import kernels as K
-from .params import flat_grad_of, shadow
+from .params import flat_grad_of, fused_group, shadow
 
 _seed_counter = itertools.count(0x5EED)
 
@@ -229,14 +229,15 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 # ================================================================================ attention core
 def _attn_fwd(q, k, v, H, scale, keep_raw):
-    """q (S2,B,Lq,HD) contiguous; k, v (B,Lk,HD) with unit inner stride (row stride free).
+    """q (S2,B,Lq,HD), k, v (B,Lk,HD): unit inner stride, every other stride free (they may be
+    column slices of one fused QKV projection buffer).
     Returns O (B,Lq,S2*HD), P (B,H,S2,Lq,Lk) and raw scaled logits (or None)."""
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
     S = torch.empty((B, H, S2, Lq, Lk), dtype=q.dtype, device=q.device)
     s_lay = (S2 * Lq * Lk, Lq * Lk, H * S2 * Lq * Lk)
-    L.gemm(q, k, S, M=Lq, N=Lk, K=d, lda=HD, ldb=k.stride(1), ldc=Lk, batch=(H, S2, B),
+    L.gemm(q, k, S, M=Lq, N=Lk, K=d, lda=q.stride(2), ldb=k.stride(1), ldc=Lk, batch=(H, S2, B),
            sa=(d, q.stride(0) if S2 > 1 else 0, q.stride(1)), sb=(d, 0, k.stride(0)), sc=s_lay,
            alpha=scale)
     raw = None
@@ -251,8 +252,9 @@ def _attn_fwd(q, k, v, H, scale, keep_raw):
     return O, P, raw
 
 
-def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None):
-    """Gradients of _attn_fwd.  d*_out may be preallocated (strided) destinations."""
+def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, dq_accumulate=False):
+    """Gradients of _attn_fwd.  d*_out may be preallocated (strided) destinations; with
+    dq_accumulate the query gradient is added to dq_out (two attentions sharing one query set)."""
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
@@ -274,11 +276,11 @@ def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None):
     # dQ = dS K
     L.gemm(dS, k, dQ, M=Lq, N=d, K=Lk, lda=Lk, ldb=k.stride(1), ldc=dQ.stride(2), trans_b=True,
            batch=(H, S2, B), sa=s_lay, sb=(d, 0, k.stride(0)),
-           sc=(d, dQ.stride(0) if S2 > 1 else 0, dQ.stride(1)))
+           sc=(d, dQ.stride(0) if S2 > 1 else 0, dQ.stride(1)), residual=dQ if dq_accumulate else None)
     # dK = sum_set dS_set^T Q_set
     for s in range(S2):
         dSs, qs = dS[:, :, s], q[s]
-        L.gemm(dSs, qs, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=HD, ldc=dK.stride(1), trans_a=True,
+        L.gemm(dSs, qs, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=qs.stride(1), ldc=dK.stride(1), trans_a=True,
                trans_b=True, batch=(H, B), sa=(s_lay[0], s_lay[2]), sb=(d, qs.stride(0)),
                sc=(d, dK.stride(0)), residual=dK if s > 0 else None)
     return dQ, dK, dV
@@ -308,6 +310,168 @@ class AttentionFn(Function):
 
 def attention(q, k, v, H, scale):
     return AttentionFn.apply(q, k, v, H, scale)
+
+
+# ---- fused query / key / value projections -----------------------------------------------------
+# The three projections of one input share a GEMM when their weights sit back to back in the flat
+# parameter buffer (params.fused_group): one launch forward, one for dX (which also sums the three
+# input gradients autograd would otherwise add), one for dW with the bias gradients riding on it.
+# Without a flat store the same buffers are filled by three launches each.
+def _qkv_fwd(xc2, ws, bs, out2):
+    """out2 [rows, 3E] = xc2 [rows, D] @ cat(ws)^T + cat(bs)."""
+    E = ws[0].shape[0]
+    fw, fb = fused_group(ws), fused_group(bs)
+    if fw is not None and fb is not None:
+        K.mm(xc2, fw[2], out2, bias=fb[0])
+    else:
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            K.mm(xc2, shadow(w), out2[:, i * E:(i + 1) * E], bias=b.detach())
+
+
+def _qkv_bwd(g2, xc2, ws, bs, need_dx=True):
+    """g2 [rows, 3E] -> dx [rows, D]; parameter gradients accumulated in place when possible.
+    Returns (dx, [dw_i], [db_i]) with None for everything that was accumulated."""
+    E = ws[0].shape[0]
+    fw, fb = fused_group(ws), fused_group(bs)
+    dx = None
+    if fw is not None and fb is not None:
+        if need_dx:
+            dx = K.mm(g2, fw[2], tb=True)
+        if g2.dtype == torch.bfloat16:
+            K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True, colsum_a=fb[1])
+        else:
+            K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True)
+            K.colsum(g2, fb[1], accumulate=True)
+        return dx, [None] * 3, [None] * 3
+    dws, dbs = [], []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        gi = g2[:, i * E:(i + 1) * E]
+        if need_dx:
+            dx = K.mm(gi, shadow(w), tb=True) if dx is None else K.mm(gi, shadow(w), dx, tb=True, res=dx)
+        dw, db = _wbgrad(w, b, gi, xc2)
+        dws.append(dw)
+        dbs.append(db)
+    return dx, dws, dbs
+
+
+class QKVProjFn(Function):
+    """QKV (B, L, 3E) = [query(x), key(x), value(x)] in one buffer (model/PMMA/attention.py:109-111)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv):
+        xc = K.to_compute(x)
+        D, E = xc.shape[-1], wq.shape[0]
+        out = torch.empty(xc.shape[:-1] + (3 * E,), dtype=xc.dtype, device=xc.device)
+        _qkv_fwd(xc.view(-1, D), (wq, wk, wv), (bq, bk, bv), out.view(-1, 3 * E))
+        ctx.save_for_backward(xc, wq, wk, wv, bq, bk, bv)
+        ctx.xdt = x.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        xc, wq, wk, wv, bq, bk, bv = ctx.saved_tensors
+        D, E = xc.shape[-1], wq.shape[0]
+        g2 = K.to_compute(g).view(-1, 3 * E)
+        dx, dws, dbs = _qkv_bwd(g2, xc.view(-1, D), (wq, wk, wv), (bq, bk, bv), ctx.needs_input_grad[0])
+        dx = None if dx is None else _back(dx, ctx.xdt, xc.shape)
+        return dx, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2]
+
+
+class PairedQKVFn(Function):
+    """QKV (2, B, L, 3E): slab 0 = [query, key, value](prot), slab 1 = [query_mol, key_mol,
+    value_mol](mol) (model/PMMA/attention.py:91-98), so the paired attention addresses both query
+    sets and both K/V pairs of one buffer through strides."""
+
+    @staticmethod
+    def forward(ctx, xp, xm, *params):
+        ap, am = K.to_compute(xp), K.to_compute(xm)
+        wp, bp = params[0:6:2], params[1:6:2]
+        wm, bm = params[6:12:2], params[7:12:2]
+        D, E = ap.shape[-1], wp[0].shape[0]
+        out = torch.empty((2,) + tuple(ap.shape[:-1]) + (3 * E,), dtype=ap.dtype, device=ap.device)
+        _qkv_fwd(ap.view(-1, D), wp, bp, out[0].view(-1, 3 * E))
+        _qkv_fwd(am.view(-1, D), wm, bm, out[1].view(-1, 3 * E))
+        ctx.save_for_backward(ap, am, *params)
+        ctx.dts = (xp.dtype, xm.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        ap, am, *params = ctx.saved_tensors
+        wp, bp = params[0:6:2], params[1:6:2]
+        wm, bm = params[6:12:2], params[7:12:2]
+        D, E = ap.shape[-1], wp[0].shape[0]
+        gc = K.to_compute(g)
+        dxp, dwp, dbp = _qkv_bwd(gc[0].view(-1, 3 * E), ap.view(-1, D), wp, bp, ctx.needs_input_grad[0])
+        dxm, dwm, dbm = _qkv_bwd(gc[1].view(-1, 3 * E), am.view(-1, D), wm, bm, ctx.needs_input_grad[1])
+        grads = []
+        for dw, db in zip(dwp, dbp):
+            grads += [dw, db]
+        for dw, db in zip(dwm, dbm):
+            grads += [dw, db]
+        return (None if dxp is None else _back(dxp, ctx.dts[0], ap.shape),
+                None if dxm is None else _back(dxm, ctx.dts[1], am.shape), *grads)
+
+
+class SelfAttnCoreFn(Function):
+    """softmax(q k^T scale) v on a fused (B, L, 3E) QKV buffer -> (B, L, E); the backward writes
+    dq / dk / dv straight into the three column blocks of one (B, L, 3E) gradient."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, scale):
+        c = K.to_compute(qkv)
+        E = c.shape[-1] // 3
+        O, P, _ = _attn_fwd(c[None, :, :, :E], c[:, :, E:2 * E], c[:, :, 2 * E:], H, scale, False)
+        ctx.save_for_backward(c, P)
+        ctx.meta = (H, scale, qkv.dtype)
+        return O
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gO):
+        c, P = ctx.saved_tensors
+        H, scale, dt = ctx.meta
+        E = c.shape[-1] // 3
+        d = torch.empty_like(c)
+        _attn_bwd(K.to_compute(gO), c[None, :, :, :E], c[:, :, E:2 * E], c[:, :, 2 * E:], P, H, scale,
+                  dq_out=d[None, :, :, :E], dk_out=d[:, :, E:2 * E], dv_out=d[:, :, 2 * E:])
+        return _back(d, dt), None, None
+
+
+class PairedAttnCoreFn(Function):
+    """The four attention maps of the paired block (model/PMMA/attention.py:44-88) on a fused
+    (2, B, L, 3E) QKV buffer: both query sets against the protein K/V -> op (B, L, 2E) =
+    cat(attn, attn_p), and against the molecule K/V -> om (B, L, 2E) = (attn_p', attn') in swapped
+    order.  The backward fills one (2, B, L, 3E) gradient; the query gradient of the second
+    attention is accumulated onto the first in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, scale):
+        c = K.to_compute(qkv)
+        E = c.shape[-1] // 3
+        Q = c[:, :, :, :E]
+        op, Pp, _ = _attn_fwd(Q, c[0, :, :, E:2 * E], c[0, :, :, 2 * E:], H, scale, False)
+        om, Pm, _ = _attn_fwd(Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], H, scale, False)
+        ctx.save_for_backward(c, Pp, Pm)
+        ctx.meta = (H, scale, qkv.dtype)
+        return op, om
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gop, gom):
+        c, Pp, Pm = ctx.saved_tensors
+        H, scale, dt = ctx.meta
+        E = c.shape[-1] // 3
+        Q = c[:, :, :, :E]
+        d = torch.empty_like(c)
+        dQ = d[:, :, :, :E]
+        _attn_bwd(K.to_compute(gop), Q, c[0, :, :, E:2 * E], c[0, :, :, 2 * E:], Pp, H, scale,
+                  dq_out=dQ, dk_out=d[0, :, :, E:2 * E], dv_out=d[0, :, :, 2 * E:])
+        _attn_bwd(K.to_compute(gom), Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], Pm, H, scale,
+                  dq_out=dQ, dk_out=d[1, :, :, E:2 * E], dv_out=d[1, :, :, 2 * E:], dq_accumulate=True)
+        return _back(d, dt), None, None
 
 
 class PairedQFn(Function):

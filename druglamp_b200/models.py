@@ -92,7 +92,11 @@ class DrugLAMPBase(nn.Module):
     def flatten_parameters(self) -> FlatParams:
         """Re-home all parameters in one flat buffer (call after ``.cuda()``): one cast kernel
         refreshes every bf16 shadow and one all-reduce covers every gradient."""
-        self._flat = FlatParams(self)
+        groups = []
+        for m in self.modules():
+            if hasattr(m, "fused_parameter_groups"):
+                groups += m.fused_parameter_groups()
+        self._flat = FlatParams(self, groups=groups)
         return self._flat
 
     # ---- shared pieces of the three forwards ------------------------------------------------------

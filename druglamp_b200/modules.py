@@ -160,28 +160,39 @@ class Attention(nn.Module):
         H = self.num_attention_heads
         scale = 1.0 / math.sqrt(self.attn_head_size)
         if mol is None:
-            q = Fn.linear(hidden_states, self.query.weight, self.query.bias)
-            k = Fn.linear(hidden_states, self.key.weight, self.key.bias)
-            v = Fn.linear(hidden_states, self.value.weight, self.value.bias)
-            o = Fn.attention(q.unsqueeze(0), k, v, H, scale)
+            # query / key / value in one (B, L, 3E) buffer: one GEMM when the weights are adjacent
+            # in the flat parameter store (fused_parameter_groups), three otherwise
+            qkv = Fn.QKVProjFn.apply(hidden_states, self.query.weight, self.query.bias, self.key.weight,
+                                     self.key.bias, self.value.weight, self.value.bias)
+            o = Fn.SelfAttnCoreFn.apply(qkv, H, scale)
             attn = Fn.linear(o, self.out.weight, self.out.bias, residual=residual)
             return attn, None, None
         if hidden_states.shape[1] != mol.shape[1]:
             raise ValueError("paired attention needs equal sequence lengths (as in the reference)")
-        # set 0 = protein queries, set 1 = molecule queries; each stream's K/V is read once
-        Q = Fn.PairedQFn.apply(hidden_states, self.query.weight, self.query.bias,
-                               mol, self.query_mol.weight, self.query_mol.bias)
-        kp = Fn.linear(hidden_states, self.key.weight, self.key.bias)
-        vp = Fn.linear(hidden_states, self.value.weight, self.value.bias)
-        km = Fn.linear(mol, self.key_mol.weight, self.key_mol.bias)
-        vm = Fn.linear(mol, self.value_mol.weight, self.value_mol.bias)
-        op = Fn.attention(Q, kp, vp, H, scale)      # [A(q_prot), A(q_mol)] = cat(attn, attn_p)
-        om = Fn.attention(Q, km, vm, H, scale)      # [A(q_prot), A(q_mol)] = (attn_p, attn): swapped
+        # one (2, B, L, 3E) buffer: slab 0 = q/k/v of the protein stream, slab 1 = of the molecule
+        # stream; set 0 = protein queries, set 1 = molecule queries; each stream's K/V is read once
+        qkv = Fn.PairedQKVFn.apply(hidden_states, mol,
+                                   self.query.weight, self.query.bias, self.key.weight, self.key.bias,
+                                   self.value.weight, self.value.bias,
+                                   self.query_mol.weight, self.query_mol.bias, self.key_mol.weight,
+                                   self.key_mol.bias, self.value_mol.weight, self.value_mol.bias)
+        # op = [A(q_prot), A(q_mol)] on the protein K/V = cat(attn, attn_p);
+        # om = the same query sets on the molecule K/V = (attn_p, attn): swapped
+        op, om = Fn.PairedAttnCoreFn.apply(qkv, H, scale)
         tp = Fn.FcCatFn.apply(op, self.fc.weight, self.fc.bias, False)
         tm = Fn.FcCatFn.apply(om, self.fc_mol.weight, self.fc_mol.bias, True)
         attn_prot = Fn.linear(tp, self.out.weight, self.out.bias, residual=residual)
         attn_mol = Fn.linear(tm, self.out_mol.weight, self.out_mol.bias, residual=residual_mol)
         return attn_prot, attn_mol, None, None
+
+    def fused_parameter_groups(self):
+        """Parameter lists a FlatParams store should lay out back to back (params.fused_group)."""
+        g = [[self.query.weight, self.key.weight, self.value.weight],
+             [self.query.bias, self.key.bias, self.value.bias]]
+        if hasattr(self, "query_mol"):
+            g += [[self.query_mol.weight, self.key_mol.weight, self.value_mol.weight],
+                  [self.query_mol.bias, self.key_mol.bias, self.value_mol.bias]]
+        return g
 
 
 class PMMABlock(nn.Module):

@@ -24,6 +24,7 @@ from . import kernels as K
 _CACHE = WeakIdKeyDictionary()      # Parameter -> [version, ptr, shadow]
 _FLAT = WeakIdKeyDictionary()       # Parameter -> weakref to its FlatParams store
 _BY_PTR: Dict[int, "weakref.ref"] = {}                              # data_ptr of a flat view -> Parameter
+_GROUPS: Dict[tuple, tuple] = {}     # data_ptrs of a fused parameter group -> (weakref store, offset, shape)
 
 
 def flat_grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
@@ -66,9 +67,18 @@ class FlatParams:
 
     ALIGN = 64  # elements; keeps every view 256-byte aligned (TMA needs 16 B)
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, groups=None):
+        """groups: lists of parameters to lay out back to back (e.g. the query / key / value weights
+        of one attention block), so that :func:`fused_group` can hand a GEMM the concatenated
+        [sum out_i, in] matrix, its gradient and its bf16 shadow as plain views -- three projections
+        of one input become one launch forward and one per gradient."""
         params: List[torch.nn.Parameter] = []
         seen = set()
+        for grp in (groups or []):
+            for p in grp:
+                if id(p) not in seen and p.dtype == torch.float32:
+                    seen.add(id(p))
+                    params.append(p)
         for p in module.parameters():
             if id(p) not in seen and p.dtype == torch.float32:
                 seen.add(id(p))
@@ -96,6 +106,18 @@ class FlatParams:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
                 _FLAT[p] = weakref.ref(self)
                 _BY_PTR[p.data_ptr()] = weakref.ref(p)
+        # fusable groups: members adjacent without padding gaps, same trailing shape
+        off_of = {id(p): o for p, o in zip(params, self.offsets)}
+        self.groups: Dict[tuple, tuple] = {}
+        for grp in (groups or []):
+            ok = all(id(p) in off_of for p in grp) and len({tuple(p.shape[1:]) for p in grp}) == 1
+            for a, b in zip(grp[:-1], grp[1:]):
+                ok = ok and off_of[id(b)] == off_of[id(a)] + a.numel()
+            if ok:
+                rows = sum(p.shape[0] for p in grp)
+                ent = (off_of[id(grp[0])], (rows,) + tuple(grp[0].shape[1:]))
+                self.groups[tuple(id(p) for p in grp)] = ent
+                _GROUPS[tuple(p.data_ptr() for p in grp)] = (weakref.ref(self),) + ent
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -128,6 +150,33 @@ class FlatParams:
             return p.detach()
         self.sync()
         return self._views16[id(p)]
+
+
+def fused_group(ps):
+    """(weights, grad, shadow) views of the parameters `ps` concatenated along dim 0, when they were
+    laid out as one group of a FlatParams store (else None).  `shadow` is in the compute dtype."""
+    key = tuple(p.data_ptr() for p in ps)           # device addresses: robust to re-wrapped tensors
+    ent = _GROUPS.get(key)
+    if ent is None:
+        return None
+    fp = ent[0]()
+    if fp is None:                                   # the store is gone (addresses may be reused)
+        _GROUPS.pop(key, None)
+        return None
+    o, shape = ent[1], ent[2]
+    if any(p.dtype != torch.float32 for p in ps) or fp.flat.data_ptr() + 4 * o != key[0]:
+        return None
+    n = 1
+    for d in shape:
+        n *= d
+    w = fp.flat[o:o + n].view(shape)
+    g = fp.grad[o:o + n].view(shape)
+    if K.compute_dtype() == torch.bfloat16:
+        fp.sync()
+        sh = fp.shadow16[o:o + n].view(shape)
+    else:
+        sh = w
+    return w, g, sh
 
 
 class FlatAdamW:

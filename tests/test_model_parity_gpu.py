@@ -119,22 +119,30 @@ def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
     assert not bad, "; ".join(bad)
 
 
-def test_flat_parameter_store_gives_identical_results():
-    fx = load_golden("druglamp_eval_b2.npz")
-    m0, _, a = run_product(fx, torch.bfloat16, flat=False)
-    m, _, b = run_product(fx, torch.bfloat16, flat=True)
-    assert torch.equal(a["score"], b["score"])
+@pytest.mark.parametrize("case,dtype,tol", [("druglamp_eval_b2.npz", torch.float32, 1e-4),
+                                            ("druglamp2c2p_train_b16.npz", torch.float32, 1e-4),
+                                            ("druglamp_eval_b2.npz", torch.bfloat16, 3e-2)])
+def test_flat_parameter_store_gives_identical_results(case, dtype, tol):
+    """The flat store changes HOW gradients are produced, not what they are: weight / bias gradients
+    are accumulated in place (dl_gemm accumulate / colsum_a), and the query / key / value weights of
+    every attention block are laid out back to back so their three projections, input gradients and
+    weight gradients are single GEMMs (params.fused_group).  In fp32 both routes agree to summation
+    order (1e-4 of the largest gradient); in bf16 the fused route rounds the three input-gradient
+    contributions once instead of three times, so the comparison is at bf16 resolution."""
+    fx = load_golden(case)
+    m0, _, a = run_product(fx, dtype, flat=False)
+    m, _, b = run_product(fx, dtype, flat=True)
+    assert torch.equal(a["score"], b["score"])          # the forward is the same arithmetic either way
     assert m._flat.grad.abs().sum().item() > 0          # gradients landed in the flat buffer
-    # in flat mode weight/bias gradients are accumulated in place by dl_gemm / dl_colsum
-    # (accumulate=1) instead of autograd's add: same values up to atomic summation order
+    assert len(m._flat.groups) >= 12                    # q/k/v weight and bias groups of the attention blocks
     p0 = dict(m0.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in m0.parameters() if p.grad is not None)
     for name, p in m.named_parameters():
         g0 = p0[name].grad
         if g0 is None:
             assert float(p.grad.abs().sum()) == 0.0, name
             continue
-        scale = float(g0.abs().max()) + 1e-12
-        assert float((p.grad - g0).abs().max()) <= 2e-3 * scale + 1e-7, name
+        assert float((p.grad - g0).abs().max()) <= tol * gmax, name
 
 
 def test_cm_loss_and_margin_schedule_match_reference():
