@@ -153,7 +153,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          mul_mode: int = MUL_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
          precise: Optional[bool] = None, split_k: int = 0, conv_taps: int = 0, conv_left: int = 0,
-         kred: bool = False, kred_shift: int = 0, accumulate: bool = False,
+         kred: int = 0, kred_shift: int = 0, accumulate: bool = False,
          colsum_a: Optional[torch.Tensor] = None) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:

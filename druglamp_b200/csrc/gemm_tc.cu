@@ -75,6 +75,7 @@ struct GemmParams {
   int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work
   int conv_cin, conv_left;      // implicit-GEMM conv1d on A (0 = off): channels per tap, left padding
   int kred_kpb, kred_shift;     // K-reduction over batch[2] (0 = off): K-blocks per batch, B row shift
+  int kred_tap;                 // 1: batch dim 0 is a convolution tap that also shifts B's rows
   float alpha;
   uint32_t idesc;
 };
@@ -422,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kbi = T.kb_begin + kb;
             const int rb = (int)p.fd_kred.div((uint32_t)kbi);
             ka = (kbi - rb * p.kred_kpb) * C::KE;
-            kbb = ka + T.b0 + p.kred_shift;
+            kbb = ka + (p.kred_tap ? T.b0 : 0) + p.kred_shift;
             a4r = c4r = rb;
           }
           if (!p.a_mn) {
@@ -799,7 +800,7 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)k_total;
   p.nb0 = (int)a->batch[0]; p.nb1 = (int)a->batch[1];
   p.conv_cin = conv_cin; p.conv_left = a->conv_left;
-  p.kred_kpb = kred_kpb; p.kred_shift = a->kred_shift;
+  p.kred_kpb = kred_kpb; p.kred_shift = a->kred_shift; p.kred_tap = a->kred == 1;
   if (kred) { p.a_on[2] = p.b_on[2] = 1; }
   if (a->accumulate && splits == 1) {     // C += result through the residual path (same layout)
     p.res = a->C;

@@ -262,12 +262,10 @@ def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, d
     dV = dv_out if dv_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
     dK = dk_out if dk_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
     dQ = dq_out if dq_out is not None else torch.empty_like(q)
-    # dV = sum_set P_set^T dO_set
-    for s in range(S2):
-        Ps, dOs = P[:, :, s], dO[:, :, s * HD:(s + 1) * HD]
-        L.gemm(Ps, dOs, dV, M=Lk, N=d, K=Lq, lda=Lk, ldb=S2 * HD, ldc=dV.stride(1), trans_a=True,
-               trans_b=True, batch=(H, B), sa=(s_lay[0], s_lay[2]), sb=(d, Lq * S2 * HD),
-               sc=(d, dV.stride(0)), residual=dV if s > 0 else None)
+    # dV = sum_set P_set^T dO_set: the query-set dimension is reduced inside one GEMM (kred = 2)
+    L.gemm(P, dO, dV, M=Lk, N=d, K=Lq, lda=Lk, ldb=S2 * HD, ldc=dV.stride(1), trans_a=True,
+           trans_b=True, batch=(H, B, S2), sa=(s_lay[0], s_lay[2], s_lay[1]), sb=(d, Lq * S2 * HD, HD),
+           sc=(d, dV.stride(0), 0), kred=2)
     # dP = dO V^T, then dS = scale * P * (dP - rowsum(P dP)) in place
     dP = torch.empty_like(P)
     L.gemm(dO, v, dP, M=Lq, N=Lk, K=d, lda=S2 * HD, ldb=v.stride(1), ldc=Lk, batch=(H, S2, B),
@@ -277,12 +275,11 @@ def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, d
     L.gemm(dS, k, dQ, M=Lq, N=d, K=Lk, lda=Lk, ldb=k.stride(1), ldc=dQ.stride(2), trans_b=True,
            batch=(H, S2, B), sa=s_lay, sb=(d, 0, k.stride(0)),
            sc=(d, dQ.stride(0) if S2 > 1 else 0, dQ.stride(1)), residual=dQ if dq_accumulate else None)
-    # dK = sum_set dS_set^T Q_set
-    for s in range(S2):
-        dSs, qs = dS[:, :, s], q[s]
-        L.gemm(dSs, qs, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=qs.stride(1), ldc=dK.stride(1), trans_a=True,
-               trans_b=True, batch=(H, B), sa=(s_lay[0], s_lay[2]), sb=(d, qs.stride(0)),
-               sc=(d, dK.stride(0)), residual=dK if s > 0 else None)
+    # dK = sum_set dS_set^T Q_set, likewise
+    L.gemm(dS, q, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=q.stride(2), ldc=dK.stride(1), trans_a=True,
+           trans_b=True, batch=(H, B, S2), sa=(s_lay[0], s_lay[2], s_lay[1]),
+           sb=(d, q.stride(1), q.stride(0) if S2 > 1 else Lq * q.stride(2)),
+           sc=(d, dK.stride(0), 0), kred=2)
     return dQ, dK, dV
 
 

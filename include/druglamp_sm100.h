@@ -100,7 +100,9 @@ typedef struct dl_gemm_args {
    * batch, K = k * cin enumerates (tap, channel) and the A tile of tap t is rows m + t - conv_left,
    * rows outside [0, L) read as zero; B = weights [cout, k * cin].  kred = 1 (weight gradient): both
    * operands MN-major, K = L rows per batch[2] entry, batch[2] is REDUCED over, batch[0] is the
-   * tap and shifts B's rows by b0 + kred_shift (zero outside [0, L)); C is [taps, M, N]. */
+   * tap and shifts B's rows by b0 + kred_shift (zero outside [0, L)); C is [taps, M, N].
+   * kred = 2: the same K-reduction over batch[2] without the tap shift (batch[0] is an ordinary
+   * batch dim): sums over the stacked query sets in the paired attention's dK / dV. */
   int32_t conv_taps, conv_left;
   int32_t kred, kred_shift;
   int32_t accumulate; /* 1: C += result (plain fp32 outputs only) -- weight gradients land directly in
