@@ -191,16 +191,25 @@ template <typename T> __device__ __forceinline__ float gelu_grad(float x) {
   }
 }
 
-// counter-based uniform in [0,1): splitmix64 of (seed, element index).  Dropout masks are a pure
-// function of (seed, logical index) so backward regenerates them instead of storing them.
-__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
-  // 32-bit avalanche (three multiplies) of (seed, index): the epilogues call this per element
-  uint32_t h = (uint32_t)idx ^ (uint32_t)seed;
-  h = (h ^ (uint32_t)(idx >> 32) * 0x9E3779B1u) * 0x85EBCA77u + (uint32_t)(seed >> 32);
+// Dropout masks are a pure function of (seed, logical element index), so backward regenerates them
+// instead of storing them.  One counter-based 32-bit hash decides TWO neighbouring elements (its
+// 16-bit halves against a 16-bit threshold; p is honoured to 1/65536 and the survivors are scaled by
+// the exact inverse of the realised keep probability): the GEMM epilogues, which are instruction
+// bound, pay half a hash per element.
+__device__ __forceinline__ uint32_t drop_hash(unsigned long long seed, unsigned long long pair) {
+  // 32-bit avalanche (three multiplies) of (seed, pair index)
+  uint32_t h = (uint32_t)pair ^ (uint32_t)seed;
+  h = (h ^ (uint32_t)(pair >> 32) * 0x9E3779B1u) * 0x85EBCA77u + (uint32_t)(seed >> 32);
   h ^= h >> 15; h *= 0xC2B2AE3Du;
   h ^= h >> 13; h *= 0x27D4EB2Fu;
   h ^= h >> 16;
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
+__host__ __device__ __forceinline__ float drop_scale(uint32_t thr) { return 65536.f / (float)(65536u - thr); }
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr) {
+  const uint32_t h = drop_hash(seed, idx >> 1);
+  return ((idx & 1ull) ? (h >> 16) : (h & 0xffffu)) >= thr;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

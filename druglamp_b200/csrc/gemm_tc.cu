@@ -223,6 +223,7 @@ struct EpiFlags {
   bool wide_c, wide_r, wide_p;       // one 32-byte access per 16 bf16 legal
   bool atomic, simple;
   float drop_inv;
+  uint32_t drop_thr;
 };
 
 template <typename TC>
@@ -244,7 +245,8 @@ __device__ __forceinline__ EpiFlags make_epi_flags(const GemmParams& p) {
   f.atomic = p.splits > 1;
   f.simple = !p.bias && !p.preact && !p.aux && !p.res && p.act == DL_ACT_NONE &&
              p.mul_mode == DL_MUL_NONE && p.drop_p == 0.f && !f.atomic && p.dbg == 0;
-  f.drop_inv = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  f.drop_thr = drop_threshold(p.drop_p);
+  f.drop_inv = p.drop_p > 0.f ? drop_scale(f.drop_thr) : 1.f;
   return f;
 }
 
@@ -292,8 +294,17 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
     }
     if (p.drop_p > 0.f) {
       const unsigned long long e = ((unsigned long long)zidx * p.M + row) * p.N + col;
+      if ((e & 1ull) == 0) {                     // aligned pairs: eight hashes for sixteen elements
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] *= hash_uniform(p.drop_seed, e + j) >= p.drop_p ? f.drop_inv : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t h = drop_hash(p.drop_seed, (e >> 1) + k);
+          x[2 * k] *= (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
+          x[2 * k + 1] *= (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] *= drop_keep(p.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
+      }
     }
     if (Res) {
       float r[16];

@@ -385,10 +385,11 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
                                unsigned long long seed) {
   pdl_trigger();
   pdl_wait();
-  const float inv = 1.f / (1.f - p);
+  const uint32_t thr = drop_threshold(p);
+  const float inv = drop_scale(thr);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const float keep = hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    const float keep = drop_keep(seed, (unsigned long long)i, thr) ? inv : 0.f;
     stf<T>(y, i, ldf<T>(x, i) * keep);
   }
 }
@@ -447,13 +448,14 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
                                unsigned long long seed) {
   pdl_trigger();
   pdl_wait();
-  const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const uint32_t thr = drop_threshold(p);
+  const float inv = p > 0.f ? drop_scale(thr) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = ldf<T>(dy, i);
     if (act == DL_ACT_GELU) v *= gelu_grad<T>(ldf<T>(pre, i));
     else if (act == DL_ACT_RELU) v = ldf<T>(pre, i) > 0.f ? v : 0.f;
-    if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    if (p > 0.f) v *= drop_keep(seed, (unsigned long long)i, thr) ? inv : 0.f;
     stf<T>(g, i, v);
   }
 }
@@ -509,11 +511,12 @@ __global__ void add_pe_kernel(const T* __restrict__ x, const float* __restrict__
                               unsigned long long seed) {
   pdl_trigger();
   pdl_wait();
-  const float inv = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const uint32_t thr = drop_threshold(p);
+  const float inv = p > 0.f ? drop_scale(thr) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = ldf<T>(x, i) + pe[i % period];
-    if (p > 0.f) v *= hash_uniform(seed, (unsigned long long)i) >= p ? inv : 0.f;
+    if (p > 0.f) v *= drop_keep(seed, (unsigned long long)i, thr) ? inv : 0.f;
     stf<T>(y, i, v);
   }
 }
