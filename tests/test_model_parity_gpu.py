@@ -65,8 +65,8 @@ def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
     # (`bf16_autocast_*_dev`, make_golden.py), and an ensemble of 12 autocast runs with the weights
     # perturbed by half a bf16 ulp spreads the loss over 3e-4..8.7e-2 and the logits over 0.12..0.99
     # (bf16_noise_floor.npz, make_noise_floor.py).  The product's bf16 result is one more draw from
-    # that distribution, so there the logits and the loss are bounded by 1.5x the ensemble maximum
-    # (never tighter than the 2e-2 bar); the eval-mode fixture (running statistics) carries the
+    # that heavy-tailed distribution (12 draws: mean 3.5e-2, sigma 3.0e-2 for the loss), so there the
+    # logits and the loss are bounded by 2x the ensemble maximum (never tighter than the 2e-2 bar); the eval-mode fixture (running statistics) carries the
     # strict 2e-2 logit / loss bar and the gradient check.
     noisy = dtype == torch.bfloat16 and bool(int(fx["meta_training"]))
     stol = ltol = tol
@@ -75,7 +75,7 @@ def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
         key = case[:-len(".npz")]
         sdev = max(float(fx["bf16_autocast_score_dev"]), float(nf[key + "/score_dev"].max()))
         ldev = max(float(fx["bf16_autocast_loss_dev"]), float(nf[key + "/loss_dev"].max()))
-        stol, ltol = max(tol, 1.5 * sdev), max(tol, 1.5 * ldev)
+        stol, ltol = max(tol, 2.0 * sdev), max(tol, 2.0 * ldev)
     if noisy:
         # intermediates (three stacked train-mode BatchNorms in the GCN, 92 % identical rows) sit at
         # ~5e-2 in bf16 and move a little from run to run (atomic reduction order): diagnostic bound
