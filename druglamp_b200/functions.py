@@ -283,32 +283,6 @@ def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, d
     return dQ, dK, dV
 
 
-class AttentionFn(Function):
-    """softmax(q k^T * scale) v for `S2` stacked query sets sharing one K/V (the PMMA paired
-    attention, model/PMMA/attention.py:44-88, and plain MHSA :109-122 with S2 = 1).
-    q (S2,B,L,H*d) -> O (B,L,S2*H*d): set s fills columns [s*H*d, (s+1)*H*d)."""
-
-    @staticmethod
-    def forward(ctx, q, k, v, H, scale):
-        qc, kc, vc = K.to_compute(q), K.to_compute(k), K.to_compute(v)
-        O, P, _ = _attn_fwd(qc, kc, vc, H, scale, False)
-        ctx.save_for_backward(qc, kc, vc, P)
-        ctx.meta = (H, scale, q.dtype, k.dtype, v.dtype)
-        return O
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, gO):
-        qc, kc, vc, P = ctx.saved_tensors
-        H, scale, qdt, kdt, vdt = ctx.meta
-        dQ, dK, dV = _attn_bwd(K.to_compute(gO), qc, kc, vc, P, H, scale)
-        return _back(dQ, qdt), _back(dK, kdt), _back(dV, vdt), None, None
-
-
-def attention(q, k, v, H, scale):
-    return AttentionFn.apply(q, k, v, H, scale)
-
-
 # ---- fused query / key / value projections -----------------------------------------------------
 # The three projections of one input share a GEMM when their weights sit back to back in the flat
 # parameter buffer (params.fused_group): one launch forward, one for dX (which also sums the three
@@ -469,38 +443,6 @@ class PairedAttnCoreFn(Function):
         _attn_bwd(K.to_compute(gom), Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], Pm, H, scale,
                   dq_out=dQ, dk_out=d[1, :, :, E:2 * E], dv_out=d[1, :, :, 2 * E:], dq_accumulate=True)
         return _back(d, dt), None, None
-
-
-class PairedQFn(Function):
-    """Q[0] = x0 W0^T + b0, Q[1] = x1 W1^T + b1 written into one (2,B,L,D) buffer so the paired
-    attention can address both query sets with a batch stride (no torch.stack copy)."""
-
-    @staticmethod
-    def forward(ctx, x0, w0, b0, x1, w1, b1):
-        a0, a1 = K.to_compute(x0), K.to_compute(x1)
-        Bn, Lr, D = a0.shape
-        N = w0.shape[0]
-        Q = torch.empty((2, Bn, Lr, N), dtype=a0.dtype, device=a0.device)
-        K.mm(a0.view(-1, D), shadow(w0), Q[0].view(-1, N), bias=b0)
-        K.mm(a1.view(-1, D), shadow(w1), Q[1].view(-1, N), bias=b1)
-        ctx.save_for_backward(a0, w0, a1, w1)
-        ctx.biases = (b0, b1)
-        ctx.dts = (x0.dtype, x1.dtype)
-        return Q
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, gQ):
-        a0, w0, a1, w1 = ctx.saved_tensors
-        g = K.to_compute(gQ)
-        N, D = w0.shape
-        g0, g1 = g[0].view(-1, N), g[1].view(-1, N)
-        dx0 = _back(K.mm(g0, shadow(w0), tb=True), ctx.dts[0], a0.shape)
-        dx1 = _back(K.mm(g1, shadow(w1), tb=True), ctx.dts[1], a1.shape)
-        b0, b1 = ctx.biases
-        dw0, db0 = _wbgrad(w0, b0, g0, a0.view(-1, D))
-        dw1, db1 = _wbgrad(w1, b1, g1, a1.view(-1, D))
-        return dx0, dw0, db0, dx1, dw1, db1
 
 
 class FcCatFn(Function):
