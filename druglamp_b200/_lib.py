@@ -50,7 +50,7 @@ _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint
 SIGNATURES = {
     "dl_gemm": [C.POINTER(GemmArgs), _P],
     "dl_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
-    "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
+    "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],
     "dl_softmax_bwd": [_P, _P, _P, _I64, _I32, _I64, _F, _I32, _P],
     "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _I32, _P],

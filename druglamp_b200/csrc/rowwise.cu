@@ -69,7 +69,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                     const float* __restrict__ rstd_in, T* __restrict__ dx,
+                     const float* __restrict__ rstd_in, T* __restrict__ dx, const T* __restrict__ dx_add,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
   pdl_trigger();
   pdl_wait();
@@ -109,6 +109,10 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
       o.y = rstd * (dg[j].y - c1 - xh[j].y * c2);
       o.z = rstd * (dg[j].z - c1 - xh[j].z * c2);
       o.w = rstd * (dg[j].w - c1 - xh[j].w * c2);
+      if (dx_add) {                          // the residual branch's gradient joins here
+        const float4 a = ld4<T>(dx_add + r * C + c0);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
       st4<T>(dx + r * C + c0, o);
     }
   }
@@ -547,18 +551,19 @@ int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* y, floa
 
 template <typename T>
 int ln_bwd_dispatch(const void* dy, const void* x, const float* g, const float* mean,
-                    const float* rstd, void* dx, float* dg, float* db, long long rows, int cols,
-                    cudaStream_t st) {
+                    const float* rstd, void* dx, const void* dx_add, float* dg, float* db, long long rows,
+                    int cols, cudaStream_t st) {
   int grid = row_grid(rows);
   if (grid > sm_count() * 2) grid = sm_count() * 2;   // fewer blocks -> fewer atomics
   const int th = kWarpsPerBlock * 32;
   const T *dyy = (const T*)dy, *xx = (const T*)x;
   T* dxx = (T*)dx;
+  const T* add = (const T*)dx_add;
   switch (cols / 128) {
-    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 1>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 2>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 4>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
-    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 8>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, dg, db, rows); break;
+    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 1>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 2>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 4>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 8>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
     default: return set_error(-1, "dl_layernorm_bwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_bwd_kernel");
@@ -583,17 +588,17 @@ extern "C" int dl_layernorm_fwd(const void* x, const float* gamma, const float* 
 }
 
 extern "C" int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma,
-                                const float* mean, const float* rstd, void* dx, float* dgamma,
-                                float* dbeta, int64_t rows, int32_t cols, int32_t accumulate,
-                                int32_t dtype, void* stream) {
+                                const float* mean, const float* rstd, void* dx, const void* dx_add,
+                                float* dgamma, float* dbeta, int64_t rows, int32_t cols,
+                                int32_t accumulate, int32_t dtype, void* stream) {
   DL_REQUIRE(dy && x && gamma && mean && rstd && dx, "dl_layernorm_bwd: null pointer");
   DL_REQUIRE(rows >= 0 && cols > 0 && cols % 128 == 0, "dl_layernorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (dgamma && !accumulate) DL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, st));
   if (dbeta && !accumulate) DL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, st));
   if (rows == 0) return 0;
-  return dtype == DL_BF16 ? ln_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st)
-                          : ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
+  return dtype == DL_BF16 ? ln_bwd_dispatch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dx_add, dgamma, dbeta, rows, cols, st)
+                          : ln_bwd_dispatch<float>(dy, x, gamma, mean, rstd, dx, dx_add, dgamma, dbeta, rows, cols, st);
 }
 
 extern "C" int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols, int64_t ld,

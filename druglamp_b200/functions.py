@@ -227,6 +227,40 @@ def layer_norm(x, gamma, beta, eps=1e-5):
     return LayerNormFn.apply(x, gamma, beta, eps)
 
 
+class LayerNormResFn(Function):
+    """(LayerNorm(x), x): the pre-norm residual pattern ``x + f(LN(x))`` (model/PMMA/block.py:33-47).
+    Handing the skip connection out of the same Function lets the backward add its gradient to the
+    LayerNorm's input gradient inside dl_layernorm_bwd instead of in autograd's separate add pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xc = K.to_compute(x)
+        y, mean, rstd = K.layernorm_fwd(xc, gamma.detach(), beta.detach(), eps)
+        ctx.save_for_backward(xc, gamma, beta, mean, rstd)
+        ctx.xdt = x.dtype
+        return y, x.view_as(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gres):
+        xc, gamma, beta, mean, rstd = ctx.saved_tensors
+        add = None
+        if gres is not None:
+            add = K.to_compute(gres).view(xc.shape)
+        tg, tb = _grad_target(gamma), _grad_target(beta)
+        if tg is not None and tb is not None:
+            dx, _, _ = K.layernorm_bwd(K.to_compute(gy), xc, gamma.detach(), mean, rstd, acc_into=(tg, tb),
+                                       dx_add=add)
+            return _back(dx, ctx.xdt), None, None, None
+        dx, dg, db = K.layernorm_bwd(K.to_compute(gy), xc, gamma.detach(), mean, rstd, dx_add=add)
+        return _back(dx, ctx.xdt), dg, db, None
+
+
+def layer_norm_res(x, gamma, beta, eps=1e-5):
+    """-> (LayerNorm(x), x) with the skip connection's gradient fused into the LayerNorm backward."""
+    return LayerNormResFn.apply(x, gamma, beta, eps)
+
+
 # ================================================================================ attention core
 def _attn_fwd(q, k, v, H, scale, keep_raw):
     """q (S2,B,Lq,HD), k, v (B,Lk,HD): unit inner stride, every other stride free (they may be

@@ -147,8 +147,9 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, save: bool = True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True, acc_into=None):
-    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True, acc_into=None, dx_add=None):
+    """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to.
+    dx_add: a tensor shaped like x that is added to dx (the skip connection's gradient)."""
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     dx = torch.empty_like(x)
     dg = db = None
@@ -158,7 +159,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True, acc_i
         dg = torch.empty(cols, dtype=torch.float32, device=x.device)
         db = torch.empty_like(dg)
     L.call("dl_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-           rstd.data_ptr(), dx.data_ptr(), L.ptr(dg), L.ptr(db), rows, cols, int(acc_into is not None), L.dt(x))
+           rstd.data_ptr(), dx.data_ptr(), L.ptr(dx_add), L.ptr(dg), L.ptr(db), rows, cols,
+           int(acc_into is not None), L.dt(x))
     return dx, dg, db
 
 

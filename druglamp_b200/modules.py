@@ -214,15 +214,26 @@ class PMMABlock(nn.Module):
     def _ln(x, m):
         return Fn.layer_norm(x, m.weight, m.bias, m.eps)
 
+    @staticmethod
+    def _ln_res(x, m):
+        """(LayerNorm(x), x): the skip connection leaves through the same Function, so its gradient
+        is added inside the LayerNorm backward kernel."""
+        return Fn.layer_norm_res(x, m.weight, m.bias, m.eps)
+
     def forward(self, prot, mol=None):
         if mol is None:
-            prot, w, gw = self.attn(self._ln(prot, self.attention_norm), residual=prot)
-            prot = self.ffn(self._ln(prot, self.ffn_norm), residual=prot)
+            h, res = self._ln_res(prot, self.attention_norm)
+            prot, w, gw = self.attn(h, residual=res)
+            h, res = self._ln_res(prot, self.ffn_norm)
+            prot = self.ffn(h, residual=res)
             return prot, w, gw
-        prot, mol, w, gw = self.attn(self._ln(prot, self.attention_norm), self._ln(mol, self.att_norm_mol),
-                                     residual=prot, residual_mol=mol)
-        prot = self.ffn(self._ln(prot, self.ffn_norm), residual=prot)
-        mol = self.ffn_mol(self._ln(mol, self.ffn_norm_mol), residual=mol)
+        hp, rp = self._ln_res(prot, self.attention_norm)
+        hm, rm = self._ln_res(mol, self.att_norm_mol)
+        prot, mol, w, gw = self.attn(hp, hm, residual=rp, residual_mol=rm)
+        hp, rp = self._ln_res(prot, self.ffn_norm)
+        prot = self.ffn(hp, residual=rp)
+        hm, rm = self._ln_res(mol, self.ffn_norm_mol)
+        mol = self.ffn_mol(hm, residual=rm)
         return prot, mol, w, gw
 
 

@@ -127,10 +127,13 @@ int dl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
                      float* rstd, int64_t rows, int32_t cols, float eps, int32_t dtype,
                      void* stream);
 /* dgamma/dbeta ([cols] fp32; may be NULL): overwritten, or added to when accumulate != 0 (the
- * parameter's .grad buffer itself, torch's AccumulateGrad semantics without the extra add). */
+ * parameter's .grad buffer itself, torch's AccumulateGrad semantics without the extra add).
+ * dx_add ([rows, cols], may be NULL; may alias dx): added to dx -- in a pre-norm residual block
+ * (model/PMMA/block.py:33-47) the gradient of the skip connection joins the LayerNorm's input
+ * gradient here instead of in a separate add pass. */
 int dl_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
-                     const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows,
-                     int32_t cols, int32_t accumulate, int32_t dtype, void* stream);
+                     const float* rstd, void* dx, const void* dx_add, float* dgamma, float* dbeta,
+                     int64_t rows, int32_t cols, int32_t accumulate, int32_t dtype, void* stream);
 
 /* softmax over the last dim of a [rows, cols<=1024] matrix with row stride ld; in-place allowed.
  * Replaces F.softmax in PGCA (model/PGCA/guided_cross_attention_model.py:308) and

@@ -36,6 +36,10 @@ def test_layernorm_fwd_bwd(dtype, tol, cols):
     _close(dx, xr.grad, tol, "dx")
     _close(dg, gr.grad, max(tol, 1e-4), "dgamma")
     _close(db, br.grad, max(tol, 1e-4), "dbeta")
+    # dx_add: the skip connection's gradient joins inside the kernel (pre-norm residual blocks)
+    extra = torch.randn(rows, cols, device="cuda").to(dtype)
+    dx2, _, _ = K.layernorm_bwd(dy, x, g, mean, rstd, dx_add=extra)
+    _close(dx2, xr.grad + extra.double(), tol, "dx + skip")
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
