@@ -140,3 +140,58 @@ def make_batch(batch_size: int, seed: int = 1234, n_drug_feature: int = 384,
             meta[b]["Y"] = int(y[b])
         seen[key] = int(y[b])
     return Batch(graph, torch.from_numpy(vp), torch.from_numpy(y), xd, xp, meta, n_atoms, prot_len)
+
+
+# reference utils.py:345-371 (CHARPROTSET): letter -> 1..25 in this order, everything else padding (0)
+_PROT_ALPHABET = "ACBEDGFIHKMLONQPSRUTWVYXZ"
+
+
+def batch_from_records(records, seed: int = 0, n_drug_feature: int = 384, n_prot_feature: int = 640) -> Batch:
+    """A batch from dataset rows ``{"smiles", "protein", "y"}`` (the shipped CSV columns) without
+    RDKit / DGL / LLM checkpoints: residue tokens and labels are the real ones (``utils.py:392-412``
+    tiling, 1022-residue truncation of ``handler/dataset.py:36``); the heavy-atom count is read off
+    the SMILES string; bond topology, atom features and the LLM embedding rows are synthetic but a
+    pure function of the strings, so the same molecule / protein always gets the same tensors."""
+    import zlib
+    B = len(records)
+    feats = np.zeros((B, MAX_NODES, NODE_FEATS), dtype=np.float32)
+    src_all, dst_all = [], []
+    vp = np.zeros((B, SEQ_LEN), dtype=np.float64)
+    xp = torch.zeros(B, SEQ_LEN, n_prot_feature, dtype=torch.float32)
+    xd = torch.zeros(B, MAX_NODES, n_drug_feature, dtype=torch.float32)
+    n_atoms = np.zeros(B, dtype=np.int64)
+    prot_len = np.zeros(B, dtype=np.int64)
+    y = np.zeros(B, dtype=np.int64)
+    meta = []
+    for b, r in enumerate(records):
+        smi, seq = r["smiles"], r["protein"][:MAX_RESIDUES]
+        hs, hp = zlib.crc32(smi.encode()), zlib.crc32(seq.encode())
+        # heavy atoms: element symbols start with an upper-case letter (H is implicit); Cl / Br count once
+        n = sum(1 for i, c in enumerate(smi) if c.isupper() and c != "H") + sum(smi.count(a) for a in "cnos")
+        n = int(np.clip(n, 4, 290))
+        n_atoms[b] = n
+        ent = np.random.default_rng([seed, 1, hs])
+        cols = ent.integers(0, 74, size=(n, 8))
+        feats[b, np.arange(n)[:, None], cols] = 1.0
+        feats[b, n:, 74] = 1.0
+        s, d = _molecule_edges(ent, n)
+        loops_real, loops_all = list(range(n)), list(range(MAX_NODES))
+        src_all.append(np.asarray(s + loops_real + loops_all, dtype=np.int64) + b * MAX_NODES)
+        dst_all.append(np.asarray(d + loops_real + loops_all, dtype=np.int64) + b * MAX_NODES)
+        L = len(seq)
+        prot_len[b] = L
+        toks = np.array([_PROT_ALPHABET.find(c.upper()) + 1 for c in seq], dtype=np.float64)
+        gp = torch.Generator().manual_seed(int(seed) * 1000003 + 2 * hp + 1)
+        emb = torch.randn(L + 2, n_prot_feature, generator=gp)
+        for i in range(SEQ_LEN // (L + 2)):
+            st = i * (L + 2)
+            vp[b, st + 1: st + 1 + L] = toks
+            xp[b, st: st + L + 2] = emb
+        gd = torch.Generator().manual_seed(int(seed) * 1000003 + 2 * hs)
+        rows = min(n + 2, MAX_NODES)
+        xd[b, :rows] = torch.randn(rows, n_drug_feature, generator=gd)
+        y[b] = int(r["y"])
+        meta.append({"Drug_ID": f"D{hs}", "Prot_ID": f"P{hp}", "Y": int(r["y"])})
+    graph = BatchedMolGraph(torch.from_numpy(np.concatenate(src_all)), torch.from_numpy(np.concatenate(dst_all)),
+                            B * MAX_NODES, B, torch.from_numpy(feats.reshape(B * MAX_NODES, NODE_FEATS)))
+    return Batch(graph, torch.from_numpy(vp), torch.from_numpy(y), xd, xp, meta, n_atoms, prot_len)
