@@ -168,3 +168,39 @@ def test_cm_loss_and_margin_schedule_match_reference():
                     assert e <= max(50 * tol, 5e-2), (dtype, k, e)
             cm.step()
     D.set_compute_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_long_sequence_batch_256_equals_its_chunks(dtype, tol):
+    """BASELINE.json configs[3] shape (protein 1022 residues + CLS/SEP tiled to 2304, drug 290 atoms,
+    batch 256): too large for the CPU oracle, so parity is carried by a size-independent property.
+    In eval mode (BatchNorm on running statistics) pairs do not interact, hence the logits of the
+    256-pair batch must equal those of its four 64-pair chunks; the padding masks are checked
+    bit-exactly against numpy on the full batch."""
+    from druglamp_b200.synth import make_batch
+    b = make_batch(256, seed=99, min_prot=1022, max_prot=1022, max_atoms=290)
+    m = build_product("DrugLAMP", dtype)
+    try:
+        m.eval()
+        bc = b.to("cuda")
+        with torch.no_grad():
+            full = m(*bc.model_inputs(), mode="eval")[2].float()
+            bit = m._masks(bc.xd, bc.xp)[0]
+            parts = []
+            from druglamp_b200.graph import BatchedMolGraph
+            c = b
+            for i in range(0, 256, 64):
+                sel = slice(i * 512, (i + 64) * 512)
+                e = (c.graph.src >= i * 512) & (c.graph.src < (i + 64) * 512)
+                g = BatchedMolGraph(c.graph.src[e] - i * 512, c.graph.dst[e] - i * 512, 64 * 512, 64,
+                                    c.graph.ndata["h"][sel]).to("cuda")
+                parts.append(m(g, c.vp[i:i + 64].cuda(), c.xd[i:i + 64].cuda(), c.xp[i:i + 64].cuda(),
+                               mode="eval")[2].float())
+        chunks = torch.cat(parts)
+        scale = float(full.abs().max()) + 1e-12
+        assert float((full - chunks).abs().max()) <= tol * scale
+        assert np.array_equal(bit.cpu().numpy(), (b.xp.numpy().sum(-1) == 0).astype(np.float32))
+        assert torch.isfinite(full).all()
+    finally:
+        import druglamp_b200 as D
+        D.set_compute_dtype(torch.float32)
