@@ -18,54 +18,120 @@ __host__ int row_grid(long long rows) {
 }
 
 // ------------------------------------------------------------------ LayerNorm
-// VEC = cols / 128 float4 chunks per lane (cols is a multiple of 128, <= 1024)
-template <typename T, int VEC>
+// One warp per row, C = 128..1024 columns.  A lane owns EPL = C/32 elements, fetched as 16-byte
+// vectors (8 bf16 / 4 fp32; 8-byte for the 128-wide bf16 case): vector k of lane l covers columns
+// k*32*V + l*V .. +V, so every warp access is one contiguous 512-byte (or 256-byte) run.  Two rows
+// are in flight per warp iteration so the loads of one overlap the shuffle reductions of the other.
+template <typename T, int C>
+struct LnLayout {
+  static constexpr int EPL = C / 32;
+  static constexpr int VMAX = 16 / (int)sizeof(T);
+  static constexpr int V = VMAX < EPL ? VMAX : EPL;
+  static constexpr int NV = EPL / V;
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void ln_load(const T* p, float* out) {
+  if constexpr (V == 8) {
+    float t[8];
+    ldv(reinterpret_cast<const __nv_bfloat16*>(p), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = t[i];
+  } else {
+    const float4 f = ld4<T>(p);
+    out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = f.w;
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void ln_store(T* p, const float* in) {
+  if constexpr (V == 8) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = in[i];
+    stv(reinterpret_cast<__nv_bfloat16*>(p), t);
+  } else {
+    st4<T>(p, make_float4(in[0], in[1], in[2], in[3]));
+  }
+}
+
+template <typename T, int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, float eps) {
   pdl_trigger();
   pdl_wait();
-  constexpr int C = VEC * 128;
+  using LY = LnLayout<T, C>;
+  constexpr int EPL = LY::EPL, V = LY::V, NV = LY::NV;
+  constexpr int R = EPL <= 16 ? 2 : 1;
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    float4 v[VEC];
-    float s = 0.f;
+  for (long long r0 = warp0; r0 < rows; r0 += R * nwarps) {
+    float v[R][EPL], s[R];
+    bool on[R];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      v[j] = ld4<T>(x + r * C + (j * 32 + lane) * 4);
-      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    for (int u = 0; u < R; ++u) {
+      const long long r = r0 + u * nwarps;
+      on[u] = r < rows;
+      s[u] = 0.f;
+      if (on[u]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) ln_load<T, V>(x + r * C + k * 32 * V + lane * V, v[u] + k * V);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) v[u][e] = 0.f;
+      }
     }
-    const float mean = warp_sum(s) * (1.f / C);
-    float q = 0.f;
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      q += a * a + b * b + c * c + d * d;
+    for (int u = 0; u < R; ++u) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) s[u] += v[u][e];
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int c0 = (j * 32 + lane) * 4;
-      const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
-      const float4 b = *reinterpret_cast<const float4*>(beta + c0);
-      float4 o;
-      o.x = (v[j].x - mean) * rstd * g.x + b.x;
-      o.y = (v[j].y - mean) * rstd * g.y + b.y;
-      o.z = (v[j].z - mean) * rstd * g.z + b.z;
-      o.w = (v[j].w - mean) * rstd * g.w + b.w;
-      st4<T>(y + r * C + c0, o);
+    for (int u = 0; u < R; ++u) mean[u] = warp_sum(s[u]) * (1.f / C);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { const float d = v[u][e] - mean[u]; q += d * d; }
+      s[u] = q;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) rstd[u] = rsqrtf(warp_sum(s[u]) * (1.f / C) + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = k * 32 * V + lane * V;
+      float g[V], b[V];
+#pragma unroll
+      for (int e = 0; e < V; e += 4) {
+        const float4 gg = *reinterpret_cast<const float4*>(gamma + c0 + e);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + c0 + e);
+        g[e] = gg.x; g[e + 1] = gg.y; g[e + 2] = gg.z; g[e + 3] = gg.w;
+        b[e] = bb.x; b[e + 1] = bb.y; b[e + 2] = bb.z; b[e + 3] = bb.w;
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (!on[u]) continue;
+        float o[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = (v[u][k * V + e] - mean[u]) * rstd[u] * g[e] + b[e];
+        ln_store<T, V>(y + (r0 + u * nwarps) * C + c0, o);
+      }
     }
     if (lane == 0) {
-      if (mean_out) mean_out[r] = mean;
-      if (rstd_out) rstd_out[r] = rstd;
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (!on[u]) continue;
+        if (mean_out) mean_out[r0 + u * nwarps] = mean[u];
+        if (rstd_out) rstd_out[r0 + u * nwarps] = rstd[u];
+      }
     }
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
@@ -73,65 +139,92 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
   pdl_trigger();
   pdl_wait();
-  constexpr int C = VEC * 128;
-  __shared__ float red[kWarpsPerBlock][32 * 4 + 4];
+  using LY = LnLayout<T, C>;
+  constexpr int EPL = LY::EPL, V = LY::V, NV = LY::NV;
+  constexpr int R = EPL <= 8 ? 2 : 1;
+  __shared__ float red[kWarpsPerBlock][C];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + w;
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-  float4 ag[VEC], ab[VEC];
+  float ag[EPL], ab[EPL], gm[EPL];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) ag[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    float4 xh[VEC], dg[VEC];
-    float s1 = 0.f, s2 = 0.f;
+  for (int e = 0; e < EPL; ++e) { ag[e] = 0.f; ab[e] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int c0 = (j * 32 + lane) * 4;
-      const float4 xv = ld4<T>(x + r * C + c0);
-      const float4 dv = ld4<T>(dy + r * C + c0);
-      const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
-      xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
-                          (xv.w - mean) * rstd);
-      dg[j] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
-      s1 += dg[j].x + dg[j].y + dg[j].z + dg[j].w;
-      s2 += dg[j].x * xh[j].x + dg[j].y * xh[j].y + dg[j].z * xh[j].z + dg[j].w * xh[j].w;
-      ag[j].x += dv.x * xh[j].x; ag[j].y += dv.y * xh[j].y;
-      ag[j].z += dv.z * xh[j].z; ag[j].w += dv.w * xh[j].w;
-      ab[j].x += dv.x; ab[j].y += dv.y; ab[j].z += dv.z; ab[j].w += dv.w;
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int e = 0; e < V; e += 4) {
+      const float4 gg = *reinterpret_cast<const float4*>(gamma + k * 32 * V + lane * V + e);
+      gm[k * V + e] = gg.x; gm[k * V + e + 1] = gg.y; gm[k * V + e + 2] = gg.z; gm[k * V + e + 3] = gg.w;
     }
-    const float c1 = warp_sum(s1) * (1.f / C), c2 = warp_sum(s2) * (1.f / C);
+  }
+  for (long long r0 = warp0; r0 < rows; r0 += R * nwarps) {
+    float xh[R][EPL], dg[R][EPL], s1[R], s2[R], rs[R];
+    bool on[R];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int c0 = (j * 32 + lane) * 4;
-      float4 o;
-      o.x = rstd * (dg[j].x - c1 - xh[j].x * c2);
-      o.y = rstd * (dg[j].y - c1 - xh[j].y * c2);
-      o.z = rstd * (dg[j].z - c1 - xh[j].z * c2);
-      o.w = rstd * (dg[j].w - c1 - xh[j].w * c2);
-      if (dx_add) {                          // the residual branch's gradient joins here
-        const float4 a = ld4<T>(dx_add + r * C + c0);
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    for (int u = 0; u < R; ++u) {
+      const long long r = r0 + u * nwarps;
+      on[u] = r < rows;
+      s1[u] = s2[u] = 0.f;
+      rs[u] = 0.f;
+      if (on[u]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          ln_load<T, V>(x + r * C + k * 32 * V + lane * V, xh[u] + k * V);
+          ln_load<T, V>(dy + r * C + k * 32 * V + lane * V, dg[u] + k * V);
+        }
+        const float mean = mean_in[r];
+        rs[u] = rstd_in[r];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const float h = (xh[u][e] - mean) * rs[u], d = dg[u][e];
+          xh[u][e] = h;
+          ag[e] += d * h;
+          ab[e] += d;
+          dg[u][e] = d * gm[e];
+          s1[u] += dg[u][e];
+          s2[u] += dg[u][e] * h;
+        }
       }
-      st4<T>(dx + r * C + c0, o);
+    }
+    float c1[R], c2[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) { c1[u] = warp_sum(s1[u]) * (1.f / C); c2[u] = warp_sum(s2[u]) * (1.f / C); }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      if (!on[u]) continue;
+      const long long r = r0 + u * nwarps;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = k * 32 * V + lane * V;
+        float o[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) o[e] = rs[u] * (dg[u][k * V + e] - c1[u] - xh[u][k * V + e] * c2[u]);
+        if (dx_add) {                        // the residual branch's gradient joins here
+          float a[V];
+          ln_load<T, V>(dx_add + r * C + c0, a);
+#pragma unroll
+          for (int e = 0; e < V; ++e) o[e] += a[e];
+        }
+        ln_store<T, V>(dx + r * C + c0, o);
+      }
     }
   }
   // block-reduce the per-warp column partials, then one atomic per column per block
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    for (int pass = 0; pass < 2; ++pass) {
-      const float4 a = pass == 0 ? ag[j] : ab[j];
-      __syncthreads();
-      red[w][lane * 4 + 0] = a.x; red[w][lane * 4 + 1] = a.y;
-      red[w][lane * 4 + 2] = a.z; red[w][lane * 4 + 3] = a.w;
-      __syncthreads();
-      if (threadIdx.x < 128) {
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) red[w][k * 32 * V + lane * V + e] = pass == 0 ? ag[k * V + e] : ab[k * V + e];
+    }
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst) {
+      for (int c = threadIdx.x; c < C; c += kWarpsPerBlock * 32) {
         float t = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < kWarpsPerBlock; ++ww) t += red[ww][threadIdx.x];
-        // threadIdx.x = l*4 + e  ->  column (j*32 + l)*4 + e = j*128 + threadIdx.x
-        float* dst = pass == 0 ? dgamma : dbeta;
-        if (dst) atomicAdd(dst + j * 128 + threadIdx.x, t);
+        for (int ww = 0; ww < kWarpsPerBlock; ++ww) t += red[ww][c];
+        atomicAdd(dst + c, t);
       }
     }
   }
@@ -538,10 +631,10 @@ int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* y, floa
   const T* xx = (const T*)x;
   T* yy = (T*)y;
   switch (cols / 128) {
-    case 1: DL_LAUNCH((layernorm_fwd_kernel<T, 1>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 2: DL_LAUNCH((layernorm_fwd_kernel<T, 2>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 4: DL_LAUNCH((layernorm_fwd_kernel<T, 4>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
-    case 8: DL_LAUNCH((layernorm_fwd_kernel<T, 8>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 1: DL_LAUNCH((layernorm_fwd_kernel<T, 128>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 2: DL_LAUNCH((layernorm_fwd_kernel<T, 256>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 4: DL_LAUNCH((layernorm_fwd_kernel<T, 512>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
+    case 8: DL_LAUNCH((layernorm_fwd_kernel<T, 1024>), grid, th, 0, st, xx, g, b, yy, mean, rstd, rows, eps); break;
     default: return set_error(-1, "dl_layernorm_fwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_fwd_kernel");
@@ -560,10 +653,10 @@ int ln_bwd_dispatch(const void* dy, const void* x, const float* g, const float* 
   T* dxx = (T*)dx;
   const T* add = (const T*)dx_add;
   switch (cols / 128) {
-    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 1>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 2>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 4>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 8>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 128>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 256>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 512>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 1024>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
     default: return set_error(-1, "dl_layernorm_bwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_bwd_kernel");
