@@ -557,6 +557,41 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
   }
 }
 
+// 16-byte vector variant (n % V == 0, 16-byte aligned pointers): V = 8 bf16 / 4 fp32 elements per
+// thread and step, one dropout hash per two elements.
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ g,
+                   long long nvec, int act, float p, unsigned long long seed) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = VecWidth<T>::N;
+  const uint32_t thr = drop_threshold(p);
+  const float inv = p > 0.f ? drop_scale(thr) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[V];
+    ldv(dy + i * V, v);
+    if (act != DL_ACT_NONE) {
+      float a[V];
+      ldv(pre + i * V, a);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        v[j] = act == DL_ACT_GELU ? v[j] * gelu_grad<T>(a[j]) : (a[j] > 0.f ? v[j] : 0.f);
+    }
+    if (p > 0.f) {
+      const unsigned long long e2 = (unsigned long long)i * (V / 2);      // i * V is even
+#pragma unroll
+      for (int k = 0; k < V / 2; ++k) {
+        const uint32_t h = drop_hash(seed, e2 + k);
+        v[2 * k] *= (h & 0xffffu) >= thr ? inv : 0.f;
+        v[2 * k + 1] *= (h >> 16) >= thr ? inv : 0.f;
+      }
+    }
+    stv(g + i * V, v);
+  }
+}
+
 // AdamW over one flat fp32 buffer (torch.optim.AdamW semantics: decoupled weight decay, bias
 // correction from the device-side step counter) that also refreshes the bf16 shadow the GEMMs read.
 __global__ void adamw_tick_kernel(long long* step) {
@@ -847,6 +882,18 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
   DL_REQUIRE(dy && g && (act == DL_ACT_NONE || pre) && p >= 0.f && p < 1.f, "dl_act_bwd: bad arguments");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const int vec = dtype == DL_BF16 ? 8 : 4;
+  if (n % vec == 0 && (((uintptr_t)dy | (uintptr_t)pre | (uintptr_t)g) & 15) == 0) {
+    const long long nvec = n / vec;
+    const int vgrid = ew_grid(nvec, 256);
+    if (dtype == DL_BF16)
+      DL_LAUNCH((act_bwd_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, nvec, act, p, seed);
+    else
+      DL_LAUNCH((act_bwd_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, nvec, act, p, seed);
+    DL_LAUNCH_CHECK("act_bwd_vec_kernel");
+    count_launch();
+    return 0;
+  }
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
     DL_LAUNCH((act_bwd_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed);
