@@ -72,7 +72,8 @@ struct GemmParams {
   int a_mn, b_mn;
   int c_bf16;
   int act, mul_mode;
-  int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work
+  int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work,
+                                // 3 plain stores without the lane transpose (A/B measurements)
   int conv_cin, conv_left;      // implicit-GEMM conv1d on A (0 = off): channels per tap, left padding
   int kred_kpb, kred_shift;     // K-reduction over batch[2] (0 = off): K-blocks per batch, B row shift
   int kred_tap;                 // 1: batch dim 0 is a convolution tap that also shifts B's rows
@@ -244,7 +245,7 @@ __device__ __forceinline__ EpiFlags make_epi_flags(const GemmParams& p) {
   f.wide_p = f.wide_c && addr_ok(p.preact, 32) && addr_ok(p.aux, 32);
   f.atomic = p.splits > 1;
   f.simple = !p.bias && !p.preact && !p.aux && !p.res && p.act == DL_ACT_NONE &&
-             p.mul_mode == DL_MUL_NONE && p.drop_p == 0.f && !f.atomic && p.dbg == 0;
+             p.mul_mode == DL_MUL_NONE && p.drop_p == 0.f && !f.atomic && (p.dbg == 0 || p.dbg == 3);
   f.drop_thr = drop_threshold(p.drop_p);
   f.drop_inv = p.drop_p > 0.f ? drop_scale(f.drop_thr) : 1.f;
   return f;
@@ -344,6 +345,62 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, const EpiFla
   const long long rrow = rbase + (long long)row * p.ldr;
   constexpr int W = BN / kColSplit;
   constexpr int STEP = (SIMPLE && W >= 32) ? 32 : 16;
+  if constexpr (SIMPLE && sizeof(TC) == 2 && W == 64) {
+    // Plain bf16 stores of a full 64-column slice: thread = row would make every store
+    // instruction touch 32 different 128-byte lines (32 bytes of each).  A 4x4 register transpose
+    // inside each group of four lanes (two shuffle stages) gives lane 4g+j chunk j of rows
+    // 4g..4g+3, so one instruction writes 8 rows x 128 contiguous bytes: a quarter of the
+    // line accesses the L1 has to process.
+    if (f.wide_c && n0 + col_begin + W <= p.N && p.dbg != 3) {       // warp-uniform
+      uint32_t P[4][8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_q + (uint32_t)(col_begin + 32 * h), v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[16 * c + 2 * k]) * p.alpha,
+                                                            __uint_as_float(v[16 * c + 2 * k + 1]) * p.alpha);
+            P[2 * h + c][k] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+        }
+      }
+      const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t y = __shfl_xor_sync(0xffffffffu, b0 ? P[c][k] : P[c + 1][k], 1);
+          if (b0) P[c][k] = y; else P[c + 1][k] = y;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t y = __shfl_xor_sync(0xffffffffu, b1 ? P[c][k] : P[c + 2][k], 2);
+          if (b1) P[c][k] = y; else P[c + 2][k] = y;
+        }
+      }
+      // P[i] = chunk (lane & 3) of row (lane & ~3) + i
+      TC* Cp = reinterpret_cast<TC*>(p.C);
+      const int rg = row0 + (lane & ~3);
+      const long long cofs = cbase + n0 + col_begin + 16 * (lane & 3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (rg + i < p.M) {
+          TC* dst = Cp + cofs + (long long)(rg + i) * p.ldc;
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                       :: "l"(dst), "r"(P[i][0]), "r"(P[i][1]), "r"(P[i][2]), "r"(P[i][3]),
+                          "r"(P[i][4]), "r"(P[i][5]), "r"(P[i][6]), "r"(P[i][7]) : "memory");
+        }
+      }
+      return;
+    }
+  }
 #pragma unroll 1
   for (int c0 = col_begin; c0 < col_begin + W; c0 += STEP) {
     const int col = n0 + c0;
