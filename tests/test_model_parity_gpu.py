@@ -204,3 +204,31 @@ def test_long_sequence_batch_256_equals_its_chunks(dtype, tol):
     finally:
         import druglamp_b200 as D
         D.set_compute_dtype(torch.float32)
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """Every kernel is launched with programmatic stream serialization and waits for its producer
+    (griddepcontrol.wait) before touching memory.  A step in a fresh process with DL_NO_PDL=1 must
+    give the same logits bit for bit and the same gradients up to atomic summation order."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys, json\n"
+        "sys.path.insert(0, '.')\n"
+        "from tests.test_model_parity_gpu import run_product\n"
+        "from tests.util import load_golden\n"
+        "m, b, o = run_product(load_golden('druglamp2c2p_train_b16.npz'), torch.bfloat16, flat=True)\n"
+        "g = m._flat.grad\n"
+        "print(json.dumps({'score': o['score'].float().flatten().tolist(), 'gsum': float(g.double().sum()),\n"
+        "                  'gabs': float(g.double().abs().sum()), 'gmax': float(g.abs().max())}))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for no_pdl in ("0", "1"):
+        env = dict(os.environ, DL_NO_PDL=no_pdl)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(__import__("json").loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert a["score"] == b["score"]
+    assert abs(a["gabs"] - b["gabs"]) <= 1e-4 * a["gabs"] and abs(a["gmax"] - b["gmax"]) <= 1e-3 * a["gmax"]
