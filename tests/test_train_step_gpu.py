@@ -1,0 +1,68 @@
+"""GPU: the training step bench.py times (druglamp_b200/train.py).
+
+* the CUDA-graph replay of a captured step is the same computation as the eager step;
+* FlatAdamW over the flat parameter buffer follows torch.optim.AdamW (the optimiser the reference
+  builds in main.py:158-160) applied to the same gradients."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(dtype, seed=3):
+    import druglamp_b200 as D
+    from druglamp_b200.models import DrugLAMP
+    D.set_compute_dtype(dtype)
+    torch.manual_seed(seed)
+    m = DrugLAMP(384, 640).cuda()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0                      # replayed graphs bake the dropout seed in
+    m.train()
+    return m
+
+
+def test_graph_replay_equals_eager_steps_and_flat_adamw_follows_torch_adamw():
+    import druglamp_b200 as D
+    from druglamp_b200.modules import binary_cross_entropy
+    from druglamp_b200.synth import make_batch
+    from druglamp_b200.train import StaticBatch, TrainStep
+    try:
+        b = make_batch(8, seed=5)
+        sb = StaticBatch(b, torch.device("cuda"))
+        # (a) five eager steps
+        ma = _model(torch.float32)
+        ta = TrainStep(ma, lr=1e-3, weight_decay=1e-2)
+        la = [float(ta.eager(sb)) for _ in range(5)]
+        # (b) capture (two eager warm-up steps) + three replays
+        mb = _model(torch.float32)
+        tb = TrainStep(mb, lr=1e-3, weight_decay=1e-2)
+        tb.capture(sb, warmup=2)
+        lb = [float(tb.replay(sb)) for _ in range(3)]
+        # (lr 1e-3 on 8 pairs is a stiff problem: the losses swing 0.73 -> 0.02 in five steps and
+        # summation-order differences of the split-K atomics grow to ~4e-4 by the last steps)
+        assert la[0] > 0 and all(abs(x - y) <= 5e-3 * abs(x) for x, y in zip(la[2:], lb)), (la, lb)
+        fa, fb = ta.flat.flat, tb.flat.flat
+        assert float((fa - fb).abs().max()) <= 2e-3
+        # (c) plain autograd + torch.optim.AdamW on an identically initialised, un-flattened model
+        mc = _model(torch.float32)
+        opt = torch.optim.AdamW(mc.parameters(), lr=1e-3, weight_decay=1e-2)
+        lc = []
+        for _ in range(5):
+            opt.zero_grad(set_to_none=True)
+            out = mc(*sb.model_inputs())
+            _, loss = binary_cross_entropy(out[4], sb.y)
+            loss.backward()
+            opt.step()
+            lc.append(float(loss.detach()))
+        assert all(abs(x - y) <= 1e-2 * abs(x) for x, y in zip(la, lc)), (la, lc)
+        pa = dict(ma.named_parameters())
+        worst = 0.0
+        for name, p in mc.named_parameters():
+            if p.grad is None:
+                continue
+            worst = max(worst, float((pa[name] - p).abs().max()))
+        assert worst <= 2e-3, worst            # parameters moved by ~5 * lr = 5e-3 each; Adam's sign-like
+        # update turns gradient noise on near-zero gradients into O(lr) differences
+    finally:
+        D.set_compute_dtype(torch.float32)
