@@ -41,7 +41,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
         ("split_k", C.c_int32), ("conv_taps", C.c_int32), ("conv_left", C.c_int32),
         ("kred", C.c_int32), ("kred_shift", C.c_int32), ("accumulate", C.c_int32),
-        ("colsum_a", C.c_void_p),
+        ("colsum_a", C.c_void_p), ("drop_seed_step", C.c_void_p),
     ]
 
 
@@ -54,14 +54,14 @@ SIGNATURES = {
     "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],
     "dl_softmax_bwd": [_P, _P, _P, _I64, _I32, _I64, _F, _I32, _P],
     "dl_colsum": [_P, _P, _I64, _I32, _I64, _I32, _I32, _P],
-    "dl_dropout": [_P, _P, _I64, _F, _U64, _I32, _P],
-    "dl_act_bwd": [_P, _P, _P, _I64, _I32, _F, _U64, _I32, _P],
+    "dl_dropout": [_P, _P, _I64, _F, _U64, _P, _I32, _P],
+    "dl_act_bwd": [_P, _P, _P, _I64, _I32, _F, _U64, _P, _I32, _P],
     "dl_act_fwd": [_P, _P, _I64, _I32, _I32, _P],
     "dl_l2norm_fwd": [_P, _P, _P, _I64, _I32, _F, _I32, _P],
     "dl_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_cast": [_P, _I32, _P, _I32, _I64, _P],
     "dl_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _P],
-    "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _I32, _P],
+    "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _P, _I32, _P],
     "dl_spmm_norm": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _I32, _P],
     "dl_batchnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P],
@@ -168,7 +168,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
                  M, N, K, lda, ldb, ldc, _I64x3(*b), _3(sa), _3(sb), _3(sc), ldr, _3(sr),
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
                  mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k,
-                 conv_taps, conv_left, int(kred), kred_shift, int(accumulate), ptr(colsum_a))
+                 conv_taps, conv_left, int(kred), kred_shift, int(accumulate), ptr(colsum_a),
+                 ptr(DROPOUT_STEP) if drop_p > 0 else None)
     if PROFILE is None:
         check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
         return
@@ -183,6 +184,10 @@ def replay_gemm(rec) -> None:
     """Re-issue a recorded dl_gemm launch on the current stream (bench.py roofline pass)."""
     check(lib().dl_gemm(C.byref(rec["args"]), stream_ptr()), "dl_gemm")
 
+
+# device step counter (int64 scalar tensor) that advances every dropout seed per training step; set
+# by kernels.set_dropout_step (train.TrainStep points it at the optimiser's step counter)
+DROPOUT_STEP = None
 
 # bench.py sets this to a list to record every dl_gemm launch of one step
 PROFILE = None

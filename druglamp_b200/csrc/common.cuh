@@ -207,6 +207,13 @@ __device__ __forceinline__ uint32_t drop_hash(unsigned long long seed, unsigned 
 }
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
 __host__ __device__ __forceinline__ float drop_scale(uint32_t thr) { return 65536.f / (float)(65536u - thr); }
+// The effective seed of a launch: the host seed advanced by a device-resident step counter (or
+// unchanged when there is none), so a CUDA-graph replay draws a fresh mask every step while the
+// forward and the backward of one step -- which read the counter before the optimiser bumps it --
+// regenerate the same one.
+__device__ __forceinline__ unsigned long long drop_seed_at(unsigned long long seed, const long long* ctr) {
+  return ctr ? seed + (unsigned long long)(*ctr) * 0x9E3779B97F4A7C15ull : seed;
+}
 __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr) {
   const uint32_t h = drop_hash(seed, idx >> 1);
   return ((idx & 1ull) ? (h >> 16) : (h & 0xffffu)) >= thr;

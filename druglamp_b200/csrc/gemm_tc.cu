@@ -62,6 +62,7 @@ struct GemmParams {
   long long ldc, sc[3];
   long long ldr, sr[3];
   unsigned long long drop_seed;
+  const long long* drop_step;   // device step counter mixed into the seed (or NULL)
   float drop_p;
   int M, N, K;
   int nb0, nb1;                 // extents of the two fastest batch dims
@@ -225,6 +226,7 @@ struct EpiFlags {
   bool atomic, simple;
   float drop_inv;
   uint32_t drop_thr;
+  unsigned long long drop_seed;      // host seed advanced by the device step counter
 };
 
 template <typename TC>
@@ -247,6 +249,7 @@ __device__ __forceinline__ EpiFlags make_epi_flags(const GemmParams& p) {
   f.simple = !p.bias && !p.preact && !p.aux && !p.res && p.act == DL_ACT_NONE &&
              p.mul_mode == DL_MUL_NONE && p.drop_p == 0.f && !f.atomic && (p.dbg == 0 || p.dbg == 3);
   f.drop_thr = drop_threshold(p.drop_p);
+  f.drop_seed = drop_seed_at(p.drop_seed, p.drop_p > 0.f ? p.drop_step : nullptr);
   f.drop_inv = p.drop_p > 0.f ? drop_scale(f.drop_thr) : 1.f;
   return f;
 }
@@ -298,13 +301,13 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
       if ((e & 1ull) == 0) {                     // aligned pairs: eight hashes for sixteen elements
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t h = drop_hash(p.drop_seed, (e >> 1) + k);
+          const uint32_t h = drop_hash(f.drop_seed, (e >> 1) + k);
           x[2 * k] *= (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
           x[2 * k + 1] *= (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] *= drop_keep(p.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
+        for (int j = 0; j < 16; ++j) x[j] *= drop_keep(f.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
       }
     }
     if (Res) {
@@ -864,7 +867,7 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
     p.a_on[i] = a->sa[i] != 0;
     p.b_on[i] = a->sb[i] != 0;
   }
-  p.drop_seed = a->drop_seed; p.drop_p = a->drop_p;
+  p.drop_seed = a->drop_seed; p.drop_p = a->drop_p; p.drop_step = (const long long*)a->drop_seed_step;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)k_total;
   p.nb0 = (int)a->batch[0]; p.nb1 = (int)a->batch[1];
   p.conv_cin = conv_cin; p.conv_left = a->conv_left;

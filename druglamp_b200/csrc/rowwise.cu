@@ -479,9 +479,10 @@ colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long ro
 
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p,
-                               unsigned long long seed) {
+                               unsigned long long seed, const long long* __restrict__ ctr) {
   pdl_trigger();
   pdl_wait();
+  seed = drop_seed_at(seed, ctr);
   const uint32_t thr = drop_threshold(p);
   const float inv = drop_scale(thr);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -542,9 +543,10 @@ l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre,
                                T* __restrict__ g, long long n, int act, float p,
-                               unsigned long long seed) {
+                               unsigned long long seed, const long long* __restrict__ ctr) {
   pdl_trigger();
   pdl_wait();
+  seed = drop_seed_at(seed, ctr);
   const uint32_t thr = drop_threshold(p);
   const float inv = p > 0.f ? drop_scale(thr) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -562,9 +564,11 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ p
 template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ g,
-                   long long nvec, int act, float p, unsigned long long seed) {
+                   long long nvec, int act, float p, unsigned long long seed,
+                   const long long* __restrict__ ctr) {
   pdl_trigger();
   pdl_wait();
+  seed = drop_seed_at(seed, ctr);
   constexpr int V = VecWidth<T>::N;
   const uint32_t thr = drop_threshold(p);
   const float inv = p > 0.f ? drop_scale(thr) : 1.f;
@@ -640,9 +644,10 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long l
 template <typename T>
 __global__ void add_pe_kernel(const T* __restrict__ x, const float* __restrict__ pe,
                               T* __restrict__ y, long long n, long long period, float p,
-                              unsigned long long seed) {
+                              unsigned long long seed, const long long* __restrict__ ctr) {
   pdl_trigger();
   pdl_wait();
+  seed = drop_seed_at(seed, ctr);
   const uint32_t thr = drop_threshold(p);
   const float inv = p > 0.f ? drop_scale(thr) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -818,16 +823,17 @@ extern "C" int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, 
   return 0;
 }
 
-extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int32_t dtype,
+extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed,
+                          const int64_t* seed_step, int32_t dtype,
                           void* stream) {
   DL_REQUIRE(x && y && p >= 0.f && p < 1.f, "dl_dropout: bad arguments");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    DL_LAUNCH((dropout_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
+    DL_LAUNCH((dropout_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed, (const long long*)seed_step);
   else
-    DL_LAUNCH((dropout_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, n, p, seed);
+    DL_LAUNCH((dropout_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, n, p, seed, (const long long*)seed_step);
   DL_LAUNCH_CHECK("dropout_kernel");
   count_launch();
   return 0;
@@ -878,7 +884,7 @@ extern "C" int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, v
 }
 
 extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
-                          uint64_t seed, int32_t dtype, void* stream) {
+                          uint64_t seed, const int64_t* seed_step, int32_t dtype, void* stream) {
   DL_REQUIRE(dy && g && (act == DL_ACT_NONE || pre) && p >= 0.f && p < 1.f, "dl_act_bwd: bad arguments");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -887,18 +893,18 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
     const long long nvec = n / vec;
     const int vgrid = ew_grid(nvec, 256);
     if (dtype == DL_BF16)
-      DL_LAUNCH((act_bwd_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, nvec, act, p, seed);
+      DL_LAUNCH((act_bwd_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, nvec, act, p, seed, (const long long*)seed_step);
     else
-      DL_LAUNCH((act_bwd_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, nvec, act, p, seed);
+      DL_LAUNCH((act_bwd_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, nvec, act, p, seed, (const long long*)seed_step);
     DL_LAUNCH_CHECK("act_bwd_vec_kernel");
     count_launch();
     return 0;
   }
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    DL_LAUNCH((act_bwd_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed);
+    DL_LAUNCH((act_bwd_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)g, n, act, p, seed, (const long long*)seed_step);
   else
-    DL_LAUNCH((act_bwd_kernel<float>), grid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, n, act, p, seed);
+    DL_LAUNCH((act_bwd_kernel<float>), grid, 256, 0, st, (const float*)dy, (const float*)pre, (float*)g, n, act, p, seed, (const long long*)seed_step);
   DL_LAUNCH_CHECK("act_bwd_kernel");
   count_launch();
   return 0;
@@ -942,15 +948,15 @@ extern "C" int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_o
 }
 
 extern "C" int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period,
-                         float p, uint64_t seed, int32_t dtype, void* stream) {
+                         float p, uint64_t seed, const int64_t* seed_step, int32_t dtype, void* stream) {
   DL_REQUIRE(x && pe && y && period > 0 && p >= 0.f && p < 1.f, "dl_add_pe: bad arguments");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
-    DL_LAUNCH((add_pe_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed);
+    DL_LAUNCH((add_pe_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed, (const long long*)seed_step);
   else
-    DL_LAUNCH((add_pe_kernel<float>), grid, 256, 0, st, (const float*)x, pe, (float*)y, n, period, p, seed);
+    DL_LAUNCH((add_pe_kernel<float>), grid, 256, 0, st, (const float*)x, pe, (float*)y, n, period, p, seed, (const long long*)seed_step);
   DL_LAUNCH_CHECK("add_pe_kernel");
   count_launch();
   return 0;

@@ -29,6 +29,15 @@ def compute_dtype() -> torch.dtype:
     return _compute_dtype
 
 
+def set_dropout_step(counter: Optional[torch.Tensor]) -> None:
+    """A device-resident int64 step counter (or None) that every dropout launch mixes into its seed
+    ON THE DEVICE: a captured CUDA graph then draws a fresh mask on every replay, while the forward
+    and backward of one step (the counter moves in the optimiser update) regenerate the same one."""
+    if counter is not None and (counter.dtype != torch.int64 or counter.numel() != 1 or not counter.is_cuda):
+        raise TypeError("the dropout step counter must be a CUDA int64 scalar tensor")
+    L.DROPOUT_STEP = counter
+
+
 def _ld(t: torch.Tensor) -> int:
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError(f"expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
@@ -95,7 +104,7 @@ def act_bwd(dy: torch.Tensor, pre: Optional[torch.Tensor], act: int, drop=(0.0, 
         return dy
     g = torch.empty_like(dy)
     L.call("dl_act_bwd", dy.data_ptr(), None if pre is None else pre.data_ptr(), g.data_ptr(),
-           dy.numel(), act, drop[0], drop[1], L.dt(dy))
+           dy.numel(), act, drop[0], drop[1], L.ptr(L.DROPOUT_STEP), L.dt(dy))
     return g
 
 
@@ -124,13 +133,14 @@ def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     if p == 0.0:
         return x
     y = torch.empty_like(x)
-    L.call("dl_dropout", x.data_ptr(), y.data_ptr(), x.numel(), p, seed, L.dt(x))
+    L.call("dl_dropout", x.data_ptr(), y.data_ptr(), x.numel(), p, seed, L.ptr(L.DROPOUT_STEP), L.dt(x))
     return y
 
 
 def add_pe(x: torch.Tensor, pe: torch.Tensor, p: float = 0.0, seed: int = 0) -> torch.Tensor:
     y = torch.empty_like(x)
-    L.call("dl_add_pe", x.data_ptr(), pe.data_ptr(), y.data_ptr(), x.numel(), pe.numel(), p, seed, L.dt(x))
+    L.call("dl_add_pe", x.data_ptr(), pe.data_ptr(), y.data_ptr(), x.numel(), pe.numel(), p, seed,
+           L.ptr(L.DROPOUT_STEP), L.dt(x))
     return y
 
 

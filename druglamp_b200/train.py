@@ -117,10 +117,18 @@ class TrainStep:
 
     # ---- pieces ---------------------------------------------------------------------------------
     def _fwd_bwd(self, sb: StaticBatch) -> None:
+        from . import kernels as K
         self.flat.zero_grad()
-        out = self.model(*sb.model_inputs())
-        _, loss = binary_cross_entropy(out[4], sb.y)
-        loss.backward()
+        # dropout seeds advance with the optimiser's device-side step counter, so a replayed graph
+        # draws fresh masks every step (forward and backward of one step read the same value: the
+        # counter moves in _update)
+        K.set_dropout_step(self.opt.step_count)
+        try:
+            out = self.model(*sb.model_inputs())
+            _, loss = binary_cross_entropy(out[4], sb.y)
+            loss.backward()
+        finally:
+            K.set_dropout_step(None)
         self.loss.copy_(loss.detach())
 
     def _reduce(self) -> None:

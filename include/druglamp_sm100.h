@@ -111,6 +111,10 @@ typedef struct dl_gemm_args {
                          computed from the A tiles while they sit in shared memory.  For a weight
                          gradient dW = dY^T X (A = dY) this is the bias gradient, so nn.Linear's
                          backward needs no separate pass over dY (fp32 [M], accumulated into). */
+  const int64_t* drop_seed_step; /* or NULL.  Device-resident step counter: the dropout seed of this launch
+                         is drop_seed + *drop_seed_step * 0x9E3779B97F4A7C15, read on the device, so a
+                         captured CUDA graph draws a fresh mask on every replay (the same pointer is given
+                         to the backward's dl_act_bwd / dl_gemm of that step). */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
@@ -150,8 +154,9 @@ int dl_colsum(const void* x, float* out, int64_t rows, int32_t cols, int64_t ld,
               int32_t dtype, void* stream);
 
 /* y = x * keep/(1-p), keep(i) = hash(seed, i) >= p (nn.Dropout of PMMA, model/PMMA/mlp.py:47,49,
- * model/PMMA/embed.py:42,52; the mask is recomputed from the seed in backward). */
-int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int32_t dtype,
+ * model/PMMA/embed.py:42,52; the mask is recomputed from the seed in backward).  seed_step (device
+ * pointer or NULL) advances the seed per training step: see dl_gemm_args.drop_seed_step. */
+int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const int64_t* seed_step, int32_t dtype,
                void* stream);
 /* y = act(x) elementwise (the ReLU inside Mean2Embed, model/cross_modality.py:166-171). */
 int dl_act_fwd(const void* x, void* y, int64_t n, int32_t act, int32_t dtype, void* stream);
@@ -162,7 +167,7 @@ int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, void* dx, in
                   int32_t cols, int32_t dtype, void* stream);
 /* g = dy * act'(pre) * dropout_mask(seed): backward of the dl_gemm epilogue's act + dropout. */
 int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
-               uint64_t seed, int32_t dtype, void* stream);
+               uint64_t seed, const int64_t* seed_step, int32_t dtype, void* stream);
 /* One AdamW step over a flat fp32 parameter buffer (torch.optim.AdamW semantics; the reference
  * builds AdamW in main.py:158-160).  grad is multiplied by grad_scale first (1/world_size after a
  * sum all-reduce); *step (device int64) is incremented; shadow_bf16 (optional) receives the
@@ -173,7 +178,7 @@ int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
 /* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
 int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
-              uint64_t seed, int32_t dtype, void* stream);
+              uint64_t seed, const int64_t* seed_step, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Molecular GCN (model/basic_model.py:545-638 GraphConv norm='both'; :411-436 GCNLayer).

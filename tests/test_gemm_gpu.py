@@ -131,7 +131,7 @@ def test_three_batch_dims_with_broadcast_and_dropout(dtype):
     _lib.gemm(x, w, y0, M=256, N=128, K=128, lda=128, ldb=128, ldc=128)
     _lib.gemm(x, w, y1, M=256, N=128, K=128, lda=128, ldb=128, ldc=128, drop_p=0.25, drop_seed=77)
     y2 = torch.empty_like(y0)
-    _lib.call("dl_dropout", y0.data_ptr(), y2.data_ptr(), y0.numel(), 0.25, 77, _lib.dt(y0))
+    _lib.call("dl_dropout", y0.data_ptr(), y2.data_ptr(), y0.numel(), 0.25, 77, None, _lib.dt(y0))
     torch.cuda.synchronize()
     assert torch.equal(y1, y2)
     frac = (y1 == 0).float().mean().item()

@@ -331,3 +331,32 @@ def test_packed_collate_expands_bit_exactly_like_the_reference_pads():
     torch.cuda.synchronize()
     assert torch.equal(sb.xp.cpu(), b.xp) and torch.equal(sb.xd.cpu(), b.xd) and torch.equal(sb.vp.cpu(), b.vp)
     assert n < dense_bytes / 2
+
+
+def test_dropout_step_counter_advances_masks_consistently():
+    """With a device step counter every dropout launch derives its seed on the device: the GEMM
+    epilogue, dl_dropout and the backward's dl_act_bwd agree at one counter value, and a new value
+    gives a different mask with nothing changed on the host (what a CUDA-graph replay sees)."""
+    from druglamp_b200 import _lib, kernels as K
+    torch.manual_seed(2)
+    x = torch.randn(256, 128, device="cuda").to(torch.bfloat16)
+    w = torch.eye(128, device="cuda").to(torch.bfloat16)
+    ctr = torch.zeros((), dtype=torch.int64, device="cuda")
+    K.set_dropout_step(ctr)
+    try:
+        masks = []
+        for step in (0, 1, 1, 2):
+            ctr.fill_(step)
+            y = torch.empty_like(x)
+            _lib.gemm(x, w, y, M=256, N=128, K=128, lda=128, ldb=128, ldc=128, drop_p=0.25, drop_seed=77)
+            d = K.dropout(x, 0.25, 77)
+            g = K.act_bwd(x, None, K.ACT_NONE, (0.25, 77))
+            assert torch.equal(y, d) and torch.equal(d, g)
+            masks.append(d != 0)
+        assert torch.equal(masks[1], masks[2])
+        assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[3])
+        keep = torch.stack(masks).float().mean().item()
+        assert abs(keep - 0.75) < 0.01
+    finally:
+        K.set_dropout_step(None)
+    assert torch.equal(K.dropout(x, 0.25, 77) != 0, K.dropout(x, 0.25, 77) != 0)
