@@ -584,16 +584,16 @@ embed_fill_bwd_kernel(const TokT* __restrict__ tok, const T* __restrict__ g, flo
   float* mine = acc + w * per_warp + lane * 4;
   const long long w0 = (long long)blockIdx.x * 8 + w, nw = (long long)gridDim.x * 8;
   long long r = w0;
-  for (; r + 3 * nw < rows; r += 4 * nw) {           // four rows of loads in flight
-    float4 gv[4];
-    int v[4];
+  for (; r + 7 * nw < rows; r += 8 * nw) {           // eight rows of loads in flight
+    float4 gv[8];
+    int v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       gv[u] = ld4<T>(g + (r + u * nw) * kEmbW + lane * 4);
       v[u] = tok_index(tok, r + u * nw);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       if (v[u] < 0 || v[u] >= vocab) continue;
       float4* a = reinterpret_cast<float4*>(mine + v[u] * kEmbW);
       float4 t = *a;

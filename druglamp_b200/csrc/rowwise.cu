@@ -658,6 +658,41 @@ __global__ void add_pe_kernel(const T* __restrict__ x, const float* __restrict__
   }
 }
 
+// 16-byte vector variant (n, period multiples of V; aligned pointers)
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_pe_vec_kernel(const T* __restrict__ x, const float* __restrict__ pe, T* __restrict__ y,
+                  long long nvec, long long period, float p, unsigned long long seed,
+                  const long long* __restrict__ ctr) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = VecWidth<T>::N;
+  seed = drop_seed_at(seed, ctr);
+  const uint32_t thr = drop_threshold(p);
+  const float inv = p > 0.f ? drop_scale(thr) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[V];
+    ldv(x + i * V, v);
+    const float* q = pe + (i * V) % period;
+#pragma unroll
+    for (int j = 0; j < V; j += 4) {
+      const float4 e = *reinterpret_cast<const float4*>(q + j);
+      v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
+    }
+    if (p > 0.f) {
+      const unsigned long long e2 = (unsigned long long)i * (V / 2);
+#pragma unroll
+      for (int k = 0; k < V / 2; ++k) {
+        const uint32_t h = drop_hash(seed, e2 + k);
+        v[2 * k] *= (h & 0xffffu) >= thr ? inv : 0.f;
+        v[2 * k + 1] *= (h >> 16) >= thr ? inv : 0.f;
+      }
+    }
+    stv(y + i * V, v);
+  }
+}
+
 int ew_grid(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)sm_count() * 16;
@@ -952,6 +987,18 @@ extern "C" int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int
   DL_REQUIRE(x && pe && y && period > 0 && p >= 0.f && p < 1.f, "dl_add_pe: bad arguments");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const int vec = dtype == DL_BF16 ? 8 : 4;
+  if (n % vec == 0 && period % vec == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)pe) & 15) == 0) {
+    const long long nvec = n / vec;
+    const int vgrid = ew_grid(nvec, 256);
+    if (dtype == DL_BF16)
+      DL_LAUNCH((add_pe_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, nvec, period, p, seed, (const long long*)seed_step);
+    else
+      DL_LAUNCH((add_pe_vec_kernel<float>), vgrid, 256, 0, st, (const float*)x, pe, (float*)y, nvec, period, p, seed, (const long long*)seed_step);
+    DL_LAUNCH_CHECK("add_pe_vec_kernel");
+    count_launch();
+    return 0;
+  }
   const int grid = ew_grid(n, 256);
   if (dtype == DL_BF16)
     DL_LAUNCH((add_pe_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)x, pe, (__nv_bfloat16*)y, n, period, p, seed, (const long long*)seed_step);
