@@ -11,7 +11,10 @@ pairs, gradients are all-reduced once per step over NCCL.
 
 One JSON line on rank 0:
   value     whole-job pairs/s with inputs resident in HBM (CUDA-graph replay, CUDA events, max over ranks)
-  e2e       same metric through the public API with HOST inputs: pinned H2D of every input + D2H of the loss
+  e2e       same metric through the public API with HOST inputs: pinned H2D of every input + D2H of the
+            loss every step; the LLM embeddings cross PCIe as the dataset yields them (packed rows,
+            druglamp_b200/collate.py) and are padded / tiled on the device like the reference collate
+  e2e_dense the same with the reference collate's dense fp32 tensors crossing PCIe (6.9 MB/pair)
   roofline  the dominant kernel (dl_gemm's tcgen05 kernel): algorithmic FLOPs / CUDA-event time of
             every launch in one instrumented step, against the measured bf16 peak
   cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores (N=1 only)
