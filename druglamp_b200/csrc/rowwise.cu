@@ -401,6 +401,114 @@ softmax_bwd_vec_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __r
   }
 }
 
+// Ragged variants: any cols <= NCH * 256 on rows padded to a multiple of 8 elements (a key length
+// such as 290 stored with a 296-element row stride).  Same lane -> 8-element-run mapping; runs that
+// lie fully inside the row use the 16-byte accesses, the one run that straddles `cols` is handled
+// element by element (so nothing outside [0, cols) is read as data or written), later runs are skipped.
+template <typename T>
+__device__ __forceinline__ void ld8_ragged(const T* row, int col0, int cols, float fill, float (&x)[8]) {
+  if (col0 + 8 <= cols) {
+    ld8<T>(row + col0, x);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = col0 + j < cols ? ldf<T>(row, col0 + j) : fill;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8_ragged(T* row, int col0, int cols, const float (&x)[8]) {
+  if (col0 + 8 <= cols) {
+    st8<T>(row + col0, x);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (col0 + j < cols) stf<T>(row, col0 + j, x[j]);
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_fwd_ragged_kernel(const T* __restrict__ s, T* __restrict__ p, long long rows, int cols,
+                          long long ld) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float v[NCH][8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      ld8_ragged<T>(s + r * ld, c * 256 + lane * 8, cols, -INFINITY, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, v[c][j]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[c][j] = __expf(v[c][j] - m); sum += v[c][j]; }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] *= inv;
+      st8_ragged<T>(p + r * ld, c * 256 + lane * 8, cols, v[c]);
+    }
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_bwd_ragged_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds,
+                          long long rows, int cols, long long ld, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float pv[NCH][8], dv[NCH][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      ld8_ragged<T>(p + r * ld, c * 256 + lane * 8, cols, 0.f, pv[c]);
+      ld8_ragged<T>(dp + r * ld, c * 256 + lane * 8, cols, 0.f, dv[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += pv[c][j] * dv[c][j];
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[c][j] = scale * pv[c][j] * (dv[c][j] - dot);
+      st8_ragged<T>(ds + r * ld, c * 256 + lane * 8, cols, dv[c]);
+    }
+  }
+}
+
+template <typename T>
+static void softmax_fwd_ragged(const void* s, void* p, long long rows, int cols, long long ld, int grid,
+                               int th, cudaStream_t st) {
+  switch ((cols + 255) / 256) {
+    case 1: DL_LAUNCH((softmax_fwd_ragged_kernel<T, 1>), grid, th, 0, st, (const T*)s, (T*)p, rows, cols, ld); break;
+    case 2: DL_LAUNCH((softmax_fwd_ragged_kernel<T, 2>), grid, th, 0, st, (const T*)s, (T*)p, rows, cols, ld); break;
+    case 3: DL_LAUNCH((softmax_fwd_ragged_kernel<T, 3>), grid, th, 0, st, (const T*)s, (T*)p, rows, cols, ld); break;
+    default: DL_LAUNCH((softmax_fwd_ragged_kernel<T, 4>), grid, th, 0, st, (const T*)s, (T*)p, rows, cols, ld); break;
+  }
+}
+template <typename T>
+static void softmax_bwd_ragged(const void* p, const void* dp, void* ds, long long rows, int cols,
+                               long long ld, float scale, int grid, int th, cudaStream_t st) {
+  switch ((cols + 255) / 256) {
+    case 1: DL_LAUNCH((softmax_bwd_ragged_kernel<T, 1>), grid, th, 0, st, (const T*)p, (const T*)dp, (T*)ds, rows, cols, ld, scale); break;
+    case 2: DL_LAUNCH((softmax_bwd_ragged_kernel<T, 2>), grid, th, 0, st, (const T*)p, (const T*)dp, (T*)ds, rows, cols, ld, scale); break;
+    case 3: DL_LAUNCH((softmax_bwd_ragged_kernel<T, 3>), grid, th, 0, st, (const T*)p, (const T*)dp, (T*)ds, rows, cols, ld, scale); break;
+    default: DL_LAUNCH((softmax_bwd_ragged_kernel<T, 4>), grid, th, 0, st, (const T*)p, (const T*)dp, (T*)ds, rows, cols, ld, scale); break;
+  }
+}
+
 // ------------------------------------------------------------------ column sums
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -785,6 +893,9 @@ extern "C" int dl_softmax_fwd(const void* s, void* p, int64_t rows, int32_t cols
       if (cols == 256) DL_LAUNCH((softmax_fwd_vec_kernel<float, 1>), grid, th, 0, st, (const float*)s, (float*)p, rows, ld);
       else DL_LAUNCH((softmax_fwd_vec_kernel<float, 2>), grid, th, 0, st, (const float*)s, (float*)p, rows, ld);
     }
+  } else if (al && cols >= 64 && cols <= 1024) {
+    if (dtype == DL_BF16) softmax_fwd_ragged<__nv_bfloat16>(s, p, rows, cols, ld, grid, th, st);
+    else softmax_fwd_ragged<float>(s, p, rows, cols, ld, grid, th, st);
   } else if (dtype == DL_BF16)
     DL_LAUNCH((softmax_fwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)s, (__nv_bfloat16*)p, rows, cols, ld);
   else
@@ -810,6 +921,9 @@ extern "C" int dl_softmax_bwd(const void* p, const void* dp, void* ds, int64_t r
       if (cols == 256) DL_LAUNCH((softmax_bwd_vec_kernel<float, 1>), grid, th, 0, st, (const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
       else DL_LAUNCH((softmax_bwd_vec_kernel<float, 2>), grid, th, 0, st, (const float*)p, (const float*)dp, (float*)ds, rows, ld, scale);
     }
+  } else if (al && cols >= 64 && cols <= 1024) {
+    if (dtype == DL_BF16) softmax_bwd_ragged<__nv_bfloat16>(p, dp, ds, rows, cols, ld, scale, grid, th, st);
+    else softmax_bwd_ragged<float>(p, dp, ds, rows, cols, ld, scale, grid, th, st);
   } else if (dtype == DL_BF16)
     DL_LAUNCH((softmax_bwd_kernel<__nv_bfloat16>), grid, th, 0, st, (const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, rows, cols, ld, scale);
   else

@@ -262,6 +262,16 @@ def layer_norm_res(x, gamma, beta, eps=1e-5):
 
 
 # ================================================================================ attention core
+def _score_buf(B, H, S2, Lq, Lk, like):
+    """(B,H,S2,Lq,Lk) score / probability map whose rows are padded to the 16-byte stride TMA
+    needs (a key length such as 290 is legal for GuidedCrossAttention); the pad columns are never
+    read: every consumer addresses the map with extent Lk."""
+    q = 16 // like.element_size()
+    Lkp = (Lk + q - 1) // q * q
+    full = torch.empty((B, H, S2, Lq, Lkp), dtype=like.dtype, device=like.device)
+    return full if Lkp == Lk else full[..., :Lk]
+
+
 def _attn_fwd(q, k, v, H, scale, keep_raw):
     """q (S2,B,Lq,HD), k, v (B,Lk,HD): unit inner stride, every other stride free (they may be
     column slices of one fused QKV projection buffer).
@@ -269,19 +279,20 @@ def _attn_fwd(q, k, v, H, scale, keep_raw):
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
-    S = torch.empty((B, H, S2, Lq, Lk), dtype=q.dtype, device=q.device)
-    s_lay = (S2 * Lq * Lk, Lq * Lk, H * S2 * Lq * Lk)
-    L.gemm(q, k, S, M=Lq, N=Lk, K=d, lda=q.stride(2), ldb=k.stride(1), ldc=Lk, batch=(H, S2, B),
+    S = _score_buf(B, H, S2, Lq, Lk, q)
+    ldp = S.stride(3)
+    s_lay = (S.stride(1), S.stride(2), S.stride(0))       # batch order (head, set, pair)
+    L.gemm(q, k, S, M=Lq, N=Lk, K=d, lda=q.stride(2), ldb=k.stride(1), ldc=ldp, batch=(H, S2, B),
            sa=(d, q.stride(0) if S2 > 1 else 0, q.stride(1)), sb=(d, 0, k.stride(0)), sc=s_lay,
            alpha=scale)
     raw = None
     if keep_raw:
         raw = S
-        P = K.softmax_fwd(S, out=torch.empty_like(S))
+        P = K.softmax_fwd(S, out=_score_buf(B, H, S2, Lq, Lk, q))
     else:
         P = K.softmax_fwd(S)
     O = torch.empty((B, Lq, S2 * HD), dtype=q.dtype, device=q.device)
-    L.gemm(P, v, O, M=Lq, N=d, K=Lk, lda=Lk, ldb=v.stride(1), ldc=S2 * HD, trans_b=True,
+    L.gemm(P, v, O, M=Lq, N=d, K=Lk, lda=ldp, ldb=v.stride(1), ldc=S2 * HD, trans_b=True,
            batch=(H, S2, B), sa=s_lay, sb=(d, 0, v.stride(0)), sc=(d, HD, Lq * S2 * HD))
     return O, P, raw
 
@@ -292,25 +303,26 @@ def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, d
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
-    s_lay = (S2 * Lq * Lk, Lq * Lk, H * S2 * Lq * Lk)
+    ldp = P.stride(3)
+    s_lay = (P.stride(1), P.stride(2), P.stride(0))
     dV = dv_out if dv_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
     dK = dk_out if dk_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
     dQ = dq_out if dq_out is not None else torch.empty_like(q)
     # dV = sum_set P_set^T dO_set: the query-set dimension is reduced inside one GEMM (kred = 2)
-    L.gemm(P, dO, dV, M=Lk, N=d, K=Lq, lda=Lk, ldb=S2 * HD, ldc=dV.stride(1), trans_a=True,
+    L.gemm(P, dO, dV, M=Lk, N=d, K=Lq, lda=ldp, ldb=S2 * HD, ldc=dV.stride(1), trans_a=True,
            trans_b=True, batch=(H, B, S2), sa=(s_lay[0], s_lay[2], s_lay[1]), sb=(d, Lq * S2 * HD, HD),
            sc=(d, dV.stride(0), 0), kred=2)
     # dP = dO V^T, then dS = scale * P * (dP - rowsum(P dP)) in place
-    dP = torch.empty_like(P)
-    L.gemm(dO, v, dP, M=Lq, N=Lk, K=d, lda=S2 * HD, ldb=v.stride(1), ldc=Lk, batch=(H, S2, B),
+    dP = _score_buf(B, H, S2, Lq, Lk, P)
+    L.gemm(dO, v, dP, M=Lq, N=Lk, K=d, lda=S2 * HD, ldb=v.stride(1), ldc=ldp, batch=(H, S2, B),
            sa=(d, HD, Lq * S2 * HD), sb=(d, 0, v.stride(0)), sc=s_lay)
     dS = K.softmax_bwd(P, dP, scale)
     # dQ = dS K
-    L.gemm(dS, k, dQ, M=Lq, N=d, K=Lk, lda=Lk, ldb=k.stride(1), ldc=dQ.stride(2), trans_b=True,
+    L.gemm(dS, k, dQ, M=Lq, N=d, K=Lk, lda=ldp, ldb=k.stride(1), ldc=dQ.stride(2), trans_b=True,
            batch=(H, S2, B), sa=s_lay, sb=(d, 0, k.stride(0)),
            sc=(d, dQ.stride(0) if S2 > 1 else 0, dQ.stride(1)), residual=dQ if dq_accumulate else None)
     # dK = sum_set dS_set^T Q_set, likewise
-    L.gemm(dS, q, dK, M=Lk, N=d, K=Lq, lda=Lk, ldb=q.stride(2), ldc=dK.stride(1), trans_a=True,
+    L.gemm(dS, q, dK, M=Lk, N=d, K=Lq, lda=ldp, ldb=q.stride(2), ldc=dK.stride(1), trans_a=True,
            trans_b=True, batch=(H, B, S2), sa=(s_lay[0], s_lay[2], s_lay[1]),
            sb=(d, q.stride(1), q.stride(0) if S2 > 1 else Lq * q.stride(2)),
            sc=(d, dK.stride(0), 0), kred=2)
@@ -563,7 +575,9 @@ class PGCAFn(Function):
         out = K.mm(O.view(-1, E), shadow(out_w), bias=out_b.detach()).view(Bn, Lq, E)
         ctx.save_for_backward(qb, kb, vb, in_w, out_w, Qp, KV, P, O, in_b, out_b)
         ctx.meta = (H, scale, shared, query.dtype, key.dtype, value.dtype)
-        raw = raw.view(Bn, H, Lq, Sk)
+        raw = raw[:, :, 0]                                             # (N, H, L, S)
+        if not raw.is_contiguous():
+            raw = raw.contiguous()                                     # padded rows (S % 8 != 0)
         ctx.mark_non_differentiable(raw)
         return out.transpose(0, 1), raw
 

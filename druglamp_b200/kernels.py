@@ -174,19 +174,36 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, need_param_grads: bool = True, acc_i
     return dx, dg, db
 
 
+def _row_ld(t: torch.Tensor) -> int:
+    """Row stride of a (..., rows, cols) tensor whose leading dims collapse onto evenly spaced rows."""
+    if t.dim() < 2:
+        return t.shape[-1]
+    ld = t.stride(-2)
+    assert t.stride(-1) == 1 and ld >= t.shape[-1]
+    run = ld
+    for size, stride in zip(reversed(t.shape[:-1]), reversed(t.stride()[:-1])):
+        assert size == 1 or stride == run, "softmax rows must be evenly spaced"
+        run *= size
+    return ld
+
+
 def softmax_fwd(s: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """softmax over the last dim of a contiguous tensor (in place when out is None)."""
+    """softmax over the last dim (in place when out is None).  The rows may be padded: the row
+    stride is ``s.stride(-2)`` and ``out`` must share the layout."""
     cols = s.shape[-1]
     out = s if out is None else out
-    L.call("dl_softmax_fwd", s.data_ptr(), out.data_ptr(), s.numel() // cols, cols, cols, L.dt(s))
+    ld = _row_ld(s)
+    assert out.stride() == s.stride()
+    L.call("dl_softmax_fwd", s.data_ptr(), out.data_ptr(), s.numel() // cols, cols, ld, L.dt(s))
     return out
 
 
 def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     """in place on dp: dp <- scale * p * (dp - sum(p * dp))."""
     cols = p.shape[-1]
-    L.call("dl_softmax_bwd", p.data_ptr(), dp.data_ptr(), dp.data_ptr(), p.numel() // cols, cols, cols,
-           scale, L.dt(p))
+    assert dp.stride() == p.stride()
+    L.call("dl_softmax_bwd", p.data_ptr(), dp.data_ptr(), dp.data_ptr(), p.numel() // cols, cols,
+           _row_ld(p), scale, L.dt(p))
     return dp
 
 

@@ -59,6 +59,32 @@ def test_softmax_fwd_bwd(dtype, tol, cols):
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("cols", [70, 290, 513, 1000])
+def test_softmax_padded_rows_leave_the_padding_untouched(dtype, tol, cols):
+    """Rows padded to a 16-byte stride (the score maps of a key length such as 290): the ragged
+    vector kernels must give the same result and never write the pad columns."""
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(2)
+    ld = (cols + 7) // 8 * 8 + 8                                     # at least one full pad run
+    full = (torch.randn(5, 41, ld, device="cuda") * 3).to(dtype)
+    full[..., cols:] = 777.0
+    s = full[..., :cols]
+    dp_full = torch.randn(5, 41, ld, device="cuda").to(dtype)
+    dp_full[..., cols:] = 555.0
+    out_full = torch.full_like(full, 333.0)
+    p = K.softmax_fwd(s, out=out_full[..., :cols])
+    sr = s.double().requires_grad_(True)
+    pr = F.softmax(sr, dim=-1)
+    _close(p, pr, tol, "p")
+    assert (out_full[..., cols:] == 333.0).all() and (full[..., cols:] == 777.0).all()
+    dpv = dp_full[..., :cols]
+    (gr,) = torch.autograd.grad(pr, sr, dpv.double())
+    ds = K.softmax_bwd(p, dpv, 0.5)
+    _close(ds, 0.5 * gr, max(tol, 1e-4) * 2, "ds")
+    assert (dp_full[..., cols:] == 555.0).all() and (out_full[..., cols:] == 333.0).all()
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
 def test_colsum_actbwd_dropout_cast_addpe(dtype, tol):
     from druglamp_b200 import kernels as K
     torch.manual_seed(2)
