@@ -7,6 +7,7 @@ bf16 -> bf16 tensor cores); parameters stay fp32 masters with compute-dtype shad
 """
 from __future__ import annotations
 
+import contextlib
 import itertools
 from typing import Optional
 
@@ -24,6 +25,27 @@ _seed_counter = itertools.count(0x5EED)
 def next_seed() -> int:
     """A fresh dropout seed; masks are regenerated from it in backward."""
     return (next(_seed_counter) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
+_forward_only = False
+
+
+@contextlib.contextmanager
+def forward_only():
+    """Forward-only scoring (druglamp_b200/infer.py): inside, the Functions skip the stores that
+    only a backward pass reads (GELU / ReLU pre-activations).  A Function's forward cannot see the
+    caller's grad mode (it always runs with grad disabled and ``needs_input_grad`` ignores
+    ``torch.no_grad``), hence the explicit switch."""
+    global _forward_only
+    prev, _forward_only = _forward_only, True
+    try:
+        yield
+    finally:
+        _forward_only = prev
+
+
+def _needs_backward(ctx) -> bool:
+    return (not _forward_only) and any(ctx.needs_input_grad)
 
 
 def _back(g: Optional[torch.Tensor], like_dtype: torch.dtype, shape=None):
@@ -109,8 +131,7 @@ class LinearFn(Function):
             wc = torch.nn.functional.pad(wc, pad)
         bias = None if b is None else _pad_cols(b.detach(), Np)
         out = torch.empty((x2.shape[0], Np), dtype=x2.dtype, device=x2.device)
-        need_grad = any(ctx.needs_input_grad)
-        pre = torch.empty_like(out) if (act != K.ACT_NONE and need_grad) else None
+        pre = torch.empty_like(out) if (act != K.ACT_NONE and _needs_backward(ctx)) else None
         r2 = None
         if residual is not None:
             r2 = _pad_cols(K.to_compute(residual).view(-1, residual.shape[-1]), Np)
@@ -170,8 +191,9 @@ class FFNFn(Function):
         x2 = K.to_compute(x).view(-1, xs[-1])
         w1c, w2c = shadow(w1), shadow(w2)
         M, Dh = x2.shape[0], w1.shape[0]
-        pre1 = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
-        hd = torch.empty_like(pre1)
+        hd = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
+        # forward-only scoring (no_grad): the pre-activation is never read, skip its store
+        pre1 = torch.empty_like(hd) if _needs_backward(ctx) else None
         K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1))
         r2 = K.to_compute(residual).view(-1, w2.shape[0]) if residual is not None else None
         y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
@@ -636,8 +658,8 @@ class MHLAFn(Function):
         Bn, Lr, E = vc.shape
         v2 = vc.view(-1, E)
         D, Hh = w1.shape[0], w2.shape[0]
-        pre1 = torch.empty((v2.shape[0], D), dtype=vc.dtype, device=vc.device)
-        h = torch.empty_like(pre1)
+        h = torch.empty((v2.shape[0], D), dtype=vc.dtype, device=vc.device)
+        pre1 = torch.empty_like(h) if _needs_backward(ctx) else None
         K.mm(v2, shadow(w1), h, bias=b1, act=K.ACT_GELU, pre=pre1)
         logits = K.mm(h, shadow(w2), bias=b2).view(Bn, Lr, Hh)
         g_ = None if gamma is None else gamma.detach()

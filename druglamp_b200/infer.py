@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
+from .functions import forward_only
 from .modules import binary_cross_entropy
 from .train import StaticBatch
 
@@ -27,7 +28,7 @@ class InferStep:
     def eager(self, sb: StaticBatch):
         """(probabilities (B,), loss) of one batch; tensors are overwritten by the next call on the
         same batch when it is replayed from a graph."""
-        with torch.no_grad():
+        with torch.no_grad(), forward_only():
             out = self.model(*sb.model_inputs(), mode="eval")
             n, loss = binary_cross_entropy(out[2], sb.y)
         return n, loss
