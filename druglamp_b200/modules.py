@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import copy
 import math
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn
@@ -20,7 +20,6 @@ import torch.nn.functional as F
 from . import functions as Fn
 from . import kernels as K
 from .graph import BatchedMolGraph
-from .params import shadow
 
 
 # ================================================================================ PGCA (H6)

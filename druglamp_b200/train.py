@@ -12,7 +12,7 @@ equivalent of the classification step only and is what ``bench.py`` times.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 

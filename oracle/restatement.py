@@ -18,7 +18,7 @@ reference arm may import this module.  The product never does.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import numpy as np
 import torch

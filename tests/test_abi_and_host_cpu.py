@@ -3,7 +3,6 @@ declares; argument errors are reported through the error channel without touchin
 host-side mirror keeps the reference's state_dict contract, config keys, margin schedule, label
 matrix construction and MLM mask sampler."""
 import ctypes
-import json
 import os
 import re
 
@@ -189,3 +188,31 @@ def test_pack_rows_host_layout_and_errors():
     b = make_batch(3, seed=5)
     d, p = b.llm_blocks()
     assert torch.equal(R.tail_pad(d, 512), b.xd) and torch.equal(R.repeat_pad(p, 2304), b.xp)
+
+
+def test_score_map_row_padding_and_softmax_row_stride_host_logic():
+    """functions._score_buf pads the rows of the attention score maps to the 16-byte stride TMA needs
+    (key length 290 -> 296 bf16 / 292 fp32 elements) without changing the logical shape, and
+    kernels._row_ld accepts exactly the layouts whose rows are evenly spaced."""
+    import pytest
+    import torch
+    from druglamp_b200 import functions as Fn
+    from druglamp_b200 import kernels as K
+    for dtype, ld in ((torch.bfloat16, 296), (torch.float32, 292)):
+        s = Fn._score_buf(3, 1, 1, 7, 290, torch.empty(1, dtype=dtype))
+        assert s.shape == (3, 1, 1, 7, 290) and s.stride() == (7 * ld, 7 * ld, 7 * ld, ld, 1)
+        assert K._row_ld(s) == ld and not s.is_contiguous()
+    s = Fn._score_buf(2, 4, 2, 5, 512, torch.empty(1, dtype=torch.bfloat16))
+    assert s.is_contiguous() and K._row_ld(s) == 512
+    assert K._row_ld(torch.empty(9)) == 9
+    with pytest.raises(AssertionError):
+        K._row_ld(torch.empty(4, 6, 16)[:, :3])            # rows not evenly spaced across dim 0
+    with pytest.raises(AssertionError):
+        K._row_ld(torch.empty(4, 16).t())                  # inner stride != 1
+    # the forward-only switch nests and restores
+    assert not Fn._forward_only
+    with Fn.forward_only():
+        with Fn.forward_only():
+            assert Fn._forward_only
+        assert Fn._forward_only
+    assert not Fn._forward_only
