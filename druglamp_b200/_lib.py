@@ -45,10 +45,28 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("lse", C.c_void_p),
+        ("raw", C.c_void_p), ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dvec", C.c_void_p), ("dq_scratch", C.c_void_p),
+        ("B", C.c_int64), ("H", C.c_int64), ("S2", C.c_int64), ("Lq", C.c_int64), ("Lk", C.c_int64),
+        ("d", C.c_int64),
+        ("q_ld", C.c_int64), ("q_sb", C.c_int64), ("q_ss", C.c_int64),
+        ("k_ld", C.c_int64), ("k_sb", C.c_int64), ("v_ld", C.c_int64), ("v_sb", C.c_int64),
+        ("o_ld", C.c_int64), ("o_sb", C.c_int64), ("o_ss", C.c_int64),
+        ("dq_ld", C.c_int64), ("dq_sb", C.c_int64), ("dq_ss", C.c_int64),
+        ("dk_ld", C.c_int64), ("dk_sb", C.c_int64), ("dv_ld", C.c_int64), ("dv_sb", C.c_int64),
+        ("raw_ld", C.c_int64), ("scale", C.c_float), ("dq_accumulate", C.c_int32),
+    ]
+
+
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
 # name -> argtypes; must list every compute entry point declared in include/druglamp_sm100.h
 SIGNATURES = {
     "dl_gemm": [C.POINTER(GemmArgs), _P],
+    "dl_attn_fwd": [C.POINTER(AttnArgs), _P],
+    "dl_attn_bwd": [C.POINTER(AttnArgs), _P],
     "dl_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
     "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],

@@ -297,10 +297,17 @@ def _score_buf(B, H, S2, Lq, Lk, like):
 def _attn_fwd(q, k, v, H, scale, keep_raw):
     """q (S2,B,Lq,HD), k, v (B,Lk,HD): unit inner stride, every other stride free (they may be
     column slices of one fused QKV projection buffer).
-    Returns O (B,Lq,S2*HD), P (B,H,S2,Lq,Lk) and raw scaled logits (or None)."""
+    Returns O (B,Lq,S2*HD), the tensor the backward needs besides O (the fused kernel's row
+    log-sum-exp (S2,B,H,Lq) fp32, or the probability map P (B,H,S2,Lq,Lk) of the unfused path) and
+    the raw scaled logits (B,H,S2,Lq,Lk) (or None)."""
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
+    if K.attn_supported(q, k, H) and (S2 == 1 or not keep_raw):
+        # ONE tcgen05 kernel: scores, softmax and p.v never leave the SM; only the row
+        # log-sum-exp is kept for the backward (which recomputes the probabilities)
+        O, lse, raw = K.attn_fwd(q, k, v, H, scale, want_raw=keep_raw)
+        return O, lse, (None if raw is None else raw.unsqueeze(2))
     S = _score_buf(B, H, S2, Lq, Lk, q)
     ldp = S.stride(3)
     s_lay = (S.stride(1), S.stride(2), S.stride(0))       # batch order (head, set, pair)
@@ -319,12 +326,19 @@ def _attn_fwd(q, k, v, H, scale, keep_raw):
     return O, P, raw
 
 
-def _attn_bwd(dO, q, k, v, P, H, scale, dq_out=None, dk_out=None, dv_out=None, dq_accumulate=False):
-    """Gradients of _attn_fwd.  d*_out may be preallocated (strided) destinations; with
-    dq_accumulate the query gradient is added to dq_out (two attentions sharing one query set)."""
+def _attn_bwd(dO, q, k, v, P, O, H, scale, dq_out=None, dk_out=None, dv_out=None, dq_accumulate=False):
+    """Gradients of _attn_fwd (P = its second result, O its first).  d*_out may be preallocated
+    (strided) destinations; with dq_accumulate the query gradient is added to dq_out (two
+    attentions sharing one query set)."""
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
     d = HD // H
+    if P.dtype == torch.float32 and P.dim() == 4 and q.dtype == torch.bfloat16:     # fused: P is the lse
+        dV = dv_out if dv_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+        dK = dk_out if dk_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+        dQ = dq_out if dq_out is not None else torch.empty((S2, B, Lq, HD), dtype=q.dtype, device=q.device)
+        K.attn_bwd(dO, q, k, v, O, P, H, scale, dQ, dK, dV, dq_accumulate=dq_accumulate)
+        return dQ, dK, dV
     ldp = P.stride(3)
     s_lay = (P.stride(1), P.stride(2), P.stride(0))
     dV = dv_out if dv_out is not None else torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
@@ -463,18 +477,18 @@ class SelfAttnCoreFn(Function):
         c = K.to_compute(qkv)
         E = c.shape[-1] // 3
         O, P, _ = _attn_fwd(c[None, :, :, :E], c[:, :, E:2 * E], c[:, :, 2 * E:], H, scale, False)
-        ctx.save_for_backward(c, P)
+        ctx.save_for_backward(c, P, O)
         ctx.meta = (H, scale, qkv.dtype)
         return O
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gO):
-        c, P = ctx.saved_tensors
+        c, P, O = ctx.saved_tensors
         H, scale, dt = ctx.meta
         E = c.shape[-1] // 3
         d = torch.empty_like(c)
-        _attn_bwd(K.to_compute(gO), c[None, :, :, :E], c[:, :, E:2 * E], c[:, :, 2 * E:], P, H, scale,
+        _attn_bwd(K.to_compute(gO), c[None, :, :, :E], c[:, :, E:2 * E], c[:, :, 2 * E:], P, O, H, scale,
                   dq_out=d[None, :, :, :E], dk_out=d[:, :, E:2 * E], dv_out=d[:, :, 2 * E:])
         return _back(d, dt), None, None
 
@@ -493,22 +507,22 @@ class PairedAttnCoreFn(Function):
         Q = c[:, :, :, :E]
         op, Pp, _ = _attn_fwd(Q, c[0, :, :, E:2 * E], c[0, :, :, 2 * E:], H, scale, False)
         om, Pm, _ = _attn_fwd(Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], H, scale, False)
-        ctx.save_for_backward(c, Pp, Pm)
+        ctx.save_for_backward(c, Pp, Pm, op, om)
         ctx.meta = (H, scale, qkv.dtype)
         return op, om
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gop, gom):
-        c, Pp, Pm = ctx.saved_tensors
+        c, Pp, Pm, op, om = ctx.saved_tensors
         H, scale, dt = ctx.meta
         E = c.shape[-1] // 3
         Q = c[:, :, :, :E]
         d = torch.empty_like(c)
         dQ = d[:, :, :, :E]
-        _attn_bwd(K.to_compute(gop), Q, c[0, :, :, E:2 * E], c[0, :, :, 2 * E:], Pp, H, scale,
+        _attn_bwd(K.to_compute(gop), Q, c[0, :, :, E:2 * E], c[0, :, :, 2 * E:], Pp, op, H, scale,
                   dq_out=dQ, dk_out=d[0, :, :, E:2 * E], dv_out=d[0, :, :, 2 * E:])
-        _attn_bwd(K.to_compute(gom), Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], Pm, H, scale,
+        _attn_bwd(K.to_compute(gom), Q, c[1, :, :, E:2 * E], c[1, :, :, 2 * E:], Pm, om, H, scale,
                   dq_out=dQ, dk_out=d[1, :, :, E:2 * E], dv_out=d[1, :, :, 2 * E:], dq_accumulate=True)
         return _back(d, dt), None, None
 
@@ -614,7 +628,7 @@ class PGCAFn(Function):
         d_out_w, d_out_b = _wbgrad(out_w, out_b, g, O.view(-1, E))
         dO = K.mm(g, shadow(out_w), tb=True).view(Bn, Lq, E)
         dKV = torch.empty_like(KV)
-        dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, H, scale,
+        dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, O, H, scale,
                               dk_out=dKV[:, :, :E], dv_out=dKV[:, :, E:])
         wi = shadow(in_w)
         dq2, dkv2 = dQp.view(-1, E), dKV.view(-1, 2 * E)

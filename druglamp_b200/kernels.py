@@ -207,6 +207,69 @@ def softmax_bwd(p: torch.Tensor, dp: torch.Tensor, scale: float = 1.0) -> torch.
     return dp
 
 
+# ----------------------------------------------------------------------------- fused attention
+ATTN_MAX_KEYS = 512
+
+
+def attn_supported(q: torch.Tensor, k: torch.Tensor, H: int) -> bool:
+    """dl_attn_* serves bf16, head dim 64 / 128 and up to 512 keys (what DrugLAMP uses); other
+    shapes run the same math as separate dl_gemm / dl_softmax launches."""
+    d = q.shape[-1] // H
+    return q.dtype == torch.bfloat16 and d in (64, 128) and k.shape[1] <= ATTN_MAX_KEYS
+
+
+def _attn_args(q, k, v, o, lse, H, scale):
+    S2, B, Lq, HD = q.shape
+    a = L.AttnArgs()
+    a.q, a.k, a.v, a.o, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
+    a.B, a.H, a.S2, a.Lq, a.Lk, a.d = B, H, S2, Lq, k.shape[1], HD // H
+    a.q_ld, a.q_sb, a.q_ss = q.stride(2), q.stride(1), q.stride(0) if S2 > 1 else 0
+    a.k_ld, a.k_sb, a.v_ld, a.v_sb = k.stride(1), k.stride(0), v.stride(1), v.stride(0)
+    a.o_ld, a.o_sb, a.o_ss = o.stride(1), o.stride(0), HD
+    a.scale = scale
+    for t in (q, k, v, o):
+        if t.stride(-1) != 1 or t.dtype != torch.bfloat16:
+            raise ValueError("dl_attn needs bf16 operands with unit inner stride")
+    return a
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, H: int, scale: float, want_raw: bool = False):
+    """q (S2, B, Lq, H*d), k / v (B, Lk, H*d) bf16 views (unit inner stride, the rest free).
+    -> O (B, Lq, S2*H*d), lse (S2, B, H, Lq) fp32 [log2 domain], raw (B, H, Lq, Lk) | None."""
+    S2, B, Lq, HD = q.shape
+    Lk = k.shape[1]
+    o = torch.empty((B, Lq, S2 * HD), dtype=q.dtype, device=q.device)
+    lse = torch.empty((S2, B, H, Lq), dtype=torch.float32, device=q.device)
+    a = _attn_args(q, k, v, o, lse, H, scale)
+    raw = None
+    if want_raw:
+        raw = torch.empty((B, H, Lq, Lk), dtype=q.dtype, device=q.device)
+        a.raw, a.raw_ld = raw.data_ptr(), Lk
+    L.check(L.lib().dl_attn_fwd(L.C.byref(a), L.stream_ptr()), "dl_attn_fwd")
+    return o, lse, raw
+
+
+def attn_bwd(d_o: torch.Tensor, q, k, v, o, lse, H: int, scale: float, dq: torch.Tensor, dk: torch.Tensor,
+             dv: torch.Tensor, dq_accumulate: bool = False) -> None:
+    """Gradients of attn_fwd into the (strided) destinations dq (like q), dk, dv (like k, v)."""
+    S2, B, Lq, HD = q.shape
+    d = HD // H
+    if d_o.stride() != o.stride() or d_o.dtype != o.dtype:
+        raise ValueError("dl_attn_bwd: d_o must share o's layout")
+    a = _attn_args(q, k, v, o, lse, H, scale)
+    a.d_o = d_o.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.dq_ld, a.dq_sb, a.dq_ss = dq.stride(2), dq.stride(1), dq.stride(0) if S2 > 1 else 0
+    a.dk_ld, a.dk_sb, a.dv_ld, a.dv_sb = dk.stride(1), dk.stride(0), dv.stride(1), dv.stride(0)
+    dvec = torch.empty((S2, B, H, Lq), dtype=torch.float32, device=q.device)
+    a.dvec = dvec.data_ptr()
+    if k.shape[1] > 128:
+        scratch = torch.empty((S2, B, H, Lq, d), dtype=torch.float32, device=q.device)
+        a.dq_scratch = scratch.data_ptr()
+    a.dq_accumulate = int(dq_accumulate)
+    L.check(L.lib().dl_attn_bwd(L.C.byref(a), L.stream_ptr()), "dl_attn_bwd")
+
+
 # ----------------------------------------------------------------------------- GCN
 def spmm_norm(indptr, indices, norm_src, norm_dst, h: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(h)

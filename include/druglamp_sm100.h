@@ -120,6 +120,51 @@ typedef struct dl_gemm_args {
 int dl_gemm(const dl_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused scaled-dot-product attention (bf16; tcgen05 score / p.v tiles with the softmax between
+ * them done out of tensor memory; no score or probability map in HBM).  One call serves
+ *   - GuidedCrossAttention's core (model/PGCA/guided_cross_attention_model.py:290,307-311):
+ *     H = 1, d = 128, raw != NULL returns the scaled pre-softmax logits (:307,:319-320);
+ *   - the paired attention of PMMA (model/PMMA/attention.py:44-88): S2 = 2 stacked query sets
+ *     (own + other stream) against ONE key/value set, output columns [set*o_ss + h*d, +d) =
+ *     cat(attn, attn_p) as :81 builds it;
+ *   - plain multi-head self attention (model/PMMA/attention.py:109-122).
+ * Layouts (elements, bf16, unit column stride; every stride a multiple of 8 elements):
+ *   q[set, b, row, h*d + c] at q + set*q_ss + b*q_sb + row*q_ld;   k / v [b, key, h*d + c] likewise;
+ *   o, d_o [b, row, set*o_ss + h*d + c];   dq / dk / dv mirror q / k / v with their own strides.
+ *   lse: fp32 [S2, B, H, Lq], log2-domain row log-sum-exp of the scaled logits (saved by forward,
+ *   read by backward).  raw: bf16 (B, H, Lq, raw_ld).
+ * Limits: d in {64, 128}, Lk <= 512 (one query tile's whole score row lives in tensor memory).
+ * Backward workspaces: dvec fp32 [S2, B, H, Lq]; dq_scratch fp32 [S2, B, H, Lq, d] (only touched
+ * when Lk > 128).  dq_accumulate != 0 adds to the existing dq (the second K/V set of the paired
+ * block shares its query gradient with the first).
+ */
+typedef struct dl_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;            /* forward: output; backward: the forward's output */
+  float* lse;         /* forward: output; backward: input */
+  void* raw;          /* forward only, or NULL */
+  const void* d_o;    /* backward */
+  void* dq;
+  void* dk;
+  void* dv;
+  float* dvec;        /* backward workspace */
+  float* dq_scratch;  /* backward workspace */
+  int64_t B, H, S2, Lq, Lk, d;
+  int64_t q_ld, q_sb, q_ss;
+  int64_t k_ld, k_sb, v_ld, v_sb;
+  int64_t o_ld, o_sb, o_ss;
+  int64_t dq_ld, dq_sb, dq_ss, dk_ld, dk_sb, dv_ld, dv_sb;
+  int64_t raw_ld;
+  float scale;
+  int32_t dq_accumulate;
+} dl_attn_args;
+
+int dl_attn_fwd(const dl_attn_args* args, void* stream);
+int dl_attn_bwd(const dl_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound; one warp per row, 128-bit vector loads, warp-shuffle reductions).
  * `dtype` is the activation dtype (x, y, dy, dx); statistics and parameters are fp32.
  */

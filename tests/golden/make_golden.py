@@ -55,7 +55,28 @@ def load_det(m):
     return shapes
 
 
-def run_model(kind, B, seed, training):
+# Parameters whose COMPLETE reference gradients the batch-64 fixture keeps (every module family of
+# the path: GCN, CNN, adaptors, PGCA, MHLA, PMMA paired + plain blocks, encoder norm, MLP head).
+FULL_GRADS = [
+    "drug_extractor.init_transform.weight", "drug_extractor.gnn.gnn_layers.0.graph_conv.weight",
+    "drug_extractor.gnn.gnn_layers.2.res_connection.weight", "drug_extractor.gnn.gnn_layers.1.bn_layer.weight",
+    "protein_extractor.conv2.bias", "protein_extractor.bn3.weight", "protein_extractor.embedding.weight",
+    "lin_d2.weight", "p_norm.weight", "lin_p2.bias",
+    "v_gca.in_proj_weight", "v_gca.out_proj.weight", "x_gca.in_proj_bias", "x_gca.out_proj.bias",
+    "v_mhla.lin2.weight", "x_mhla.lin1.bias", "v_gca_norm.weight",
+    "pmma.embeddings.pe_prot", "pmma.embeddings.mol_embeddings.bias",
+    "pmma.encoder.layer_with_mol.0.attn.query.weight", "pmma.encoder.layer_with_mol.0.attn.key_mol.bias",
+    "pmma.encoder.layer_with_mol.0.attn.fc_mol.bias", "pmma.encoder.layer_with_mol.1.attn.value.weight",
+    "pmma.encoder.layer_with_mol.1.ffn.fc2.bias", "pmma.encoder.layer_with_mol.1.ffn_norm_mol.weight",
+    "pmma.encoder.layer_with_mol.2.attn.query.bias", "pmma.encoder.layer_with_mol.2.attention_norm.weight",
+    "pmma.encoder.layer_with_mol.3.attn.out.bias", "pmma.encoder.layer_with_mol.3.ffn.fc1.bias",
+    "pmma.encoder.encoder_norm.weight", "mlp_classifier.fc3.bias", "mlp_classifier.fc4.weight",
+    "mlp_classifier.bn1.weight",
+]
+FULL_PAIRS = (0, 63)     # pairs whose complete vd / vp rows are kept
+
+
+def run_model(kind, B, seed, training, full=False):
     torch.manual_seed(0)
     m = build(kind)
     from model.basic_model import binary_cross_entropy
@@ -82,6 +103,14 @@ def run_model(kind, B, seed, training):
         if p.grad is not None:
             fx["grad/" + k] = digest(p.grad)
             gnames.append(k)
+    if full:
+        # complete tensors, not digests: the bench configuration's parity pin (bf16 included)
+        for k in FULL_GRADS:
+            fx["fullgrad/" + k] = dict(m.named_parameters())[k].grad.detach().float().numpy()
+        for i in FULL_PAIRS:
+            fx[f"full_vd/{i}"] = vd[i].detach().float().numpy()
+            fx[f"full_vp/{i}"] = vp[i].detach().float().numpy()
+            fx[f"full_A_v_gca/{i}"] = m.A_v_gca[i].detach().float().numpy().astype(np.float16)
     for k, v in m.state_dict().items():
         if "running_" in k:
             fx["buf/" + k] = digest(v)
@@ -163,6 +192,15 @@ def run_ssl(m, ssl):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    which = set(sys.argv[1:]) or {"b64", "small"}
+    if "b64" in which:
+        # the configuration bench.py times: full DrugLAMP, 64 pairs, train mode (dropout 0 for parity)
+        fx, *_ = run_model("DrugLAMP", 64, 21, True, full=True)
+        np.savez_compressed(os.path.join(HERE, "druglamp_train_b64_full.npz"), **fx)
+        print("druglamp train b64: loss", fx["loss"], "autocast dev", fx["bf16_autocast_score_dev"],
+              fx["bf16_autocast_loss_dev"])
+    if "small" not in which:
+        return
     fx, m, b, cp, ssl = run_model("DrugLAMP2C2P", 16, 7, True)
     fx.update(run_cm(m, b, cp))
     np.savez_compressed(os.path.join(HERE, "druglamp2c2p_train_b16.npz"), **fx)

@@ -119,6 +119,62 @@ def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
     assert not bad, "; ".join(bad)
 
 
+def _cos(a, b):
+    a = a.double().flatten().cpu()
+    b = b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("dtype,tol,gcos,gnorm", [(torch.float32, 1e-3, 0.99999, 1e-2),
+                                                   (torch.bfloat16, 2e-2, 0.999, 5e-2)])
+def test_bench_configuration_b64_train_matches_reference(dtype, tol, gcos, gnorm):
+    """The configuration bench.py times -- full DrugLAMP, 64 pairs, TRAIN mode (batch statistics in
+    every BatchNorm), flat parameter store -- against complete tensors of the unmodified reference
+    (tests/golden/druglamp_train_b64_full.npz, make_golden.py b64): all 64 logits, the loss, complete
+    vd / vp / raw PGCA maps of two pairs and 33 complete parameter gradients covering every module
+    family.  Bars: logits (relative to max |logit|) and loss within 1e-3 in fp32 and 2e-2 in bf16
+    (north_star); every gradient tensor's cosine to the reference >= 0.99999 / 0.999 and its norm
+    within 1 % / 5 %."""
+    fx = load_golden("druglamp_train_b64_full.npz")
+    m, b, o = run_product(fx, dtype, flat=True)
+    try:
+        rep, bad = [], []
+
+        def check(name, err, bar):
+            rep.append(f"{name}={err:.2e}")
+            if not err <= bar:
+                bad.append(f"{name}: {err:.3e} > {bar:g}")
+
+        sc = o["score"].detach().double().cpu().numpy()
+        check("score", np.abs(sc - fx["score"]).max() / np.abs(fx["score"]).max(), tol)
+        check("loss", abs(o["loss"].item() - float(fx["loss"])) / abs(float(fx["loss"])), tol)
+        assert np.array_equal(o["ssl"]["fill_bit_p"].cpu().numpy().astype(np.uint8), fx["fill_bit_p"])
+        for i in (0, 63):
+            for nm, t in (("vd", o["vd"]), ("vp", o["vp"]), ("A_v_gca", m.A_v_gca)):
+                g = torch.from_numpy(fx[f"full_{nm}/{i}"].astype(np.float32))
+                e = float((t[i].detach().float().cpu().reshape(g.shape) - g).abs().max() / g.abs().max())
+                check(f"{nm}[{i}]", e, 2.5 * tol if nm != "A_v_gca" else 4 * tol)
+        params = dict(m.named_parameters())
+        worst_c, worst_n = 1.0, 0.0
+        for k in fx:
+            if not k.startswith("fullgrad/"):
+                continue
+            g = torch.from_numpy(fx[k])
+            mine = params[k[9:]].grad
+            assert mine is not None, k
+            c = _cos(mine, g)
+            nr = abs(float(mine.double().norm().cpu() / g.double().norm()) - 1.0)
+            worst_c, worst_n = min(worst_c, c), max(worst_n, nr)
+            if c < gcos or nr > gnorm:
+                bad.append(f"{k[9:]}: cos {c:.6f} norm dev {nr:.3e}")
+        rep.append(f"grad cos min={worst_c:.6f} norm dev max={worst_n:.2e}")
+        print(" | ".join(rep))
+        assert not bad, "; ".join(bad)
+    finally:
+        import druglamp_b200 as D
+        D.set_compute_dtype(torch.float32)
+
+
 @pytest.mark.parametrize("case,dtype,tol", [("druglamp_eval_b2.npz", torch.float32, 1e-4),
                                             ("druglamp2c2p_train_b16.npz", torch.float32, 1e-4),
                                             ("druglamp_eval_b2.npz", torch.bfloat16, 3e-2)])
