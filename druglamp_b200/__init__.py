@@ -20,6 +20,7 @@ def patch_reference() -> None:
 
     from . import modules as M
     from . import ssl as S
+    M.RETURN_CALLER_DTYPE = True      # the reference's own fp32 layers sit between the replaced modules
     bm = importlib.import_module("model.basic_model")
     bm.MolecularGCN = M.MolecularGCN
     bm.GuidedCrossAttention = M.GuidedCrossAttention

@@ -211,8 +211,14 @@ __host__ __device__ __forceinline__ float drop_scale(uint32_t thr) { return 6553
 // unchanged when there is none), so a CUDA-graph replay draws a fresh mask every step while the
 // forward and the backward of one step -- which read the counter before the optimiser bumps it --
 // regenerate the same one.
+// The step is mixed in through splitmix64 (not added with the multiplier the host uses to space
+// consecutive launch seeds): launch i at step t must not reuse the mask of launch i+1 at step t-1.
 __device__ __forceinline__ unsigned long long drop_seed_at(unsigned long long seed, const long long* ctr) {
-  return ctr ? seed + (unsigned long long)(*ctr) * 0x9E3779B97F4A7C15ull : seed;
+  if (!ctr) return seed;
+  unsigned long long z = seed ^ ((unsigned long long)(*ctr) * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
 __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr) {
   const uint32_t h = drop_hash(seed, idx >> 1);

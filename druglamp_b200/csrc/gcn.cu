@@ -39,6 +39,113 @@ spmm_norm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices
   st4<T>(out + (size_t)row * 128 + lane * 4, acc);
 }
 
+// ---------------------------------------------------------------- CSR construction on the device
+// (src, dst) edge list -> CSR by destination and by source in STABLE edge order (bit-identical to a
+// host argsort(stable) + bincount), the two deg.clamp(1)^-1/2 vectors of GraphConv
+// (model/basic_model.py:596-603,623-630) and the validity flags.  Four small launches, no host sync:
+// count degrees (atomics) -> scan -> scatter edge ids (atomic cursors) -> per-row sort by edge id.
+__global__ void csr_count_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
+                                 long long n_edges, long long n_nodes, int* __restrict__ cnt_in,
+                                 int* __restrict__ cnt_out, int* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long s = src[e], d = dst[e];
+    if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) { atomicAdd(flags + 1, 1); continue; }
+    atomicAdd(cnt_in + d, 1);
+    atomicAdd(cnt_out + s, 1);
+  }
+}
+
+// one block: exclusive scan of both degree arrays, norms, zero-in-degree count; the degree arrays are
+// zeroed afterwards (they become the scatter cursors)
+__global__ void __launch_bounds__(1024)
+csr_scan_kernel(int* __restrict__ cnt_in, int* __restrict__ cnt_out, long long n_nodes,
+                int* __restrict__ indptr, int* __restrict__ indptr_t, float* __restrict__ norm_src,
+                float* __restrict__ norm_dst, int* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int part[2][1024];
+  const int t = threadIdx.x;
+  const long long chunk = (n_nodes + 1023) / 1024;
+  const long long i0 = t * chunk, i1 = i0 + chunk < n_nodes ? i0 + chunk : n_nodes;
+  int a = 0, b = 0, zero_in = 0;
+  for (long long i = i0; i < i1; ++i) {
+    a += cnt_in[i];
+    b += cnt_out[i];
+    zero_in += cnt_in[i] == 0;
+  }
+  part[0][t] = a;
+  part[1][t] = b;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {      // Hillis-Steele inclusive scan of the per-thread sums
+    const int va = t >= o ? part[0][t - o] : 0, vb = t >= o ? part[1][t - o] : 0;
+    __syncthreads();
+    part[0][t] += va;
+    part[1][t] += vb;
+    __syncthreads();
+  }
+  int pa = part[0][t] - a, pb = part[1][t] - b;
+  for (long long i = i0; i < i1; ++i) {
+    const int ci = cnt_in[i], co = cnt_out[i];
+    indptr[i] = pa;
+    indptr_t[i] = pb;
+    pa += ci;
+    pb += co;
+    norm_dst[i] = rsqrtf((float)(ci > 1 ? ci : 1));
+    norm_src[i] = rsqrtf((float)(co > 1 ? co : 1));
+    cnt_in[i] = 0;
+    cnt_out[i] = 0;
+  }
+  if (t == 1023) {
+    indptr[n_nodes] = part[0][1023];
+    indptr_t[n_nodes] = part[1][1023];
+  }
+  if (zero_in) atomicAdd(flags, zero_in);
+}
+
+__global__ void csr_scatter_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
+                                   long long n_edges, long long n_nodes, const int* __restrict__ indptr,
+                                   const int* __restrict__ indptr_t, int* __restrict__ cur_in,
+                                   int* __restrict__ cur_out, int* __restrict__ eid_in, int* __restrict__ eid_out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long s = src[e], d = dst[e];
+    if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) continue;
+    eid_in[indptr[d] + atomicAdd(cur_in + d, 1)] = (int)e;
+    eid_out[indptr_t[s] + atomicAdd(cur_out + s, 1)] = (int)e;
+  }
+}
+
+// one thread per node and direction: order the row's edge ids (rows are a handful of entries:
+// insertion sort), then replace them by the neighbour at the other end
+__global__ void csr_finish_kernel(const long long* __restrict__ src, const long long* __restrict__ dst,
+                                  long long n_nodes, const int* __restrict__ indptr,
+                                  const int* __restrict__ indptr_t, int* __restrict__ eid_in,
+                                  int* __restrict__ eid_out, int* __restrict__ indices, int* __restrict__ indices_t) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_nodes) return;
+  const bool t = i >= n_nodes;
+  const long long row = t ? i - n_nodes : i;
+  const int* ptr = t ? indptr_t : indptr;
+  int* eid = t ? eid_out : eid_in;
+  const long long* other = t ? dst : src;
+  int* out = t ? indices_t : indices;
+  const int e0 = ptr[row], e1 = ptr[row + 1];
+  for (int a = e0 + 1; a < e1; ++a) {
+    const int v = eid[a];
+    int b = a - 1;
+    while (b >= e0 && eid[b] > v) { eid[b + 1] = eid[b]; --b; }
+    eid[b + 1] = v;
+  }
+  for (int a = e0; a < e1; ++a) out[a] = (int)other[eid[a]];
+}
+
 // ---------------------------------------------------------------- BatchNorm statistics
 // sums[0:C] += sum_r a[r,c] ; sums[C:2C] += sum_r a[r,c]*b[r,c]
 //   forward : a = x, b = x            -> sum, sum of squares
@@ -456,6 +563,39 @@ extern "C" int dl_spmm_norm(const int32_t* indptr, const int32_t* indices, const
 
 // workspace: 2*cols doubles (zeroed here).  training != 0: batch statistics (+ running update when
 // running_mean != NULL); training == 0: statistics from the running buffers.
+extern "C" int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_nodes,
+                            int32_t* indptr, int32_t* indices, int32_t* indptr_t, int32_t* indices_t,
+                            float* norm_src, float* norm_dst, int32_t* flags, int32_t* workspace,
+                            void* stream) {
+  using namespace dl;
+  DL_REQUIRE(src && dst && indptr && indices && indptr_t && indices_t && norm_src && norm_dst && flags && workspace,
+             "dl_csr_build: null pointer");
+  DL_REQUIRE(n_nodes >= 1 && n_edges >= 0 && n_nodes < (1ll << 30) && n_edges < (1ll << 31), "dl_csr_build: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* cnt_in = workspace;
+  int* cnt_out = workspace + n_nodes;
+  int* eid_in = workspace + 2 * n_nodes;
+  int* eid_out = eid_in + n_edges;
+  DL_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(2 * n_nodes) * sizeof(int), st));
+  DL_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+  const int eg = n_edges > 0 ? (int)((n_edges + 255) / 256 < 1184 ? (n_edges + 255) / 256 : 1184) : 1;
+  DL_LAUNCH(csr_count_kernel, eg, 256, 0, st, (const long long*)src, (const long long*)dst, (long long)n_edges,
+            (long long)n_nodes, cnt_in, cnt_out, flags);
+  DL_LAUNCH_CHECK("csr_count_kernel");
+  DL_LAUNCH(csr_scan_kernel, 1, 1024, 0, st, cnt_in, cnt_out, (long long)n_nodes, indptr, indptr_t, norm_src,
+            norm_dst, flags);
+  DL_LAUNCH_CHECK("csr_scan_kernel");
+  DL_LAUNCH(csr_scatter_kernel, eg, 256, 0, st, (const long long*)src, (const long long*)dst, (long long)n_edges,
+            (long long)n_nodes, (const int*)indptr, (const int*)indptr_t, cnt_in, cnt_out, eid_in, eid_out);
+  DL_LAUNCH_CHECK("csr_scatter_kernel");
+  DL_LAUNCH(csr_finish_kernel, (int)((2 * n_nodes + 255) / 256), 256, 0, st, (const long long*)src,
+            (const long long*)dst, (long long)n_nodes, (const int*)indptr, (const int*)indptr_t, eid_in, eid_out,
+            indices, indices_t);
+  DL_LAUNCH_CHECK("csr_finish_kernel");
+  count_launch(4);
+  return 0;
+}
+
 extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
                                 float* mean, float* rstd, float* running_mean, float* running_var,
                                 int64_t* num_batches_tracked, double* workspace, int64_t rows,

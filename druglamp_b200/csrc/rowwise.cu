@@ -714,7 +714,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ shadow, long long n,
                              const long long* __restrict__ step, float lr, float b1, float b2,
-                             float eps, float wd, float grad_scale) {
+                             float eps, float wd, float grad_scale,
+                             const unsigned char* __restrict__ active) {
   pdl_trigger();
   pdl_wait();
   const float t = (float)(*step);
@@ -722,6 +723,9 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
+    // parameters that received no gradient this step are skipped entirely (no decay, moments
+    // untouched), like torch.optim.AdamW skips p.grad is None
+    if (active != nullptr && active[i >> 6] == 0) continue;
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.f - lr * wd);
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -1062,7 +1066,7 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
 extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                              void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1,
                              float beta2, float eps, float weight_decay, float grad_scale,
-                             void* stream) {
+                             const uint8_t* active_blocks, void* stream) {
   DL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "dl_adamw_step: null pointer");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1070,7 +1074,8 @@ extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, fl
   DL_LAUNCH_CHECK("adamw_tick_kernel");
   DL_LAUNCH(adamw_kernel, ew_grid(n, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq,
                                                 (__nv_bfloat16*)shadow_bf16, n, (const long long*)step,
-                                                lr, beta1, beta2, eps, weight_decay, grad_scale);
+                                                lr, beta1, beta2, eps, weight_decay, grad_scale,
+                                                (const unsigned char*)active_blocks);
   DL_LAUNCH_CHECK("adamw_kernel");
   count_launch(2);
   return 0;

@@ -17,14 +17,21 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 from . import kernels as K
-from .params import flat_grad_of, fused_group, shadow
+from .params import flat_grad_of, fused_group, mark_touched, shadow
 
 _seed_counter = itertools.count(0x5EED)
+_seed_stream = 0
+
+
+def set_seed_stream(rank: int) -> None:
+    """Give every data-parallel rank its own dropout stream (folded into each launch seed)."""
+    global _seed_stream
+    _seed_stream = (int(rank) * 0xA24BAED4963EE407) & 0xFFFFFFFFFFFFFFFF
 
 
 def next_seed() -> int:
     """A fresh dropout seed; masks are regenerated from it in backward."""
-    return (next(_seed_counter) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    return ((next(_seed_counter) * 0x9E3779B97F4A7C15) ^ _seed_stream) & 0xFFFFFFFFFFFFFFFF
 
 
 _forward_only = False
@@ -93,6 +100,20 @@ def _wbgrad(wp, bp, g, x):
         K.mm(g, x, tw, ta=True, tb=True, accumulate=True, colsum_a=tb)
         return None, None
     return _wgrad(wp, g, x), (None if bp is None else _bgrad(bp, g))
+
+
+class CastFn(Function):
+    """dtype conversion with the dl_cast kernel (the gradient is converted back)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.xdt = x.dtype
+        return K.cast(x, dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return _back(g.contiguous(), ctx.xdt), None
 
 
 # ================================================================================ Linear
@@ -388,6 +409,8 @@ def _qkv_bwd(g2, xc2, ws, bs, need_dx=True):
     fw, fb = fused_group(ws), fused_group(bs)
     dx = None
     if fw is not None and fb is not None:
+        for t in tuple(ws) + tuple(bs):
+            mark_touched(t)
         if need_dx:
             dx = K.mm(g2, fw[2], tb=True)
         if g2.dtype == torch.bfloat16:

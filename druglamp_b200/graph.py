@@ -87,6 +87,9 @@ class BatchedMolGraph:
         g = object.__new__(BatchedMolGraph)
         g._n, g.batch_size = self._n, self.batch_size
         g._zero_in = self._zero_in
+        if self._zero_in is None:
+            self.check_no_zero_in_degree_quiet()
+        g._zero_in = self._zero_in
         for k in ("src", "dst", "indptr", "indices", "indptr_t", "indices_t",
                   "in_deg", "out_deg", "norm_dst", "norm_src"):
             setattr(g, k, getattr(self, k).to(device, **kw))
@@ -103,8 +106,81 @@ class BatchedMolGraph:
         h = g.ndata["h"] if "h" in g.ndata else None
         return cls(src, dst, g.num_nodes(), g.batch_size, h)
 
+    # ---- device-side construction (no host sync: usable on an input pipeline's copy stream) --------
+    @classmethod
+    def from_edges_device(cls, src: torch.Tensor, dst: torch.Tensor, num_nodes: int, batch_size: int,
+                          h: Optional[torch.Tensor] = None) -> "BatchedMolGraph":
+        """Build the carrier from CUDA int64 edge lists with ``dl_csr_build`` (hand-written kernels:
+        degree count, scan, stable scatter) instead of torch argsort / bincount and their host
+        round-trips.  Produces exactly what ``__init__`` builds on the host."""
+        if not (src.is_cuda and dst.is_cuda and src.dtype == torch.int64 and dst.dtype == torch.int64):
+            raise TypeError("from_edges_device needs CUDA int64 src / dst")
+        g = object.__new__(cls)
+        g._n, g.batch_size = int(num_nodes), int(batch_size)
+        dev, E = src.device, int(src.numel())
+        g.src, g.dst = src.contiguous(), dst.contiguous()
+        g.ndata = {} if h is None else {"h": h}
+        i32 = dict(dtype=torch.int32, device=dev)
+        g.indptr, g.indptr_t = torch.empty(g._n + 1, **i32), torch.empty(g._n + 1, **i32)
+        g.indices, g.indices_t = torch.empty(E, **i32), torch.empty(E, **i32)
+        g.norm_src = torch.empty(g._n, dtype=torch.float32, device=dev)
+        g.norm_dst = torch.empty(g._n, dtype=torch.float32, device=dev)
+        g._flags = torch.empty(2, **i32)
+        g._ws = torch.empty(2 * g._n + 2 * E, **i32)
+        g._zero_in = None                      # unknown until someone asks (one host read, cached)
+        g.rebuild_()
+        return g
+
+    def rebuild_(self, src: Optional[torch.Tensor] = None, dst: Optional[torch.Tensor] = None) -> "BatchedMolGraph":
+        """Refill this carrier's (fixed-address) CSR buffers from new edge lists of the same length:
+        what a CUDA-graph-captured step needs when the next batch arrives as raw (src, dst)."""
+        from . import _lib as L
+        if src is not None:
+            if src.numel() != self.src.numel():
+                raise ValueError("rebuild_ needs edge lists of the captured length")
+            self.src.copy_(src, non_blocking=True)
+            self.dst.copy_(dst, non_blocking=True)
+        if not hasattr(self, "_ws"):
+            dev = self.src.device
+            self._flags = torch.empty(2, dtype=torch.int32, device=dev)
+            self._ws = torch.empty(2 * self._n + 2 * self.src.numel(), dtype=torch.int32, device=dev)
+        L.call("dl_csr_build", self.src.data_ptr(), self.dst.data_ptr(), self.src.numel(), self._n,
+               self.indptr.data_ptr(), self.indices.data_ptr(), self.indptr_t.data_ptr(),
+               self.indices_t.data_ptr(), self.norm_src.data_ptr(), self.norm_dst.data_ptr(),
+               self._flags.data_ptr(), self._ws.data_ptr())
+        self._zero_in = None
+        return self
+
+    @property
+    def in_deg(self):
+        d = self.__dict__.get("_in_deg")
+        return d if d is not None else (self.indptr[1:] - self.indptr[:-1]).long()
+
+    @in_deg.setter
+    def in_deg(self, v):
+        self.__dict__["_in_deg"] = v
+
+    @property
+    def out_deg(self):
+        d = self.__dict__.get("_out_deg")
+        return d if d is not None else (self.indptr_t[1:] - self.indptr_t[:-1]).long()
+
+    @out_deg.setter
+    def out_deg(self, v):
+        self.__dict__["_out_deg"] = v
+
+    def check_no_zero_in_degree_quiet(self) -> None:
+        if self._zero_in is None:
+            f = self._flags.tolist()
+            self._zero_in = bool(f[0])
+
     def check_no_zero_in_degree(self) -> None:
         """Mirror of the DGLError raised at ``basic_model.py:580-590``."""
+        if self._zero_in is None:              # device-built: read the kernel's flags once
+            f = self._flags.tolist()
+            if f[1]:
+                raise ValueError("edge endpoint out of range")
+            self._zero_in = bool(f[0])
         if self._zero_in:
             raise Exception("There are 0-in-degree nodes in the graph, output for those nodes "
                             "will be invalid. Adding self-loop on the input graph will resolve the issue.")

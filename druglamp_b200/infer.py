@@ -9,6 +9,8 @@ no Python between the ~120 launches.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -21,7 +23,7 @@ class InferStep:
     def __init__(self, model):
         self.model = model.eval()
         self.flat = model._flat or model.flatten_parameters()
-        self._graphs = {}
+        self._graphs = weakref.WeakKeyDictionary()      # StaticBatch -> graph: dies with the batch
         self._pool = None
         self.launches_per_step = 0
 
@@ -48,9 +50,9 @@ class InferStep:
         if self._pool is None:
             self._pool = g.pool()
         self.launches_per_step = L.launch_count() - n0
-        self._graphs[id(sb)] = (g, n, loss)
+        self._graphs[sb] = (g, n, loss)
 
     def replay(self, sb: StaticBatch):
-        g, n, loss = self._graphs[id(sb)]
+        g, n, loss = self._graphs[sb]
         g.replay()
         return n, loss

@@ -21,6 +21,20 @@ from . import functions as Fn
 from . import kernels as K
 from .graph import BatchedMolGraph
 
+# druglamp_b200.patch_reference() turns this on: the drop-in modules then return their results in
+# the CALLER's dtype.  Inside the reference's own model/DrugLAMP*.py the replaced modules alternate
+# with the reference's fp32 nn.Linear / nn.LayerNorm / MLP layers, which reject a bf16 input
+# ("mat1 and mat2 must have the same dtype"); druglamp_b200.models.* keeps everything in the compute
+# dtype and leaves it off.
+RETURN_CALLER_DTYPE = False
+
+
+def _ret(y, like):
+    if RETURN_CALLER_DTYPE and torch.is_tensor(y) and torch.is_tensor(like) and like.is_floating_point() \
+            and y.dtype != like.dtype:
+        return Fn.CastFn.apply(y, like.dtype)
+    return y
+
 
 # ================================================================================ PGCA (H6)
 class GuidedCrossAttention(nn.Module):
@@ -65,8 +79,9 @@ class GuidedCrossAttention(nn.Module):
             raise NotImplementedError("attention dropout is 0 on the DrugLAMP hot path")
         out, raw = Fn.PGCAFn.apply(query, key, value, self.in_proj_weight, self.in_proj_bias,
                                    self.out_proj.weight, self.out_proj.bias, self.num_heads)
+        out = _ret(out, query)
         if need_weights:
-            return out, raw
+            return out, _ret(raw, query)
         return out, None
 
 
@@ -90,8 +105,8 @@ class MultiHeadLinearAttention(nn.Module):
 
     def forward(self, v):
         self._check()
-        return Fn.MHLAFn.apply(v, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias,
-                               None, None, 0.0)
+        return _ret(Fn.MHLAFn.apply(v, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias,
+                                    None, None, 0.0), v)
 
     def forward_residual_norm(self, v, norm: nn.LayerNorm):
         """``norm(v + self(v))`` in one fused kernel pair (reference ``model/DrugLAMP.py:63-71``)."""
@@ -305,7 +320,8 @@ class PairedMultimodelAttention(nn.Module):
 
     def forward(self, prot, mol=None):
         embedding_output, mol = self.embeddings(prot, mol)
-        return self.encoder(embedding_output, mol)
+        encoded, w, gw = self.encoder(embedding_output, mol)
+        return _ret(encoded, prot), w, gw
 
 
 # ================================================================================ GCN (H3-H5)
@@ -426,9 +442,10 @@ class MolecularGCN(nn.Module):
     def forward(self, batch_graph):
         node_feats = batch_graph.ndata.pop('h')
         g = BatchedMolGraph.from_dgl(batch_graph)
+        h_in = node_feats
         node_feats = Fn.linear(node_feats, self.init_transform.weight)
         node_feats = self.gnn(g, node_feats)
-        return node_feats.view(batch_graph.batch_size, -1, self.output_feats)
+        return _ret(node_feats, h_in).view(batch_graph.batch_size, -1, self.output_feats)
 
 
 # ================================================================================ CrossModality (H12)

@@ -38,7 +38,20 @@ def flat_grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
         return None
     if p.data_ptr() != t.data_ptr() or p.shape != t.shape or p.grad is None or p.grad.dtype != torch.float32:
         return None
+    mark_touched(p)            # a kernel is about to accumulate this parameter's gradient in place
     return p.grad
+
+
+def mark_touched(p: torch.Tensor) -> None:
+    """Record that `p` receives a gradient in the current step (FlatAdamW updates only those)."""
+    r = _BY_PTR.get(p.data_ptr())           # by device address: robust to re-wrapped tensors
+    q = r() if r is not None else None
+    if q is None:
+        return
+    r = _FLAT.get(q)
+    fp = r() if r is not None else None
+    if fp is not None:
+        fp.touched.add(fp.index_of[id(q)])
 
 
 def shadow(p: torch.Tensor) -> torch.Tensor:
@@ -98,14 +111,24 @@ class FlatParams:
         self.shadow16: Optional[torch.Tensor] = None
         self._synced = -1
         self._views16: Dict[int, torch.Tensor] = {}
+        # Which parameters received a gradient since the last zero_grad(): torch's optimizers skip
+        # parameters whose .grad is None, but here .grad always exists (a view of the flat buffer), so
+        # the producers say so -- kernels that accumulate in place go through flat_grad_of(), and
+        # gradients that arrive through autograd's AccumulateGrad fire the hook below.
+        self.touched = set()
+        self.index_of = {id(p): i for i, p in enumerate(params)}
+        self._hooks = []
         with torch.no_grad():
-            for p, o in zip(params, self.offsets):
+            for i, (p, o) in enumerate(zip(params, self.offsets)):
                 view = self.flat[o:o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
                 _FLAT[p] = weakref.ref(self)
                 _BY_PTR[p.data_ptr()] = weakref.ref(p)
+                if p.requires_grad:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(
+                        lambda _p, i=i, t=self.touched: t.add(i)))
         # fusable groups: members adjacent without padding gaps, same trailing shape
         off_of = {id(p): o for p, o in zip(params, self.offsets)}
         self.groups: Dict[tuple, tuple] = {}
@@ -121,9 +144,19 @@ class FlatParams:
 
     def zero_grad(self) -> None:
         self.grad.zero_()
+        self.touched.clear()
         for p, o in zip(self.params, self.offsets):          # re-attach if something reset .grad
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def active_blocks(self) -> torch.Tensor:
+        """uint8 mask, one byte per ALIGN elements of the flat buffer: 1 where the owning parameter
+        was touched since the last zero_grad() (host tensor)."""
+        m = torch.zeros(self.numel // self.ALIGN, dtype=torch.uint8)
+        for i in self.touched:
+            o, n = self.offsets[i], self.params[i].numel()
+            m[o // self.ALIGN:(o + n + self.ALIGN - 1) // self.ALIGN] = 1
+        return m
 
     def sync(self, force: bool = False) -> None:
         """Refresh the bf16 shadow with one kernel if any parameter changed since the last sync."""
@@ -189,6 +222,16 @@ class FlatAdamW:
         self.exp_avg = torch.zeros_like(flat.flat)
         self.exp_avg_sq = torch.zeros_like(flat.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=flat.flat.device)
+        # device copy of FlatParams.active_blocks(); refreshed when the set of touched parameters
+        # changes (never inside a CUDA-graph capture: TrainStep.capture refreshes it before capturing)
+        self.active = torch.zeros(flat.numel // flat.ALIGN, dtype=torch.uint8, device=flat.flat.device)
+        self._active_key = None
+
+    def refresh_active(self) -> None:
+        key = frozenset(self.flat.touched)
+        if key != self._active_key:
+            self.active.copy_(self.flat.active_blocks())
+            self._active_key = key
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat.zero_grad()
@@ -197,8 +240,11 @@ class FlatAdamW:
         from . import _lib as L
         f = self.flat
         f.sync()
+        if not torch.cuda.is_current_stream_capturing():
+            self.refresh_active()
         sh = f.shadow16.data_ptr() if (f.shadow16 is not None and K.compute_dtype() == torch.bfloat16) else None
         L.call("dl_adamw_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
                self.exp_avg_sq.data_ptr(), sh, f.numel, self.step_count.data_ptr(), self.lr,
-               self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale)
+               self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
+               self.active.data_ptr())
         f.mark_synced()       # raw-pointer update: versions unchanged, shadow already fresh

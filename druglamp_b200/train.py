@@ -12,6 +12,7 @@ equivalent of the classification step only and is what ``bench.py`` times.
 """
 from __future__ import annotations
 
+import weakref
 from typing import List
 
 import torch
@@ -36,9 +37,11 @@ class StaticBatch:
         self._stage = {}                          # device staging of packed rows (load_from_packed)
 
     def tensors(self) -> List[torch.Tensor]:
+        """What crosses PCIe for one batch in the reference collate's layout: node features, tokens,
+        the dense LLM embeddings, labels and the batched graph's raw edge list (the CSR carrier is
+        rebuilt from it on the device, ``BatchedMolGraph.rebuild_``)."""
         g = self.graph
-        return [self.h, self.vp, self.xd, self.xp, self.y, g.indptr, g.indices, g.indptr_t,
-                g.indices_t, g.norm_src, g.norm_dst]
+        return [self.h, self.vp, self.xd, self.xp, self.y, g.src, g.dst]
 
     def host_copy(self, pin=True) -> List[torch.Tensor]:
         out = []
@@ -49,17 +52,19 @@ class StaticBatch:
         return out
 
     def load_from(self, host: List[torch.Tensor]) -> int:
-        """Asynchronous H2D refresh of every input buffer; returns the bytes copied."""
+        """Asynchronous H2D refresh of every input buffer, then the device-side CSR construction
+        from the edge list (dl_csr_build: no host sync); returns the bytes copied."""
         n = 0
         for dst, src in zip(self.tensors(), host):
             dst.copy_(src, non_blocking=True)
             n += src.numel() * src.element_size()
+        self.graph.rebuild_()
         return n
 
     # ---- packed wire format (druglamp_b200.collate): untiled embedding rows over PCIe ---------
     def _small(self) -> List[torch.Tensor]:
         g = self.graph
-        return [self.h, self.vp, self.y, g.indptr, g.indices, g.indptr_t, g.indices_t, g.norm_src, g.norm_dst]
+        return [self.h, self.vp, self.y, g.src, g.dst]
 
     def host_copy_packed(self, batch, pin=True) -> dict:
         """Host image of this batch with the LLM embeddings as packed rows (what the dataset yields
@@ -83,6 +88,7 @@ class StaticBatch:
         for dst, src in zip(self._small(), host["small"]):
             dst.copy_(src, non_blocking=True)
             n += src.numel() * src.element_size()
+        self.graph.rebuild_()
         for key, dense in (("xd", self.xd), ("xp", self.xp)):
             pk = host[key]
             stage = self._stage.get(key)
@@ -110,8 +116,11 @@ class TrainStep:
         self.opt = FlatAdamW(self.flat, lr=lr, weight_decay=weight_decay)
         self.world_size = world_size
         self.pg = process_group
+        if world_size > 1 and torch.distributed.is_initialized():
+            from .functions import set_seed_stream
+            set_seed_stream(torch.distributed.get_rank(process_group))
         self.loss = torch.zeros((), dtype=torch.float32, device=self.flat.flat.device)
-        self._graphs = {}
+        self._graphs = weakref.WeakKeyDictionary()      # StaticBatch -> (graph, graph): dies with the batch
         self._pool = None
         self.launches_per_step = 0
 
@@ -148,6 +157,12 @@ class TrainStep:
     def capture(self, sb: StaticBatch, warmup: int = 2) -> None:
         """Capture fwd+bwd and the optimizer update for this batch's buffers (the NCCL all-reduce
         between them stays a stream-ordered eager call)."""
+        # The warm-up steps (lazy initialisation, allocator pool) and the capture itself must not
+        # train on the capture batch: parameters, Adam moments, the step counter and every module
+        # buffer (BatchNorm running statistics) are restored afterwards.
+        opt = self.opt
+        keep = [t.clone() for t in (self.flat.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
+        bufs = [(b, b.clone()) for b in self.model.buffers()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -161,13 +176,20 @@ class TrainStep:
             self._fwd_bwd(sb)
         if self._pool is None:
             self._pool = g1.pool()
+        opt.refresh_active()          # which parameters this step's backward reaches (host -> device, not captured)
         with torch.cuda.graph(g2, pool=self._pool):
             self._update()
         self.launches_per_step = L.launch_count() - n0
-        self._graphs[id(sb)] = (g1, g2)
+        self._graphs[sb] = (g1, g2)
+        with torch.no_grad():
+            for dst, src in zip((self.flat.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_count), keep):
+                dst.copy_(src)
+            for b, c in bufs:
+                b.copy_(c)
+        self.flat.sync(force=True)
 
     def replay(self, sb: StaticBatch) -> torch.Tensor:
-        g1, g2 = self._graphs[id(sb)]
+        g1, g2 = self._graphs[sb]
         g1.replay()
         self._reduce()
         g2.replay()

@@ -112,7 +112,7 @@ typedef struct dl_gemm_args {
                          gradient dW = dY^T X (A = dY) this is the bias gradient, so nn.Linear's
                          backward needs no separate pass over dY (fp32 [M], accumulated into). */
   const int64_t* drop_seed_step; /* or NULL.  Device-resident step counter: the dropout seed of this launch
-                         is drop_seed + *drop_seed_step * 0x9E3779B97F4A7C15, read on the device, so a
+                         is splitmix64(drop_seed ^ f(*drop_seed_step)), read on the device, so a
                          captured CUDA graph draws a fresh mask on every replay (the same pointer is given
                          to the backward's dl_act_bwd / dl_gemm of that step). */
 } dl_gemm_args;
@@ -216,10 +216,15 @@ int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act,
 /* One AdamW step over a flat fp32 parameter buffer (torch.optim.AdamW semantics; the reference
  * builds AdamW in main.py:158-160).  grad is multiplied by grad_scale first (1/world_size after a
  * sum all-reduce); *step (device int64) is incremented; shadow_bf16 (optional) receives the
- * updated parameters in bf16 for the tensor-core GEMMs. */
+ * updated parameters in bf16 for the tensor-core GEMMs.  active_blocks (or NULL = all): one byte per
+ * 64 consecutive elements; a 0 skips those elements entirely -- parameters that received no gradient
+ * this step are neither decayed nor have their moments moved, as torch.optim.AdamW skips
+ * `p.grad is None` (three AdamWs over the same parameters, main.py:158-160; SSL / CM heads get no
+ * gradient from the classification loss, trainer.py:196-200). */
 int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float grad_scale, void* stream);
+                  float eps, float weight_decay, float grad_scale, const uint8_t* active_blocks,
+                  void* stream);
 int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
 /* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
 int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
@@ -236,6 +241,18 @@ int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period
 int dl_spmm_norm(const int32_t* indptr, const int32_t* indices, const float* norm_src,
                  const float* norm_dst, const void* h, void* out, int64_t n_rows, int32_t feats,
                  int32_t dtype, void* stream);
+
+/* Graph carrier built on the device from the batched molecule's edge list (what DGL hands
+ * GraphConv: g.edges(), in_degrees(), out_degrees(); model/basic_model.py:579-603,623-630):
+ * CSR by destination (indptr / indices = source ids) and by source (indptr_t / indices_t) in stable
+ * edge order -- identical to a host argsort(stable) -- plus norm_dst = clamp(in_deg, 1)^-1/2 and
+ * norm_src = clamp(out_deg, 1)^-1/2.  Duplicate edges are kept (App. A5).  flags[0] = number of
+ * zero-in-degree nodes (the DGLError condition of :580-590), flags[1] = edges with an endpoint outside
+ * [0, n_nodes) (skipped).  indptr*: [n_nodes + 1], indices*: [n_edges], workspace: 2*n_nodes +
+ * 2*n_edges int32.  No host synchronisation: the input pipeline can run it on its copy stream. */
+int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_nodes,
+                 int32_t* indptr, int32_t* indices, int32_t* indptr_t, int32_t* indices_t,
+                 float* norm_src, float* norm_dst, int32_t* flags, int32_t* workspace, void* stream);
 
 /* nn.BatchNorm1d over [rows, cols] (model/basic_model.py:401,434 bn_layer; also
  * cross_modality.py:168).  training!=0: batch statistics, running buffers updated with

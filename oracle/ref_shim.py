@@ -10,9 +10,11 @@ None of them does arithmetic on the hot path except DGL's
 published semantics -- an unweighted sum over in-edges, duplicate edges counted
 once per duplicate -- is restated by :class:`FakeGraph` with ``index_add_``.
 
-Only ``tests/golden/make_golden.py`` (fixture generation, run where
-``/root/reference`` exists) and the reference arm of ``bench.py`` use this file.
-``/root/reference`` does not exist on the GPU box; ``available()`` says so.
+Only ``tests/`` (fixture generation, the live oracle checks and the drop-in test) and the
+reference arm of ``bench.py`` use this file.  ``/root/reference`` does not exist on the GPU box:
+there the shim falls back to ``oracle/_ref`` -- the same modules byte-compiled by
+``oracle/build_ref.py`` in the build container (sourceless ``.pyc``, git-ignored, shipped by gpurun).
+``available()`` says whether either is present.
 """
 from __future__ import annotations
 
@@ -23,11 +25,30 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("DRUGLAMP_REFERENCE_ROOT", "/root/reference")
+_SRC_ROOT = os.environ.get("DRUGLAMP_REFERENCE_ROOT", "/root/reference")
+_PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    if os.path.isdir(os.path.join(_SRC_ROOT, "model")):
+        return _SRC_ROOT
+    ver = os.path.join(_PYC_ROOT, "PYTHON_VERSION")
+    if os.path.isdir(os.path.join(_PYC_ROOT, "model")) and os.path.exists(ver) and \
+            open(ver).read().strip() == "%d.%d" % sys.version_info[:2]:
+        return _PYC_ROOT
+    return _SRC_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "model"))
+
+
+def kind() -> str:
+    """"source" (the tree under /root/reference) or "pyc" (oracle/_ref, byte-compiled from it)."""
+    return "pyc" if REFERENCE_ROOT == _PYC_ROOT else "source"
 
 
 class _AttrDict(dict):

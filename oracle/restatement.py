@@ -371,10 +371,25 @@ def druglamp_forward(sd: SD, kind: str, src, dst, h, batch_size, vp, xd, xp, tra
 
 
 # --------------------------------------------------------------------------- deterministic params
+def _hash_uniform(n: int, key: int) -> np.ndarray:
+    """n reproducible pseudo-random float64 in [-1, 1): splitmix64 of (key, index) in wrapping
+    uint64 arithmetic -- a pure function of its arguments on every machine."""
+    with np.errstate(over="ignore"):
+        z = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(key & 0xFFFFFFFFFFFFFFFF)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / float(1 << 53)) - 1.0
+
+
 def deterministic_state(shapes: Dict[str, tuple], seed: int = 0) -> SD:
-    """Machine-independent parameter values: a pure arithmetic function of
-    (name, index), so the build container, the GPU box and the fixtures agree without
-    shipping 56 MB of weights.  Scale ~ 1/sqrt(fan_in) for matrices."""
+    """Machine-independent parameter values: a pure arithmetic function of (name, index), so the
+    build container, the GPU box and the fixtures agree without shipping 56 MB of weights.
+    Matrices are full-rank pseudo-random (hashed uniform) with standard deviation 0.8 / sqrt(fan_in),
+    i.e. a healthy, initialisation-like network.  (Round 1 used sinusoids of the flat index: every
+    such matrix has rank <= 4, the activations collapsed onto a few directions and the
+    normalisation layers amplified bf16 rounding to 20-70 % logit noise -- for PyTorch's own bf16
+    autocast of the reference just as much as for the product -- which pinned nothing.)"""
     out = {}
     for name in sorted(shapes):
         shp = tuple(shapes[name])
@@ -382,8 +397,7 @@ def deterministic_state(shapes: Dict[str, tuple], seed: int = 0) -> SD:
         # ssl_model.extractor.* are the same tensors as protein_extractor.* (App. B)
         hname = name.replace("ssl_model.extractor.", "protein_extractor.")
         hsh = (sum((i + 1) * ord(c) for i, c in enumerate(hname)) * 2654435761 + seed * 97) % 1000003
-        idx = np.arange(n, dtype=np.float64)
-        vals = np.sin(idx * 0.61803398875 + hsh * 0.001) + 0.5 * np.sin(idx * 0.0137 + hsh)
+        vals = _hash_uniform(n, hsh * 0x100000001B3 + 0x5851F42D4C957F2D)
         if name.endswith("num_batches_tracked"):
             out[name] = torch.zeros(shp, dtype=torch.int64)
             continue
@@ -396,7 +410,7 @@ def deterministic_state(shapes: Dict[str, tuple], seed: int = 0) -> SD:
             if ".pe_" in name:
                 vals = 0.1 * vals
             else:
-                vals = vals * (0.9 / math.sqrt(fan_in))
+                vals = vals * (0.8 * math.sqrt(3.0) / math.sqrt(fan_in))
         elif name.endswith("weight"):      # norm gains
             vals = 1.0 + 0.1 * vals
         else:                               # biases

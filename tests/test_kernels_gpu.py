@@ -386,3 +386,32 @@ def test_dropout_step_counter_advances_masks_consistently():
     finally:
         K.set_dropout_step(None)
     assert torch.equal(K.dropout(x, 0.25, 77) != 0, K.dropout(x, 0.25, 77) != 0)
+
+
+def test_csr_build_on_device_equals_host_construction():
+    """dl_csr_build (degree count -> scan -> stable scatter) against BatchedMolGraph's host
+    construction (torch argsort(stable) + bincount): indptr / indices of both directions and the
+    clamp(deg, 1)^-1/2 norms bit for bit, duplicate edges (the double self loops of App. A5) and
+    isolated nodes included; rebuild_ refills the same buffers for a second edge list."""
+    from druglamp_b200.graph import BatchedMolGraph
+    from druglamp_b200.synth import make_batch
+    b = make_batch(6, seed=17)
+    for src, dst, n in ((b.graph.src, b.graph.dst, b.graph.num_nodes()),
+                        (torch.tensor([0, 0, 3, 3, 3, 2, 5, 5]), torch.tensor([1, 1, 0, 3, 3, 2, 0, 4]), 7)):
+        host = BatchedMolGraph(src, dst, n, 1)
+        dev = BatchedMolGraph.from_edges_device(src.cuda(), dst.cuda(), n, 1)
+        for k in ("indptr", "indices", "indptr_t", "indices_t", "norm_src", "norm_dst"):
+            assert torch.equal(getattr(dev, k).cpu(), getattr(host, k)), k
+        assert torch.equal(dev.in_deg.cpu(), host.in_deg) and torch.equal(dev.out_deg.cpu(), host.out_deg)
+        dev.check_no_zero_in_degree_quiet()
+        assert dev._zero_in == host._zero_in
+    # same buffers, new edges (a permutation of the edge list changes the stable order inside rows)
+    perm = torch.randperm(b.graph.src.numel(), generator=torch.Generator().manual_seed(1))
+    s2, d2 = b.graph.src[perm], b.graph.dst[perm]
+    dev = BatchedMolGraph.from_edges_device(b.graph.src.cuda(), b.graph.dst.cuda(), b.graph.num_nodes(), 6)
+    ptr0 = dev.indices.data_ptr()
+    dev.rebuild_(s2.cuda(), d2.cuda())
+    host = BatchedMolGraph(s2, d2, b.graph.num_nodes(), 6)
+    assert dev.indices.data_ptr() == ptr0
+    for k in ("indptr", "indices", "indptr_t", "indices_t", "norm_src", "norm_dst"):
+        assert torch.equal(getattr(dev, k).cpu(), getattr(host, k)), k

@@ -55,31 +55,17 @@ def _digest_err(actual, gold, floor=0.0):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-3, 1e-2), (torch.bfloat16, 2e-2, 1e-1)])
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-3, 1e-2), (torch.bfloat16, 2e-2, 2e-1)])
 def test_forward_backward_matches_reference_fixture(case, dtype, tol, gtol):
     fx = load_golden(case)
     m, b, o = run_product(fx, dtype)
     report = []
-    # Train-mode BatchNorm over a small batch amplifies bf16 rounding noise: PyTorch's own bf16
-    # autocast moves the UNMODIFIED reference's logits by 0.2-0.7 of max|logit| on these fixtures
-    # (`bf16_autocast_*_dev`, make_golden.py), and an ensemble of 12 autocast runs with the weights
-    # perturbed by half a bf16 ulp spreads the loss over 3e-4..8.7e-2 and the logits over 0.12..0.99
-    # (bf16_noise_floor.npz, make_noise_floor.py).  The product's bf16 result is one more draw from
-    # that heavy-tailed distribution (12 draws: mean 3.5e-2, sigma 3.0e-2 for the loss), so there the
-    # logits and the loss are bounded by 2x the ensemble maximum (never tighter than the 2e-2 bar); the eval-mode fixture (running statistics) carries the
-    # strict 2e-2 logit / loss bar and the gradient check.
-    noisy = dtype == torch.bfloat16 and bool(int(fx["meta_training"]))
+    # bf16: the north_star bar (2e-2) on logits and loss in EVERY mode, train-mode batch statistics
+    # included; intermediates behind the three stacked train-mode BatchNorms of the GCN get 2x, and
+    # every parameter gradient's sampled digest stays within gtol of its own scale.
     stol = ltol = tol
-    if noisy:
-        nf = load_golden("bf16_noise_floor.npz")
-        key = case[:-len(".npz")]
-        sdev = max(float(fx["bf16_autocast_score_dev"]), float(nf[key + "/score_dev"].max()))
-        ldev = max(float(fx["bf16_autocast_loss_dev"]), float(nf[key + "/loss_dev"].max()))
-        stol, ltol = max(tol, 2.0 * sdev), max(tol, 2.0 * ldev)
-    if noisy:
-        # intermediates (three stacked train-mode BatchNorms in the GCN, 92 % identical rows) sit at
-        # ~5e-2 in bf16 and move a little from run to run (atomic reduction order): diagnostic bound
-        tol, gtol = 5 * tol, float("inf")
+    if dtype == torch.bfloat16:
+        tol = 2 * tol
     sc = o["score"].detach().double().cpu().numpy()
     s_err = np.abs(sc - fx["score"]).max() / (np.abs(fx["score"]).max() + 1e-30)
     report.append(("score", s_err, stol))
@@ -156,12 +142,18 @@ def test_bench_configuration_b64_train_matches_reference(dtype, tol, gcos, gnorm
                 check(f"{nm}[{i}]", e, 2.5 * tol if nm != "A_v_gca" else 4 * tol)
         params = dict(m.named_parameters())
         worst_c, worst_n = 1.0, 0.0
+        gmax = max(float(np.abs(fx[k]).max()) for k in fx if k.startswith("fullgrad/"))
         for k in fx:
             if not k.startswith("fullgrad/"):
                 continue
             g = torch.from_numpy(fx[k])
             mine = params[k[9:]].grad
             assert mine is not None, k
+            if float(g.abs().max()) < 1e-9 * gmax:
+                # theoretically zero (a key bias shifts every logit of a softmax row equally): the
+                # reference's own value is rounding noise, so only the magnitude is comparable
+                assert float(mine.abs().max()) < 1e-3 * gmax, k
+                continue
             c = _cos(mine, g)
             nr = abs(float(mine.double().norm().cpu() / g.double().norm()) - 1.0)
             worst_c, worst_n = min(worst_c, c), max(worst_n, nr)
