@@ -9,6 +9,7 @@ built library, or on CPU tensors, raises.
 __version__ = "0.1.0"
 
 from .kernels import compute_dtype, set_compute_dtype  # noqa: F401
+from .modules import set_gcn_precision  # noqa: F401
 
 
 def patch_reference() -> None:

@@ -49,7 +49,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("lse", C.c_void_p),
         ("raw", C.c_void_p), ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
-        ("dvec", C.c_void_p), ("dq_scratch", C.c_void_p),
+        ("dvec", C.c_void_p),
         ("B", C.c_int64), ("H", C.c_int64), ("S2", C.c_int64), ("Lq", C.c_int64), ("Lk", C.c_int64),
         ("d", C.c_int64),
         ("q_ld", C.c_int64), ("q_sb", C.c_int64), ("q_ss", C.c_int64),

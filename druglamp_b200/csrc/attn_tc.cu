@@ -22,8 +22,8 @@
 //       P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - D) * scale   -> bf16 shared-memory tiles
 //       dV += P^T dO,  dK += dS^T Q                      (accumulate over the query loop)
 //       dQ_tile (+)= dS K                                (dS^T tile read as an MN-major A operand)
-//   dQ needs the sum over key tiles: the same thread owns a dQ row in every pass, so the partial sum
-//   lives in an fp32 scratch row it wrote itself (no atomics, deterministic).
+//   dQ needs the sum over key tiles: every tile's contribution leaves as a bulk tensor operation from a
+//   shared-memory staging tile -- a plain store for the first key tile, a bf16 reduce-add for the rest.
 #include <mutex>
 
 #include "../../include/druglamp_sm100.h"
@@ -47,7 +47,6 @@ struct AttnParams {
   // backward
   __nv_bfloat16 *dQ, *dK, *dV;
   const float* dvec;
-  float* scratch;
   long long o_ld, o_sb, o_ss;
   long long dq_ld, dq_sb, dq_ss, dk_ld, dk_sb, dv_ld, dv_sb;
   long long raw_ld;
@@ -291,36 +290,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // =============================================================================== backward
-// dvec[set, b, h, row] = sum_d dO * O over the head's columns (one warp per row and head)
+// dvec[set, b, h, row] = sum_d dO * O over the head's columns: D/8 lanes per (row, head), one
+// 16-byte load of each operand per lane, shuffle reduction inside the lane group
 template <int D>
-__global__ void attn_dvec_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
-                                 float* __restrict__ dvec, long long o_ld, long long o_sb, long long o_ss,
-                                 int B, int H, int S2, int Lq) {
+__global__ void __launch_bounds__(256)
+attn_dvec_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                 float* __restrict__ dvec, long long o_ld, long long o_sb, long long o_ss,
+                 int B, int H, int S2, int Lq) {
   pdl_trigger();
   pdl_wait();
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)S2 * B * H * Lq;
-  if (w >= total) return;
-  const int row = (int)(w % Lq);
-  long long t = w / Lq;
-  const int h = (int)(t % H);
-  t /= H;
-  const int b = (int)(t % B), set = (int)(t / B);
-  const long long off = (long long)b * o_sb + (long long)row * o_ld + (long long)set * o_ss + h * D;
-  constexpr int PER = D / 32;   // 2 or 4 elements per lane
+  constexpr int G = D / 8;                           // lanes per (row, head): 8 or 16
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)S2 * B * Lq * H;
+  long long w = t / G;                               // (set, b, row, h) with h fastest: a row's heads are
+  const int part = (int)(t % G);                     // adjacent in memory, so a warp reads contiguous bytes
+  const bool ok = w < total;
+  if (!ok) w = total - 1;
+  const int h = (int)(w % H);
+  long long u = w / H;
+  const int row = (int)(u % Lq);
+  u /= Lq;
+  const int b = (int)(u % B), set = (int)(u / B);
+  const long long off = (long long)b * o_sb + (long long)row * o_ld + (long long)set * o_ss + h * D + part * 8;
+  float x[8], y[8];
+  ldv(O + off, x);
+  ldv(dO + off, y);
   float acc = 0.f;
-  if constexpr (PER == 2) {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(O + off + 2 * lane);
-    const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(dO + off + 2 * lane);
-    const float2 fa = __bfloat1622float2(a), fg = __bfloat1622float2(g);
-    acc = fa.x * fg.x + fa.y * fg.y;
-  } else {
-    const float4 fa = ld4<__nv_bfloat16>(O + off + 4 * lane), fg = ld4<__nv_bfloat16>(dO + off + 4 * lane);
-    acc = fa.x * fg.x + fa.y * fg.y + fa.z * fg.z + fa.w * fg.w;
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) dvec[w] = acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc = fmaf(x[i], y[i], acc);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (ok && part == 0) dvec[(((long long)set * B + b) * H + h) * Lq + row] = acc;
 }
 
 template <int D>
@@ -341,7 +341,7 @@ template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmdQ, const AttnParams p) {
   using C = BwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -368,6 +368,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
     ptx::prefetch_tmap(&tmdO);
+    ptx::prefetch_tmap(&tmdQ);
     ptx::mbar_init(bar_kv, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_qfull + 8 * i, 1);
@@ -477,6 +478,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ls[ts] = ok ? p.lse[vrow + q0 + ts] : INFINITY;
           ds_[ts] = ok ? p.dvec[vrow + q0 + ts] : 0.f;
         }
+        if (ts == 0) ptx::bulk_wait_read0();     // the previous dQ store has read the P^T buffer it staged in
         ptx::bar_sync(1, 32 * kSoftWarps);
         ptx::mbar_wait(bar_st, n & 1);
         ptx::tc_fence_after();
@@ -509,52 +511,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_pds);
-        // dQ tile: rows are queries now
+        // dQ tile: rows are queries now.  TMEM -> bf16 -> the (free again) P^T buffer in the TMA layout
+        // -> one bulk tensor store for the first key tile, a bf16 reduce-add (in L2) for the others and
+        // for a shared query gradient: coalesced, asynchronous, no scratch round trip
         ptx::mbar_wait(bar_dq, n & 1);
         ptx::tc_fence_after();
-        const int qrow = q0 + r;
-        const bool q_ok = qrow < p.Lq;
-        float* srow = p.scratch + ((vrow + qrow) * D + hh * (D / 2));
-        __nv_bfloat16* qdst = p.dQ + (long long)b * p.dq_sb + (long long)qrow * p.dq_ld +
-                              (long long)set * p.dq_ss + h * D + hh * (D / 2);
+        {
+          constexpr int W = D / 2;                        // columns per thread: 32 (one block half) or 64 (a block)
+          const uint32_t srow = sPT + (uint32_t)((hh * W / 64) * kBlk + r * 128);
 #pragma unroll
-        for (int g = 0; g < D / 64; ++g) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(tl + (uint32_t)(C::T_DQ + hh * (D / 2) + g * 32), v);
-          ptx::tmem_ld_wait();
-          if (q_ok) {
-            float x[32];
+          for (int g = 0; g < W / 32; ++g) {
+            uint32_t v[32], w[16];
+            ptx::tmem_ld_32x32(tl + (uint32_t)(C::T_DQ + hh * W + g * 32), v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            if (t > 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 f = *reinterpret_cast<const float4*>(srow + g * 32 + j);
-                x[j] += f.x; x[j + 1] += f.y; x[j + 2] += f.z; x[j + 3] += f.w;
-              }
-            }
-            if (t + 1 < p.nkc) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(srow + g * 32 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-            } else {
-              if (p.dq_acc) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  float y[8];
-                  ldv(qdst + g * 32 + j, y);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) x[j + k] += y[k];
-                }
-              }
-              uint32_t w[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = ptx::pack_bf16(x[2 * j], x[2 * j + 1]);
-              stg_bf16x32(qdst + g * 32, w);
-            }
+            for (int j = 0; j < 16; ++j) w[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            sts_row32(srow, ((hh * W) % 64) / 8 + g * 4, xr, w);
           }
         }
+        ptx::fence_proxy_async();
         ptx::tc_fence_before();
+        ptx::bar_sync(2, 32 * kSoftWarps);
+        if (ts == 0) {
+          const bool add = t > 0 || p.dq_acc != 0;
+#pragma unroll
+          for (int j = 0; j < C::NB; ++j) {
+            if (add) ptx::tma_reduce_add_4d(&tmdQ, sPT + j * kBlk, h * D + 64 * j, q0, b, set);
+            else ptx::tma_store_4d(&tmdQ, sPT + j * kBlk, h * D + 64 * j, q0, b, set);
+          }
+          ptx::bulk_commit();
+        }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_tfree);
       }
@@ -585,6 +571,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dkvfree);
     }
+    if (ts == 0) ptx::bulk_wait0();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -650,7 +637,7 @@ void fill_common(AttnParams& p, const dl_attn_args* a) {
   p.lse = a->lse;
   p.raw = (__nv_bfloat16*)a->raw;
   p.dQ = (__nv_bfloat16*)a->dq; p.dK = (__nv_bfloat16*)a->dk; p.dV = (__nv_bfloat16*)a->dv;
-  p.dvec = a->dvec; p.scratch = a->dq_scratch;
+  p.dvec = a->dvec;
   p.o_ld = a->o_ld; p.o_sb = a->o_sb; p.o_ss = a->o_ss;
   p.dq_ld = a->dq_ld; p.dq_sb = a->dq_sb; p.dq_ss = a->dq_ss;
   p.dk_ld = a->dk_ld; p.dk_sb = a->dk_sb; p.dv_ld = a->dv_ld; p.dv_sb = a->dv_sb;
@@ -687,7 +674,7 @@ int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
 
 template <int D>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-               AttnParams& p, const dl_attn_args* a, cudaStream_t stream) {
+               const CUtensorMap& tdq, AttnParams& p, const dl_attn_args* a, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -698,7 +685,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
     return set_error((int)attr_err, "dl_attn_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   const long long rows = (long long)p.S2 * p.B * p.H * p.Lq;
   const int threads = 256;
-  DL_LAUNCH((attn_dvec_kernel<D>), ceil_div(rows * 32, threads), threads, 0, stream,
+  DL_LAUNCH((attn_dvec_kernel<D>), ceil_div(rows * (D / 8), threads), threads, 0, stream,
             (const __nv_bfloat16*)a->o, (const __nv_bfloat16*)a->d_o, a->dvec, p.o_ld, p.o_sb, p.o_ss, p.B, p.H,
             p.S2, p.Lq);
   DL_LAUNCH_CHECK("attn_dvec_kernel");
@@ -706,7 +693,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   p.idesc_b = ptx::make_idesc(false, false, true, 128, D);      // dV += P^T dO, dK += dS^T Q
   p.idesc_c = ptx::make_idesc(false, true, true, 128, D);       // dQ = dS K
   dim3 grid((unsigned)p.H, (unsigned)p.B, 1);
-  DL_LAUNCH((attn_bwd_kernel<D>), grid, kAttnThreads, C::SMEM, stream, tq, tk, tv, tdo, p);
+  DL_LAUNCH((attn_bwd_kernel<D>), grid, kAttnThreads, C::SMEM, stream, tq, tk, tv, tdo, tdq, p);
   DL_LAUNCH_CHECK("attn_bwd_kernel");
   count_launch(2);
   return 0;
@@ -739,21 +726,20 @@ extern "C" int dl_attn_bwd(const dl_attn_args* a, void* stream_) {
   int rc = check_common(a);
   if (rc) return rc;
   DL_REQUIRE(a->d_o && a->dq && a->dk && a->dv && a->dvec, "dl_attn_bwd: d_o, dq, dk, dv and dvec must be non-null");
-  DL_REQUIRE(a->Lk <= 128 || a->dq_scratch != nullptr, "dl_attn_bwd: dq_scratch is required when Lk > 128");
-  DL_REQUIRE(((uintptr_t)a->dq_scratch & 15) == 0, "dl_attn_bwd: dq_scratch must be 16-byte aligned");
   auto ok16 = [](const void* q, long long ld, long long sb, long long ss) {
     return ((uintptr_t)q & 15) == 0 && ld % 8 == 0 && sb % 8 == 0 && ss % 8 == 0;
   };
   DL_REQUIRE(ok16(a->dq, a->dq_ld, a->dq_sb, a->dq_ss) && ok16(a->dk, a->dk_ld, a->dk_sb, 0) &&
              ok16(a->dv, a->dv_ld, a->dv_sb, 0), "dl_attn_bwd: dq / dk / dv need 16-byte aligned rows");
   const long long cols = a->H * a->d;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   if ((rc = make_map(&tq, a->q, cols, a->Lq, a->B, a->S2, a->q_ld, a->q_sb, a->q_ss, "q"))) return rc;
   if ((rc = make_map(&tk, a->k, cols, a->Lk, a->B, 1, a->k_ld, a->k_sb, 0, "k"))) return rc;
   if ((rc = make_map(&tv, a->v, cols, a->Lk, a->B, 1, a->v_ld, a->v_sb, 0, "v"))) return rc;
   if ((rc = make_map(&tdo, a->d_o, cols, a->Lq, a->B, a->S2, a->o_ld, a->o_sb, a->o_ss, "d_o"))) return rc;
+  if ((rc = make_map(&tdq, a->dq, cols, a->Lq, a->B, a->S2, a->dq_ld, a->dq_sb, a->dq_ss, "dq"))) return rc;
   AttnParams p;
   fill_common(p, a);
-  if (a->d == 64) return launch_bwd<64>(tq, tk, tv, tdo, p, a, stream);
-  return launch_bwd<128>(tq, tk, tv, tdo, p, a, stream);
+  if (a->d == 64) return launch_bwd<64>(tq, tk, tv, tdo, tdq, p, a, stream);
+  return launch_bwd<128>(tq, tk, tv, tdo, tdq, p, a, stream);
 }

@@ -93,8 +93,8 @@ csr_scan_kernel(int* __restrict__ cnt_in, int* __restrict__ cnt_out, long long n
     indptr_t[i] = pb;
     pa += ci;
     pb += co;
-    norm_dst[i] = rsqrtf((float)(ci > 1 ? ci : 1));
-    norm_src[i] = rsqrtf((float)(co > 1 ? co : 1));
+    norm_dst[i] = __fdiv_rn(1.0f, __fsqrt_rn((float)(ci > 1 ? ci : 1)));    // IEEE: equals clamp(deg,1).pow(-0.5)
+    norm_src[i] = __fdiv_rn(1.0f, __fsqrt_rn((float)(co > 1 ? co : 1)));
     cnt_in[i] = 0;
     cnt_out[i] = 0;
   }

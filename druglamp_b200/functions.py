@@ -63,6 +63,12 @@ def _back(g: Optional[torch.Tensor], like_dtype: torch.dtype, shape=None):
     return g if shape is None else g.reshape(shape)
 
 
+def _as(g: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Incoming gradient, contiguous, in the dtype this Function's forward computed in (which may
+    differ from the global compute dtype: kernels.local_compute_dtype)."""
+    return K.cast(g if g.is_contiguous() else g.contiguous(), dtype)
+
+
 def _grad_target(p):
     """The fp32 gradient buffer of a parameter that lives in a FlatParams store (None otherwise).
     Weight / bias gradients are then accumulated straight into it by the producing kernel
@@ -172,7 +178,7 @@ class LinearFn(Function):
         act, drop_p, seed, xs, xdt, rdt, has_b, w_kn, Kd, Kw, N, No, rshape = ctx.meta
         Kp = x2.shape[1]
         Np = wc.shape[1] if w_kn else wc.shape[0]
-        gy2 = K.to_compute(gy).view(-1, No)
+        gy2 = _as(gy, x2.dtype).view(-1, No)
         g = K.act_bwd(_pad_cols(gy2, Np), pre, act, (drop_p, seed))
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
@@ -733,13 +739,14 @@ class SpmmFn(Function):
         hc = K.to_compute(h)
         ctx.graph = graph
         ctx.hdt = h.dtype
+        ctx.cdt = hc.dtype
         return K.spmm_norm(graph.indptr, graph.indices, graph.norm_src, graph.norm_dst, hc)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         g = ctx.graph
-        dh = K.spmm_norm(g.indptr_t, g.indices_t, g.norm_dst, g.norm_src, K.to_compute(gy))
+        dh = K.spmm_norm(g.indptr_t, g.indices_t, g.norm_dst, g.norm_src, _as(gy, ctx.cdt))
         return _back(dh, ctx.hdt), None
 
 
@@ -767,10 +774,10 @@ class BatchNormFn(Function):
         g_ = None if gamma is None else gamma.detach()
         tg, tb = _grad_target(gamma), _grad_target(beta)
         if tg is not None and tb is not None:       # straight into the flat gradient buffer
-            dx, _, _ = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
+            dx, _, _ = K.batchnorm_bwd(_as(gy, x2.dtype).view(x2.shape), x2, g_, mean, rstd, training,
                                        acc_into=(tg, tb), relu_mask=relu)
             return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None, None
-        dx, dg, db = K.batchnorm_bwd(K.to_compute(gy).view(x2.shape), x2, g_, mean, rstd, training,
+        dx, dg, db = K.batchnorm_bwd(_as(gy, x2.dtype).view(x2.shape), x2, g_, mean, rstd, training,
                                      need_param_grads=gamma is not None, relu_mask=relu)
         return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None, None
 

@@ -29,6 +29,25 @@ def compute_dtype() -> torch.dtype:
     return _compute_dtype
 
 
+class local_compute_dtype:
+    """``with local_compute_dtype(torch.float32): ...`` -- run a sub-graph's FORWARD in another
+    compute dtype (its Functions keep the dtype of what they saved for their backward)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _compute_dtype
+        self.prev = _compute_dtype
+        if self.dtype is not None:
+            _compute_dtype = self.dtype
+
+    def __exit__(self, *exc):
+        global _compute_dtype
+        _compute_dtype = self.prev
+        return False
+
+
 def set_dropout_step(counter: Optional[torch.Tensor]) -> None:
     """A device-resident int64 step counter (or None) that every dropout launch mixes into its seed
     ON THE DEVICE: a captured CUDA graph then draws a fresh mask on every replay, while the forward
@@ -253,7 +272,6 @@ def attn_bwd(d_o: torch.Tensor, q, k, v, o, lse, H: int, scale: float, dq: torch
              dv: torch.Tensor, dq_accumulate: bool = False) -> None:
     """Gradients of attn_fwd into the (strided) destinations dq (like q), dk, dv (like k, v)."""
     S2, B, Lq, HD = q.shape
-    d = HD // H
     if d_o.stride() != o.stride() or d_o.dtype != o.dtype:
         raise ValueError("dl_attn_bwd: d_o must share o's layout")
     a = _attn_args(q, k, v, o, lse, H, scale)
@@ -263,9 +281,6 @@ def attn_bwd(d_o: torch.Tensor, q, k, v, o, lse, H: int, scale: float, dq: torch
     a.dk_ld, a.dk_sb, a.dv_ld, a.dv_sb = dk.stride(1), dk.stride(0), dv.stride(1), dv.stride(0)
     dvec = torch.empty((S2, B, H, Lq), dtype=torch.float32, device=q.device)
     a.dvec = dvec.data_ptr()
-    if k.shape[1] > 128:
-        scratch = torch.empty((S2, B, H, Lq, d), dtype=torch.float32, device=q.device)
-        a.dq_scratch = scratch.data_ptr()
     a.dq_accumulate = int(dq_accumulate)
     L.check(L.lib().dl_attn_bwd(L.C.byref(a), L.stream_ptr()), "dl_attn_bwd")
 

@@ -134,9 +134,9 @@ int dl_gemm(const dl_gemm_args* args, void* stream);
  *   lse: fp32 [S2, B, H, Lq], log2-domain row log-sum-exp of the scaled logits (saved by forward,
  *   read by backward).  raw: bf16 (B, H, Lq, raw_ld).
  * Limits: d in {64, 128}, Lk <= 512 (one query tile's whole score row lives in tensor memory).
- * Backward workspaces: dvec fp32 [S2, B, H, Lq]; dq_scratch fp32 [S2, B, H, Lq, d] (only touched
- * when Lk > 128).  dq_accumulate != 0 adds to the existing dq (the second K/V set of the paired
- * block shares its query gradient with the first).
+ * Backward workspace: dvec fp32 [S2, B, H, Lq].  dq is written by bulk tensor stores (first key tile)
+ * and bf16 reduce-adds (further key tiles); dq_accumulate != 0 makes every tile a reduce-add onto the
+ * existing dq (the second K/V set of the paired block shares its query gradient with the first).
  */
 typedef struct dl_attn_args {
   const void* q;
@@ -150,7 +150,6 @@ typedef struct dl_attn_args {
   void* dk;
   void* dv;
   float* dvec;        /* backward workspace */
-  float* dq_scratch;  /* backward workspace */
   int64_t B, H, S2, Lq, Lk, d;
   int64_t q_ld, q_sb, q_ss;
   int64_t k_ld, k_sb, v_ld, v_sb;

@@ -4,9 +4,11 @@
 
 The reference is pure Python, so "building" it means ``py_compile``: every module the hot path
 imports (``model/**``, ``utils.py``, ``configs/**``) is compiled from the sources where they lie
-under ``/root/reference`` into a sourceless ``.pyc`` tree.  No reference source is copied; the
-output directory is git-ignored (it travels to the GPU box with ``gpurun`` like the built ``.so``)
-and is importable by the same interpreter version that built it.  It lets the GPU box run
+under ``/root/reference`` into a sourceless tree of compiled code objects (``*.refbin``: the bytes
+``py_compile`` produces; not named ``.pyc`` because snapshot tools drop those like ``__pycache__``).
+No reference source is copied; the output directory is git-ignored (it travels to the GPU box with
+``gpurun`` like the built ``.so``) and is importable, through the finder in ``oracle/ref_shim.py``, by
+the same interpreter version that built it.  It lets the GPU box run
 
   * ``bench.py --impl reference`` on the reference's OWN modules (``cpu_baseline.kind = "reference"``),
   * ``tests/test_dropin_reference_gpu.py``: the reference's ``model/DrugLAMP*.py:forward`` on top of
@@ -40,7 +42,7 @@ def build(verbose: bool = False) -> str | None:
                 if f.endswith(".py"):
                     todo.append(os.path.relpath(os.path.join(d, f), SRC))
     for rel in sorted(todo):
-        dst = os.path.join(OUT, rel + "c")                 # foo.py -> foo.pyc beside where foo.py would be
+        dst = os.path.join(OUT, rel[:-3] + ".refbin")      # foo.py -> foo.refbin beside where foo.py would be
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(os.path.join(SRC, rel), cfile=dst, dfile=rel, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -13,7 +13,8 @@ once per duplicate -- is restated by :class:`FakeGraph` with ``index_add_``.
 Only ``tests/`` (fixture generation, the live oracle checks and the drop-in test) and the
 reference arm of ``bench.py`` use this file.  ``/root/reference`` does not exist on the GPU box:
 there the shim falls back to ``oracle/_ref`` -- the same modules byte-compiled by
-``oracle/build_ref.py`` in the build container (sourceless ``.pyc``, git-ignored, shipped by gpurun).
+``oracle/build_ref.py`` in the build container (sourceless code objects, git-ignored, shipped by
+gpurun) and imported through ``_RefbinFinder`` below.
 ``available()`` says whether either is present.
 """
 from __future__ import annotations
@@ -112,6 +113,42 @@ class FakeGraph:
         self.dstdata["h"] = out
 
 
+class _RefbinFinder:
+    """Meta-path finder / loader for the ``*.refbin`` tree of oracle/build_ref.py (py_compile output:
+    16-byte header + marshalled code object)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def _path(self, fullname):
+        rel = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(os.path.join(rel, "__init__.refbin")):
+            return os.path.join(rel, "__init__.refbin"), True
+        if os.path.isfile(rel + ".refbin"):
+            return rel + ".refbin", False
+        return None, False
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.util
+        f, is_pkg = self._path(fullname)
+        if f is None:
+            return None
+        spec = importlib.util.spec_from_loader(fullname, self, origin=f, is_package=is_pkg)
+        if is_pkg:
+            spec.submodule_search_locations = [os.path.dirname(f)]
+        return spec
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        with open(module.__spec__.origin, "rb") as f:
+            code = marshal.loads(f.read()[16:])
+        module.__file__ = module.__spec__.origin
+        exec(code, module.__dict__)
+
+
 _INSTALLED = False
 
 
@@ -151,7 +188,9 @@ def install() -> None:
         lu = mod("lightning_utilities", core=core)
         core.rank_zero = rz
         lu.core = core
-    if REFERENCE_ROOT not in sys.path:
+    if REFERENCE_ROOT == _PYC_ROOT:
+        sys.meta_path.insert(0, _RefbinFinder(_PYC_ROOT))
+    elif REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     _INSTALLED = True
 

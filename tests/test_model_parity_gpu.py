@@ -149,7 +149,7 @@ def test_bench_configuration_b64_train_matches_reference(dtype, tol, gcos, gnorm
             g = torch.from_numpy(fx[k])
             mine = params[k[9:]].grad
             assert mine is not None, k
-            if float(g.abs().max()) < 1e-9 * gmax:
+            if k.endswith(("key.bias", "key_mol.bias")):
                 # theoretically zero (a key bias shifts every logit of a softmax row equally): the
                 # reference's own value is rounding noise, so only the magnitude is comparable
                 assert float(mine.abs().max()) < 1e-3 * gmax, k

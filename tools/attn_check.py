@@ -25,6 +25,11 @@ CASES = [
     ("PGCA long-seq shape (ragged) + raw", 2, 1, 1, 300, 290, 128, True, "kv"),
     ("ragged small", 2, 1, 1, 77, 33, 128, True, "dense"),
     ("d64 4 chunks", 1, 2, 2, 200, 400, 64, False, "dense"),
+    # the step's real sizes (64 pairs) and the long-sequence config (256 pairs): timing cases
+    ("FULL paired PMMA", 64, 4, 2, 256, 256, 64, False, "qkv"),
+    ("FULL plain PMMA", 64, 4, 1, 256, 256, 128, False, "qkv"),
+    ("FULL PGCA", 64, 1, 1, 256, 512, 128, True, "kv"),
+    ("FULL PGCA long-seq B=256", 256, 1, 1, 1200, 290, 128, True, "kv"),
 ]
 
 
