@@ -782,12 +782,29 @@ class BatchNormFn(Function):
         return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None, None
 
 
+_bn_frozen = False
+
+
+@contextlib.contextmanager
+def frozen_bn_buffers():
+    """Inside, train-mode BatchNorms normalise with batch statistics as usual but leave their
+    running buffers alone (a feature-only pre-pass must not count a batch twice)."""
+    global _bn_frozen
+    prev, _bn_frozen = _bn_frozen, True
+    try:
+        yield
+    finally:
+        _bn_frozen = prev
+
+
 def batch_norm(x, bn: torch.nn.BatchNorm1d, relu_input: bool = False):
     """Apply an nn.BatchNorm1d module's parameters/buffers with the dl_batchnorm kernels."""
     training = bn.training or bn.running_mean is None
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                             bn.num_batches_tracked if training else None, bn.eps, momentum, training,
+    update = training and not _bn_frozen
+    return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean if (update or not training) else None,
+                             bn.running_var if (update or not training) else None,
+                             bn.num_batches_tracked if update else None, bn.eps, momentum, training,
                              relu_input)
 
 

@@ -16,7 +16,7 @@ batch, for the loss and for the gradients reaching each rank's local features.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist
@@ -24,7 +24,10 @@ from torch.autograd import Function
 
 
 class AllGatherRows(Function):
-    """Concatenate `x` (rows differ per rank allowed) from all ranks along dim 0, in rank order.
+    """Concatenate `x` from all ranks along dim 0, in rank order.  Every rank contributes the SAME
+    number of rows (data-parallel shards of one global batch), so this is ONE fixed-size
+    ``all_gather_into_tensor`` (ncclAllGather into a preallocated buffer): no size exchange, no host
+    synchronisation, capturable in a CUDA graph.
 
     Backward assumes the downstream computation is replicated on every rank and that parameter
     gradients are later *averaged* over ranks (DDP convention): each rank keeps the slice of the
@@ -35,22 +38,16 @@ class AllGatherRows(Function):
     def forward(ctx, x, group, average_downstream):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
-        n_local = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
-        sizes = [torch.zeros_like(n_local) for _ in range(world)]
-        dist.all_gather(sizes, n_local, group=group)
-        sizes = [int(s.item()) for s in sizes]
-        mx = max(sizes)
-        pad = x if x.shape[0] == mx else torch.cat([x, x.new_zeros((mx - x.shape[0],) + x.shape[1:])])
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad.contiguous(), group=group)
-        ctx.meta = (sizes, rank, world, average_downstream)
-        return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        ctx.meta = (x.shape[0], rank, world, average_downstream)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        sizes, rank, world, average_downstream = ctx.meta
-        start = sum(sizes[:rank])
-        gs = g[start:start + sizes[rank]]
+        n, rank, world, average_downstream = ctx.meta
+        gs = g[rank * n:(rank + 1) * n]
         return (gs * world if average_downstream else gs), None, None
 
 
@@ -60,14 +57,28 @@ def all_gather_rows(x: torch.Tensor, group=None, average_downstream: bool = True
     return AllGatherRows.apply(x, group, average_downstream)
 
 
-def all_gather_meta(meta: List[dict], group=None) -> List[dict]:
-    """Rank-ordered concatenation of the per-pair metadata (ids and labels are tiny: host objects)."""
+def _id64(s) -> int:
+    """Stable 63-bit hash of an entity id (str or int): ids travel as int64, not as pickled objects."""
+    import hashlib
+    return int.from_bytes(hashlib.blake2b(str(s).encode(), digest_size=8).digest(), "little") >> 1
+
+
+def all_gather_meta(meta: List[dict], group=None, device=None) -> List[dict]:
+    """Rank-ordered concatenation of the per-pair metadata as ONE fixed-size tensor collective: each
+    pair contributes (hash64(Prot_ID), hash64(Drug_ID), Y) as an int64 row.  The label matrix only
+    needs id EQUALITY, which the hashes preserve.  (When every rank can enumerate the whole global
+    batch itself -- a DistributedSampler with a shared seed does -- no exchange is needed at all:
+    pass the global meta list to ``CrossModality.prepare`` directly; bench.py --config 2c2p does.)"""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return list(meta)
-    out: List[Optional[List[dict]]] = [None] * dist.get_world_size(group)
-    dist.all_gather_object(out, [{"Prot_ID": m["Prot_ID"], "Drug_ID": m["Drug_ID"], "Y": int(m["Y"])} for m in meta],
-                           group=group)
-    return [m for part in out for m in part]
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+    loc = torch.tensor([[_id64(m["Prot_ID"]), _id64(m["Drug_ID"]), int(m["Y"])] for m in meta],
+                       dtype=torch.int64, device=device)
+    out = torch.empty((world * loc.shape[0], 3), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, loc, group=group)
+    return [{"Prot_ID": p, "Drug_ID": d, "Y": y} for p, d, y in out.cpu().tolist()]
 
 
 def global_cross_modality_loss(cm, prot, aug_prot, drug, aug_drug, meta, group=None, pool_fn=None,

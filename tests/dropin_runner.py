@@ -27,6 +27,10 @@ def main():
     from tests.util import load_golden, digest
 
     fx = load_golden(fixture)
+    # the reference's own layers (ProteinCNN, adaptors, MLP head) run in torch here: full fp32, like the
+    # CPU run that recorded the fixtures
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     ref_shim.install()
     D.patch_reference()
     D.set_compute_dtype(torch.float32 if mode == "f32" else torch.bfloat16)
@@ -52,7 +56,7 @@ def main():
     vd, vp, ssl_input, cm_input, score = m(g, b.vp.cuda(), b.xd.cuda(), b.xp.cuda())   # trainer.py:196
     n, loss = bm.binary_cross_entropy(score, b.y.cuda())                               # trainer.py:199
     more = (cm_input is not None)
-    loss.backward(retain_graph=more)                                                     # trainer.py:200
+    loss.backward(retain_graph=True)                                                     # trainer.py:200 (SSL / CM follow)
     torch.cuda.synchronize()
     out = {"kind": kind, "mode": mode, "launches": _lib.launch_count() - n0,
            "score_dtype": str(score.dtype), "vd_dtype": str(vd.dtype),
