@@ -53,7 +53,7 @@ struct AttnParams {
   int B, H, S2, Lq, Lk;
   int nkc;                 // 128-key chunks
   int nqt;                 // 128-query tiles per set
-  int raw_vec;             // raw rows allow 16-byte stores
+  int raw_vec;             // raw rows are 4-byte aligned (even row stride): two logits per store
   int dq_acc;
   float scale, c1;         // c1 = scale * log2(e)
   uint32_t idesc_a, idesc_b, idesc_c;
@@ -208,19 +208,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
         }
-        if (p.raw != nullptr && row_ok && nvalid > 0) {
-          __nv_bfloat16* dst = p.raw + (((long long)b * p.H + h) * p.Lq + qrow) * p.raw_ld + col;
-          if (p.raw_vec && nvalid >= 32) {
-            uint32_t w[16];
+        if (p.raw != nullptr && nvalid > 0) {       // warp-uniform
+          // raw scaled logits: transpose the warp's 32 x 32 block through shared memory (the second P
+          // buffer is idle until pass B) so that 16 lanes write 64 contiguous bytes of ONE row --
+          // thread = row would touch 32 different rows per store instruction
+          uint32_t* stg = reinterpret_cast<uint32_t*>(smem + C::KV_BYTES + 2 * kBlk) + (warp - 2) * (16 * 33);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              w[j] = ptx::pack_bf16(__uint_as_float(v[2 * j]) * p.scale, __uint_as_float(v[2 * j + 1]) * p.scale);
-            stg_bf16x32(dst, w);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = __float2bfloat16_rn(__uint_as_float(v[j]) * p.scale);
+          for (int j = 0; j < 16; ++j)
+            stg[j * 33 + lane] = ptx::pack_bf16(__uint_as_float(v[2 * j]) * p.scale, __uint_as_float(v[2 * j + 1]) * p.scale);
+          __syncwarp();
+          const int hl = lane >> 4, wl = lane & 15;
+          const int colw = col + 2 * wl;
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {
+            const int rr = 2 * it + hl;
+            const int grow = q0 + quad * 32 + rr;
+            const uint32_t word = stg[wl * 33 + rr];
+            if (grow < p.Lq && colw < p.Lk) {
+              __nv_bfloat16* dst = p.raw + (((long long)b * p.H + h) * p.Lq + grow) * p.raw_ld + colw;
+              if (p.raw_vec && colw + 1 < p.Lk) {
+                *reinterpret_cast<uint32_t*>(dst) = word;
+              } else {
+                reinterpret_cast<unsigned short*>(dst)[0] = (unsigned short)(word & 0xffffu);
+                if (colw + 1 < p.Lk) reinterpret_cast<unsigned short*>(dst)[1] = (unsigned short)(word >> 16);
+              }
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -645,7 +659,7 @@ void fill_common(AttnParams& p, const dl_attn_args* a) {
   p.B = (int)a->B; p.H = (int)a->H; p.S2 = (int)a->S2; p.Lq = (int)a->Lq; p.Lk = (int)a->Lk;
   p.nkc = (int)((a->Lk + 127) / 128);
   p.nqt = (int)((a->Lq + 127) / 128);
-  p.raw_vec = a->raw != nullptr && a->raw_ld % 8 == 0 && ((uintptr_t)a->raw & 15) == 0;
+  p.raw_vec = a->raw != nullptr && a->raw_ld % 2 == 0 && ((uintptr_t)a->raw & 3) == 0;
   p.dq_acc = a->dq_accumulate;
   p.scale = a->scale;
   p.c1 = a->scale * 1.4426950408889634f;

@@ -562,8 +562,9 @@ class CrossModality(nn.Module):
     def latents_from_pooled(self, prot, aug_prot, drug, aug_drug, targets: CMTargets):
         """Unit-norm latents of the unique entities from the per-pair sequence means (B, hidden).
         Selecting the unique rows after the mean equals the reference's select-then-mean."""
-        prot, aug_prot = prot[targets.p_idx], aug_prot[targets.p_idx]
-        drug, aug_drug = drug[targets.d_idx], aug_drug[targets.d_idx]
+        # index_select: its backward is an index_add_ (no sort, no host sync: CUDA-graph capturable)
+        prot, aug_prot = prot.index_select(0, targets.p_idx), aug_prot.index_select(0, targets.p_idx)
+        drug, aug_drug = drug.index_select(0, targets.d_idx), aug_drug.index_select(0, targets.d_idx)
         pe = torch.cat([self._embed(prot, self.prot2latent), self._embed(aug_prot, self.aug_prot2latent)], -1)
         de = torch.cat([self._embed(drug, self.drug2latent), self._embed(aug_drug, self.aug_drug2latent)], -1)
         pl = Fn.L2NormFn.apply(Fn.linear(pe, self.to_prot_latent.weight))
