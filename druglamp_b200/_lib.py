@@ -41,7 +41,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("mul_mode", C.c_int32), ("tile_n", C.c_int32), ("precise", C.c_int32),
         ("split_k", C.c_int32), ("conv_taps", C.c_int32), ("conv_left", C.c_int32),
         ("kred", C.c_int32), ("kred_shift", C.c_int32), ("accumulate", C.c_int32),
-        ("colsum_a", C.c_void_p), ("drop_seed_step", C.c_void_p),
+        ("colsum_a", C.c_void_p), ("drop_seed_step", C.c_void_p), ("pre_mode", C.c_int32),
     ]
 
 
@@ -173,7 +173,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          sr=(0, 0, 0), drop_p: float = 0.0, drop_seed: int = 0, tile_n: int = 0,
          precise: Optional[bool] = None, split_k: int = 0, conv_taps: int = 0, conv_left: int = 0,
          kred: int = 0, kred_shift: int = 0, accumulate: bool = False,
-         colsum_a: Optional[torch.Tensor] = None) -> None:
+         colsum_a: Optional[torch.Tensor] = None, pre_mode: int = 0) -> None:
     """Raw strided/batched GEMM (see ``dl_gemm`` in the header); all extents in elements."""
     if A.dtype != B.dtype:
         raise TypeError(f"A and B must share a dtype ({A.dtype} vs {B.dtype})")
@@ -188,7 +188,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
                  drop_seed, drop_p, alpha, dt(A), dt(out), int(trans_a), int(trans_b), act,
                  mul_mode, tile_n, int(FP32_PRECISE if precise is None else precise), split_k,
                  conv_taps, conv_left, int(kred), kred_shift, int(accumulate), ptr(colsum_a),
-                 ptr(DROPOUT_STEP) if drop_p > 0 else None)
+                 ptr(DROPOUT_STEP) if drop_p > 0 else None, int(pre_mode))
     if PROFILE is None:
         check(lib().dl_gemm(C.byref(a), stream_ptr()), "dl_gemm")
         return

@@ -179,6 +179,20 @@ template <typename T> __device__ __forceinline__ float gelu_fwd(float x) {
     return gelu_erf(x);
   }
 }
+// value and derivative together (one tanh): the forward epilogue that stores d/dx for the backward
+template <typename T> __device__ __forceinline__ void gelu_fwd_grad(float x, float& y, float& d) {
+  if constexpr (sizeof(T) == 2) {
+    const float u = x * x;
+    const float t = tanh_approx(x * fmaf(u, 0.044715f * 0.7978845608f, 0.7978845608f));
+    const float hx = 0.5f * x;
+    y = fmaf(hx, t, hx);
+    const float dz = fmaf(u, 3.0f * 0.044715f * 0.7978845608f, 0.7978845608f);
+    d = fmaf(hx * fmaf(-t, t, 1.0f), dz, fmaf(0.5f, t, 0.5f));
+  } else {
+    y = gelu_erf(x);
+    d = gelu_erf_grad(x);
+  }
+}
 template <typename T> __device__ __forceinline__ float gelu_grad(float x) {
   if constexpr (sizeof(T) == 2) {
     const float u = x * x;

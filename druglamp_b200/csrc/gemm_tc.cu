@@ -73,6 +73,7 @@ struct GemmParams {
   int a_mn, b_mn;
   int c_bf16;
   int act, mul_mode;
+  int pre_mode;                 // 0: preact = pre-activation; 1: preact = d(dropout(act(v)))/dv (backward's multiplier)
   int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work,
                                 // 3 plain stores without the lane transpose (A/B measurements)
   int conv_cin, conv_left;      // implicit-GEMM conv1d on A (0 = off): channels per tap, left padding
@@ -282,13 +283,26 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
     }
-    if (Pre) store16<TC>(Pre + off, x, full && f.vec_p, nvalid, f.wide_p);
+    const bool deriv = Pre != nullptr && p.pre_mode == 1;
+    float dact[16];                                  // d act / dv, later times the dropout factor
+    if (Pre && !deriv) store16<TC>(Pre + off, x, full && f.vec_p, nvalid, f.wide_p);
     if (p.act == DL_ACT_GELU) {
+      if (deriv) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
+        for (int j = 0; j < 16; ++j) gelu_fwd_grad<TC>(x[j], x[j], dact[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
+      }
     } else if (p.act == DL_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+      for (int j = 0; j < 16; ++j) {
+        if (deriv) dact[j] = x[j] > 0.f ? 1.f : 0.f;
+        x[j] = fmaxf(x[j], 0.f);
+      }
+    } else if (deriv) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dact[j] = 1.f;
     }
     if (p.mul_mode != DL_MUL_NONE) {
       float m[16];
@@ -302,14 +316,22 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t h = drop_hash(f.drop_seed, (e >> 1) + k);
-          x[2 * k] *= (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
-          x[2 * k + 1] *= (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
+          const float m0 = (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
+          const float m1 = (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
+          x[2 * k] *= m0;
+          x[2 * k + 1] *= m1;
+          if (deriv) { dact[2 * k] *= m0; dact[2 * k + 1] *= m1; }
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] *= drop_keep(f.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const float m = drop_keep(f.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
+          x[j] *= m;
+          if (deriv) dact[j] *= m;
+        }
       }
     }
+    if (deriv) store16<TC>(Pre + off, dact, full && f.vec_p, nvalid, f.wide_p);
     if (Res) {
       float r[16];
       load16<TC>(Res + rrow + col, r, full && f.vec_r, nvalid, f.wide_r);
@@ -784,6 +806,8 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   DL_REQUIRE(a->mul_mode == DL_MUL_NONE || a->mul_aux != nullptr, "dl_gemm: mul_mode set without mul_aux");
   DL_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "dl_gemm: drop_p must be in [0, 1)");
   DL_REQUIRE(a->act >= 0 && a->act <= 2 && a->mul_mode >= 0 && a->mul_mode <= 3, "dl_gemm: bad act / mul_mode");
+  DL_REQUIRE(a->pre_mode == 0 || (a->pre_mode == 1 && a->mul_mode == DL_MUL_NONE),
+             "dl_gemm: pre_mode must be 0 or 1 (1 excludes mul_aux)");
   if (a->M == 0 || a->N == 0) return 0;
   const bool f32 = a->dtype_ab == DL_F32;
   const int sms = sm_count();
@@ -887,6 +911,7 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   p.a_mn = a->trans_a != 0; p.b_mn = a->trans_b != 0;
   p.c_bf16 = a->dtype_c == DL_BF16;
   p.act = a->act; p.mul_mode = a->mul_mode; p.alpha = a->alpha;
+  p.pre_mode = a->pre_mode;
   static const int dbg_mode = [] { const char* e = getenv("DL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_mode;
   p.idesc = 0;

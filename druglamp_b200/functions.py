@@ -221,7 +221,8 @@ class FFNFn(Function):
         hd = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
         # forward-only scoring (no_grad): the pre-activation is never read, skip its store
         pre1 = torch.empty_like(hd) if _needs_backward(ctx) else None
-        K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1))
+        # pre1 receives d hd / d pre = gelu'(pre) * dropout factor (pre_mode 1): the backward multiplies
+        K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1), pre_mode=1)
         r2 = K.to_compute(residual).view(-1, w2.shape[0]) if residual is not None else None
         y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
         ctx.save_for_backward(x2, w1, w2, pre1, hd)
@@ -238,7 +239,7 @@ class FFNFn(Function):
         g2 = K.act_bwd(gy2, None, K.ACT_NONE, (p, seed2))
         b1p, b2p = ctx.biases
         dw2, db2 = _wbgrad(w2, b2p, g2, hd)
-        dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD, drop=(p, seed1))
+        dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
         dw1, db1 = _wbgrad(w1, b1p, dpre1, x2)
         dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs) if ctx.needs_input_grad[0] else None
         dres = _back(gy2, rdt, gy.shape) if rdt is not None else None
@@ -703,7 +704,7 @@ class MHLAFn(Function):
         D, Hh = w1.shape[0], w2.shape[0]
         h = torch.empty((v2.shape[0], D), dtype=vc.dtype, device=vc.device)
         pre1 = torch.empty_like(h) if _needs_backward(ctx) else None
-        K.mm(v2, shadow(w1), h, bias=b1, act=K.ACT_GELU, pre=pre1)
+        K.mm(v2, shadow(w1), h, bias=b1, act=K.ACT_GELU, pre=pre1, pre_mode=1)      # pre1 = gelu'(lin1(v))
         logits = K.mm(h, shadow(w2), bias=b2).view(Bn, Lr, Hh)
         g_ = None if gamma is None else gamma.detach()
         b_ = None if beta is None else beta.detach()
@@ -724,7 +725,7 @@ class MHLAFn(Function):
         dl2 = dlogits.view(-1, Hh)
         b1, b2 = ctx.biases
         dw2, db2 = _wbgrad(w2, b2, dl2, h)
-        dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_GELU_GRAD)
+        dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
         dw1, db1 = _wbgrad(w1, b1, dpre1, vc.view(-1, E))
         dv = K.mm(dpre1, shadow(w1), tb=True, res=dv_direct.view(-1, E)).view(Bn, Lr, E)
         return _back(dv, ctx.vdt), dw1, db1, dw2, db2, dg, db, None

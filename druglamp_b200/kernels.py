@@ -87,7 +87,8 @@ def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, 
        tb: bool = False, bias=None, act: int = ACT_NONE, pre: Optional[torch.Tensor] = None,
        mul_aux=None, mul_mode: int = MUL_NONE, res: Optional[torch.Tensor] = None,
        drop: Tuple[float, int] = (0.0, 0), alpha: float = 1.0, out_dtype=None,
-       tile_n: int = 0, accumulate: bool = False, colsum_a: Optional[torch.Tensor] = None) -> torch.Tensor:
+       tile_n: int = 0, accumulate: bool = False, colsum_a: Optional[torch.Tensor] = None,
+       pre_mode: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * op(a) @ op(b)).  colsum_a (fp32 [M], bf16 operands, ta=True):
     += column sums of a, i.e. the bias gradient when this is a weight-gradient GEMM.
 
@@ -106,7 +107,7 @@ def mm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, 
     L.gemm(a, b, out, M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b), ldc=_ld(out), trans_a=ta, trans_b=tb,
            alpha=alpha, bias=bias, act=act, preact_out=pre, mul_aux=mul_aux, mul_mode=mul_mode,
            residual=res, ldr=ldr, drop_p=drop[0], drop_seed=drop[1], tile_n=tile_n, accumulate=accumulate,
-           colsum_a=colsum_a)
+           colsum_a=colsum_a, pre_mode=pre_mode)
     return out
 
 

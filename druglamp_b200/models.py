@@ -122,7 +122,9 @@ class DrugLAMPBase(nn.Module):
         return mhla.forward_residual_norm(m, norm), A
 
     def _head(self, f):
-        f = Fn.SitePoolFn.apply(f, f.shape[1]).view(f.shape[0], f.shape[2])     # torch.mean(f, dim=1)
+        from . import modules as M
+        with K.local_compute_dtype(torch.float32 if M.HEAD_PRECISION == "fp32" else None):
+            f = Fn.SitePoolFn.apply(f, f.shape[1]).view(f.shape[0], f.shape[2])     # torch.mean(f, dim=1)
         return self.mlp_classifier(f)
 
     def _masks(self, xd, xp, need_xd=True):

@@ -36,6 +36,10 @@ RETURN_CALLER_DTYPE = False
 # 1.3 % of the step's FLOPs, so by default its activations stay fp32 (TF32x3 GEMMs) whatever the
 # compute dtype of the rest; "compute" follows set_compute_dtype.
 GCN_PRECISION = "fp32"
+# The decoder head (mean over the sequence -> MLP with three train-mode BatchNorm1d over the PAIRS of the
+# batch, model/basic_model.py:196-215) works on 64 rows: 0.04 % of the FLOPs, but every BatchNorm over 64
+# samples re-amplifies the rounding of its input.  It runs in fp32 as well.
+HEAD_PRECISION = "fp32"
 
 
 def set_gcn_precision(mode: str) -> None:
@@ -43,6 +47,13 @@ def set_gcn_precision(mode: str) -> None:
     if mode not in ("fp32", "compute"):
         raise ValueError("GCN precision must be 'fp32' or 'compute'")
     GCN_PRECISION = mode
+
+
+def set_head_precision(mode: str) -> None:
+    global HEAD_PRECISION
+    if mode not in ("fp32", "compute"):
+        raise ValueError("head precision must be 'fp32' or 'compute'")
+    HEAD_PRECISION = mode
 
 
 def _ret(y, like):
@@ -661,7 +672,8 @@ class MLP(nn.Module):
         self.fc4 = nn.Linear(out_dim, binary)
 
     def forward(self, x):
-        for i in (1, 2, 3):
-            fc, bn = getattr(self, f"fc{i}"), getattr(self, f"bn{i}")
-            x = Fn.batch_norm(Fn.linear(x, fc.weight, fc.bias, K.ACT_GELU), bn)
-        return Fn.linear(x, self.fc4.weight, self.fc4.bias).float()
+        with K.local_compute_dtype(torch.float32 if HEAD_PRECISION == "fp32" else None):
+            for i in (1, 2, 3):
+                fc, bn = getattr(self, f"fc{i}"), getattr(self, f"bn{i}")
+                x = Fn.batch_norm(Fn.linear(x, fc.weight, fc.bias, K.ACT_GELU), bn)
+            return Fn.linear(x, self.fc4.weight, self.fc4.bias).float()

@@ -115,6 +115,11 @@ typedef struct dl_gemm_args {
                          is splitmix64(drop_seed ^ f(*drop_seed_step)), read on the device, so a
                          captured CUDA graph draws a fresh mask on every replay (the same pointer is given
                          to the backward's dl_act_bwd / dl_gemm of that step). */
+  int32_t pre_mode;   /* what preact_out receives.  0: the pre-activation v (after bias).  1: the derivative of
+                         this epilogue's elementwise part, d dropout(act(v)) / dv = act'(v) * keep / (1 - p): the
+                         backward's dX GEMM then multiplies by it (DL_MUL_VALUE) instead of re-evaluating
+                         gelu' and the dropout hash per element -- the epilogue of the 4x-wide FFN gradient
+                         (model/PMMA/mlp.py:45-49) is instruction-bound, the forward has the values at hand. */
 } dl_gemm_args;
 
 int dl_gemm(const dl_gemm_args* args, void* stream);
