@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdruglamp_sm100.so")
+# DRUGLAMP_LIB: an alternative build of the same ABI (A/B measurements on one box)
+LIB_PATH = os.environ.get("DRUGLAMP_LIB") or os.path.join(HERE, "libdruglamp_sm100.so")
 
 DL_F32, DL_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2

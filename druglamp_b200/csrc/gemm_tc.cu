@@ -256,7 +256,7 @@ __device__ __forceinline__ EpiFlags make_epi_flags(const GemmParams& p) {
 }
 
 // 16 accumulator columns of one row -> global memory, with the fused element-wise work.
-template <typename TC, bool SIMPLE>
+template <typename TC, bool SIMPLE, bool DERIV = false>
 __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f, const uint32_t* v,
                                          int row, int col, long long crow, long long rrow,
                                          unsigned zidx) {
@@ -283,11 +283,11 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
 #pragma unroll
       for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
     }
-    const bool deriv = Pre != nullptr && p.pre_mode == 1;
-    float dact[16];                                  // d act / dv, later times the dropout factor
-    if (Pre && !deriv) store16<TC>(Pre + off, x, full && f.vec_p, nvalid, f.wide_p);
+    constexpr bool deriv = DERIV;                    // preact_out = d dropout(act(v)) / dv (pre_mode 1): its own
+    float dact[DERIV ? 16 : 1];                      // instantiation, so the common epilogues keep their registers
+    if (!deriv && Pre) store16<TC>(Pre + off, x, full && f.vec_p, nvalid, f.wide_p);
     if (p.act == DL_ACT_GELU) {
-      if (deriv) {
+      if constexpr (deriv) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) gelu_fwd_grad<TC>(x[j], x[j], dact[j]);
       } else {
@@ -297,10 +297,10 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
     } else if (p.act == DL_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if (deriv) dact[j] = x[j] > 0.f ? 1.f : 0.f;
+        if constexpr (deriv) dact[j] = x[j] > 0.f ? 1.f : 0.f;
         x[j] = fmaxf(x[j], 0.f);
       }
-    } else if (deriv) {
+    } else if constexpr (deriv) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) dact[j] = 1.f;
     }
@@ -320,18 +320,18 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
           const float m1 = (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
           x[2 * k] *= m0;
           x[2 * k + 1] *= m1;
-          if (deriv) { dact[2 * k] *= m0; dact[2 * k + 1] *= m1; }
+          if constexpr (deriv) { dact[2 * k] *= m0; dact[2 * k + 1] *= m1; }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float m = drop_keep(f.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
           x[j] *= m;
-          if (deriv) dact[j] *= m;
+          if constexpr (deriv) dact[j] *= m;
         }
       }
     }
-    if (deriv) store16<TC>(Pre + off, dact, full && f.vec_p, nvalid, f.wide_p);
+    if constexpr (deriv) store16<TC>(Pre + off, dact, full && f.vec_p, nvalid, f.wide_p);
     if (Res) {
       float r[16];
       load16<TC>(Res + rrow + col, r, full && f.vec_r, nvalid, f.wide_r);
@@ -360,7 +360,7 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
 // One warp's 32-row x (BN/4)-column slice of a tile, straight from tensor memory to global memory:
 // thread = row (the tcgen05.ld 32x32b layout).  Every 32-byte sector a thread touches is written
 // (or read) in full.  Plain stores (SIMPLE) pull 32 columns per tensor-memory round trip.
-template <typename TC, int BN, bool SIMPLE>
+template <typename TC, int BN, bool SIMPLE, bool DERIV = false>
 __device__ __forceinline__ void epilogue_slice(const GemmParams& p, const EpiFlags& f, uint32_t tmem_q,
                                                int lane, int row0, int n0, int col_begin,
                                                long long cbase, long long rbase, unsigned zidx) {
@@ -435,9 +435,9 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, const EpiFla
     else ptx::tmem_ld_32x16(tmem_q + (uint32_t)c0, v);                        // before any divergence
     ptx::tmem_ld_wait();
     if (!row_ok) continue;
-    finish16<TC, SIMPLE>(p, f, v, row, col, crow, rrow, zidx);
+    finish16<TC, SIMPLE, DERIV>(p, f, v, row, col, crow, rrow, zidx);
     if constexpr (STEP == 32) {
-      if (col + 16 < p.N) finish16<TC, SIMPLE>(p, f, v + 16, row, col + 16, crow, rrow, zidx);
+      if (col + 16 < p.N) finish16<TC, SIMPLE, DERIV>(p, f, v + 16, row, col + 16, crow, rrow, zidx);
     }
   }
 }
@@ -665,9 +665,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.dbg == 2) {
       } else if (p.c_bf16) {
         if (ef.simple) epilogue_slice<__nv_bfloat16, BN, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+        else if (p.pre_mode == 1 && p.preact) epilogue_slice<__nv_bfloat16, BN, false, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
         else epilogue_slice<__nv_bfloat16, BN, false>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
       } else {
         if (ef.simple) epilogue_slice<float, BN, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
+        else if (p.pre_mode == 1 && p.preact) epilogue_slice<float, BN, false, true>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
         else epilogue_slice<float, BN, false>(p, ef, tmem_q, lane, row0, T.n0, cb, cbase, rbase, T.zb);
       }
       ptx::tc_fence_before();

@@ -164,6 +164,7 @@ class LinearFn(Function):
             r2 = _pad_cols(K.to_compute(residual).view(-1, residual.shape[-1]), Np)
         K.mm(x2, wc, out, tb=w_kn, bias=bias, act=act, pre=pre, res=r2, drop=(drop_p, seed))
         ctx.save_for_backward(x2, wc, pre)
+        ctx.precise = L.FP32_PRECISE
         ctx.params = (w, b)
         No = Np if keep_pad else N
         ctx.meta = (act, drop_p, seed, xs, x.dtype, None if residual is None else residual.dtype,
@@ -174,6 +175,11 @@ class LinearFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
+        with K.fp32_precise(ctx.precise):
+            return LinearFn._backward(ctx, gy)
+
+    @staticmethod
+    def _backward(ctx, gy):
         x2, wc, pre = ctx.saved_tensors
         act, drop_p, seed, xs, xdt, rdt, has_b, w_kn, Kd, Kw, N, No, rshape = ctx.meta
         Kp = x2.shape[1]

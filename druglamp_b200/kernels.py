@@ -31,20 +31,41 @@ def compute_dtype() -> torch.dtype:
 
 class local_compute_dtype:
     """``with local_compute_dtype(torch.float32): ...`` -- run a sub-graph's FORWARD in another
-    compute dtype (its Functions keep the dtype of what they saved for their backward)."""
+    compute dtype (its Functions keep the dtype of what they saved for their backward).  When the
+    surrounding mode is bf16, the fp32 island's GEMMs run as plain TF32 (one MMA pass, fp32
+    accumulation and fp32 storage -- the precision the reference itself selects, main.py:43) instead of
+    the 3xTF32 split of the fp32 parity mode; LinearFn remembers the choice for its backward."""
 
     def __init__(self, dtype):
         self.dtype = dtype
 
     def __enter__(self):
         global _compute_dtype
-        self.prev = _compute_dtype
+        self.prev, self.prev_precise = _compute_dtype, L.FP32_PRECISE
         if self.dtype is not None:
+            if self.dtype == torch.float32 and _compute_dtype == torch.bfloat16:
+                L.FP32_PRECISE = False
             _compute_dtype = self.dtype
 
     def __exit__(self, *exc):
         global _compute_dtype
         _compute_dtype = self.prev
+        L.FP32_PRECISE = self.prev_precise
+        return False
+
+
+class fp32_precise:
+    """Temporarily select 3xTF32 (True) or plain TF32 (False) for fp32 GEMM operands."""
+
+    def __init__(self, flag):
+        self.flag = flag
+
+    def __enter__(self):
+        self.prev = L.FP32_PRECISE
+        L.FP32_PRECISE = self.flag
+
+    def __exit__(self, *exc):
+        L.FP32_PRECISE = self.prev
         return False
 
 
