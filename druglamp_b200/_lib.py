@@ -83,8 +83,8 @@ SIGNATURES = {
     "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _P, _I32, _P],
     "dl_csr_build": [_P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dl_spmm_norm": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],
-    "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _I32, _P],
-    "dl_batchnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P],
+    "dl_batchnorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _F, _F, _I32, _F, _I32, _P],
+    "dl_batchnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _I32, _P],
     "dl_embed_fill_fwd": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_embed_fill_bwd": [_P, _I32, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_fillbit_pool": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _I32, _P],

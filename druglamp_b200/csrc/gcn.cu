@@ -364,6 +364,20 @@ bn_colstats_vec_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
   }
 }
 
+// The LAST row stands for `w` identical rows (the molecular GCN's virtual nodes):
+// add the (w - 1) missing copies to the column sums.
+template <typename T>
+__global__ void bn_lastrow_fix_kernel(const T* __restrict__ xlast, double* __restrict__ sums, int cols, double wm1) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < cols) {
+    const double v = (double)Cvt<T>::to_f(xlast[c]);
+    sums[c] += wm1 * v;
+    sums[cols + c] += wm1 * v * v;
+  }
+}
+
 // y = (x - mean) * rstd * gamma + beta.  FINALIZE: mean / rstd come from the fp64 column sums
 // (biased variance); the first row block also stores them for the backward pass and updates the
 // running statistics (momentum, unbiased variance) and num_batches_tracked.
@@ -374,7 +388,7 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
                     const float* __restrict__ beta, float* __restrict__ running_mean,
                     float* __restrict__ running_var, long long* __restrict__ nbt, T* __restrict__ y,
                     long long rows, int cols, long long rows_per_block, int tpr, float eps,
-                    float momentum) {
+                    float momentum, double count) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = VecWidth<T>::N;
@@ -388,8 +402,8 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
   for (int j = 0; j < V; ++j) {
     float mu, rs;
     if (FINALIZE) {
-      const double m = sums[c + j] / (double)rows;
-      double var = sums[cols + c + j] / (double)rows - m * m;
+      const double m = sums[c + j] / count;            // count = rows, or the weighted row count
+      double var = sums[cols + c + j] / count - m * m;
       if (var < 0.0) var = 0.0;
       mu = (float)m;
       rs = (float)(1.0 / sqrt(var + (double)eps));
@@ -397,7 +411,7 @@ bn_apply_vec_kernel(const T* __restrict__ x, const double* __restrict__ sums, fl
         mean[c + j] = mu;
         rstd[c + j] = rs;
         if (running_mean) {
-          const double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+          const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
           running_mean[c + j] = (1.f - momentum) * running_mean[c + j] + momentum * mu;
           running_var[c + j] = (1.f - momentum) * running_var[c + j] + momentum * (float)unb;
         }
@@ -443,7 +457,7 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                         const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, long long rows, int cols, long long rows_per_block,
-                        int tpr, int training, int acc, int relu) {
+                        int tpr, int training, int acc, int relu, double count, float last_w) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = VecWidth<T>::N;
@@ -463,9 +477,11 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
     }
     k0[j] = g * rs;
     mu_[j] = mu;
-    m1[j] = training ? (float)(sdy / (double)rows) : 0.f;
-    k1[j] = training ? rs * (float)(sdyx / (double)rows) : 0.f;
+    m1[j] = training ? (float)(sdy / count) : 0.f;
+    k1[j] = training ? rs * (float)(sdyx / count) : 0.f;
   }
+  // last_w > 1: the last row stands for last_w identical rows and its dy is already the SUM of their
+  // gradients, so the batch-statistics correction applies last_w times to it
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   long long r = r0 + rsub;
@@ -478,9 +494,10 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
+      const float w = (r + u * rpp == rows - 1) ? last_w : 1.f;
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float t = k0[j] * (d[u][j] - m1[j] - (xv[u][j] - mu_[j]) * k1[j]);
+        const float t = k0[j] * (d[u][j] - w * (m1[j] + (xv[u][j] - mu_[j]) * k1[j]));
         d[u][j] = (relu && !(xv[u][j] > 0.f)) ? 0.f : t;
       }
       stv(dx + (r + u * rpp) * cols + c, d[u]);
@@ -490,9 +507,10 @@ bn_bwd_apply_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const
     float d[V], xv[V];
     ldv(dy + r * cols + c, d);
     ldv(x + r * cols + c, xv);
+    const float w = (r == rows - 1) ? last_w : 1.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float t = k0[j] * (d[j] - m1[j] - (xv[j] - mu_[j]) * k1[j]);
+      const float t = k0[j] * (d[j] - w * (m1[j] + (xv[j] - mu_[j]) * k1[j]));
       d[j] = (relu && !(xv[j] > 0.f)) ? 0.f : t;
     }
     stv(dx + r * cols + c, d);
@@ -600,8 +618,10 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
                                 float* mean, float* rstd, float* running_mean, float* running_var,
                                 int64_t* num_batches_tracked, double* workspace, int64_t rows,
                                 int32_t cols, float eps, float momentum, int32_t training,
-                                int32_t dtype, void* stream) {
+                                float last_row_weight, int32_t dtype, void* stream) {
   DL_REQUIRE(x && y && mean && rstd, "dl_batchnorm_fwd: null pointer");
+  const bool weighted = last_row_weight > 1.f;
+  const double count = weighted ? (double)rows - 1.0 + (double)last_row_weight : (double)rows;
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_fwd: cols must be a positive multiple of 4 and rows >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   ColSlice g;
@@ -613,25 +633,31 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
       DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
       if (dtype == DL_BF16) {
         DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
-        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, true>), grid, 256, 0, st, (const __nv_bfloat16*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        if (weighted)
+          DL_LAUNCH((bn_lastrow_fix_kernel<__nv_bfloat16>), ceil_div(cols, 128), 128, 0, st, (const __nv_bfloat16*)x + (rows - 1) * cols, workspace, cols, (double)last_row_weight - 1.0);
+        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, true>), grid, 256, 0, st, (const __nv_bfloat16*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum, count);
       } else {
         DL_LAUNCH((bn_colstats_vec_kernel<float, false>), grid, 256, 0, st, (const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g.rpb, g.tpr);
-        DL_LAUNCH((bn_apply_vec_kernel<float, true>), grid, 256, 0, st, (const float*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        if (weighted)
+          DL_LAUNCH((bn_lastrow_fix_kernel<float>), ceil_div(cols, 128), 128, 0, st, (const float*)x + (rows - 1) * cols, workspace, cols, (double)last_row_weight - 1.0);
+        DL_LAUNCH((bn_apply_vec_kernel<float, true>), grid, 256, 0, st, (const float*)x, workspace, mean, rstd, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum, count);
       }
+      if (weighted) count_launch();
       DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_apply_vec_kernel");
       count_launch(2);
     } else {
       DL_REQUIRE(running_mean && running_var, "dl_batchnorm_fwd: eval mode needs running statistics");
       DL_LAUNCH(bn_eval_stats_kernel, ceil_div(cols, 128), 128, 0, st, running_mean, running_var, mean, rstd, cols, eps);
       if (dtype == DL_BF16)
-        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_apply_vec_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (__nv_bfloat16*)y, rows, cols, g.rpb, g.tpr, eps, momentum, count);
       else
-        DL_LAUNCH((bn_apply_vec_kernel<float, false>), grid, 256, 0, st, (const float*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum);
+        DL_LAUNCH((bn_apply_vec_kernel<float, false>), grid, 256, 0, st, (const float*)x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, (float*)y, rows, cols, g.rpb, g.tpr, eps, momentum, count);
       DL_LAUNCH_CHECK("bn_eval_stats_kernel / bn_apply_vec_kernel");
       count_launch(2);
     }
     return 0;
   }
+  DL_REQUIRE(!weighted, "dl_batchnorm_fwd: last_row_weight needs cols %% (16 / element size) == 0 and 16-byte aligned tensors");
   if (training) {
     DL_REQUIRE(workspace != nullptr, "dl_batchnorm_fwd: workspace required in training mode");
     DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
@@ -664,9 +690,12 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
 extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma,
                                 const float* mean, const float* rstd, void* dx, float* dgamma,
                                 float* dbeta, double* workspace, int64_t rows, int32_t cols,
-                                int32_t training, int32_t accumulate, int32_t relu_mask, int32_t dtype,
-                                void* stream) {
+                                int32_t training, int32_t accumulate, int32_t relu_mask,
+                                float last_row_weight, int32_t dtype, void* stream) {
   DL_REQUIRE(dy && x && mean && rstd && dx && workspace, "dl_batchnorm_bwd: null pointer");
+  const bool weighted = last_row_weight > 1.f;
+  const double count = weighted ? (double)rows - 1.0 + (double)last_row_weight : (double)rows;
+  const float last_w = weighted ? last_row_weight : 1.f;
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
@@ -675,16 +704,16 @@ extern "C" int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamm
     const dim3 vgrid(g.xb, g.yb);
     if (dtype == DL_BF16) {
       DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, true>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      DL_LAUNCH((bn_bwd_apply_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<__nv_bfloat16>), vgrid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, workspace, (__nv_bfloat16*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask, count, last_w);
     } else {
       DL_LAUNCH((bn_colstats_vec_kernel<float, true>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, workspace, rows, cols, g.rpb, g.tpr);
-      DL_LAUNCH((bn_bwd_apply_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask);
+      DL_LAUNCH((bn_bwd_apply_vec_kernel<float>), vgrid, 256, 0, st, (const float*)dy, (const float*)x, mean, rstd, gamma, workspace, (float*)dx, dgamma, dbeta, rows, cols, g.rpb, g.tpr, training, accumulate, relu_mask, count, last_w);
     }
     DL_LAUNCH_CHECK("bn_colstats_vec_kernel / bn_bwd_apply_vec_kernel");
     count_launch(2);
     return 0;
   }
-  DL_REQUIRE(!relu_mask, "dl_batchnorm_bwd: relu_mask needs cols %% (16 / element size) == 0 and 16-byte aligned tensors");
+  DL_REQUIRE(!relu_mask && !weighted, "dl_batchnorm_bwd: relu_mask / last_row_weight need cols %% (16 / element size) == 0 and 16-byte aligned tensors");
   dim3 grid; long long rpb;
   stats_grid(rows, cols, &grid, &rpb);
   if (dtype == DL_BF16)

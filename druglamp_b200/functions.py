@@ -328,7 +328,7 @@ def _score_buf(B, H, S2, Lq, Lk, like):
     return full if Lkp == Lk else full[..., :Lk]
 
 
-def _attn_fwd(q, k, v, H, scale, keep_raw):
+def _attn_fwd(q, k, v, H, scale, keep_raw, out=None):
     """q (S2,B,Lq,HD), k, v (B,Lk,HD): unit inner stride, every other stride free (they may be
     column slices of one fused QKV projection buffer).
     Returns O (B,Lq,S2*HD), the tensor the backward needs besides O (the fused kernel's row
@@ -340,8 +340,10 @@ def _attn_fwd(q, k, v, H, scale, keep_raw):
     if K.attn_supported(q, k, H) and (S2 == 1 or not keep_raw):
         # ONE tcgen05 kernel: scores, softmax and p.v never leave the SM; only the row
         # log-sum-exp is kept for the backward (which recomputes the probabilities)
-        O, lse, raw = K.attn_fwd(q, k, v, H, scale, want_raw=keep_raw)
+        O, lse, raw = K.attn_fwd(q, k, v, H, scale, want_raw=keep_raw, out=out)
         return O, lse, (None if raw is None else raw.unsqueeze(2))
+    if out is not None:
+        raise ValueError("a preallocated output needs the fused attention kernel")
     S = _score_buf(B, H, S2, Lq, Lk, q)
     ldp = S.stride(3)
     s_lay = (S.stride(1), S.stride(2), S.stride(0))       # batch order (head, set, pair)
@@ -617,11 +619,29 @@ class FcCatFn(Function):
 
 
 # ================================================================================ PGCA
+def _rows(t: torch.Tensor, seq_first: bool) -> torch.Tensor:
+    """A (L, N, E) tensor as the [L*N, E] row matrix of the chosen row order, in the compute dtype:
+    seq_first keeps the reference's own (l, n) order (no copy for a contiguous input), otherwise the
+    rows run (n, l) (no copy when the input is a permuted view of a batch-first tensor)."""
+    Lr, Nr, E = t.shape
+    return K.to_compute(t if seq_first else t.transpose(0, 1)).view(Lr * Nr, E)
+
+
+def _blc(rows: torch.Tensor, Lr: int, Nr: int, seq_first: bool) -> torch.Tensor:
+    """The (N, L, C) view of a row matrix built by _rows (strided when seq_first)."""
+    C_ = rows.shape[1]
+    return rows.view(Lr, Nr, C_).permute(1, 0, 2) if seq_first else rows.view(Nr, Lr, C_)
+
+
 class PGCAFn(Function):
     """GuidedCrossAttention forward/backward (model/PGCA/guided_cross_attention_model.py:124-329,
     the enc-dec in-proj branch :138-162): in-proj GEMMs, scaled q k^T with the RAW logits kept
     (:307,:319-320), softmax, p v, out-proj.  Inputs are sequence-first (L,N,E) like the
-    reference; the torch.equal host sync of :138 does not exist here."""
+    reference; the torch.equal host sync of :138 does not exist here.
+
+    The projections are row-order agnostic and the attention kernel addresses its operands through
+    strides, so a contiguous sequence-first input (what the reference API hands over, e.g. the
+    1200 x 290 long-sequence configuration) is processed in place -- no (L,N,E) <-> (N,L,E) copies."""
 
     @staticmethod
     def forward(ctx, query, key, value, in_w, in_b, out_w, out_b, H):
@@ -629,68 +649,76 @@ class PGCAFn(Function):
         Sk = key.shape[0]
         shared = (key.data_ptr() == value.data_ptr() and key.stride() == value.stride()
                   and key.shape == value.shape)
-        qb = K.to_compute(query.transpose(0, 1))                      # (B, L, E)
-        kb = K.to_compute(key.transpose(0, 1))                        # (B, S, E)
-        vb = kb if shared else K.to_compute(value.transpose(0, 1))
+        fused_ok = K.compute_dtype() == torch.bfloat16 and (E // H) in (64, 128) and Sk <= K.ATTN_MAX_KEYS
+        sf = bool(fused_ok and query.is_contiguous() and key.is_contiguous() and value.is_contiguous()
+                  and not query.transpose(0, 1).is_contiguous())
+        q2, k2 = _rows(query, sf), _rows(key, sf)
+        v2 = k2 if shared else _rows(value, sf)
         wi = shadow(in_w)
         ib = in_b.detach()
-        Qp = K.mm(qb.view(-1, E), wi[:E], bias=ib[:E]).view(1, Bn, Lq, E)
-        KV = torch.empty((Bn, Sk, 2 * E), dtype=qb.dtype, device=qb.device)
+        Q2 = K.mm(q2, wi[:E], bias=ib[:E])
+        KV2 = torch.empty((k2.shape[0], 2 * E), dtype=q2.dtype, device=q2.device)
         if shared:
-            K.mm(kb.view(-1, E), wi[E:], KV.view(-1, 2 * E), bias=ib[E:])
+            K.mm(k2, wi[E:], KV2, bias=ib[E:])
         else:
-            K.mm(kb.view(-1, E), wi[E:2 * E], KV.view(-1, 2 * E)[:, :E], bias=ib[E:2 * E])
-            K.mm(vb.view(-1, E), wi[2 * E:], KV.view(-1, 2 * E)[:, E:], bias=ib[2 * E:])
-        Kp, Vp = KV[:, :, :E], KV[:, :, E:]
+            K.mm(k2, wi[E:2 * E], KV2[:, :E], bias=ib[E:2 * E])
+            K.mm(v2, wi[2 * E:], KV2[:, E:], bias=ib[2 * E:])
+        Qp, KV = _blc(Q2, Lq, Bn, sf)[None], _blc(KV2, Sk, Bn, sf)
         scale = float(E // H) ** -0.5
-        O, P, raw = _attn_fwd(Qp, Kp, Vp, H, scale, True)
-        out = K.mm(O.view(-1, E), shadow(out_w), bias=out_b.detach()).view(Bn, Lq, E)
-        ctx.save_for_backward(qb, kb, vb, in_w, out_w, Qp, KV, P, O, in_b, out_b)
-        ctx.meta = (H, scale, shared, query.dtype, key.dtype, value.dtype)
+        O2 = torch.empty((q2.shape[0], E), dtype=q2.dtype, device=q2.device) if sf else None
+        O, P, raw = _attn_fwd(Qp, KV[:, :, :E], KV[:, :, E:], H, scale, True,
+                              out=None if O2 is None else _blc(O2, Lq, Bn, sf))
+        if O2 is None:
+            O2 = O.view(-1, E)
+        out2 = K.mm(O2, shadow(out_w), bias=out_b.detach())
+        ctx.save_for_backward(q2, k2, v2, in_w, out_w, Q2, KV2, P, O2, in_b, out_b)
+        ctx.meta = (H, scale, shared, sf, query.dtype, key.dtype, value.dtype, Lq, Sk, Bn)
         raw = raw[:, :, 0]                                             # (N, H, L, S)
         if not raw.is_contiguous():
             raw = raw.contiguous()                                     # padded rows (S % 8 != 0)
         ctx.mark_non_differentiable(raw)
-        return out.transpose(0, 1), raw
+        return (out2.view(Lq, Bn, E) if sf else out2.view(Bn, Lq, E).transpose(0, 1)), raw
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout, _graw):
-        qb, kb, vb, in_w, out_w, Qp, KV, P, O, in_b, out_b = ctx.saved_tensors
-        H, scale, shared, qdt, kdt, vdt = ctx.meta
-        Bn, Lq, E = qb.shape
-        Sk = kb.shape[1]
-        g = K.to_compute(gout.transpose(0, 1)).view(-1, E)             # (B*L, E)
-        d_out_w, d_out_b = _wbgrad(out_w, out_b, g, O.view(-1, E))
-        dO = K.mm(g, shadow(out_w), tb=True).view(Bn, Lq, E)
-        dKV = torch.empty_like(KV)
-        dQp, _, _ = _attn_bwd(dO, Qp, KV[:, :, :E], KV[:, :, E:], P, O, H, scale,
-                              dk_out=dKV[:, :, :E], dv_out=dKV[:, :, E:])
+        q2, k2, v2, in_w, out_w, Q2, KV2, P, O2, in_b, out_b = ctx.saved_tensors
+        H, scale, shared, sf, qdt, kdt, vdt, Lq, Sk, Bn = ctx.meta
+        E = q2.shape[1]
+        g = _rows(gout, sf)                                            # [L*N, E] in the forward's row order
+        d_out_w, d_out_b = _wbgrad(out_w, out_b, g, O2)
+        dO2 = K.mm(g, shadow(out_w), tb=True)
+        dQ2, dKV2 = torch.empty_like(Q2), torch.empty_like(KV2)
+        KV, dKV = _blc(KV2, Sk, Bn, sf), _blc(dKV2, Sk, Bn, sf)
+        _attn_bwd(_blc(dO2, Lq, Bn, sf), _blc(Q2, Lq, Bn, sf)[None], KV[:, :, :E], KV[:, :, E:], P,
+                  _blc(O2, Lq, Bn, sf), H, scale, dq_out=_blc(dQ2, Lq, Bn, sf)[None],
+                  dk_out=dKV[:, :, :E], dv_out=dKV[:, :, E:])
         wi = shadow(in_w)
-        dq2, dkv2 = dQp.view(-1, E), dKV.view(-1, 2 * E)
+
+        def back(rows, Lr, dt):                                        # row matrix -> (L, N, E) gradient
+            t = _back(rows, dt)
+            return t.view(Lr, Bn, E) if sf else t.view(Bn, Lr, E).transpose(0, 1)
         # the packed in-proj gradients go straight into the flat gradient buffer when there is one
         tw, tb_ = _grad_target(in_w), _grad_target(in_b)
         acc = tw is not None and tb_ is not None
         d_in_w = tw if acc else torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
         d_in_b = tb_ if acc else torch.empty(3 * E, dtype=torch.float32, device=g.device)
-        fuse = acc and dq2.dtype == torch.bfloat16      # bias gradients summed inside the dW GEMMs
-        K.mm(dq2, qb.view(-1, E), d_in_w[:E], ta=True, tb=True, accumulate=acc,
-             colsum_a=d_in_b[:E] if fuse else None)
+        fuse = acc and dQ2.dtype == torch.bfloat16      # bias gradients summed inside the dW GEMMs
+        K.mm(dQ2, q2, d_in_w[:E], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[:E] if fuse else None)
         if not fuse:
-            K.colsum(dq2, d_in_b[:E], accumulate=acc)
+            K.colsum(dQ2, d_in_b[:E], accumulate=acc)
         if not (fuse and shared):
-            K.colsum(dkv2, d_in_b[E:], accumulate=acc)
-        dquery = _back(K.mm(dq2, wi[:E], tb=True).view(Bn, Lq, E), qdt).transpose(0, 1)
+            K.colsum(dKV2, d_in_b[E:], accumulate=acc)
+        dquery = back(K.mm(dQ2, wi[:E], tb=True), Lq, qdt)
         if shared:
-            K.mm(dkv2, kb.view(-1, E), d_in_w[E:], ta=True, tb=True, accumulate=acc,
-                 colsum_a=d_in_b[E:] if fuse else None)
-            dkey = _back(K.mm(dkv2, wi[E:], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
+            K.mm(dKV2, k2, d_in_w[E:], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[E:] if fuse else None)
+            dkey = back(K.mm(dKV2, wi[E:], tb=True), Sk, kdt)
             dvalue = None
         else:
-            K.mm(dkv2[:, :E], kb.view(-1, E), d_in_w[E:2 * E], ta=True, tb=True, accumulate=acc)
-            K.mm(dkv2[:, E:], vb.view(-1, E), d_in_w[2 * E:], ta=True, tb=True, accumulate=acc)
-            dkey = _back(K.mm(dkv2[:, :E], wi[E:2 * E], tb=True).view(Bn, Sk, E), kdt).transpose(0, 1)
-            dvalue = _back(K.mm(dkv2[:, E:], wi[2 * E:], tb=True).view(Bn, Sk, E), vdt).transpose(0, 1)
+            K.mm(dKV2[:, :E], k2, d_in_w[E:2 * E], ta=True, tb=True, accumulate=acc)
+            K.mm(dKV2[:, E:], v2, d_in_w[2 * E:], ta=True, tb=True, accumulate=acc)
+            dkey = back(K.mm(dKV2[:, :E], wi[E:2 * E], tb=True), Sk, kdt)
+            dvalue = back(K.mm(dKV2[:, E:], wi[2 * E:], tb=True), Sk, vdt)
         if acc:
             d_in_w = d_in_b = None
         return dquery, dkey, dvalue, d_in_w, d_in_b, d_out_w, d_out_b, None
@@ -757,36 +785,62 @@ class SpmmFn(Function):
         return _back(dh, ctx.hdt), None
 
 
+class ExpandVirtualFn(Function):
+    """(R + 1, C) compact rows -> (N, C): real rows to their slots, the representative virtual row
+    (the last one) to every other slot (graph.CompactMolGraph).  Backward: the real rows' gradients,
+    and for the representative the SUM over all the slots it stands for."""
+
+    @staticmethod
+    def forward(ctx, xc, real_idx, n_full):
+        R = real_idx.numel()
+        out = xc[R].expand(n_full, xc.shape[1]).contiguous()
+        out.index_copy_(0, real_idx, xc[:R])
+        ctx.save_for_backward(real_idx)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (real_idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        real = g.index_select(0, real_idx)
+        virt = K.colsum(g) - K.colsum(real)                  # fp32 column sums (dl_colsum)
+        return torch.cat((real, virt.to(g.dtype).unsqueeze(0))), None, None
+
+
 class BatchNormFn(Function):
     """nn.BatchNorm1d over (rows, C) with the module's buffers updated in place."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, relu_input=False):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, relu_input=False,
+                last_row_weight=1.0):
         """relu_input: x is the output of a ReLU whose own backward is skipped (Conv1dSameFn with
-        mask_in_bwd=False); the mask (x > 0) is applied to dx inside the BatchNorm backward kernel."""
+        mask_in_bwd=False); the mask (x > 0) is applied to dx inside the BatchNorm backward kernel.
+        last_row_weight w > 1: the last row stands for w identical rows (dl_batchnorm_fwd)."""
         xc = K.to_compute(x)
         x2 = xc.view(-1, xc.shape[-1])
         g_ = None if gamma is None else gamma.detach()
         b_ = None if beta is None else beta.detach()
-        y, mean, rstd = K.batchnorm_fwd(x2, g_, b_, running_mean, running_var, nbt, eps, momentum, training)
+        y, mean, rstd = K.batchnorm_fwd(x2, g_, b_, running_mean, running_var, nbt, eps, momentum, training,
+                                        last_row_weight if training else 1.0)
         ctx.save_for_backward(x2, gamma, beta, mean, rstd)
-        ctx.meta = (training, x.dtype, x.shape, bool(relu_input))
+        ctx.meta = (training, x.dtype, x.shape, bool(relu_input), float(last_row_weight) if training else 1.0)
         return y.view(xc.shape)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x2, gamma, beta, mean, rstd = ctx.saved_tensors
-        training, xdt, xshape, relu = ctx.meta
+        training, xdt, xshape, relu, lrw = ctx.meta
         g_ = None if gamma is None else gamma.detach()
         tg, tb = _grad_target(gamma), _grad_target(beta)
         if tg is not None and tb is not None:       # straight into the flat gradient buffer
             dx, _, _ = K.batchnorm_bwd(_as(gy, x2.dtype).view(x2.shape), x2, g_, mean, rstd, training,
-                                       acc_into=(tg, tb), relu_mask=relu)
-            return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None, None
+                                       acc_into=(tg, tb), relu_mask=relu, last_row_weight=lrw)
+            return _back(dx, xdt, xshape), None, None, None, None, None, None, None, None, None, None
         dx, dg, db = K.batchnorm_bwd(_as(gy, x2.dtype).view(x2.shape), x2, g_, mean, rstd, training,
-                                     need_param_grads=gamma is not None, relu_mask=relu)
-        return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None, None
+                                     need_param_grads=gamma is not None, relu_mask=relu, last_row_weight=lrw)
+        return _back(dx, xdt, xshape), dg, db, None, None, None, None, None, None, None, None
 
 
 _bn_frozen = False
@@ -804,7 +858,7 @@ def frozen_bn_buffers():
         _bn_frozen = prev
 
 
-def batch_norm(x, bn: torch.nn.BatchNorm1d, relu_input: bool = False):
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu_input: bool = False, last_row_weight: float = 1.0):
     """Apply an nn.BatchNorm1d module's parameters/buffers with the dl_batchnorm kernels."""
     training = bn.training or bn.running_mean is None
     momentum = 0.1 if bn.momentum is None else bn.momentum
@@ -812,7 +866,7 @@ def batch_norm(x, bn: torch.nn.BatchNorm1d, relu_input: bool = False):
     return BatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean if (update or not training) else None,
                              bn.running_var if (update or not training) else None,
                              bn.num_batches_tracked if update else None, bn.eps, momentum, training,
-                             relu_input)
+                             relu_input, last_row_weight)
 
 
 # ================================================================================ glue

@@ -94,6 +94,8 @@ class BatchedMolGraph:
                   "in_deg", "out_deg", "norm_dst", "norm_src"):
             setattr(g, k, getattr(self, k).to(device, **kw))
         g.ndata = {k: v.to(device, **kw) for k, v in self.ndata.items()}
+        c = self.compact()
+        g.__dict__["_compact"] = None if c is None else c.to(device, **kw)
         return g
 
     # ---- constructors -----------------------------------------------------------
@@ -105,6 +107,45 @@ class BatchedMolGraph:
         src, dst = g.edges()
         h = g.ndata["h"] if "h" in g.ndata else None
         return cls(src, dst, g.num_nodes(), g.batch_size, h)
+
+    # ---- virtual-node dedup ------------------------------------------------------------
+    def compact(self):
+        """-> CompactMolGraph or None.  Every molecule is padded to 512 nodes with VIRTUAL nodes
+        (dataset.py:214-222): isolated, one self loop, one and the same feature row -- 92 % of all
+        rows.  Isolated identical rows stay identical through every GCN layer, so the layer needs
+        evaluating once for them.  The compact graph keeps the real nodes plus ONE representative
+        virtual node (the last row) and remembers how many rows it stands for; BatchNorm counts it
+        that often (dl_batchnorm last_row_weight) and the result is expanded back to all N rows, so
+        nothing is dropped or masked.  Built on the host (collate time) from CPU tensors; None when
+        the graph was assembled on the device or has no such nodes."""
+        c = self.__dict__.get("_compact", False)
+        if c is not False:
+            return c
+        c = None
+        h = self.ndata.get("h")
+        if h is not None and not self.src.is_cuda and not h.is_cuda and self._n > 1:
+            ind, outd = self.in_deg, self.out_deg
+            first_src = torch.full((self._n,), -1, dtype=torch.int64)
+            has = ind > 0
+            first_src[has] = self.indices[self.indptr[:-1][has].long()].long()
+            cand = (ind == 1) & (outd == 1) & (first_src == torch.arange(self._n))
+            if int(cand.sum()) >= 2:
+                rep = int(torch.nonzero(cand)[0])
+                virt = cand & (h == h[rep]).all(dim=1)
+                m = int(virt.sum())
+                if m >= 2:
+                    real_idx = torch.nonzero(~virt).flatten()
+                    R = int(real_idx.numel())
+                    new_id = torch.full((self._n,), -1, dtype=torch.int64)
+                    new_id[real_idx] = torch.arange(R)
+                    keep = ~virt[self.src]
+                    src_c = torch.cat((new_id[self.src[keep]], torch.tensor([R])))
+                    dst_c = torch.cat((new_id[self.dst[keep]], torch.tensor([R])))
+                    assert int(src_c.min()) >= 0 and int(dst_c.min()) >= 0    # virtual nodes are isolated
+                    c = CompactMolGraph(BatchedMolGraph(src_c, dst_c, R + 1, self.batch_size),
+                                        torch.cat((real_idx, torch.tensor([rep]))), real_idx, m, self._n)
+        self.__dict__["_compact"] = c
+        return c
 
     # ---- device-side construction (no host sync: usable on an input pipeline's copy stream) --------
     @classmethod
@@ -184,3 +225,20 @@ class BatchedMolGraph:
         if self._zero_in:
             raise Exception("There are 0-in-degree nodes in the graph, output for those nodes "
                             "will be invalid. Adding self-loop on the input graph will resolve the issue.")
+
+
+class CompactMolGraph:
+    """Real nodes + one representative virtual node (row R) of a BatchedMolGraph (see compact())."""
+
+    def __init__(self, graph: BatchedMolGraph, gather: torch.Tensor, real_idx: torch.Tensor, n_virtual: int,
+                 n_full: int):
+        self.graph, self.gather, self.real_idx = graph, gather, real_idx
+        self.n_virtual, self.n_full = int(n_virtual), int(n_full)
+
+    def to(self, device, **kw) -> "CompactMolGraph":
+        return CompactMolGraph(self.graph.to(device, **kw), self.gather.to(device, **kw),
+                               self.real_idx.to(device, **kw), self.n_virtual, self.n_full)
+
+    def tensors(self):
+        g = self.graph
+        return [self.gather, self.real_idx, g.indptr, g.indices, g.indptr_t, g.indices_t, g.norm_src, g.norm_dst]

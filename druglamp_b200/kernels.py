@@ -36,15 +36,15 @@ class local_compute_dtype:
     accumulation and fp32 storage -- the precision the reference itself selects, main.py:43) instead of
     the 3xTF32 split of the fp32 parity mode; LinearFn remembers the choice for its backward."""
 
-    def __init__(self, dtype):
-        self.dtype = dtype
+    def __init__(self, dtype, precise=None):
+        self.dtype, self.precise = dtype, precise
 
     def __enter__(self):
         global _compute_dtype
         self.prev, self.prev_precise = _compute_dtype, L.FP32_PRECISE
         if self.dtype is not None:
             if self.dtype == torch.float32 and _compute_dtype == torch.bfloat16:
-                L.FP32_PRECISE = False
+                L.FP32_PRECISE = False if self.precise is None else bool(self.precise)
             _compute_dtype = self.dtype
 
     def __exit__(self, *exc):
@@ -274,12 +274,17 @@ def _attn_args(q, k, v, o, lse, H, scale):
     return a
 
 
-def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, H: int, scale: float, want_raw: bool = False):
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, H: int, scale: float, want_raw: bool = False,
+             out: Optional[torch.Tensor] = None):
     """q (S2, B, Lq, H*d), k / v (B, Lk, H*d) bf16 views (unit inner stride, the rest free).
-    -> O (B, Lq, S2*H*d), lse (S2, B, H, Lq) fp32 [log2 domain], raw (B, H, Lq, Lk) | None."""
+    -> O (B, Lq, S2*H*d), lse (S2, B, H, Lq) fp32 [log2 domain], raw (B, H, Lq, Lk) | None.
+    `out`: a preallocated (B, Lq, S2*H*d) destination with free row / pair strides (e.g. a view of a
+    sequence-first buffer)."""
     S2, B, Lq, HD = q.shape
     Lk = k.shape[1]
-    o = torch.empty((B, Lq, S2 * HD), dtype=q.dtype, device=q.device)
+    o = out if out is not None else torch.empty((B, Lq, S2 * HD), dtype=q.dtype, device=q.device)
+    if tuple(o.shape) != (B, Lq, S2 * HD):
+        raise ValueError("attn_fwd: out must be (B, Lq, S2*H*d)")
     lse = torch.empty((S2, B, H, Lq), dtype=torch.float32, device=q.device)
     a = _attn_args(q, k, v, o, lse, H, scale)
     raw = None
@@ -316,7 +321,7 @@ def spmm_norm(indptr, indices, norm_src, norm_dst, h: torch.Tensor) -> torch.Ten
 
 
 def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, eps: float,
-                  momentum: float, training: bool):
+                  momentum: float, training: bool, last_row_weight: float = 1.0):
     rows, cols = x.shape
     y = torch.empty_like(x)
     mean = torch.empty(cols, dtype=torch.float32, device=x.device)
@@ -324,12 +329,12 @@ def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, 
     ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
     L.call("dl_batchnorm_fwd", x.data_ptr(), L.ptr(gamma), L.ptr(beta), y.data_ptr(), mean.data_ptr(),
            rstd.data_ptr(), L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt), ws.data_ptr(), rows, cols,
-           eps, momentum, int(training), L.dt(x))
+           eps, momentum, int(training), float(last_row_weight), L.dt(x))
     return y, mean, rstd
 
 
 def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True, acc_into=None,
-                  relu_mask: bool = False):
+                  relu_mask: bool = False, last_row_weight: float = 1.0):
     """acc_into = (dgamma, dbeta) fp32 gradient buffers to ADD the parameter gradients to.
     relu_mask: x is a ReLU output; dx is additionally multiplied by (x > 0)."""
     rows, cols = x.shape
@@ -343,7 +348,7 @@ def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bo
         db = torch.empty_like(dg)
     L.call("dl_batchnorm_bwd", dy.data_ptr(), x.data_ptr(), L.ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
            dx.data_ptr(), L.ptr(dg), L.ptr(db), ws.data_ptr(), rows, cols, int(training),
-           int(acc_into is not None), int(relu_mask), L.dt(x))
+           int(acc_into is not None), int(relu_mask), float(last_row_weight), L.dt(x))
     return dx, dg, db
 
 

@@ -41,7 +41,8 @@ class StaticBatch:
         the dense LLM embeddings, labels and the batched graph's raw edge list (the CSR carrier is
         rebuilt from it on the device, ``BatchedMolGraph.rebuild_``)."""
         g = self.graph
-        return [self.h, self.vp, self.xd, self.xp, self.y, g.src, g.dst]
+        c = g.compact()
+        return [self.h, self.vp, self.xd, self.xp, self.y, g.src, g.dst] + ([] if c is None else c.tensors())
 
     def host_copy(self, pin=True) -> List[torch.Tensor]:
         out = []
@@ -64,7 +65,8 @@ class StaticBatch:
     # ---- packed wire format (druglamp_b200.collate): untiled embedding rows over PCIe ---------
     def _small(self) -> List[torch.Tensor]:
         g = self.graph
-        return [self.h, self.vp, self.y, g.src, g.dst]
+        c = g.compact()
+        return [self.h, self.vp, self.y, g.src, g.dst] + ([] if c is None else c.tensors())
 
     def host_copy_packed(self, batch, pin=True) -> dict:
         """Host image of this batch with the LLM embeddings as packed rows (what the dataset yields

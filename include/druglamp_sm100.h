@@ -261,18 +261,24 @@ int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_
 /* nn.BatchNorm1d over [rows, cols] (model/basic_model.py:401,434 bn_layer; also
  * cross_modality.py:168).  training!=0: batch statistics, running buffers updated with
  * `momentum` (unbiased variance) and *num_batches_tracked += 1 when given; training==0: running
- * statistics.  mean/rstd: [cols] outputs saved for backward.  workspace: 2*cols doubles. */
+ * statistics.  mean/rstd: [cols] outputs saved for backward.  workspace: 2*cols doubles.
+ * last_row_weight w > 1 (training only): the LAST row stands for w identical rows -- the molecular
+ * GCN's virtual nodes, 92 % of the 512 slots per molecule, all carry one and the same row at every
+ * layer, so the layer is evaluated once for them: batch statistics count that row w
+ * times (N = rows - 1 + w).  In the backward the last row's dy is the SUM of the w copies' gradients
+ * and its dx the sum of their input gradients.  w <= 1 turns it off. */
 int dl_batchnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                      float* rstd, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, double* workspace, int64_t rows, int32_t cols,
-                     float eps, float momentum, int32_t training, int32_t dtype, void* stream);
+                     float eps, float momentum, int32_t training, float last_row_weight, int32_t dtype,
+                     void* stream);
 /* accumulate != 0: dgamma/dbeta are added to (the parameters' .grad buffers).  relu_mask != 0: x is
  * a ReLU output (ProteinCNN conv -> ReLU -> BN, model/basic_model.py:174-178) and dx is also
  * multiplied by (x > 0), so the activation's backward needs no pass of its own. */
 int dl_batchnorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                      const float* rstd, void* dx, float* dgamma, float* dbeta, double* workspace,
                      int64_t rows, int32_t cols, int32_t training, int32_t accumulate,
-                     int32_t relu_mask, int32_t dtype, void* stream);
+                     int32_t relu_mask, float last_row_weight, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Model glue.

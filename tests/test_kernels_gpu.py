@@ -417,3 +417,72 @@ def test_csr_build_on_device_equals_host_construction():
     assert dev.indices.data_ptr() == ptr0
     for k in ("indptr", "indices", "indptr_t", "indices_t"):
         assert torch.equal(getattr(dev, k).cpu(), getattr(host, k)), k
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_batchnorm_weighted_last_row_equals_expanded_batch(dtype, tol):
+    """dl_batchnorm last_row_weight = w: the last row stands for w identical rows (the molecular GCN's
+    virtual nodes).  Forward statistics, running buffers, dx, dgamma and dbeta must equal
+    nn.BatchNorm1d on the batch with that row written out w times -- the last row's dy being the sum
+    of the copies' gradients and its dx the sum of their input gradients."""
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(9)
+    R, w, cols = 700, 333, 128
+    x = (torch.randn(R + 1, cols, device="cuda") * 0.7 + 2.0).to(dtype)       # |mean| >> std like the GCN
+    dy_real = torch.randn(R, cols, device="cuda")
+    dy_copies = torch.randn(w, cols, device="cuda")
+    dy = torch.cat((dy_real, dy_copies.sum(0, keepdim=True))).to(dtype)
+    bn = torch.nn.BatchNorm1d(cols).cuda().double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    g, b = bn.weight.detach().float(), bn.bias.detach().float()
+    rm, rv = bn.running_mean.detach().float().clone(), bn.running_var.detach().float().clone()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    y, mean, rstd = K.batchnorm_fwd(x, g, b, rm, rv, nbt, 1e-5, 0.1, True, last_row_weight=float(w))
+    dx, dg, db = K.batchnorm_bwd(dy, x, g, mean, rstd, True, last_row_weight=float(w))
+    xe = torch.cat((x[:R], x[R:].expand(w, cols))).double().requires_grad_(True)
+    ye = bn(xe)
+    dye = torch.cat((dy[:R].double(), dy_copies.double()))
+    ye.backward(dye)
+    _close(y[:R], ye[:R], tol, "y real")
+    _close(y[R], ye[R], tol, "y virtual")
+    _close(dx[:R], xe.grad[:R], max(tol, 2e-5), "dx real")
+    _close(dx[R], xe.grad[R:].sum(0), max(tol, 5e-5), "dx virtual (summed)")
+    _close(dg, bn.weight.grad, max(tol, 1e-4), "dgamma")
+    _close(db, bn.bias.grad, max(tol, 1e-4), "dbeta")
+    _close(rm, bn.running_mean, 1e-4, "running_mean")
+    _close(rv, bn.running_var, 1e-4, "running_var")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 2e-2)])
+def test_gcn_virtual_node_dedup_equals_dense_evaluation(dtype, tol):
+    """MolecularGCN on real nodes + one representative virtual node (graph.compact, weighted BatchNorm,
+    expansion) against the dense evaluation of all B*512 rows: outputs and every parameter gradient."""
+    import druglamp_b200 as D
+    from druglamp_b200 import modules as M
+    from druglamp_b200.synth import make_batch
+    D.set_compute_dtype(dtype)
+    try:
+        b = make_batch(6, seed=31)
+        c = b.graph.compact()
+        assert c is not None and c.n_virtual + c.real_idx.numel() == 6 * 512
+        res = {}
+        for dedup in (False, True):
+            M.GCN_DEDUP = dedup
+            torch.manual_seed(2)
+            m = M.MolecularGCN(75, 128, True, [128] * 3, None).cuda().train()
+            g = b.graph.to("cuda")
+            g.ndata["h"] = b.graph.ndata["h"].cuda()
+            out = m(g)
+            gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).cuda().to(out.dtype)
+            out.backward(gy)
+            res[dedup] = (out.detach().float(), {k: p.grad.clone() for k, p in m.named_parameters()},
+                          m.gnn.gnn_layers[2].bn_layer.running_var.clone())
+        _close(res[True][0], res[False][0], tol, "vd")
+        _close(res[True][2], res[False][2], 1e-3, "running_var")
+        for k, gd in res[False][1].items():
+            _close(res[True][1][k], gd, max(tol, 1e-3), k)
+    finally:
+        M.GCN_DEDUP = True
+        D.set_compute_dtype(torch.float32)
