@@ -41,7 +41,7 @@ from .train import StaticBatch
 
 def _pool(seq: torch.Tensor) -> torch.Tensor:
     """mean over the sequence axis (``cross_modality.py:151-154``) -> (B, hidden), fp32."""
-    return Fn.SitePoolFn.apply(seq, seq.shape[1]).view(seq.shape[0], seq.shape[2]).float()
+    return Fn.seq_mean(seq).float()
 
 
 class ContrastiveStep:

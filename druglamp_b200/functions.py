@@ -884,6 +884,17 @@ class SitePoolFn(Function):
         return _back(K.site_pool_bwd(K.to_compute(gy), S), xdt), None
 
 
+def seq_mean(x: torch.Tensor) -> torch.Tensor:
+    """torch.mean(x, dim=1) of (B, L, C) -> (B, C) with the dl_site_pool kernels.  A mean over a long
+    sequence is taken in two stages (16 interleaved groups, then the 16 partial means): one stage would
+    leave B*C/4 threads looping serially over L strided rows."""
+    B, Lr, C_ = x.shape
+    if Lr % 16 == 0 and Lr > 16:
+        x = SitePoolFn.apply(x, Lr // 16)                 # (B, 16, C): mean over s of x[b, s*16 + j]
+        Lr = 16
+    return SitePoolFn.apply(x, Lr).view(B, C_)
+
+
 class AddPEFn(Function):
     """dropout(x + pe) (model/PMMA/embed.py:51-52)."""
 

@@ -123,8 +123,11 @@ class DrugLAMPBase(nn.Module):
 
     def _head(self, f):
         from . import modules as M
+        B, Lr, C_ = f.shape
+        if Lr % 16 == 0 and Lr > 16:
+            f = Fn.SitePoolFn.apply(f, Lr // 16)            # first stage of torch.mean(f, dim=1), compute dtype
         with K.local_compute_dtype(torch.float32 if M.HEAD_PRECISION == "fp32" else None):
-            f = Fn.SitePoolFn.apply(f, f.shape[1]).view(f.shape[0], f.shape[2])     # torch.mean(f, dim=1)
+            f = Fn.SitePoolFn.apply(f, f.shape[1]).view(B, C_)                      # second stage, head precision
         return self.mlp_classifier(f)
 
     def _masks(self, xd, xp, need_xd=True):

@@ -574,7 +574,7 @@ class CrossModality(nn.Module):
 
     @staticmethod
     def _pool(seq):
-        return Fn.SitePoolFn.apply(seq, seq.shape[1]).view(seq.shape[0], seq.shape[2])    # mean over L
+        return Fn.seq_mean(seq)                                                           # mean over L
 
     @staticmethod
     def _embed(x, m2e):

@@ -93,7 +93,7 @@ def global_cross_modality_loss(cm, prot, aug_prot, drug, aug_drug, meta, group=N
     from . import functions as Fn
     if pool_fn is None:
         def pool_fn(seq):
-            return Fn.SitePoolFn.apply(seq, seq.shape[1]).view(seq.shape[0], seq.shape[2])
+            return Fn.seq_mean(seq)
     pooled = [all_gather_rows(pool_fn(t), group, average_downstream) for t in (prot, aug_prot, drug, aug_drug)]
     targets = cm.prepare(all_gather_meta(meta, group))
     if targets.G.device != pooled[0].device:
