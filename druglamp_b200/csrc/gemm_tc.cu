@@ -73,6 +73,8 @@ struct GemmParams {
   int a_mn, b_mn;
   int c_bf16;
   int act, mul_mode;
+  int in_on[3];                 // TMA epilogue: 0 when the elementwise input broadcasts over that batch dim
+  int tma_in;                   // TMA epilogue: 0 none, 1 mul_aux, 2 residual arrives through the slab
   int pre_mode;                 // 0: preact = pre-activation; 1: preact = d(dropout(act(v)))/dv (backward's multiplier)
   int dbg;                      // bring-up only (DL_GEMM_DEBUG env): 1 no C stores, 2 no epilogue work,
                                 // 3 plain stores without the lane transpose (A/B measurements)
@@ -88,8 +90,16 @@ struct GemmParams {
 // landed stage in place as hi = x & 0xffffe000 and lo = x - hi (exact) before the issuer runs
 // three MMAs per K step (hi*hi + lo*hi + hi*lo): fp32-grade products on the tensor cores.  The
 // conversion is elementwise, so it is independent of the swizzled layout.
-template <int BN, bool TF32, bool SPLIT = false>
+// TMAEPI (bf16 output, BN = 256): the epilogue leaves through shared memory.  Every epilogue warp owns a
+// 4 KB slab [32 rows x 128 B, SWIZZLE_128B]; an elementwise input (mul_aux or residual) arrives in it by
+// TMA while the tile's MMAs still run, the warp reads its rows from it, writes the finished bf16 rows
+// back into it and one lane issues a bulk tensor store.  Thread = row addressing of global memory makes
+// every load / store instruction touch 32 different 128-byte lines (the L1 retires about one per
+// cycle: 2048 cycles per 128 x 256 tile and operand, as long as the tile's MMAs at K = 256); through
+// shared memory the same bytes cost a few hundred cycles and no LSU address traffic at all.
+template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false>
 struct Cfg {
+  static_assert(!TMAEPI || (BN == 256 && !TF32), "TMA epilogue: bf16 operands, 256-wide tiles");
   static constexpr int ELEM = TF32 ? 4 : 2;
   static constexpr int KE = 128 / ELEM;   // K elements per K-block
   static constexpr int UK = 32 / ELEM;    // K elements per tcgen05.mma
@@ -98,14 +108,14 @@ struct Cfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;             // what TMA delivers per stage
   static constexpr int STAGE_BYTES = SPLIT ? 2 * LOAD_BYTES : LOAD_BYTES;
-  static constexpr int STAGES = SPLIT ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4))
-                                      : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int EPI_BYTES = 0;                               // epilogue goes TMEM -> registers -> global
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int STAGES = TMAEPI ? 3 : SPLIT ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4))
+                                               : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int EPI_BYTES = TMAEPI ? kEpiWarps * 4096 : 0;   // per-warp staging slabs
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static_assert((3 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier area");
+  static_assert((3 * STAGES + 4 + kEpiWarps) * 8 + 8 <= BAR_BYTES, "barrier area");
 };
 
 struct Tile {
@@ -442,11 +452,107 @@ __device__ __forceinline__ void epilogue_slice(const GemmParams& p, const EpiFla
   }
 }
 
-template <int BN, bool TF32, bool SPLIT>
+// TMA epilogue: 16 accumulator columns of one row -> this thread's row of the warp's shared-memory
+// slab (two 16-byte chunks, SWIZZLE_128B), with the same fused element-wise work as finish16.  An
+// elementwise input (p.tma_in: 1 = mul_aux, 2 = residual) is read from the very chunks it overwrites.
+template <bool DERIV>
+__device__ __forceinline__ void tma_chunk16(const GemmParams& p, const EpiFlags& f, const uint32_t* v, int row,
+                                            bool row_ok, int col, long long crow, unsigned zidx,
+                                            uint32_t slab_row, int chunk0, int xr) {
+  using TC = __nv_bfloat16;
+  const int nvalid = min(16, p.N - col);
+  if (nvalid <= 0) return;                           // warp-uniform: the store clips these columns
+  const bool full = nvalid == 16;
+  TC* Pre = reinterpret_cast<TC*>(p.preact);
+  float x[16];
+  if (p.bias) {
+    float b[16];
+    load16<float>(p.bias + col, b, full && f.vec_b, nvalid);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha + b[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+  }
+  float dact[DERIV ? 16 : 1];
+  if (!DERIV && Pre && row_ok) store16<TC>(Pre + crow + col, x, full && f.vec_p, nvalid, f.wide_p);
+  if (p.act == DL_ACT_GELU) {
+    if constexpr (DERIV) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gelu_fwd_grad<TC>(x[j], x[j], dact[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
+    }
+  } else if (p.act == DL_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if constexpr (DERIV) dact[j] = x[j] > 0.f ? 1.f : 0.f;
+      x[j] = fmaxf(x[j], 0.f);
+    }
+  } else if constexpr (DERIV) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dact[j] = 1.f;
+  }
+  const uint32_t a0 = slab_row + (uint32_t)((chunk0 ^ xr) << 4), a1 = slab_row + (uint32_t)(((chunk0 + 1) ^ xr) << 4);
+  float in[16];
+  if (p.tma_in != 0) {
+    uint32_t w0[4], w1[4];
+    ptx::lds128(a0, w0);
+    ptx::lds128(a1, w1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      in[2 * k] = __uint_as_float(w0[k] << 16);
+      in[2 * k + 1] = __uint_as_float(w0[k] & 0xffff0000u);
+      in[8 + 2 * k] = __uint_as_float(w1[k] << 16);
+      in[8 + 2 * k + 1] = __uint_as_float(w1[k] & 0xffff0000u);
+    }
+  }
+  if (p.tma_in == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = apply_mul<TC>(x[j], in[j], p.mul_mode);
+  }
+  if (p.drop_p > 0.f) {
+    const unsigned long long e = ((unsigned long long)zidx * p.M + row) * p.N + col;
+    if ((e & 1ull) == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t h = drop_hash(f.drop_seed, (e >> 1) + k);
+        const float m0 = (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
+        const float m1 = (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
+        x[2 * k] *= m0;
+        x[2 * k + 1] *= m1;
+        if constexpr (DERIV) { dact[2 * k] *= m0; dact[2 * k + 1] *= m1; }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float m = drop_keep(f.drop_seed, e + j, f.drop_thr) ? f.drop_inv : 0.f;
+        x[j] *= m;
+        if constexpr (DERIV) dact[j] *= m;
+      }
+    }
+  }
+  if constexpr (DERIV) {
+    if (row_ok) store16<TC>(Pre + crow + col, dact, full && f.vec_p, nvalid, f.wide_p);
+  }
+  if (p.tma_in == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] += in[j];
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = ptx::pack_bf16(x[2 * k], x[2 * k + 1]);
+  ptx::sts128(a0, w[0], w[1], w[2], w[3]);
+  ptx::sts128(a1, w[4], w[5], w[6], w[7]);
+}
+
+template <int BN, bool TF32, bool SPLIT, bool TMAEPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmIn,
                const GemmParams p) {
-  using C = Cfg<BN, TF32, SPLIT>;
+  using C = Cfg<BN, TF32, SPLIT, TMAEPI>;
   static_assert(!SPLIT || TF32, "SPLIT applies to fp32 operands");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -458,7 +564,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_conv = bar_empty + 8 * C::STAGES;              // [STAGES] hi/lo split done
   const uint32_t bar_tfull = bar_conv + 8 * C::STAGES;              // [2] accumulator ready
   const uint32_t bar_tempty = bar_tfull + 16;                       // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 4);
+  const uint32_t bar_in = bar_tempty + 16;                          // [kEpiWarps] TMA epilogue: input slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 4 + kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
@@ -474,6 +581,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_tfull + 8 * i, 1);
       ptx::mbar_init(bar_tempty + 8 * i, kEpiWarps);
+    }
+    for (int i = 0; i < kEpiWarps; ++i) ptx::mbar_init(bar_in + 8 * i, 1);
+    if constexpr (TMAEPI) {
+      ptx::prefetch_tmap(&tmC);
+      if (p.tma_in) ptx::prefetch_tmap(&tmIn);
     }
     ptx::fence_barrier_init();
   }
@@ -579,7 +691,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = we >> 2;                     // which column slice of the tile
     const EpiFlags ef = p.c_bf16 ? make_epi_flags<__nv_bfloat16>(p) : make_epi_flags<float>(p);
-    uint32_t it = 0, ti = 0;
+    uint32_t it = 0, ti = 0, in_phase = 0;
     for (int tl = blockIdx.x; tl < p.total_tiles; tl += gridDim.x, ++ti) {
       const Tile T = decode_tile<BN, C::KE>(p, tl);
       if constexpr (SPLIT) {
@@ -656,6 +768,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
+      if constexpr (TMAEPI) {
+        // the warp's slab: wait until the previous tile's store has read it, then (optionally) start
+        // the elementwise input's load -- it lands while this tile's MMAs still run
+        const uint32_t slab = base_addr + C::STAGES * C::STAGE_BYTES + (uint32_t)we * 4096u;
+        const int cb = half * (BN / kColSplit), row0 = T.m0 + q * 32;
+        const bool live = T.n0 + cb < p.N;                               // warp-uniform
+        if (lane == 0) ptx::bulk_wait_read0();
+        __syncwarp();
+        if (p.tma_in && live && lane == 0) {
+          ptx::mbar_arrive_expect_tx(bar_in + 8 * we, 4096);
+          ptx::tma_load_5d(slab, &tmIn, bar_in + 8 * we, T.n0 + cb, row0, p.in_on[0] ? T.b0 : 0,
+                           p.in_on[1] ? T.b1 : 0, p.in_on[2] ? T.b2 : 0);
+        }
+        ptx::mbar_wait(bar_tfull + 8 * ab, aph);
+        ptx::tc_fence_after();
+        if (p.tma_in && live) ptx::mbar_wait(bar_in + 8 * we, in_phase), in_phase ^= 1u;
+        const long long cbase = (long long)T.b0 * p.sc[0] + (long long)T.b1 * p.sc[1] + (long long)T.b2 * p.sc[2];
+        const uint32_t tmem_q = tmem + ab * BN + ((uint32_t)(q * 32) << 16);
+        const int row = row0 + lane;
+        const bool row_ok = row < p.M;
+        const long long crow = cbase + (long long)row * p.ldc;
+        const uint32_t slab_row = slab + (uint32_t)lane * 128u;
+        const bool deriv = p.pre_mode == 1 && p.preact != nullptr;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(tmem_q + (uint32_t)(cb + 16 * j), v);
+          ptx::tmem_ld_wait();
+          if (deriv) tma_chunk16<true>(p, ef, v, row, row_ok, T.n0 + cb + 16 * j, crow, T.zb, slab_row, 2 * j, lane & 7);
+          else tma_chunk16<false>(p, ef, v, row, row_ok, T.n0 + cb + 16 * j, crow, T.zb, slab_row, 2 * j, lane & 7);
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (live) {
+            ptx::tma_store_5d(&tmC, slab, T.n0 + cb, row0, T.b0, T.b1, T.b2);
+            ptx::bulk_commit();
+          }
+          ptx::mbar_arrive(bar_tempty + 8 * ab);
+        }
+        continue;
+      }
       ptx::mbar_wait(bar_tfull + 8 * ab, aph);
       ptx::tc_fence_after();
       const long long cbase = (long long)T.b0 * p.sc[0] + (long long)T.b1 * p.sc[1] + (long long)T.b2 * p.sc[2];
@@ -675,6 +830,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * ab);
+    }
+    if constexpr (TMAEPI) {
+      if (lane == 0) ptx::bulk_wait0();          // the slabs must outlive the stores that read them
     }
   }
   ptx::tc_fence_before();
@@ -736,14 +894,36 @@ int make_operand_map(CUtensorMap* m, const void* ptr, bool f32, bool mn_major, l
   return 0;
 }
 
-template <int BN, bool TF32, bool SPLIT = false>
+// bf16 [.., rows, cols] tensor as the epilogue's slabs see it: box = 64 columns x 32 rows, SWIZZLE_128B
+int make_epi_map(CUtensorMap* m, const void* ptr, long long cols, long long rows, long long ld,
+                 const int64_t* nb, const long long* s, const char* name) {
+  cuuint64_t dims[5] = {(cuuint64_t)cols, (cuuint64_t)rows, 1, 1, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)(ld * 2), 0, 0, 0};
+  const long long dummy = rows * ld;
+  for (int i = 0; i < 3; ++i) {
+    dims[2 + i] = (cuuint64_t)(s[i] ? nb[i] : 1);
+    strides[1 + i] = (cuuint64_t)((s[i] ? s[i] : dummy) * 2);
+  }
+  cuuint32_t box[5] = {64, 32, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn fn = encode_fn();
+  DL_REQUIRE(fn != nullptr, "dl_gemm: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(-2, "dl_gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
+  return 0;
+}
+
+template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long long batch,
-           cudaStream_t stream) {
-  using C = Cfg<BN, TF32, SPLIT>;
+           cudaStream_t stream, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmIn = nullptr) {
+  using C = Cfg<BN, TF32, SPLIT, TMAEPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, SPLIT>,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   });
   if (attr_err != cudaSuccess)
@@ -764,7 +944,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long l
   p.fd_kred.init((uint32_t)(p.kred_kpb > 0 ? p.kred_kpb : 1));
   p.total_tiles = (int)total;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  DL_LAUNCH((gemm_tc_kernel<BN, TF32, SPLIT>), grid, kGemmThreads, C::SMEM, stream, tmA, tmB, p);
+  DL_LAUNCH((gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI>), grid, kGemmThreads, C::SMEM, stream, tmA, tmB,
+            tmC ? *tmC : tmA, tmIn ? *tmIn : tmA, p);
   DL_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
@@ -917,6 +1098,34 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   static const int dbg_mode = [] { const char* e = getenv("DL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg_mode;
   p.idesc = 0;
+  p.tma_in = 0;
+  p.in_on[0] = p.in_on[1] = p.in_on[2] = 0;
+  // Epilogue through shared memory + bulk tensor stores (see Cfg): bf16 output tiles of width 256 whose
+  // main loop is short enough (K <= 1024) for the epilogue to matter, at most one elementwise input.
+  static const bool tma_epi_off = [] { const char* e = getenv("DL_GEMM_NO_TMA_EPI"); return e && atoi(e) != 0; }();
+  auto al8 = [](long long v) { return v % 8 == 0; };
+  const bool tma_epi = !tma_epi_off && !f32 && p.c_bf16 && bn == 256 && splits == 1 && !conv && !kred &&
+                       dbg_mode == 0 && nkb <= 16 && ((uintptr_t)a->C & 15) == 0 && al8(a->ldc) && al8(a->sc[0]) &&
+                       al8(a->sc[1]) && al8(a->sc[2]) && !(a->mul_aux && a->residual) &&
+                       (!a->mul_aux || ((uintptr_t)a->mul_aux & 15) == 0) &&
+                       (!a->residual || (((uintptr_t)a->residual & 15) == 0 && al8(p.ldr) && al8(p.sr[0]) &&
+                                         al8(p.sr[1]) && al8(p.sr[2])));
+  if (tma_epi) {
+    CUtensorMap tmC, tmIn;
+    rc = make_epi_map(&tmC, a->C, a->N, a->M, a->ldc, a->batch, p.sc, "C");
+    if (rc) return rc;
+    if (a->mul_aux) {
+      p.tma_in = 1;
+      for (int i = 0; i < 3; ++i) p.in_on[i] = p.sc[i] != 0;
+      rc = make_epi_map(&tmIn, a->mul_aux, a->N, a->M, a->ldc, a->batch, p.sc, "mul_aux");
+    } else if (a->residual) {
+      p.tma_in = 2;
+      for (int i = 0; i < 3; ++i) p.in_on[i] = p.sr[i] != 0;
+      rc = make_epi_map(&tmIn, a->residual, a->N, a->M, p.ldr, a->batch, p.sr, "residual");
+    }
+    if (rc) return rc;
+    return launch<256, false, false, true>(tmA, tmB, p, batch, stream, &tmC, p.tma_in ? &tmIn : nullptr);
+  }
   if (f32 && a->precise) {
     if (bn == 64) return launch<64, true, true>(tmA, tmB, p, batch, stream);
     if (bn == 128) return launch<128, true, true>(tmA, tmB, p, batch, stream);

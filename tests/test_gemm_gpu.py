@@ -185,3 +185,48 @@ def test_weight_gradient_with_fused_bias_gradient(M, N, K, tile_n):
     with pytest.raises(RuntimeError, match="colsum_a"):
         _lib.gemm(dY.float(), X.float(), dW, M=M, N=N, K=K, lda=M, ldb=N, ldc=N, trans_a=True,
                   trans_b=True, accumulate=True, colsum_a=db)
+
+
+@pytest.mark.parametrize("case", [
+    dict(M=1000, N=1024, K=256, bias=True, act=1, preact=True),                 # fc1-type: GELU + pre-activation
+    dict(M=640, N=512, K=256, mul_mode=3),                                      # backward multiplier (DL_MUL_VALUE)
+    dict(M=777, N=256, K=1024, bias=True, residual=True),                       # fc2-type: residual through the slab
+    dict(M=300, N=648, K=128, bias=True, pad=8),                                # ragged N (third tile 136 wide), padded rows
+    dict(M=256, N=768, K=256, bias=True, batch=(2, 3)),                         # batched C
+    dict(M=130, N=256, K=64),                                                   # plain store, ragged M
+])
+def test_tma_store_epilogue_matches_float64(case):
+    """bf16 outputs of 256-wide tiles leave through shared memory + bulk tensor stores, the elementwise
+    input (mul_aux / residual) arrives by TMA (gemm_tc.cu Cfg TMAEPI): every fused-epilogue flavour of
+    that path against float64, with integer operands (exact) and random ones; DL_GEMM_NO_TMA_EPI=1 is
+    the per-thread-store path the same cases ran on before."""
+    for integer in (True, False):
+        err, scale, pre_err = run_case(dtype=torch.bfloat16, trans_a=False, trans_b=False, integer=integer, **case)
+        if integer and not case.get("act") and not case.get("mul_mode"):
+            assert err <= 2e-2 * scale, (case, err, scale)       # exact products, one bf16 rounding of the result
+        else:
+            assert err <= 2e-2 * scale, (case, err, scale)
+        if pre_err is not None:
+            assert pre_err <= 1e-2 * scale + 4e-3 * max(scale, 1.0), (case, pre_err)
+
+
+def test_tma_epilogue_residual_in_place_and_broadcast():
+    """residual aliasing C (FcCatFn's second half-GEMM) and a batch-broadcast residual (positional
+    embeddings: sr = 0 with ldr != 0) through the TMA epilogue."""
+    from druglamp_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 512, 256, 128
+    A = torch.randint(-2, 3, (M, K), generator=g, device="cuda").to(torch.bfloat16)
+    B = torch.randint(-2, 3, (N, K), generator=g, device="cuda").to(torch.bfloat16)
+    C0 = torch.randint(-4, 5, (M, N), generator=g, device="cuda").to(torch.bfloat16)
+    Cc = C0.clone()
+    _lib.gemm(A, B, Cc, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, residual=Cc)
+    ref = A.double() @ B.double().t() + C0.double()
+    assert torch.equal(Cc.double(), ref.to(torch.bfloat16).double())
+    # 3 batches of A against one B, residual (M, N) shared by all batches
+    A3 = torch.randint(-2, 3, (3, M, K), generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.empty((3, M, N), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(A3, B, out, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, batch=(3, 1, 1), sa=(M * K, 0, 0), sb=(0, 0, 0),
+              sc=(M * N, 0, 0), residual=C0, ldr=N, sr=(0, 0, 0))
+    ref3 = A3.double() @ B.double().t() + C0.double()
+    assert torch.equal(out.double(), ref3.to(torch.bfloat16).double())
