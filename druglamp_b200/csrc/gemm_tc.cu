@@ -1101,10 +1101,16 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   p.tma_in = 0;
   p.in_on[0] = p.in_on[1] = p.in_on[2] = 0;
   // Epilogue through shared memory + bulk tensor stores (see Cfg): bf16 output tiles of width 256 whose
-  // main loop is short enough (K <= 1024) for the epilogue to matter, at most one elementwise input.
+  // main loop is short enough (K <= 1024) for the epilogue to matter, exactly one elementwise input.
   static const bool tma_epi_off = [] { const char* e = getenv("DL_GEMM_NO_TMA_EPI"); return e && atoi(e) != 0; }();
   auto al8 = [](long long v) { return v % 8 == 0; };
-  const bool tma_epi = !tma_epi_off && !f32 && p.c_bf16 && bn == 256 && splits == 1 && !conv && !kred &&
+  // Measured on B200 (same box, DL_GEMM_NO_TMA_EPI A/B): with an elementwise input the slab path wins
+  // (16384x1024x256 * aux 29.0 -> 26.6 us, 16384x2048x512 * aux 56.1 -> 49.7 us: the input's HBM latency
+  // hides behind the MMAs instead of sitting in front of every 16-column chunk); without one the
+  // slab's store -> reuse chain is longer than a K = 256 main loop and the direct stores win, so those
+  // launches keep them.
+  const bool tma_epi = !tma_epi_off && (a->mul_aux || a->residual) && !(a->preact_out && a->pre_mode == 1) &&
+                       !f32 && p.c_bf16 && bn == 256 && splits == 1 && !conv && !kred &&
                        dbg_mode == 0 && nkb <= 16 && ((uintptr_t)a->C & 15) == 0 && al8(a->ldc) && al8(a->sc[0]) &&
                        al8(a->sc[1]) && al8(a->sc[2]) && !(a->mul_aux && a->residual) &&
                        (!a->mul_aux || ((uintptr_t)a->mul_aux & 15) == 0) &&

@@ -96,8 +96,28 @@ class DrugLAMPBase(nn.Module):
         for m in self.modules():
             if hasattr(m, "fused_parameter_groups"):
                 groups += m.fused_parameter_groups()
-        self._flat = FlatParams(self, groups=groups)
+        pmma_ids = {id(p) for p in self.pmma.parameters()}
+        groups = [g for g in groups if all(id(p) in pmma_ids for p in g)] + \
+                 [g for g in groups if not all(id(p) in pmma_ids for p in g)]
+        self._flat = FlatParams(self, groups=groups, first=list(self.pmma.parameters()))
         return self._flat
+
+    def _watch_pmma_inputs(self, *tensors):
+        """TrainStep's overlap hook: call `_pmma_grads_ready` once the gradients of PMMA's inputs have
+        been computed, i.e. when every PMMA (and decoder-head) parameter gradient is final."""
+        cb = getattr(self, "_pmma_grads_ready", None)
+        if cb is None or not torch.is_grad_enabled():
+            return
+        uniq = [t for i, t in enumerate(tensors) if t.requires_grad and all(t is not u for u in tensors[:i])]
+        pending = [len(uniq)]
+
+        def hook(g):
+            pending[0] -= 1
+            if pending[0] == 0:
+                cb()
+            return g
+        for t in uniq:
+            t.register_hook(hook)
 
     # ---- shared pieces of the three forwards ------------------------------------------------------
     def _protein_branch(self, vp, fill_bit_p):
@@ -157,6 +177,7 @@ class DrugLAMP(DrugLAMPBase):
         xpa, xda = self._llm_adaptors(xp_pool, xd_lin)
         mv, self.A_v_gca = self._guided(self.v_gca, self.v_mhla, self.v_gca_norm, vpf, vd)
         mx, self.A_x_gca = self._guided(self.x_gca, self.x_mhla, self.x_gca_norm, xpa, xda)
+        self._watch_pmma_inputs(mx, mv)
         f, self.attn, self.guide_attn = self.pmma(mx, mv)
         score = self._head(f)
         return vd, vpf, xda, xpa, ssl, score
@@ -193,6 +214,7 @@ class DrugLAMPwoLLM(DrugLAMPBase):
         ssl = {'vp': vp, 'xp': None, 'fill_bit_p': bit_p, 'vd': vd, 'xd': None, 'p_mode': 'vp'}
         vpf = self._protein_branch(vp, bit_p)
         mv, self.A_v_gca = self._guided(self.v_gca, self.v_mhla, self.v_gca_norm, vpf, vd)
+        self._watch_pmma_inputs(mv)
         f, self.attn, self.guide_attn = self.pmma(mv, mv)
         score = self._head(f)
         if mode == "train":

@@ -482,7 +482,9 @@ class MolecularGCN(nn.Module):
                 x = self.gnn(cg.graph, x, last_row_weight=float(cg.n_virtual))
             node_feats = Fn.ExpandVirtualFn.apply(x, cg.real_idx, cg.n_full)
         else:
-            with K.local_compute_dtype(fp32):
+            # dense fallback (a graph assembled on the device, or one without virtual nodes): the weight
+            # gradients sum tens of thousands of identical rows, plain TF32 shows there -- 3xTF32 as well
+            with K.local_compute_dtype(fp32, precise=True):
                 node_feats = Fn.linear(node_feats, self.init_transform.weight)
                 node_feats = self.gnn(g, node_feats)
         return _ret(node_feats, h_in).view(batch_graph.batch_size, -1, self.output_feats)

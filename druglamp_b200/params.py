@@ -80,7 +80,7 @@ class FlatParams:
 
     ALIGN = 64  # elements; keeps every view 256-byte aligned (TMA needs 16 B)
 
-    def __init__(self, module: torch.nn.Module, groups=None):
+    def __init__(self, module: torch.nn.Module, groups=None, first=None):
         """groups: lists of parameters to lay out back to back (e.g. the query / key / value weights
         of one attention block), so that :func:`fused_group` can hand a GEMM the concatenated
         [sum out_i, in] matrix, its gradient and its bf16 shadow as plain views -- three projections
@@ -92,6 +92,14 @@ class FlatParams:
                 if id(p) not in seen and p.dtype == torch.float32:
                     seen.add(id(p))
                     params.append(p)
+        # `first`: parameters to place directly behind the groups, so that [0, head_numel) is one
+        # contiguous range (the PMMA parameters: their gradients are complete long before the rest of
+        # the backward, and that range is all-reduced while the rest still runs)
+        for p in (first or []):
+            if id(p) not in seen and p.dtype == torch.float32:
+                seen.add(id(p))
+                params.append(p)
+        n_head = len(params)
         for p in module.parameters():
             if id(p) not in seen and p.dtype == torch.float32:
                 seen.add(id(p))
@@ -106,6 +114,7 @@ class FlatParams:
             self.offsets.append(off)
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
+        self.head_numel = self.offsets[n_head] if n_head < len(params) else off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
         self.shadow16: Optional[torch.Tensor] = None

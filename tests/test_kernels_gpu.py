@@ -481,9 +481,7 @@ def test_gcn_virtual_node_dedup_equals_dense_evaluation(dtype, tol):
                           m.gnn.gnn_layers[2].bn_layer.running_var.clone())
         _close(res[True][0], res[False][0], tol, "vd")
         _close(res[True][2], res[False][2], 1e-3, "running_var")
-        # in bf16 mode the dense fp32 island runs plain TF32 and the compact one 3xTF32; the weight
-        # gradients sum ~3000 identical virtual rows, so the TF32 rounding shows at the 5e-2 level
-        gtol = 1e-3 if dtype == torch.float32 else 1e-1
+        gtol = 1e-3 if dtype == torch.float32 else 2e-2      # bf16 mode: the incoming gradient is bf16
         for k, gd in res[False][1].items():
             _close(res[True][1][k], gd, gtol, k)
     finally:
