@@ -340,7 +340,12 @@ def run_gpu(args):
     if rank == 0:
         pk = peaks()
 
-        def local_step():                      # no collective: only rank 0 runs this pass
+        # only rank 0 runs this pass, so it must not contain a collective: the overlapped gradient
+        # all-reduce lives inside _fwd_bwd and is switched off here
+        ts.overlap = False
+        model._pmma_grads_ready = None
+
+        def local_step():
             ts._fwd_bwd(batches[0])
             ts._update()
         local_step()

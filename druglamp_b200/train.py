@@ -163,8 +163,9 @@ class TrainStep:
 
     def _reduce_head(self) -> None:
         """Called from inside the backward (models._watch_pmma_inputs): PMMA's gradients are final."""
-        main = torch.cuda.current_stream()
-        self._comm.wait_stream(main)
+        self._comm.wait_stream(torch.cuda.current_stream())
+        for s in getattr(self.model, "_branch_streams", []):    # the hook may fire on either branch stream
+            self._comm.wait_stream(s)
         with torch.cuda.stream(self._comm):
             torch.distributed.all_reduce(self.flat.grad[:self.flat.head_numel], group=self.pg)
         self._joined = False
