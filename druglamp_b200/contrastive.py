@@ -103,7 +103,8 @@ class ContrastiveStep:
             total = cls * cls_scale
             for i, k in enumerate(("prot", "aug_prot", "drug", "aug_drug")):
                 total = total + (_pool(cp[k]) * dp[i]).sum()
-            total.backward()
+            with Fn.deferred_weight_grads():
+                total.backward()
         finally:
             K.set_dropout_step(None)
         self.cls_loss.add_(cls.detach() * cls_scale)

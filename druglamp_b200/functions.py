@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import contextlib
 import itertools
+import os
 from typing import Optional
 
 import torch
@@ -80,11 +81,77 @@ def _grad_target(p):
     return g if (g is not None and g.is_contiguous()) else None
 
 
+# ---- deferred parameter gradients -------------------------------------------------------------------
+# Nothing in the backward reads a parameter gradient, yet the weight-gradient GEMMs (split-K over
+# 16k-32k rows, a third of the step's GEMM time) sit in the middle of the dX chain.  Inside
+# `deferred_weight_grads()` every kernel that ACCUMULATES INTO THE FLAT GRADIENT BUFFER is issued on a
+# side stream that waits for its operands; the caller's stream only waits for that stream when the
+# context closes (train.TrainStep: right after loss.backward()).  Outside the context nothing changes:
+# a user who reads p.grad after backward() sees stream-ordered results as with any PyTorch module.
+_wgrad_defer = None
+
+
+class deferred_weight_grads:
+    """Context: parameter-gradient kernels with a flat-buffer destination run on `stream` (created on
+    first use); closing the context makes the current stream wait for them."""
+
+    _streams = {}
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled and os.environ.get("DL_NO_WGRAD_STREAM", "0") == "0"
+        self.stream = None
+        self.keep = []          # operands stay referenced until the join: the autograd engine adds
+        #                         gradients IN PLACE into a buffer it holds the last reference to
+
+    def __enter__(self):
+        global _wgrad_defer
+        self._prev, _wgrad_defer = _wgrad_defer, (self if self.enabled else None)
+        return self
+
+    def join(self, stream=None):
+        """`stream` (default: the current one) waits for every deferred kernel issued so far."""
+        if self.stream is not None:
+            (stream or torch.cuda.current_stream()).wait_stream(self.stream)
+
+    def __exit__(self, *exc):
+        global _wgrad_defer
+        _wgrad_defer = self._prev
+        self.join()
+        self.keep.clear()
+        return False
+
+    @contextlib.contextmanager
+    def on(self, *reads):
+        cur = torch.cuda.current_stream()
+        if self.stream is None:
+            dev = cur.device
+            self.stream = self._streams.get(dev) or self._streams.setdefault(dev, torch.cuda.Stream(dev))
+        s = self.stream
+        s.wait_stream(cur)
+        for t in reads:
+            if t is not None:
+                t.record_stream(s)
+                self.keep.append(t)
+        with torch.cuda.stream(s):
+            yield
+
+
+@contextlib.contextmanager
+def _param_grad_stream(*reads):
+    """Where the kernels inside may run: the deferred stream when a deferral is active."""
+    if _wgrad_defer is None:
+        yield
+    else:
+        with _wgrad_defer.on(*reads):
+            yield
+
+
 def _wgrad(p, a, b):
     """dW = a^T b (both stored [rows, features]); into p.grad when possible."""
     tgt = _grad_target(p)
     if tgt is not None and tgt.dim() == 2:
-        K.mm(a, b, tgt, ta=True, tb=True, accumulate=True)
+        with _param_grad_stream(a, b):
+            K.mm(a, b, tgt, ta=True, tb=True, accumulate=True)
         return None
     return K.mm(a, b, ta=True, tb=True, out_dtype=torch.float32)
 
@@ -92,7 +159,8 @@ def _wgrad(p, a, b):
 def _bgrad(p, g):
     tgt = _grad_target(p)
     if tgt is not None:
-        K.colsum(g, tgt, accumulate=True)
+        with _param_grad_stream(g):
+            K.colsum(g, tgt, accumulate=True)
         return None
     return K.colsum(g)
 
@@ -103,7 +171,8 @@ def _wbgrad(wp, bp, g, x):
     streams through shared memory (dl_gemm colsum_a), which is the bias gradient."""
     tw, tb = _grad_target(wp), _grad_target(bp)
     if tw is not None and tw.dim() == 2 and tb is not None and g.dtype == torch.bfloat16:
-        K.mm(g, x, tw, ta=True, tb=True, accumulate=True, colsum_a=tb)
+        with _param_grad_stream(g, x):
+            K.mm(g, x, tw, ta=True, tb=True, accumulate=True, colsum_a=tb)
         return None, None
     return _wgrad(wp, g, x), (None if bp is None else _bgrad(bp, g))
 
@@ -428,11 +497,12 @@ def _qkv_bwd(g2, xc2, ws, bs, need_dx=True):
             mark_touched(t)
         if need_dx:
             dx = K.mm(g2, fw[2], tb=True)
-        if g2.dtype == torch.bfloat16:
-            K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True, colsum_a=fb[1])
-        else:
-            K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True)
-            K.colsum(g2, fb[1], accumulate=True)
+        with _param_grad_stream(g2, xc2):
+            if g2.dtype == torch.bfloat16:
+                K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True, colsum_a=fb[1])
+            else:
+                K.mm(g2, xc2, fw[1], ta=True, tb=True, accumulate=True)
+                K.colsum(g2, fb[1], accumulate=True)
         return dx, [None] * 3, [None] * 3
     dws, dbs = [], []
     for i, (w, b) in enumerate(zip(ws, bs)):
@@ -607,8 +677,9 @@ class FcCatFn(Function):
             tw, tb_ = _grad_target(w), _grad_target(ctx.bias)
             if tw is not None and tb_ is not None and g.dtype == torch.bfloat16:
                 # crosswise halves straight into the flat gradient; the first GEMM also sums g's columns
-                K.mm(g, o2[:, :D], tw[:, D:], ta=True, tb=True, accumulate=True, colsum_a=tb_)
-                K.mm(g, o2[:, D:], tw[:, :D], ta=True, tb=True, accumulate=True)
+                with _param_grad_stream(g, o2):
+                    K.mm(g, o2[:, :D], tw[:, D:], ta=True, tb=True, accumulate=True, colsum_a=tb_)
+                    K.mm(g, o2[:, D:], tw[:, :D], ta=True, tb=True, accumulate=True)
                 dw = db = None
             else:
                 dw = torch.empty((N, D2), dtype=torch.float32, device=g.device)
@@ -704,19 +775,22 @@ class PGCAFn(Function):
         d_in_w = tw if acc else torch.empty((3 * E, E), dtype=torch.float32, device=g.device)
         d_in_b = tb_ if acc else torch.empty(3 * E, dtype=torch.float32, device=g.device)
         fuse = acc and dQ2.dtype == torch.bfloat16      # bias gradients summed inside the dW GEMMs
-        K.mm(dQ2, q2, d_in_w[:E], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[:E] if fuse else None)
-        if not fuse:
-            K.colsum(dQ2, d_in_b[:E], accumulate=acc)
-        if not (fuse and shared):
-            K.colsum(dKV2, d_in_b[E:], accumulate=acc)
+        with (_param_grad_stream(dQ2, q2, dKV2, k2, v2) if acc else contextlib.nullcontext()):
+            K.mm(dQ2, q2, d_in_w[:E], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[:E] if fuse else None)
+            if not fuse:
+                K.colsum(dQ2, d_in_b[:E], accumulate=acc)
+            if not (fuse and shared):
+                K.colsum(dKV2, d_in_b[E:], accumulate=acc)
+            if shared:
+                K.mm(dKV2, k2, d_in_w[E:], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[E:] if fuse else None)
+            else:
+                K.mm(dKV2[:, :E], k2, d_in_w[E:2 * E], ta=True, tb=True, accumulate=acc)
+                K.mm(dKV2[:, E:], v2, d_in_w[2 * E:], ta=True, tb=True, accumulate=acc)
         dquery = back(K.mm(dQ2, wi[:E], tb=True), Lq, qdt)
         if shared:
-            K.mm(dKV2, k2, d_in_w[E:], ta=True, tb=True, accumulate=acc, colsum_a=d_in_b[E:] if fuse else None)
             dkey = back(K.mm(dKV2, wi[E:], tb=True), Sk, kdt)
             dvalue = None
         else:
-            K.mm(dKV2[:, :E], k2, d_in_w[E:2 * E], ta=True, tb=True, accumulate=acc)
-            K.mm(dKV2[:, E:], v2, d_in_w[2 * E:], ta=True, tb=True, accumulate=acc)
             dkey = back(K.mm(dKV2[:, :E], wi[E:2 * E], tb=True), Sk, kdt)
             dvalue = back(K.mm(dKV2[:, E:], wi[2 * E:], tb=True), Sk, vdt)
         if acc:

@@ -18,6 +18,7 @@ from typing import List
 import torch
 
 from . import _lib as L
+from . import functions as Fn
 from .graph import BatchedMolGraph
 from .modules import binary_cross_entropy
 from .params import FlatAdamW
@@ -148,7 +149,9 @@ class TrainStep:
         try:
             out = self.model(*sb.model_inputs())
             _, loss = binary_cross_entropy(out[4], sb.y)
-            loss.backward()
+            # weight-gradient GEMMs leave the dX chain for a side stream; joined when the context closes
+            with Fn.deferred_weight_grads():
+                loss.backward()
         finally:
             K.set_dropout_step(None)
         self.loss.copy_(loss.detach())
@@ -166,6 +169,8 @@ class TrainStep:
         self._comm.wait_stream(torch.cuda.current_stream())
         for s in getattr(self.model, "_branch_streams", []):    # the hook may fire on either branch stream
             self._comm.wait_stream(s)
+        if Fn._wgrad_defer is not None:                          # PMMA's deferred weight gradients
+            Fn._wgrad_defer.join(self._comm)
         with torch.cuda.stream(self._comm):
             torch.distributed.all_reduce(self.flat.grad[:self.flat.head_numel], group=self.pg)
         self._joined = False

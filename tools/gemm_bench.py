@@ -48,20 +48,22 @@ def make(M, N, K, batch, ta, tb, dtype=torch.bfloat16):
     sb = (N * K, N * K * batch[0], N * K * batch[0] * batch[1])
     sc = (M * N, M * N * batch[0], M * N * batch[0] * batch[1])
 
-    def run(tile_n=0):
+    def run(tile_n=0, split_k=0):
+        # weight-gradient shapes accumulate into C like the model does (no memset in the timing)
         _lib.gemm(A, B, C, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=N, trans_a=bool(ta), trans_b=bool(tb),
-                  batch=batch, sa=sa, sb=sb, sc=sc, tile_n=tile_n)
+                  batch=batch, sa=sa, sb=sb, sc=sc, tile_n=tile_n, split_k=split_k,
+                  accumulate=bool(ta and tb and nb == 1))
     return run
 
 
-def bench(shape, tile_n=0, reps=20):
+def bench(shape, tile_n=0, reps=20, split_k=0):
     run = make(*shape)
-    run(tile_n)
+    run(tile_n, split_k)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(reps):
-            run(tile_n)
+            run(tile_n, split_k)
     g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -83,6 +85,23 @@ if __name__ == "__main__":
         for _ in range(3):
             run()
         torch.cuda.synchronize()
+    elif len(sys.argv) > 1 and sys.argv[1] == "--splitk":
+        # split-K factor sweep on the weight-gradient shapes of the step (K = rows of the batch)
+        wg = [(1024, 256, 16384), (256, 1024, 16384), (256, 256, 16384), (768, 256, 16384), (2048, 512, 16384),
+              (512, 2048, 16384), (1536, 512, 16384), (512, 512, 16384), (256, 512, 16384), (128, 128, 16384),
+              (256, 128, 32768), (256, 392, 32768), (256, 648, 16384), (648, 128, 16384)]
+        for (M, N, K) in wg:
+            s = (M, N, K, (1, 1, 1), 1, 1)
+            line = f"{str((M, N, K)):24s}"
+            for tn in (0, 128, 256):
+                for sk in (0, 8, 12, 18, 24, 36, 48, 72):
+                    try:
+                        us, tf = bench(s, tn, split_k=sk)
+                        line += f" | bn{tn} sk{sk}: {us:6.1f}"
+                    except Exception as e:  # noqa: BLE001
+                        line += f" | bn{tn} sk{sk}: ERR"
+                line += "\n" + " " * 24
+            print(line, flush=True)
     else:
         for s in SHAPES:
             line = f"{str(s):60s}"
