@@ -132,7 +132,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 }
 
 template <typename T, int C>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, C <= 512 ? 2 : 1)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, T* __restrict__ dx, const T* __restrict__ dx_add,
@@ -141,7 +141,10 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
   pdl_wait();
   using LY = LnLayout<T, C>;
   constexpr int EPL = LY::EPL, V = LY::V, NV = LY::NV;
-  constexpr int R = EPL <= 8 ? 2 : 1;
+  // rows in flight per warp: the grid is capped (atomics), so memory-level parallelism has to come from
+  // the warp itself -- 4 rows (C <= 256) / 2 rows (C = 512) of x and dy are loaded before the first
+  // reduction starts
+  constexpr int R = EPL <= 8 ? 4 : (EPL <= 16 ? 2 : 1);
   __shared__ float red[kWarpsPerBlock][C];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + w;

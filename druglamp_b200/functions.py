@@ -35,6 +35,34 @@ def next_seed() -> int:
     return ((next(_seed_counter) * 0x9E3779B97F4A7C15) ^ _seed_stream) & 0xFFFFFFFFFFFFFFFF
 
 
+# ---- branch streams -----------------------------------------------------------------------------------
+# Independent branches of the forward (drug / protein extractors and their guided attentions; the
+# protein and molecule streams of the paired PMMA blocks) are issued on two CUDA streams.  autograd runs
+# every backward node on the stream of its forward, so the backward forks the same way.  Works eagerly
+# and inside a CUDA-graph capture (the side stream joins the capture through its wait on the capturing
+# stream).  DL_NO_BRANCH_STREAMS=1 turns it off (A/B measurements).
+BRANCH_STREAMS = os.environ.get("DL_NO_BRANCH_STREAMS", "0") == "0"
+_branch_streams = {}
+
+
+def branch_stream(like: torch.Tensor):
+    """The side stream for `like`'s device (None when branch streams are off or `like` is not on a GPU)."""
+    if not BRANCH_STREAMS or not like.is_cuda:
+        return None
+    s = _branch_streams.get(like.device)
+    if s is None:
+        s = _branch_streams[like.device] = torch.cuda.Stream(like.device)
+    return s
+
+
+def crosses(stream, *tensors):
+    """Tensors allocated on one stream and read on another: tell the caching allocator, so their blocks
+    are not handed out again on the allocating stream while the reader is still pending."""
+    for t in tensors:
+        if torch.is_tensor(t) and t.is_cuda:
+            t.record_stream(stream)
+
+
 _forward_only = False
 
 
@@ -551,8 +579,18 @@ class PairedQKVFn(Function):
         wm, bm = params[6:12:2], params[7:12:2]
         D, E = ap.shape[-1], wp[0].shape[0]
         out = torch.empty((2,) + tuple(ap.shape[:-1]) + (3 * E,), dtype=ap.dtype, device=ap.device)
-        _qkv_fwd(ap.view(-1, D), wp, bp, out[0].view(-1, 3 * E))
-        _qkv_fwd(am.view(-1, D), wm, bm, out[1].view(-1, 3 * E))
+        side = branch_stream(ap)
+        if side is None:
+            _qkv_fwd(ap.view(-1, D), wp, bp, out[0].view(-1, 3 * E))
+            _qkv_fwd(am.view(-1, D), wm, bm, out[1].view(-1, 3 * E))
+        else:                                   # the molecule slab on the side stream, joined before the core
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _qkv_fwd(am.view(-1, D), wm, bm, out[1].view(-1, 3 * E))
+            _qkv_fwd(ap.view(-1, D), wp, bp, out[0].view(-1, 3 * E))
+            main.wait_stream(side)
+            crosses(side, out)
         ctx.save_for_backward(ap, am, *params)
         ctx.dts = (xp.dtype, xm.dtype)
         return out
@@ -565,8 +603,19 @@ class PairedQKVFn(Function):
         wm, bm = params[6:12:2], params[7:12:2]
         D, E = ap.shape[-1], wp[0].shape[0]
         gc = K.to_compute(g)
-        dxp, dwp, dbp = _qkv_bwd(gc[0].view(-1, 3 * E), ap.view(-1, D), wp, bp, ctx.needs_input_grad[0])
-        dxm, dwm, dbm = _qkv_bwd(gc[1].view(-1, 3 * E), am.view(-1, D), wm, bm, ctx.needs_input_grad[1])
+        side = branch_stream(gc)
+        if side is None:
+            dxp, dwp, dbp = _qkv_bwd(gc[0].view(-1, 3 * E), ap.view(-1, D), wp, bp, ctx.needs_input_grad[0])
+            dxm, dwm, dbm = _qkv_bwd(gc[1].view(-1, 3 * E), am.view(-1, D), wm, bm, ctx.needs_input_grad[1])
+        else:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                crosses(side, gc)
+                dxm, dwm, dbm = _qkv_bwd(gc[1].view(-1, 3 * E), am.view(-1, D), wm, bm, ctx.needs_input_grad[1])
+            dxp, dwp, dbp = _qkv_bwd(gc[0].view(-1, 3 * E), ap.view(-1, D), wp, bp, ctx.needs_input_grad[0])
+            main.wait_stream(side)          # autograd hands both results on from this node's stream
+            crosses(main, dxm)
         grads = []
         for dw, db in zip(dwp, dbp):
             grads += [dw, db]

@@ -10,8 +10,6 @@ are one pass over ``xp`` (dl_fillbit_pool), ``norm(v + mhla(v))`` is one kernel 
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
 
@@ -24,29 +22,6 @@ from .params import FlatParams
 from .ssl import SSL
 
 CONFIGS = {'LAMP': get_model_defaults}
-
-# Independent branches of the forward (and, through autograd, of the backward) on a second CUDA stream.
-# Works eagerly and inside a CUDA-graph capture (the side stream joins the capture through its
-# wait on the capturing stream).  DL_NO_BRANCH_STREAMS=1 turns it off (A/B measurements).
-BRANCH_STREAMS = os.environ.get("DL_NO_BRANCH_STREAMS", "0") == "0"
-_side_streams = {}
-
-
-def _side_stream(like: torch.Tensor):
-    if not BRANCH_STREAMS or not like.is_cuda:
-        return None
-    s = _side_streams.get(like.device)
-    if s is None:
-        s = _side_streams[like.device] = torch.cuda.Stream(like.device)
-    return s
-
-
-def _crosses(stream, *tensors):
-    """Tensors allocated on one stream and read on another: tell the caching allocator, so their blocks
-    are not handed out again on the allocating stream while the reader is still pending."""
-    for t in tensors:
-        if torch.is_tensor(t) and t.is_cuda:
-            t.record_stream(stream)
 
 
 class DrugLAMPBase(nn.Module):
@@ -195,7 +170,7 @@ class DrugLAMP(DrugLAMPBase):
     def _forward(self, vd, vp, xd, xp):
         if self._flat is not None:
             self._flat.sync()
-        side = _side_stream(xp)
+        side = Fn.branch_stream(xp)
         self._branch_streams = [] if side is None else [side]      # what the last forward used besides the caller's
         if side is None:
             vd = self.drug_extractor(vd)                                    # (B, 512, 128)
@@ -222,15 +197,15 @@ class DrugLAMP(DrugLAMPBase):
             ev_fill = main.record_event()
             with torch.cuda.stream(side):
                 side.wait_event(ev_fill)
-                _crosses(side, xp_pool)
+                Fn.crosses(side, xp_pool)
                 xpa, xda = self._llm_adaptors(xp_pool, xd_lin)
                 mx, self.A_x_gca = self._guided(self.x_gca, self.x_mhla, self.x_gca_norm, xpa, xda)
             vpf = self._protein_branch(vp, bit_p)
             main.wait_event(ev_vd)
-            _crosses(main, vd)
+            Fn.crosses(main, vd)
             mv, self.A_v_gca = self._guided(self.v_gca, self.v_mhla, self.v_gca_norm, vpf, vd)
             main.wait_stream(side)
-            _crosses(main, mx, self.A_x_gca, xpa, xda, xd_cat)
+            Fn.crosses(main, mx, self.A_x_gca, xpa, xda, xd_cat)
         ssl = {'vp': vp, 'xp': xp if xp_cat is None else xp_cat, 'fill_bit_p': bit_p, 'vd': vd, 'xd': xd_cat}
         self._watch_pmma_inputs(mx, mv)
         f, self.attn, self.guide_attn = self.pmma(mx, mv)

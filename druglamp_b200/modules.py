@@ -199,7 +199,9 @@ class Attention(nn.Module):
             raise NotImplementedError("vis=True (returning probability maps) is not on the hot path "
                                       "(DrugLAMPBase builds PMMA with vis=False)")
 
-    def forward(self, hidden_states, mol=None, residual=None, residual_mol=None):
+    def forward(self, hidden_states, mol=None, residual=None, residual_mol=None, side=None):
+        """side: the stream the molecule stream's tensors (`mol`, `residual_mol`) live on; the returned
+        molecule output stays on it (PMMABlock / Encoder join)."""
         H = self.num_attention_heads
         scale = 1.0 / math.sqrt(self.attn_head_size)
         if mol is None:
@@ -222,10 +224,20 @@ class Attention(nn.Module):
         # op = [A(q_prot), A(q_mol)] on the protein K/V = cat(attn, attn_p);
         # om = the same query sets on the molecule K/V = (attn_p, attn): swapped
         op, om = Fn.PairedAttnCoreFn.apply(qkv, H, scale)
+        if side is None:
+            tp = Fn.FcCatFn.apply(op, self.fc.weight, self.fc.bias, False)
+            tm = Fn.FcCatFn.apply(om, self.fc_mol.weight, self.fc_mol.bias, True)
+            attn_prot = Fn.linear(tp, self.out.weight, self.out.bias, residual=residual)
+            attn_mol = Fn.linear(tm, self.out_mol.weight, self.out_mol.bias, residual=residual_mol)
+            return attn_prot, attn_mol, None, None
+        core_done = torch.cuda.current_stream().record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(core_done)
+            Fn.crosses(side, om)
+            tm = Fn.FcCatFn.apply(om, self.fc_mol.weight, self.fc_mol.bias, True)
+            attn_mol = Fn.linear(tm, self.out_mol.weight, self.out_mol.bias, residual=residual_mol)
         tp = Fn.FcCatFn.apply(op, self.fc.weight, self.fc.bias, False)
-        tm = Fn.FcCatFn.apply(om, self.fc_mol.weight, self.fc_mol.bias, True)
         attn_prot = Fn.linear(tp, self.out.weight, self.out.bias, residual=residual)
-        attn_mol = Fn.linear(tm, self.out_mol.weight, self.out_mol.bias, residual=residual_mol)
         return attn_prot, attn_mol, None, None
 
     def fused_parameter_groups(self):
@@ -263,13 +275,27 @@ class PMMABlock(nn.Module):
         is added inside the LayerNorm backward kernel."""
         return Fn.layer_norm_res(x, m.weight, m.bias, m.eps)
 
-    def forward(self, prot, mol=None):
+    def forward(self, prot, mol=None, side=None):
+        """side: a second CUDA stream on which `mol` is ready; the molecule stream's LayerNorms, output
+        projection and FFN are issued there, concurrent with the protein stream's on the caller's stream,
+        and the returned `mol` stays on it (Encoder.forward joins after the last paired block)."""
         if mol is None:
             h, res = self._ln_res(prot, self.attention_norm)
             prot, w, gw = self.attn(h, residual=res)
             h, res = self._ln_res(prot, self.ffn_norm)
             prot = self.ffn(h, residual=res)
             return prot, w, gw
+        if side is not None:
+            with torch.cuda.stream(side):
+                hm, rm = self._ln_res(mol, self.att_norm_mol)
+            hp, rp = self._ln_res(prot, self.attention_norm)
+            prot, mol, w, gw = self.attn(hp, hm, residual=rp, residual_mol=rm, side=side)
+            with torch.cuda.stream(side):
+                hm, rm = self._ln_res(mol, self.ffn_norm_mol)
+                mol = self.ffn_mol(hm, residual=rm)
+            hp, rp = self._ln_res(prot, self.ffn_norm)
+            prot = self.ffn(hp, residual=rp)
+            return prot, mol, w, gw
         hp, rp = self._ln_res(prot, self.attention_norm)
         hm, rm = self._ln_res(mol, self.att_norm_mol)
         prot, mol, w, gw = self.attn(hp, hm, residual=rp, residual_mol=rm)
@@ -324,16 +350,27 @@ class Encoder(nn.Module):
     def forward(self, hidden_states, mol=None):
         attn_weights: List = []
         guided_attn_weights: List = []
+        # the molecule stream of the paired blocks runs on a second CUDA stream (Fn.branch_stream)
+        side = Fn.branch_stream(hidden_states) if mol is not None else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            Fn.crosses(side, mol)
         for i, layer_block in enumerate(self.layer_with_mol):
             if i >= 2:
                 if i == 2:
+                    if side is not None:
+                        torch.cuda.current_stream().wait_stream(side)
+                        Fn.crosses(torch.cuda.current_stream(), mol)
+                        side = None
                     hidden_states = torch.cat((hidden_states, mol), dim=-1)
                 hidden_states, weights, guided_weights = layer_block(hidden_states)
             else:
-                hidden_states, mol, weights, guided_weights = layer_block(hidden_states, mol)
+                hidden_states, mol, weights, guided_weights = layer_block(hidden_states, mol, side=side)
             if self.vis:
                 attn_weights.append(weights)
                 guided_attn_weights.append(guided_weights)
+        if side is not None:                      # fewer than three layers: nothing joined the streams yet
+            torch.cuda.current_stream().wait_stream(side)
         m = self.encoder_norm
         encoded = Fn.layer_norm(hidden_states, m.weight, m.bias, m.eps)
         return encoded, attn_weights, guided_attn_weights

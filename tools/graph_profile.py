@@ -1,7 +1,7 @@
 """Per-kernel time of the CAPTURED step (CUDA-graph replay, warm caches, PDL overlap included), from
 CUPTI kernel records via torch.profiler -- the in-situ complement of the cold, serialised ncu pass.
 
-    DL_NO_PDL=1 python tools/graph_profile.py > gpurun_out/graph_profile.txt
+    DL_NO_PDL=1 python tools/graph_profile.py [trace.json] > gpurun_out/graph_profile.txt
 
 (with programmatic dependent launch on, a kernel's recorded duration includes its wait for the
 previous kernel, so per-kernel numbers are only meaningful with DL_NO_PDL=1)
@@ -42,6 +42,8 @@ def main():
         for _ in range(REPS):
             ts.replay(sb)
         torch.cuda.synchronize()
+    if len(sys.argv) > 1:                 # chrome trace (stream = tid) for offline timeline analysis
+        prof.export_chrome_trace(sys.argv[1])
     agg = collections.defaultdict(lambda: [0, 0.0])
     t_min, t_max = None, None
     for ev in prof.events():
