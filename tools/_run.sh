@@ -1,7 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r2p.txt 2>&1; tail -3 gpurun_out/pytest_r2p.txt
-timeout 300 python bench.py --steps 50 --no-cpu-baseline > gpurun_out/bench_r2p.json 2> gpurun_out/bench_r2p.err; python -c "
-import json;d=json.load(open('gpurun_out/bench_r2p.json'));print('PMMA-STREAMS+LN', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['gemm_ms_per_step'])"
-timeout 300 python tools/graph_profile.py gpurun_out/trace_r2p.json > gpurun_out/graph_profile_r2p.md 2>&1; head -3 gpurun_out/graph_profile_r2p.md; grep layernorm_bwd gpurun_out/graph_profile_r2p.md
+timeout 600 python bench.py --config 2c2p --steps 4 --warmup 2 > gpurun_out/r2_bench_2c2p_1gpu.json 2> gpurun_out/r2_2c2p.err; tail -c 600 gpurun_out/r2_bench_2c2p_1gpu.json
+timeout 300 python bench.py --config pgca > gpurun_out/r2_bench_pgca_1gpu.json 2>> gpurun_out/r2_2c2p.err; tail -c 400 gpurun_out/r2_bench_pgca_1gpu.json
+timeout 300 python bench.py --config infer > gpurun_out/r2_bench_infer_1gpu.json 2>> gpurun_out/r2_2c2p.err; tail -c 400 gpurun_out/r2_bench_infer_1gpu.json
+DL_BENCH_DUMP=gpurun_out/gemm_profile_r2q.txt timeout 600 python bench.py > gpurun_out/bench_r2q.json 2> gpurun_out/bench_r2q.err; tail -c 1500 gpurun_out/bench_r2q.json
+timeout 300 python bench.py --impl reference --steps 6 --warmup 1 > gpurun_out/bench_ref_r2q.json 2>> gpurun_out/bench_r2q.err; cat gpurun_out/bench_ref_r2q.json | cut -c1-300
