@@ -62,6 +62,18 @@ class AttnArgs(C.Structure):
     ]
 
 
+class SmallLinearArgs(C.Structure):
+    _fields_ = [
+        ("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("pre", C.c_void_p), ("Y", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldy", C.c_int64),
+        ("w_kn", C.c_int32), ("act", C.c_int32), ("bn", C.c_int32), ("training", C.c_int32),
+        ("eps", C.c_float), ("momentum", C.c_float),
+    ]
+
+
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
 # name -> argtypes; must list every compute entry point declared in include/druglamp_sm100.h
 SIGNATURES = {
@@ -98,6 +110,8 @@ SIGNATURES = {
     "dl_cm_triplet_bwd": [_P, _P, _I64, _I64, _F, _P, _P, _P, _P],
     "dl_cross_entropy_fwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _I32, _P],
     "dl_cross_entropy_bwd": [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _P, _P, _I32, _P],
+    "dl_small_linear": [C.POINTER(SmallLinearArgs), _P],
+    "dl_head_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_bce_fwd": [_P, _P, _P, _P, _I64, _P],
     "dl_bce_bwd": [_P, _P, _P, _P, _I64, _P],
 }

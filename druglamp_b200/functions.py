@@ -305,6 +305,72 @@ class LinearFn(Function):
         return dx, dw, db, None, dres, None, None, None, None
 
 
+class HeadLayerFn(Function):
+    """y = BatchNorm1d(act(x W^T + b)) on at most K.SMALL_M rows, fp32: one layer of the decoder head
+    (model/basic_model.py:205-213) as one launch forward (dl_small_linear) and two backward
+    (dl_head_bn_act_bwd, then dX = g W by dl_small_linear); dW = g^T x is a dl_gemm that nothing
+    downstream waits for.  bn = None: plain Linear (+ activation)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, bn_w, bn_b, running_mean, running_var, nbt, eps, momentum, training, has_bn):
+        xs = x.shape
+        x2 = x.reshape(-1, xs[-1]).float().contiguous()
+        need = _needs_backward(ctx)
+        bn = (None if bn_w is None else bn_w.detach(), None if bn_b is None else bn_b.detach(), running_mean,
+              running_var, nbt, eps, momentum, training) if has_bn else None
+        y, pre, mean, rstd = K.small_linear(x2, w.detach(), None if b is None else b.detach(), act=act,
+                                            keep_pre=need and (has_bn or act != K.ACT_NONE), bn=bn)
+        ctx.save_for_backward(x2, w, pre, mean, rstd, bn_w)
+        ctx.params = (b, bn_b)
+        ctx.meta = (act, bool(training), has_bn, xs, x.dtype)
+        return y.view(*xs[:-1], w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, w, pre, mean, rstd, bn_w = ctx.saved_tensors
+        b, bn_b = ctx.params
+        act, training, has_bn, xs, xdt = ctx.meta
+        N = w.shape[0]
+        g = gy.reshape(-1, N).float().contiguous()
+        dgam = dbet = db = None
+        if pre is not None:
+            tg, tb_, tbias = _grad_target(bn_w), _grad_target(bn_b), _grad_target(b)
+            flat = (not has_bn or bn_w is None or (tg is not None and tb_ is not None)) and (b is None or tbias is not None)
+            if flat:
+                g, _, _, _ = K.head_bn_act_bwd(g, pre, None if bn_w is None else bn_w.detach(), mean, rstd, act,
+                                               training, b is not None, acc_into=(tg, tb_, tbias))
+            else:
+                g, dgam, dbet, db = K.head_bn_act_bwd(g, pre, None if bn_w is None else bn_w.detach(), mean, rstd,
+                                                      act, training, b is not None)
+        elif b is not None:
+            db = g.sum(0) if N <= K.SMALL_M else _bgrad(b, g)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _, _, _ = K.small_linear(g, w.detach(), None, w_kn=True)
+            dx = _back(dx, xdt, xs)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if N <= K.SMALL_M:       # (N, rows) x (rows, K): narrower than a TMA row -- the small-M kernel again
+                dw = K.small_linear(g.t().contiguous(), x2, None, w_kn=True)[0]
+            else:
+                dw = _wgrad(w, g, x2)
+        return dx, dw, db, None, dgam, dbet, None, None, None, None, None, None, None
+
+
+def head_layer(x, fc: torch.nn.Linear, act=K.ACT_NONE, bn: Optional[torch.nn.BatchNorm1d] = None):
+    """fc -> act -> bn (optional) on <= K.SMALL_M rows through the small-M kernels."""
+    if bn is None:
+        return HeadLayerFn.apply(x, fc.weight, fc.bias, act, None, None, None, None, None, 0.0, 0.0, False, False)
+    training = bn.training or bn.running_mean is None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    update = training and not _bn_frozen
+    keep = update or not training
+    return HeadLayerFn.apply(x, fc.weight, fc.bias, act, bn.weight, bn.bias, bn.running_mean if keep else None,
+                             bn.running_var if keep else None, bn.num_batches_tracked if update else None,
+                             bn.eps, momentum, training, True)
+
+
 def linear(x, w, b=None, act=K.ACT_NONE, residual=None, drop_p=0.0, seed=0, keep_pad=False):
     return LinearFn.apply(x, w, b, act, residual, drop_p, seed, False, keep_pad)
 

@@ -535,3 +535,57 @@ def bce_bwd(prob, y, gout):
     ds = torch.empty_like(prob)
     L.call("dl_bce_bwd", prob.data_ptr(), y.data_ptr(), gout.data_ptr(), ds.data_ptr(), prob.numel())
     return ds
+
+
+# ---- small-M dense layers (the decoder head) ---------------------------------------------------
+SMALL_M = 64
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, w_kn: bool = False, act: int = ACT_NONE,
+                 keep_pre: bool = False, bn=None):
+    """y = BatchNorm(act(x op(w) + bias)) for at most SMALL_M rows, fp32, one launch (dl_small_linear).
+    w: [N, K] (w_kn=False) or [K, N] (w_kn=True), unit inner stride.
+    bn: None or (gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, training).
+    -> (y, pre or None, mean or None, rstd or None)"""
+    M, Kd = x.shape
+    N = w.shape[1] if w_kn else w.shape[0]
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or x.stride(1) != 1 or w.stride(1) != 1:
+        raise TypeError("dl_small_linear takes fp32 operands with unit inner stride")
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    pre = torch.empty_like(y) if keep_pre else None
+    mean = rstd = None
+    a = L.SmallLinearArgs()
+    a.X, a.W, a.bias, a.pre, a.Y = x.data_ptr(), w.data_ptr(), L.ptr(bias), L.ptr(pre), y.data_ptr()
+    a.M, a.N, a.K = M, N, Kd
+    a.ldx, a.ldw, a.ldy = x.stride(0), w.stride(0), N
+    a.w_kn, a.act = int(w_kn), act
+    if bn is not None:
+        gamma, beta, rm, rv, nbt, eps, momentum, training = bn
+        mean = torch.empty(N, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        a.gamma, a.beta, a.mean, a.rstd = L.ptr(gamma), L.ptr(beta), mean.data_ptr(), rstd.data_ptr()
+        a.running_mean, a.running_var, a.num_batches_tracked = L.ptr(rm), L.ptr(rv), L.ptr(nbt)
+        a.bn, a.training, a.eps, a.momentum = 1, int(training), eps, momentum
+    L.check(L.lib().dl_small_linear(L.C.byref(a), L.stream_ptr()), "dl_small_linear")
+    return y, pre, mean, rstd
+
+
+def head_bn_act_bwd(dy, pre, gamma, mean, rstd, act: int, training: bool, has_bias: bool = True, acc_into=None):
+    """BatchNorm1d + activation backward of one head layer (dl_head_bn_act_bwd).
+    -> (g = d loss / d pre, dgamma, dbeta, dbias).  acc_into = (dgamma, dbeta, dbias) fp32 gradient
+    buffers to ADD to (entries that do not apply are None); the gradients are then returned as None."""
+    M, N = dy.shape
+    g = torch.empty_like(dy)
+    bn = mean is not None
+    if acc_into is not None:
+        dg, db, dbias = acc_into
+    else:
+        new = lambda: torch.empty(N, dtype=torch.float32, device=dy.device)       # noqa: E731
+        dg, db = (new(), new()) if (bn and gamma is not None) else (None, None)
+        dbias = new() if has_bias else None
+    L.call("dl_head_bn_act_bwd", dy.data_ptr(), pre.data_ptr(), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
+           g.data_ptr(), L.ptr(dg), L.ptr(db), L.ptr(dbias), M, N, act, int(bn), int(training),
+           int(acc_into is not None))
+    if acc_into is not None:
+        return g, None, None, None
+    return g, dg, db, dbias

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 from typing import List
 
 import torch
@@ -40,6 +41,8 @@ GCN_PRECISION = "fp32"
 # batch, model/basic_model.py:196-215) works on 64 rows: 0.04 % of the FLOPs, but every BatchNorm over 64
 # samples re-amplifies the rounding of its input.  It runs in fp32 as well.
 HEAD_PRECISION = "fp32"
+# Decoder head on <= 64 rows: one launch per layer (csrc/head.cu) instead of GEMM + BatchNorm chains.
+HEAD_SMALL_KERNELS = os.environ.get("DL_NO_HEAD_KERNELS", "0") == "0"
 # Evaluate the GCN once for all virtual nodes (graph.BatchedMolGraph.compact): ~12x fewer rows.
 GCN_DEDUP = True
 
@@ -723,6 +726,12 @@ class MLP(nn.Module):
         self.fc4 = nn.Linear(out_dim, binary)
 
     def forward(self, x):
+        rows = x.numel() // x.shape[-1]
+        if HEAD_PRECISION == "fp32" and x.is_cuda and rows <= K.SMALL_M and HEAD_SMALL_KERNELS:
+            # <= 64 pairs: each fc -> GELU -> BatchNorm1d layer is one launch (fp32 CUDA-core FMA)
+            for i in (1, 2, 3):
+                x = Fn.head_layer(x, getattr(self, f"fc{i}"), K.ACT_GELU, getattr(self, f"bn{i}"))
+            return Fn.head_layer(x, self.fc4)
         with K.local_compute_dtype(torch.float32 if HEAD_PRECISION == "fp32" else None):
             for i in (1, 2, 3):
                 fc, bn = getattr(self, f"fc{i}"), getattr(self, f"bn{i}")

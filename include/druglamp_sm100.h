@@ -371,6 +371,35 @@ int dl_bce_fwd(const float* score, const float* y, float* prob, float* loss, int
 int dl_bce_bwd(const float* prob, const float* y, const float* gout, float* dscore, int64_t n,
                void* stream);
 
+/* One dense layer on at most 64 rows, fp32, in ONE launch: Y = BatchNorm1d(act(X op(W) + bias)) -- a layer
+ * of the decoder head (model/basic_model.py:196-215: fc -> GELU -> BatchNorm1d over the PAIRS of the
+ * batch; the head is 0.04 % of the FLOPs but a serial chain between forward and backward).
+ *   w_kn = 0: W is [N, K] (nn.Linear weight, y = x W^T);  w_kn = 1: W is [K, N] (dX = g W)
+ *   pre (optional): X op(W) + bias before the activation, kept for the backward
+ *   bn != 0: BatchNorm1d over the M rows -- training != 0: batch statistics, running_mean / running_var
+ *   (optional) updated with `momentum` (unbiased variance), *num_batches_tracked += 1 (optional);
+ *   training == 0: the running statistics.  mean / rstd: [N] outputs for the backward.
+ * CUDA-core fp32 FMA (the product is latency bound at M <= 64); a CTA owns 8 output columns for all rows,
+ * which makes the batch statistics CTA-local. */
+typedef struct dl_small_linear_args {
+  const float* X; const float* W; const float* bias;
+  float* pre; float* Y;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd; float* running_mean; float* running_var; int64_t* num_batches_tracked;
+  int64_t M, N, K;
+  int64_t ldx, ldw, ldy;          /* row strides of X, W and of Y / pre (elements) */
+  int32_t w_kn, act, bn, training;
+  float eps, momentum;
+} dl_small_linear_args;
+int dl_small_linear(const dl_small_linear_args* args, void* stream);
+/* Backward of the layer's BatchNorm1d + activation (column-local): g = d loss / d pre from dy = d loss / d Y;
+ * dgamma, dbeta, dbias (each optional): parameter gradients, added to when accumulate != 0.  dX and dW
+ * follow as g W (dl_small_linear, w_kn = 1) and g^T X (dl_gemm).  Contiguous [M, N] tensors, M <= 64. */
+int dl_head_bn_act_bwd(const float* dy, const float* pre, const float* gamma, const float* mean,
+                       const float* rstd, float* g, float* dgamma, float* dbeta, float* dbias,
+                       int64_t M, int64_t N, int32_t act, int32_t bn, int32_t training,
+                       int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -487,3 +487,80 @@ def test_gcn_virtual_node_dedup_equals_dense_evaluation(dtype, tol):
     finally:
         M.GCN_DEDUP = True
         D.set_compute_dtype(torch.float32)
+
+
+# ---------------------------------------------------------------------------- small-M head kernels
+@pytest.mark.parametrize("M,N,Kd", [(64, 1024, 512), (64, 256, 1024), (16, 1024, 1024), (2, 100, 250), (64, 1, 256),
+                                    (7, 8, 1), (33, 1030, 130)])
+def test_small_linear_matches_fp64(M, N, Kd):
+    """dl_small_linear: y = x W^T + b (and the dX orientation y = g W) on <= 64 rows, fp32 FMA."""
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(M * 1000 + N)
+    x = torch.randn(M, Kd, device="cuda")
+    w = torch.randn(N, Kd, device="cuda") / Kd ** 0.5
+    b = torch.randn(N, device="cuda")
+    y, pre, _, _ = K.small_linear(x, w, b, act=K.ACT_GELU, keep_pre=True)
+    ref_pre = x.double() @ w.double().t() + b.double()
+    _close(pre, ref_pre, 2e-6, "pre")
+    _close(y, F.gelu(ref_pre), 2e-6, "gelu")
+    g = torch.randn(M, N, device="cuda")
+    dx, _, _, _ = K.small_linear(g, w, None, w_kn=True)
+    _close(dx, g.double() @ w.double(), 2e-6, "dx")
+
+
+@pytest.mark.parametrize("M", [64, 16, 2])
+@pytest.mark.parametrize("training", [True, False])
+def test_head_layer_matches_torch_linear_gelu_batchnorm(M, training):
+    """Fn.head_layer = nn.Linear -> GELU -> nn.BatchNorm1d: outputs, running buffers, every gradient."""
+    from druglamp_b200 import functions as Fn
+    from druglamp_b200 import kernels as K
+    torch.manual_seed(5 + M)
+    Kd, N = 512, 1024
+    fc, bn = torch.nn.Linear(Kd, N).cuda(), torch.nn.BatchNorm1d(N).cuda()
+    fr, br = torch.nn.Linear(Kd, N).cuda().double(), torch.nn.BatchNorm1d(N).cuda().double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+        fr.load_state_dict(fc.state_dict()); br.load_state_dict(bn.state_dict())
+    bn.train(training); br.train(training)
+    x = torch.randn(M, Kd, device="cuda", requires_grad=True)
+    xr = x.detach().double().requires_grad_(True)
+    dy = torch.randn(M, N, device="cuda")
+    y = Fn.head_layer(x, fc, K.ACT_GELU, bn)
+    y.backward(dy)
+    yr = br(F.gelu(fr(xr)))
+    yr.backward(dy.double())
+    tol = 2e-4 if (training and M == 2) else 2e-5          # two-sample statistics amplify rounding
+    _close(y, yr, tol, "y")
+    _close(x.grad, xr.grad, tol * 5, "dx")
+    _close(fc.weight.grad, fr.weight.grad, 2e-3, "dW")      # dl_gemm TF32 / 3xTF32 product over the rows
+    _close(fc.bias.grad, fr.bias.grad, tol * 5, "db")
+    _close(bn.weight.grad, br.weight.grad, tol * 5, "dgamma")
+    _close(bn.bias.grad, br.bias.grad, tol * 5, "dbeta")
+    _close(bn.running_mean, br.running_mean, 1e-5, "running_mean")
+    _close(bn.running_var, br.running_var, 1e-5, "running_var")
+    assert int(bn.num_batches_tracked) == int(br.num_batches_tracked)
+
+
+def test_decoder_head_small_kernels_equal_the_gemm_path():
+    """modules.MLP on 64 rows: the one-launch-per-layer path against the dl_gemm + dl_batchnorm path."""
+    from druglamp_b200 import modules as Mo
+    torch.manual_seed(11)
+    a, b = Mo.MLP(512, 1024, 256, 1).cuda(), Mo.MLP(512, 1024, 256, 1).cuda()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(64, 512, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = a(xa)
+    prev, Mo.HEAD_SMALL_KERNELS = Mo.HEAD_SMALL_KERNELS, False
+    try:
+        yb = b(xb)
+    finally:
+        Mo.HEAD_SMALL_KERNELS = prev
+    r = torch.randn(64, 1, device="cuda")     # (a plain sum has zero gradient through train-mode BatchNorm)
+    (ya * r).sum().backward(); (yb * r).sum().backward()
+    _close(ya, yb, 5e-3, "score")           # the GEMM path multiplies in TF32
+    _close(xa.grad, xb.grad, 2e-2, "dx")
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        _close(p.grad, q.grad, 2e-2, n)
+    for (n, p), (_, q) in zip(a.named_buffers(), b.named_buffers()):
+        _close(p, q, 5e-3, n)
