@@ -202,6 +202,32 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _teardown(world, *drop):
+    """Leave cleanly at N > 1.  The captured step graphs contain NCCL kernels; a communicator that is
+    destroyed while such graphs are alive (or while another rank is still busy) can block forever, and
+    a bench that printed its line but never exits is a hung run for the driver.  So: graphs first, then
+    a barrier, then destroy -- and a watchdog that ends the process if the teardown does not return."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    sys.stdout.flush()
+    threading.Timer(45.0, lambda: os._exit(0)).start()
+    for d in drop:
+        try:
+            d.clear()
+        except Exception:
+            pass
+    gc.collect()
+    torch.cuda.synchronize()
+    try:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    finally:
+        sys.stdout.flush()
+        os._exit(0)
+
+
 # ------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import druglamp_b200 as D
@@ -453,8 +479,7 @@ def run_gpu(args):
             line["long_run"] = {"steps": long_steps, "ms_per_step": long_ms / long_steps,
                                 "value": pairs * long_steps / (long_ms * 1e-3), "unit": UNIT}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _teardown(world, ts._graphs)
 
 
 # ------------------------------------------------------------------------------------- other configs
@@ -566,8 +591,7 @@ def run_2c2p(args):
                 "e2e": None, "gpu_launches": cs.launches * steps, "gpu_launches_per_step": cs.launches,
                 "loss": loss}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _teardown(world, cs._g_feat, cs._g_back)
 
 
 def run_pgca(args):
@@ -616,8 +640,7 @@ def run_pgca(args):
                           "algorithmic_tflops": flop / step_ms * 1e-9,
                           "raw_map_bytes": raw.numel() * raw.element_size(), "e2e": None,
                           "gpu_launches": launches * steps, "gpu_launches_per_step": launches}), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _teardown(world)
 
 
 def run_infer(args):
@@ -657,17 +680,72 @@ def run_infer(args):
                           "algorithmic_tflops_per_gpu": 8.277 * B / step_ms, "e2e": None,
                           "gpu_launches": st.launches_per_step * steps,
                           "gpu_launches_per_step": st.launches_per_step}), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _teardown(world)
+
+
+def run_trainer(args):
+    """The reference's training step with its auxiliary losses (trainer.py:179-231):
+    DrugLAMP2C2P, 64 pairs, bf16, three AdamW optimisers over all parameters, stepped eagerly (the MLM mask
+    is sampled per step and the 2C2P label matrix is built from the batch's meta dicts on the host, as the
+    reference does).  `value` = an SSL + 2C2P epoch's step; the other epoch kinds are listed beside it."""
+    import druglamp_b200 as D
+    from druglamp_b200 import _lib as L
+    from druglamp_b200.models import DrugLAMP2C2P
+    from druglamp_b200.synth import make_batch
+    from druglamp_b200.train import StaticBatch
+    from druglamp_b200.trainer_step import TrainerStep
+    rank, local, world, dev = _dist_setup()
+    D.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(1234)
+    model = DrugLAMP2C2P(384, 640).to(dev)
+    model.train()
+    model.flatten_parameters()
+    raw = [make_batch(BATCH, seed=1234 + rank * 100 + i) for i in range(N_DISTINCT_BATCHES)]
+    batches = [StaticBatch(b, dev) for b in raw]
+    steps = args.steps if args.steps is not None else 30
+    out = {}
+    launches = 0
+    for name, (ssl, cm), wiped in (("cls", (False, False), False), ("cls+ssl", (True, False), False),
+                                   ("cls+ssl+2c2p", (True, True), False),
+                                   ("cls+ssl+2c2p, wiped backward passes run too", (True, True), True)):
+        ts = TrainerStep(model, run_wiped_backward=wiped)
+        it = [0]
+
+        def step():
+            i = it[0] % len(batches)
+            ts.step(batches[i], meta=raw[i].meta, compute_ssl=ssl, compute_cm=cm)
+            it[0] += 1
+        n0 = L.launch_count()
+        step()
+        launches = L.launch_count() - n0
+        ms = _timed(step, steps, args.warmup, world)
+        out[name] = {"ms_per_step": ms / steps, "pairs_per_s": BATCH * world * steps / (ms * 1e-3),
+                     "gpu_launches_per_step": launches}
+    if rank == 0:
+        head = out["cls+ssl+2c2p"]
+        print(json.dumps({"metric": METRIC, "value": head["pairs_per_s"], "unit": UNIT, "n_gpus": world,
+                          "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": head["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                          "data": "synthetic",
+                          "config": {"workload": "reference training step with auxiliary losses (trainer.py:179-231): "
+                                                 "DrugLAMP2C2P forward, classification + SSL x0.1 + 2C2P losses, three AdamW "
+                                                 "over all parameters; eager launches (host-side mask sampling / label matrix), "
+                                                 "no gradient all-reduce in this line",
+                                     "batch_per_gpu": BATCH, "parallelism": f"replicas x{world}",
+                                     "l2_policy": f"{N_DISTINCT_BATCHES} distinct resident batches of ~440 MB rotate"},
+                          "epoch_kinds": out, "e2e": None, "gpu_launches": head["gpu_launches_per_step"] * steps,
+                          "gpu_launches_per_step": head["gpu_launches_per_step"]}), flush=True)
+    _teardown(world)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--config", default="druglamp", choices=["druglamp", "2c2p", "pgca", "infer"],
+    ap.add_argument("--config", default="druglamp", choices=["druglamp", "2c2p", "pgca", "infer", "trainer"],
                     help="druglamp = BASELINE configs[1] (the headline, default); 2c2p = configs[2]; "
-                         "pgca = configs[3]; infer = configs[4]")
+                         "pgca = configs[3]; infer = configs[4]; trainer = the reference training step with its "
+                         "SSL / 2C2P losses and three optimisers (trainer.py:179-231)")
     ap.add_argument("--global-batch", type=int, default=4096, help="--config 2c2p only")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -675,7 +753,7 @@ def main():
     ap.add_argument("--ncu-step", action="store_true", help="run one eager step in an NVTX range and exit (for ncu)")
     args = ap.parse_args()
     if args.config != "druglamp" and args.impl == "b200":
-        {"2c2p": run_2c2p, "pgca": run_pgca, "infer": run_infer}[args.config](args)
+        {"2c2p": run_2c2p, "pgca": run_pgca, "infer": run_infer, "trainer": run_trainer}[args.config](args)
         return
     if args.steps is None:
         args.steps = 200

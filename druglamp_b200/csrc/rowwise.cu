@@ -713,22 +713,38 @@ __global__ void adamw_tick_kernel(long long* step) {
   pdl_trigger();
   pdl_wait(); *step += 1; }
 
+// per-parameter step counts (torch keeps state['step'] per parameter and only advances it when the
+// parameter has a gradient): one counter per 64-element block of the flat buffer
+__global__ void adamw_tick_blocks_kernel(int* __restrict__ steps, const unsigned char* __restrict__ active,
+                                         long long nblocks) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks;
+       b += (long long)gridDim.x * blockDim.x)
+    if (active == nullptr || active[b]) steps[b] += 1;
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ shadow, long long n,
                              const long long* __restrict__ step, float lr, float b1, float b2,
                              float eps, float wd, float grad_scale,
-                             const unsigned char* __restrict__ active) {
+                             const unsigned char* __restrict__ active, const int* __restrict__ step_blocks) {
   pdl_trigger();
   pdl_wait();
   const float t = (float)(*step);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     // parameters that received no gradient this step are skipped entirely (no decay, moments
     // untouched), like torch.optim.AdamW skips p.grad is None
     if (active != nullptr && active[i >> 6] == 0) continue;
+    if (step_blocks != nullptr) {            // this parameter's own step count
+      const float tb = (float)step_blocks[i >> 6];
+      step_size = lr / (1.f - powf(b1, tb));
+      inv_sqrt_bc2 = rsqrtf(1.f - powf(b2, tb));
+    }
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.f - lr * wd);
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -1069,16 +1085,23 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
 extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                              void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1,
                              float beta2, float eps, float weight_decay, float grad_scale,
-                             const uint8_t* active_blocks, void* stream) {
+                             const uint8_t* active_blocks, int32_t* step_blocks, void* stream) {
   DL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "dl_adamw_step: null pointer");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   DL_LAUNCH(adamw_tick_kernel, 1, 1, 0, st, (long long*)step);
   DL_LAUNCH_CHECK("adamw_tick_kernel");
+  if (step_blocks) {
+    const long long nb = (n + 63) / 64;
+    DL_LAUNCH(adamw_tick_blocks_kernel, ew_grid(nb, 256), 256, 0, st, (int*)step_blocks,
+              (const unsigned char*)active_blocks, nb);
+    DL_LAUNCH_CHECK("adamw_tick_blocks_kernel");
+    count_launch();
+  }
   DL_LAUNCH(adamw_kernel, ew_grid(n, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq,
                                                 (__nv_bfloat16*)shadow_bf16, n, (const long long*)step,
                                                 lr, beta1, beta2, eps, weight_decay, grad_scale,
-                                                (const unsigned char*)active_blocks);
+                                                (const unsigned char*)active_blocks, (const int*)step_blocks);
   DL_LAUNCH_CHECK("adamw_kernel");
   count_launch(2);
   return 0;

@@ -45,13 +45,14 @@ BRANCH_STREAMS = os.environ.get("DL_NO_BRANCH_STREAMS", "0") == "0"
 _branch_streams = {}
 
 
-def branch_stream(like: torch.Tensor):
-    """The side stream for `like`'s device (None when branch streams are off or `like` is not on a GPU)."""
+def branch_stream(like: torch.Tensor, index: int = 0):
+    """Side stream `index` of `like`'s device (None when branch streams are off or `like` is not on a GPU)."""
     if not BRANCH_STREAMS or not like.is_cuda:
         return None
-    s = _branch_streams.get(like.device)
+    key = (like.device, index)
+    s = _branch_streams.get(key)
     if s is None:
-        s = _branch_streams[like.device] = torch.cuda.Stream(like.device)
+        s = _branch_streams[key] = torch.cuda.Stream(like.device)
     return s
 
 
@@ -586,7 +587,7 @@ def _qkv_bwd(g2, xc2, ws, bs, need_dx=True):
     E = ws[0].shape[0]
     fw, fb = fused_group(ws), fused_group(bs)
     dx = None
-    if fw is not None and fb is not None:
+    if fw is not None and fb is not None and _grad_target(ws[0]) is not None:     # (None: in-place gradients off)
         for t in tuple(ws) + tuple(bs):
             mark_touched(t)
         if need_dx:
@@ -1151,14 +1152,28 @@ class Conv1dSameFn(Function):
         out = torch.empty(xc.shape[:2] + (Cout,), dtype=xc.dtype, device=xc.device)
         K.conv1d_same(xc, w_taps, out, taps=k, left=left, bias=None if b is None else b.detach(),
                       act=K.ACT_RELU if relu else K.ACT_NONE)
-        ctx.save_for_backward(xc, w, out if (relu and mask_in_bwd) else None, b)
+        # the tap-reversed, transposed weight of the dX convolution only depends on the weights: it is laid
+        # out now, on a side stream, instead of in the middle of the backward's longest chain
+        wd, wd_ready = None, None
+        if _needs_backward(ctx) and ctx.needs_input_grad[0]:
+            side = branch_stream(xc)
+            cur = torch.cuda.current_stream()
+            if side is not None and side != cur:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    wd = wc.flip(2).permute(1, 2, 0).reshape(Cin, k * Cout).contiguous()
+                    wd_ready = side.record_event()
+            else:
+                wd = wc.flip(2).permute(1, 2, 0).reshape(Cin, k * Cout).contiguous()
+        ctx.save_for_backward(xc, w, out if (relu and mask_in_bwd) else None, b, wd)
+        ctx.wd_ready = wd_ready
         ctx.meta = (relu and mask_in_bwd, left, x.dtype, b is not None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        xc, w, out, b = ctx.saved_tensors
+        xc, w, out, b, wd = ctx.saved_tensors
         relu, left, xdt, has_b = ctx.meta
         Cout, Cin, k = w.shape
         g = K.to_compute(gy)
@@ -1166,12 +1181,22 @@ class Conv1dSameFn(Function):
             g = K.act_bwd(g, out, K.ACT_RELU)          # mask from the post-ReLU output (y > 0 <=> pre > 0)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wd = shadow(w).flip(2).permute(1, 2, 0).reshape(Cin, k * Cout).contiguous()
+            if wd is None:
+                wd = shadow(w).flip(2).permute(1, 2, 0).reshape(Cin, k * Cout).contiguous()
+            elif ctx.wd_ready is not None:
+                torch.cuda.current_stream().wait_event(ctx.wd_ready)
+                crosses(torch.cuda.current_stream(), wd)
             dx = torch.empty_like(xc)
             K.conv1d_same(g, wd, dx, taps=k, left=k - 1 - left)
             dx = _back(dx, xdt)
         if ctx.needs_input_grad[1]:
-            dw = K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0).contiguous()
+            tgt = _grad_target(w)
+            if tgt is not None:
+                # (taps, Cout, Cin) partial on the deferred stream, then added into the (Cout, Cin, k) gradient
+                with _param_grad_stream(g, xc):
+                    tgt.add_(K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0))
+            else:
+                dw = K.conv1d_same_wgrad(g, xc, k, left).permute(1, 2, 0).contiguous()
         if has_b and ctx.needs_input_grad[2]:
             db = _bgrad(b, g.view(-1, Cout))
         return dx, dw, db, None, None

@@ -183,14 +183,18 @@ class DrugLAMP(DrugLAMPBase):
             # Two branches that only meet at PMMA (DrugLAMP.py:55-72) run on two streams:
             #   main  fill bit + site means of xp (one pass over 5.9 MB per pair, HBM bound) -> ProteinCNN
             #         (tensor bound) -> v_gca / v_mhla
-            #   side  MolecularGCN (a few thousand rows: launch-latency bound, leaves the SMs idle) -> xd
-            #         fill bit -> LLM adaptors -> x_gca / x_mhla
+            #   side  xd fill bit -> LLM adaptors -> x_gca / x_mhla
+            #   gcn   MolecularGCN (a few thousand rows: launch-latency bound, leaves the SMs idle)
             # autograd runs every backward node on its forward stream, so the backward forks the same way.
             main = torch.cuda.current_stream()
+            gcn = Fn.branch_stream(xp, 1)          # its own stream: its backward (a serial chain of tiny
+            self._branch_streams.append(gcn)       # kernels) must not queue up behind the x branch's
+            gcn.wait_stream(main)
+            with torch.cuda.stream(gcn):
+                vd = self.drug_extractor(vd)
+                ev_vd = gcn.record_event()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                vd = self.drug_extractor(vd)
-                ev_vd = side.record_event()
                 al = Fn._align()
                 _, xd_cat, xd_lin = K.fillbit_pool(xd, 1, want_cat=True, want_pooled=True, pad_to=al)
             bit_p, xp_cat, xp_pool = K.fillbit_pool(xp, self.site_len, want_cat=not self.lazy_ssl_concat, pad_to=al)

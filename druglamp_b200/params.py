@@ -38,6 +38,10 @@ def flat_grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
         return None
     if p.data_ptr() != t.data_ptr() or p.shape != t.shape or p.grad is None or p.grad.dtype != torch.float32:
         return None
+    sr = _FLAT.get(p)
+    store = sr() if sr is not None else None
+    if store is not None and not store.inplace_grads:
+        return None
     mark_touched(p)            # a kernel is about to accumulate this parameter's gradient in place
     return p.grad
 
@@ -125,6 +129,12 @@ class FlatParams:
         # the producers say so -- kernels that accumulate in place go through flat_grad_of(), and
         # gradients that arrive through autograd's AccumulateGrad fire the hook below.
         self.touched = set()
+        # True: the backward kernels ADD weight / bias gradients straight into the flat gradient buffer
+        # and hand autograd None for those inputs -- AccumulateGrad (and with it torch DDP's reducer
+        # hooks, torch.autograd.grad, gradient hooks) never sees them.  TrainStep / ContrastiveStep
+        # all-reduce the flat buffer themselves; under torch / Lightning DDP set this to False so every
+        # parameter gradient travels through autograd as usual.
+        self.inplace_grads = True
         self.index_of = {id(p): i for i, p in enumerate(params)}
         self._hooks = []
         with torch.no_grad():
@@ -226,11 +236,17 @@ class FlatAdamW:
     parameters, their Adam moments and the bf16 shadow.  CUDA-graph capturable (the step counter
     lives on the device)."""
 
-    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 per_param_steps: bool = False):
+        """per_param_steps: keep one step count per parameter (torch's state['step']): needed when the
+        set of parameters that receive a gradient changes between steps (trainer_step.TrainerStep); with
+        a constant set (train.TrainStep) the single device counter is the same thing."""
         self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
         self.exp_avg = torch.zeros_like(flat.flat)
         self.exp_avg_sq = torch.zeros_like(flat.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=flat.flat.device)
+        self.step_blocks = (torch.zeros(flat.numel // flat.ALIGN, dtype=torch.int32, device=flat.flat.device)
+                            if per_param_steps else None)
         # device copy of FlatParams.active_blocks(); refreshed when the set of touched parameters
         # changes (never inside a CUDA-graph capture: TrainStep.capture refreshes it before capturing)
         self.active = torch.zeros(flat.numel // flat.ALIGN, dtype=torch.uint8, device=flat.flat.device)
@@ -255,5 +271,5 @@ class FlatAdamW:
         L.call("dl_adamw_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
                self.exp_avg_sq.data_ptr(), sh, f.numel, self.step_count.data_ptr(), self.lr,
                self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
-               self.active.data_ptr())
+               self.active.data_ptr(), None if self.step_blocks is None else self.step_blocks.data_ptr())
         f.mark_synced()       # raw-pointer update: versions unchanged, shadow already fresh

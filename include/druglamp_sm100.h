@@ -224,11 +224,14 @@ int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act,
  * 64 consecutive elements; a 0 skips those elements entirely -- parameters that received no gradient
  * this step are neither decayed nor have their moments moved, as torch.optim.AdamW skips
  * `p.grad is None` (three AdamWs over the same parameters, main.py:158-160; SSL / CM heads get no
- * gradient from the classification loss, trainer.py:196-200). */
+ * gradient from the classification loss, trainer.py:196-200).  step_blocks (or NULL): one int32 step
+ * count per 64 elements, advanced for the active blocks and used for THEIR bias correction -- torch keeps
+ * state['step'] per parameter, which matters when the set of parameters with a gradient changes from
+ * step to step (classification / SSL / 2C2P epochs of trainer.py:190-191); NULL = *step for everyone. */
 int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1, float beta2,
                   float eps, float weight_decay, float grad_scale, const uint8_t* active_blocks,
-                  void* stream);
+                  int32_t* step_blocks, void* stream);
 int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
 /* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
 int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
