@@ -126,9 +126,12 @@ class deferred_weight_grads:
 
     _streams = {}
 
+    N_STREAMS = int(os.environ.get("DL_WGRAD_STREAMS", "3"))
+
     def __init__(self, enabled: bool = True):
         self.enabled = enabled and os.environ.get("DL_NO_WGRAD_STREAM", "0") == "0"
-        self.stream = None
+        self.streams = []       # created on first use; kernels go to them round robin (one serial queue
+        self._next = 0          # of ~60 split-K GEMMs would otherwise drain long after the dX chain ends)
         self.keep = []          # operands stay referenced until the join: the autograd engine adds
         #                         gradients IN PLACE into a buffer it holds the last reference to
 
@@ -139,8 +142,8 @@ class deferred_weight_grads:
 
     def join(self, stream=None):
         """`stream` (default: the current one) waits for every deferred kernel issued so far."""
-        if self.stream is not None:
-            (stream or torch.cuda.current_stream()).wait_stream(self.stream)
+        for s in self.streams:
+            (stream or torch.cuda.current_stream()).wait_stream(s)
 
     def __exit__(self, *exc):
         global _wgrad_defer
@@ -152,10 +155,13 @@ class deferred_weight_grads:
     @contextlib.contextmanager
     def on(self, *reads):
         cur = torch.cuda.current_stream()
-        if self.stream is None:
+        if not self.streams:
             dev = cur.device
-            self.stream = self._streams.get(dev) or self._streams.setdefault(dev, torch.cuda.Stream(dev))
-        s = self.stream
+            if dev not in self._streams:
+                self._streams[dev] = [torch.cuda.Stream(dev) for _ in range(max(1, self.N_STREAMS))]
+            self.streams = self._streams[dev]
+        s = self.streams[self._next % len(self.streams)]
+        self._next += 1
         s.wait_stream(cur)
         for t in reads:
             if t is not None:
