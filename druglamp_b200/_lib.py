@@ -91,7 +91,8 @@ SIGNATURES = {
     "dl_l2norm_fwd": [_P, _P, _P, _I64, _I32, _F, _I32, _P],
     "dl_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P],
     "dl_cast": [_P, _I32, _P, _I32, _I64, _P],
-    "dl_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _P, _P, _P],
+    "dl_copy_rows": [_P, _I64, _P, _I64, _I64, _I64, _P],
+    "dl_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _P, _P, _I32, _P],
     "dl_add_pe": [_P, _P, _P, _I64, _I64, _F, _U64, _P, _I32, _P],
     "dl_csr_build": [_P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dl_spmm_norm": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P],

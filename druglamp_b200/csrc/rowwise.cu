@@ -729,10 +729,11 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              __nv_bfloat16* __restrict__ shadow, long long n,
                              const long long* __restrict__ step, float lr, float b1, float b2,
                              float eps, float wd, float grad_scale,
-                             const unsigned char* __restrict__ active, const int* __restrict__ step_blocks) {
+                             const unsigned char* __restrict__ active, const int* __restrict__ step_blocks,
+                             int step_offset) {
   pdl_trigger();
   pdl_wait();
-  const float t = (float)(*step);
+  const float t = (float)(*step + step_offset);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -754,6 +755,21 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
     p[i] = pi;
     if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+// dst[r, 0:bytes) = src[r, 0:bytes) for rows with independent pitches: the column halves of a
+// concatenation (forward) and of its gradient (backward), 16 bytes per thread per step
+__global__ void copy_rows_kernel(const uint4* __restrict__ src, long long src_pitch16, uint4* __restrict__ dst,
+                                 long long dst_pitch16, long long rows, int row16) {
+  pdl_trigger();
+  pdl_wait();
+  const long long n = rows * row16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row16;
+    const int c = (int)(i - r * row16);
+    dst[r * dst_pitch16 + c] = src[r * src_pitch16 + c];
   }
 }
 
@@ -1085,12 +1101,16 @@ extern "C" int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, i
 extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                              void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1,
                              float beta2, float eps, float weight_decay, float grad_scale,
-                             const uint8_t* active_blocks, int32_t* step_blocks, void* stream) {
+                             const uint8_t* active_blocks, int32_t* step_blocks, int32_t tick,
+                             void* stream) {
   DL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "dl_adamw_step: null pointer");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DL_LAUNCH(adamw_tick_kernel, 1, 1, 0, st, (long long*)step);
-  DL_LAUNCH_CHECK("adamw_tick_kernel");
+  if (tick) {
+    DL_LAUNCH(adamw_tick_kernel, 1, 1, 0, st, (long long*)step);
+    DL_LAUNCH_CHECK("adamw_tick_kernel");
+    count_launch();
+  }
   if (step_blocks) {
     const long long nb = (n + 63) / 64;
     DL_LAUNCH(adamw_tick_blocks_kernel, ew_grid(nb, 256), 256, 0, st, (int*)step_blocks,
@@ -1101,9 +1121,26 @@ extern "C" int dl_adamw_step(float* param, const float* grad, float* exp_avg, fl
   DL_LAUNCH(adamw_kernel, ew_grid(n, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq,
                                                 (__nv_bfloat16*)shadow_bf16, n, (const long long*)step,
                                                 lr, beta1, beta2, eps, weight_decay, grad_scale,
-                                                (const unsigned char*)active_blocks, (const int*)step_blocks);
+                                                (const unsigned char*)active_blocks, (const int*)step_blocks,
+                                                tick ? 0 : 1);
   DL_LAUNCH_CHECK("adamw_kernel");
-  count_launch(2);
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_copy_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch,
+                            int64_t row_bytes, int64_t rows, void* stream) {
+  DL_REQUIRE(src && dst, "dl_copy_rows: null pointer");
+  DL_REQUIRE(row_bytes > 0 && rows >= 0 && src_pitch >= row_bytes && dst_pitch >= row_bytes, "dl_copy_rows: bad extents");
+  DL_REQUIRE((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)src_pitch | (uintptr_t)dst_pitch | (uintptr_t)row_bytes) & 15) == 0,
+             "dl_copy_rows: pointers, pitches and the row length must be multiples of 16 bytes");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = rows * (row_bytes / 16);
+  DL_LAUNCH(copy_rows_kernel, ew_grid(n, 256), 256, 0, st, (const uint4*)src, (long long)(src_pitch / 16), (uint4*)dst,
+            (long long)(dst_pitch / 16), (long long)rows, (int)(row_bytes / 16));
+  DL_LAUNCH_CHECK("copy_rows_kernel");
+  count_launch();
   return 0;
 }
 

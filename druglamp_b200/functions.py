@@ -1208,6 +1208,55 @@ class Conv1dSameFn(Function):
         return dx, dw, db, None, None
 
 
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """(..., C) -> a (rows, C) view with unit inner stride and ONE row stride (a copy only when the leading
+    dimensions do not collapse)."""
+    C_ = t.shape[-1]
+    if t.stride(-1) == 1:
+        try:
+            return t.view(-1, C_)
+        except RuntimeError:
+            pass
+    return t.contiguous().view(-1, C_)
+
+
+class CatLastFn(Function):
+    """torch.cat((a, b), dim=-1) (model/DrugLAMP.py:57,66; model/PMMA/encoder.py:46) with dl_copy_rows: two
+    16-byte-vector row copies forward, and two CONTIGUOUS halves of the gradient backward (autograd's own
+    backward hands out column-slice views, which every consumer then compacts with an element-wise copy)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        Ca, Cb = a.shape[-1], b.shape[-1]
+        a2, b2 = _rows2d(a), _rows2d(b)
+        out = torch.empty((a2.shape[0], Ca + Cb), dtype=a.dtype, device=a.device)
+        K.copy_rows(a2, out[:, :Ca])
+        K.copy_rows(b2, out[:, Ca:])
+        ctx.meta = (a.shape, b.shape)
+        return out.view(*a.shape[:-1], Ca + Cb)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        ashape, bshape = ctx.meta
+        Ca, Cb = ashape[-1], bshape[-1]
+        g2 = _rows2d(g)
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = K.copy_rows(g2[:, :Ca], torch.empty((g2.shape[0], Ca), dtype=g.dtype, device=g.device)).view(ashape)
+        if ctx.needs_input_grad[1]:
+            gb = K.copy_rows(g2[:, Ca:], torch.empty((g2.shape[0], Cb), dtype=g.dtype, device=g.device)).view(bshape)
+        return ga, gb
+
+
+def cat_last(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """cat((a, b), -1); falls back to torch.cat when the shapes do not fit the 16-byte row copies."""
+    es = a.element_size()
+    ok = (a.is_cuda and a.dtype == b.dtype and a.shape[:-1] == b.shape[:-1] and (a.shape[-1] * es) % 16 == 0
+          and (b.shape[-1] * es) % 16 == 0)
+    return CatLastFn.apply(a, b) if ok else torch.cat((a, b), dim=-1)
+
+
 class TransposeFn(Function):
     """(B, R, C) -> (B, C, R) contiguous."""
 

@@ -589,3 +589,13 @@ def head_bn_act_bwd(dy, pre, gamma, mean, rstd, act: int, training: bool, has_bi
     if acc_into is not None:
         return g, None, None, None
     return g, dg, db, dbias
+
+
+def copy_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[r, :] = src[r, :] for 2-D tensors with unit inner stride and any row strides (dl_copy_rows)."""
+    if src.shape != dst.shape or src.dtype != dst.dtype or src.stride(1) != 1 or dst.stride(1) != 1:
+        raise ValueError("copy_rows needs two (rows, cols) tensors of one dtype with unit inner stride")
+    es = src.element_size()
+    L.call("dl_copy_rows", src.data_ptr(), src.stride(0) * es, dst.data_ptr(), dst.stride(0) * es,
+           src.shape[1] * es, src.shape[0])
+    return dst

@@ -138,7 +138,7 @@ class DrugLAMPBase(nn.Module):
     def _guided(gca, mhla, norm, p, d):
         """PGCA -> concat -> MHLA gate + residual + LayerNorm (DrugLAMP.py:55-71)."""
         m, A = gca(p.permute(1, 0, 2), d.permute(1, 0, 2), d.permute(1, 0, 2))
-        m = torch.cat((p.to(m.dtype), m.permute(1, 0, 2)), 2)
+        m = Fn.cat_last(p.to(m.dtype), m.permute(1, 0, 2))
         return mhla.forward_residual_norm(m, norm), A
 
     def _head(self, f):

@@ -365,7 +365,7 @@ class Encoder(nn.Module):
                         torch.cuda.current_stream().wait_stream(side)
                         Fn.crosses(torch.cuda.current_stream(), mol)
                         side = None
-                    hidden_states = torch.cat((hidden_states, mol), dim=-1)
+                    hidden_states = Fn.cat_last(hidden_states, mol)
                 hidden_states, weights, guided_weights = layer_block(hidden_states)
             else:
                 hidden_states, mol, weights, guided_weights = layer_block(hidden_states, mol, side=side)

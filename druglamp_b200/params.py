@@ -261,15 +261,24 @@ class FlatAdamW:
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat.zero_grad()
 
-    def step(self, grad_scale: float = 1.0) -> None:
+    def step(self, grad_scale: float = 1.0, lo: int = 0, hi: Optional[int] = None, tick: bool = True) -> None:
+        """One AdamW step over elements [lo, hi) of the flat buffer (default: all of it).  A step may be
+        issued as several ranges; exactly one of them -- the LAST -- ticks the step counter (the earlier ones
+        use count + 1 for their bias correction, dl_adamw_step).  lo / hi must be multiples of ALIGN."""
         from . import _lib as L
         f = self.flat
+        hi = f.numel if hi is None else hi
+        if lo % f.ALIGN or hi % f.ALIGN or not 0 <= lo <= hi <= f.numel:
+            raise ValueError("AdamW range must lie on parameter-block boundaries")
         f.sync()
         if not torch.cuda.is_current_stream_capturing():
             self.refresh_active()
-        sh = f.shadow16.data_ptr() if (f.shadow16 is not None and K.compute_dtype() == torch.bfloat16) else None
-        L.call("dl_adamw_step", f.flat.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
-               self.exp_avg_sq.data_ptr(), sh, f.numel, self.step_count.data_ptr(), self.lr,
-               self.betas[0], self.betas[1], self.eps, self.weight_decay, grad_scale,
-               self.active.data_ptr(), None if self.step_blocks is None else self.step_blocks.data_ptr())
+        bf = f.shadow16 is not None and K.compute_dtype() == torch.bfloat16
+        sh = f.shadow16.data_ptr() + 2 * lo if bf else None
+        blk = lo // f.ALIGN
+        L.call("dl_adamw_step", f.flat.data_ptr() + 4 * lo, f.grad.data_ptr() + 4 * lo,
+               self.exp_avg.data_ptr() + 4 * lo, self.exp_avg_sq.data_ptr() + 4 * lo, sh, hi - lo,
+               self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+               grad_scale, self.active.data_ptr() + blk,
+               None if self.step_blocks is None else self.step_blocks.data_ptr() + 4 * blk, int(tick))
         f.mark_synced()       # raw-pointer update: versions unchanged, shadow already fresh

@@ -122,17 +122,24 @@ class TrainStep:
         if world_size > 1 and torch.distributed.is_initialized():
             from .functions import set_seed_stream
             set_seed_stream(torch.distributed.get_rank(process_group))
-        # Gradient all-reduce overlapped with the backward: the PMMA parameters (73 % of the model, laid out
-        # first in the flat buffer) have final gradients as soon as the backward reaches PMMA's inputs;
-        # their range is reduced on a side stream while MHLA / PGCA / CNN / GCN still run, the rest
-        # right after the backward.  Both collectives are part of the captured step graph.
+        # Overlapped with the backward: the PMMA parameters (73 % of the model, laid out first in the flat
+        # buffer) have final gradients as soon as the backward reaches PMMA's inputs.  From that point an
+        # auxiliary stream (a) all-reduces their range (N > 1) and (b) runs their AdamW update, while MHLA /
+        # PGCA / CNN / GCN still run; the rest of the buffer follows the backward.  The collectives and the
+        # early update are part of the captured step graph.
         import os
-        self.overlap = (world_size > 1 and self.flat.head_numel < self.flat.numel
-                        and os.environ.get("DL_NO_OVERLAP", "0") == "0")
-        if self.overlap:
-            self._comm = torch.cuda.Stream()
-            self._joined = True
-            model._pmma_grads_ready = self._reduce_head
+        split = self.flat.head_numel < self.flat.numel
+        self.overlap = world_size > 1 and split and os.environ.get("DL_NO_OVERLAP", "0") == "0"
+        # (b) is off by default: measured on one B200 it is neutral (4.633 vs 4.622 ms) -- the update is
+        # HBM bound and only competes with the backward kernels it overlaps; DL_EARLY_UPDATE=1 turns it on
+        self.early_update = (split and (world_size == 1 or self.overlap)
+                             and os.environ.get("DL_EARLY_UPDATE", "0") == "1")
+        self._aux = torch.cuda.Stream()
+        self._comm = self._aux
+        self._joined = True
+        self._head_updated = False
+        if self.overlap or self.early_update:
+            model._pmma_grads_ready = self._pmma_ready
         self.loss = torch.zeros((), dtype=torch.float32, device=self.flat.flat.device)
         self._graphs = weakref.WeakKeyDictionary()      # StaticBatch -> (graph, graph): dies with the batch
         self._pool = None
@@ -141,7 +148,11 @@ class TrainStep:
     # ---- pieces ---------------------------------------------------------------------------------
     def _fwd_bwd(self, sb: StaticBatch) -> None:
         from . import kernels as K
-        self.flat.zero_grad()
+        main = torch.cuda.current_stream()
+        # the gradient buffer is cleared beside the forward (nothing reads it before the backward)
+        self._aux.wait_stream(main)
+        with torch.cuda.stream(self._aux):
+            self.flat.zero_grad()
         # dropout seeds advance with the optimiser's device-side step counter, so a replayed graph
         # draws fresh masks every step (forward and backward of one step read the same value: the
         # counter moves in _update)
@@ -149,30 +160,38 @@ class TrainStep:
         try:
             out = self.model(*sb.model_inputs())
             _, loss = binary_cross_entropy(out[4], sb.y)
-            # weight-gradient GEMMs leave the dX chain for a side stream; joined when the context closes
+            main.wait_stream(self._aux)
+            # weight-gradient GEMMs leave the dX chain for side streams; joined when the context closes
             with Fn.deferred_weight_grads():
                 loss.backward()
         finally:
             K.set_dropout_step(None)
         self.loss.copy_(loss.detach())
         if self.overlap:
-            main = torch.cuda.current_stream()
             if self._joined:            # the hook never fired (no PMMA gradient): reduce everything here
                 torch.distributed.all_reduce(self.flat.grad, group=self.pg)
             else:
                 torch.distributed.all_reduce(self.flat.grad[self.flat.head_numel:], group=self.pg)
-                main.wait_stream(self._comm)
-                self._joined = True
+        if not self._joined:
+            main.wait_stream(self._aux)
+            self._joined = True
 
-    def _reduce_head(self) -> None:
+    def _pmma_ready(self) -> None:
         """Called from inside the backward (models._watch_pmma_inputs): PMMA's gradients are final."""
-        self._comm.wait_stream(torch.cuda.current_stream())
-        for s in getattr(self.model, "_branch_streams", []):    # the hook may fire on either branch stream
-            self._comm.wait_stream(s)
+        aux = self._aux
+        aux.wait_stream(torch.cuda.current_stream())
+        for s in getattr(self.model, "_branch_streams", []):    # the hook may fire on any branch stream
+            aux.wait_stream(s)
         if Fn._wgrad_defer is not None:                          # PMMA's deferred weight gradients
-            Fn._wgrad_defer.join(self._comm)
-        with torch.cuda.stream(self._comm):
-            torch.distributed.all_reduce(self.flat.grad[:self.flat.head_numel], group=self.pg)
+            Fn._wgrad_defer.join(aux)
+        with torch.cuda.stream(aux):
+            if self.overlap:
+                torch.distributed.all_reduce(self.flat.grad[:self.flat.head_numel], group=self.pg)
+            if self.early_update:
+                # the counter is ticked by the final range in _update: dropout kernels of the remaining
+                # backward still read this step's value
+                self.opt.step(grad_scale=1.0 / self.world_size, lo=0, hi=self.flat.head_numel, tick=False)
+                self._head_updated = True
         self._joined = False
 
     def _reduce(self) -> None:
@@ -180,7 +199,9 @@ class TrainStep:
             torch.distributed.all_reduce(self.flat.grad, group=self.pg)
 
     def _update(self) -> None:
-        self.opt.step(grad_scale=1.0 / self.world_size)
+        lo = self.flat.head_numel if self._head_updated else 0
+        self._head_updated = False
+        self.opt.step(grad_scale=1.0 / self.world_size, lo=lo)
 
     def eager(self, sb: StaticBatch) -> torch.Tensor:
         self._fwd_bwd(sb)

@@ -217,6 +217,12 @@ int dl_l2norm_bwd(const void* dy, const void* y, const float* norm, void* dx, in
 /* g = dy * act'(pre) * dropout_mask(seed): backward of the dl_gemm epilogue's act + dropout. */
 int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act, float p,
                uint64_t seed, const int64_t* seed_step, int32_t dtype, void* stream);
+/* dst[r, 0:row_bytes) = src[r, 0:row_bytes), r < rows, rows src_pitch / dst_pitch bytes apart (all multiples
+ * of 16): the column blocks of torch.cat(..., dim=-1) (model/DrugLAMP.py:57,66, model/PMMA/encoder.py:46) and
+ * of its gradient, without PyTorch's element-wise strided copy. */
+int dl_copy_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t row_bytes,
+                 int64_t rows, void* stream);
+
 /* One AdamW step over a flat fp32 parameter buffer (torch.optim.AdamW semantics; the reference
  * builds AdamW in main.py:158-160).  grad is multiplied by grad_scale first (1/world_size after a
  * sum all-reduce); *step (device int64) is incremented; shadow_bf16 (optional) receives the
@@ -227,11 +233,15 @@ int dl_act_bwd(const void* dy, const void* pre, void* g, int64_t n, int32_t act,
  * gradient from the classification loss, trainer.py:196-200).  step_blocks (or NULL): one int32 step
  * count per 64 elements, advanced for the active blocks and used for THEIR bias correction -- torch keeps
  * state['step'] per parameter, which matters when the set of parameters with a gradient changes from
- * step to step (classification / SSL / 2C2P epochs of trainer.py:190-191); NULL = *step for everyone. */
+ * step to step (classification / SSL / 2C2P epochs of trainer.py:190-191); NULL = *step for everyone.
+ * tick != 0: *step is incremented first (one call per optimiser step does this); tick == 0: *step is left
+ * alone and the bias correction uses *step + 1 -- a RANGE of the flat buffer updated ahead of the call that
+ * ticks (train.TrainStep updates the PMMA parameters while the rest of the backward still runs; the dropout
+ * kernels of that backward keep reading the un-ticked counter). */
 int dl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   void* shadow_bf16, int64_t n, int64_t* step, float lr, float beta1, float beta2,
                   float eps, float weight_decay, float grad_scale, const uint8_t* active_blocks,
-                  int32_t* step_blocks, void* stream);
+                  int32_t* step_blocks, int32_t tick, void* stream);
 int dl_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, void* stream);
 /* y[i] = dropout(x[i] + pe[i % period])  (model/PMMA/embed.py:51-52). */
 int dl_add_pe(const void* x, const float* pe, void* y, int64_t n, int64_t period, float p,
