@@ -193,6 +193,56 @@ template <typename T> __device__ __forceinline__ void gelu_fwd_grad(float x, flo
     d = gelu_erf_grad(x);
   }
 }
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 do two fp32 lanes per issue slot) -----------------------
+// The GEMM epilogues that evaluate GELU + its derivative + two dropout factors per element are bound by
+// instruction issue (36 per element before, ncu: profiles/r2m_gemm_top_ncu.md); the floating-point part
+// of that goes through these.  Same roundings as the scalar code: fma.rn / mul.rn per lane.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n"
+      " mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+// value and derivative of GELU for two elements (bf16 storage: tanh form, packed; fp32: the scalar erf form)
+template <typename T> __device__ __forceinline__ void gelu_fwd_grad2(float2 x, float2& y, float2& d) {
+  if constexpr (sizeof(T) == 2) {
+    constexpr float c1 = 0.7978845608f, c2 = 0.044715f * 0.7978845608f;
+    const float2 u = f2_mul(x, x);
+    const float2 arg = f2_mul(x, f2_fma(u, f2(c2), f2(c1)));
+    const float2 t = make_float2(tanh_approx(arg.x), tanh_approx(arg.y));
+    const float2 hx = f2_mul(x, f2(0.5f)), nhx = f2_mul(x, f2(-0.5f));
+    y = f2_fma(hx, t, hx);
+    const float2 dz = f2_fma(u, f2(3.0f * c2), f2(c1));
+    const float2 a = f2_fma(f2_mul(nhx, t), t, hx);            // hx (1 - t^2)
+    d = f2_fma(a, dz, f2_fma(t, f2(0.5f), f2(0.5f)));
+  } else {
+    gelu_fwd_grad<T>(x.x, y.x, d.x);
+    gelu_fwd_grad<T>(x.y, y.y, d.y);
+  }
+}
+template <typename T> __device__ __forceinline__ float2 gelu_fwd2(float2 x) {
+  if constexpr (sizeof(T) == 2) {
+    constexpr float c1 = 0.7978845608f, c2 = 0.044715f * 0.7978845608f;
+    const float2 u = f2_mul(x, x);
+    const float2 arg = f2_mul(x, f2_fma(u, f2(c2), f2(c1)));
+    const float2 t = make_float2(tanh_approx(arg.x), tanh_approx(arg.y));
+    const float2 hx = f2_mul(x, f2(0.5f));
+    return f2_fma(hx, t, hx);
+  } else {
+    return make_float2(gelu_fwd<T>(x.x), gelu_fwd<T>(x.y));
+  }
+}
+
 template <typename T> __device__ __forceinline__ float gelu_grad(float x) {
   if constexpr (sizeof(T) == 2) {
     const float u = x * x;

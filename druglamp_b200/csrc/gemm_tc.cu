@@ -284,14 +284,21 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
     TC* Pre = reinterpret_cast<TC*>(p.preact);
     const TC* Aux = reinterpret_cast<const TC*>(p.aux);
     const TC* Res = reinterpret_cast<const TC*>(p.res);
+    const float2 al2 = f2(p.alpha);
     if (p.bias) {
       float b[16];
       load16<float>(p.bias + col, b, full && f.vec_b, nvalid);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha + b[j];
+      for (int j = 0; j < 16; j += 2) {
+        const float2 r = f2_fma(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al2, make_float2(b[j], b[j + 1]));
+        x[j] = r.x; x[j + 1] = r.y;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+      for (int j = 0; j < 16; j += 2) {
+        const float2 r = f2_mul(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al2);
+        x[j] = r.x; x[j + 1] = r.y;
+      }
     }
     constexpr bool deriv = DERIV;                    // preact_out = d dropout(act(v)) / dv (pre_mode 1): its own
     float dact[DERIV ? 16 : 1];                      // instantiation, so the common epilogues keep their registers
@@ -299,10 +306,17 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
     if (p.act == DL_ACT_GELU) {
       if constexpr (deriv) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gelu_fwd_grad<TC>(x[j], x[j], dact[j]);
+        for (int j = 0; j < 16; j += 2) {
+          float2 y2, d2;
+          gelu_fwd_grad2<TC>(make_float2(x[j], x[j + 1]), y2, d2);
+          x[j] = y2.x; x[j + 1] = y2.y; dact[j] = d2.x; dact[j + 1] = d2.y;
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
+        for (int j = 0; j < 16; j += 2) {
+          const float2 y2 = gelu_fwd2<TC>(make_float2(x[j], x[j + 1]));
+          x[j] = y2.x; x[j + 1] = y2.y;
+        }
       }
     } else if (p.act == DL_ACT_RELU) {
 #pragma unroll
@@ -326,11 +340,14 @@ __device__ __forceinline__ void finish16(const GemmParams& p, const EpiFlags& f,
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t h = drop_hash(f.drop_seed, (e >> 1) + k);
-          const float m0 = (h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f;
-          const float m1 = (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f;
-          x[2 * k] *= m0;
-          x[2 * k + 1] *= m1;
-          if constexpr (deriv) { dact[2 * k] *= m0; dact[2 * k + 1] *= m1; }
+          const float2 m = make_float2((h & 0xffffu) >= f.drop_thr ? f.drop_inv : 0.f,
+                                       (h >> 16) >= f.drop_thr ? f.drop_inv : 0.f);
+          const float2 xm = f2_mul(make_float2(x[2 * k], x[2 * k + 1]), m);
+          x[2 * k] = xm.x; x[2 * k + 1] = xm.y;
+          if constexpr (deriv) {
+            const float2 dm = f2_mul(make_float2(dact[2 * k], dact[2 * k + 1]), m);
+            dact[2 * k] = dm.x; dact[2 * k + 1] = dm.y;
+          }
         }
       } else {
 #pragma unroll
@@ -465,24 +482,38 @@ __device__ __forceinline__ void tma_chunk16(const GemmParams& p, const EpiFlags&
   const bool full = nvalid == 16;
   TC* Pre = reinterpret_cast<TC*>(p.preact);
   float x[16];
+  const float2 al2 = f2(p.alpha);
   if (p.bias) {
     float b[16];
     load16<float>(p.bias + col, b, full && f.vec_b, nvalid);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha + b[j];
+    for (int j = 0; j < 16; j += 2) {
+      const float2 r = f2_fma(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al2, make_float2(b[j], b[j + 1]));
+      x[j] = r.x; x[j + 1] = r.y;
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+    for (int j = 0; j < 16; j += 2) {
+      const float2 r = f2_mul(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al2);
+      x[j] = r.x; x[j + 1] = r.y;
+    }
   }
   float dact[DERIV ? 16 : 1];
   if (!DERIV && Pre && row_ok) store16<TC>(Pre + crow + col, x, full && f.vec_p, nvalid, f.wide_p);
   if (p.act == DL_ACT_GELU) {
     if constexpr (DERIV) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) gelu_fwd_grad<TC>(x[j], x[j], dact[j]);
+      for (int j = 0; j < 16; j += 2) {
+        float2 y2, d2;
+        gelu_fwd_grad2<TC>(make_float2(x[j], x[j + 1]), y2, d2);
+        x[j] = y2.x; x[j + 1] = y2.y; dact[j] = d2.x; dact[j + 1] = d2.y;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = gelu_fwd<TC>(x[j]);
+      for (int j = 0; j < 16; j += 2) {
+        const float2 y2 = gelu_fwd2<TC>(make_float2(x[j], x[j + 1]));
+        x[j] = y2.x; x[j + 1] = y2.y;
+      }
     }
   } else if (p.act == DL_ACT_RELU) {
 #pragma unroll
