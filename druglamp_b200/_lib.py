@@ -62,6 +62,16 @@ class AttnArgs(C.Structure):
     ]
 
 
+class FfnArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p),
+        ("residual", C.c_void_p), ("hidden", C.c_void_p), ("dact", C.c_void_p), ("y", C.c_void_p),
+        ("M", C.c_int64), ("D", C.c_int64), ("Dh", C.c_int64),
+        ("ldx", C.c_int64), ("ldh", C.c_int64), ("ldy", C.c_int64), ("ldr", C.c_int64),
+        ("drop_p", C.c_float), ("seed1", C.c_uint64), ("seed2", C.c_uint64), ("drop_seed_step", C.c_void_p),
+    ]
+
+
 class SmallLinearArgs(C.Structure):
     _fields_ = [
         ("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("pre", C.c_void_p), ("Y", C.c_void_p),
@@ -80,6 +90,8 @@ SIGNATURES = {
     "dl_gemm": [C.POINTER(GemmArgs), _P],
     "dl_attn_fwd": [C.POINTER(AttnArgs), _P],
     "dl_attn_bwd": [C.POINTER(AttnArgs), _P],
+    "dl_ffn_fwd": [C.POINTER(FfnArgs), _P],
+    "dl_ffn_bwd": [C.POINTER(FfnArgs), _P],
     "dl_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],
     "dl_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_softmax_fwd": [_P, _P, _I64, _I32, _I64, _I32, _P],
@@ -103,6 +115,8 @@ SIGNATURES = {
     "dl_fillbit_pool": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_expand_rows": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "dl_transpose": [_P, _P, _I64, _I32, _I32, _I32, _P],
+    "dl_bn_transpose": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P],
+    "dl_site_pool_view_bwd": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "dl_site_pool_fwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
     "dl_site_pool_bwd": [_P, _P, _I64, _I32, _I32, _I32, _I64, _I32, _P],
     "dl_mhla_gate_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _I32, _P],
@@ -216,8 +230,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
 
 
 def replay_gemm(rec) -> None:
-    """Re-issue a recorded dl_gemm launch on the current stream (bench.py roofline pass)."""
-    check(lib().dl_gemm(C.byref(rec["args"]), stream_ptr()), "dl_gemm")
+    """Re-issue a recorded tensor-core launch (dl_gemm, or the fused dl_ffn_fwd / dl_ffn_bwd) on the
+    current stream (bench.py roofline pass)."""
+    fn = rec.get("fn", "dl_gemm")
+    check(getattr(lib(), fn)(C.byref(rec["args"]), stream_ptr()), fn)
 
 
 # device step counter (int64 scalar tensor) that advances every dropout seed per training step; set

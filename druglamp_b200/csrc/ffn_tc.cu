@@ -1,0 +1,551 @@
+// dl_ffn_fwd / dl_ffn_bwd: the position-wise feed-forward network of a PMMA block (model/PMMA/mlp.py:44-50
+// with the block's residual add, model/PMMA/block.py:45-47) as ONE tcgen05 kernel per direction: two chained
+// GEMMs with the 4x-wide hidden activation kept on chip between them.
+//
+//   forward    H = dropout(gelu(X W1^T + b1))            [M, Dh]   (also stored: the backward's dW2 operand)
+//              Y = dropout(H W2^T + b2) + residual        [M, 256]
+//   backward   dP = (G W2) * dact                         [M, Dh]   (stored: the backward's dW1 operand)
+//              dX = dP W1                                 [M, 256]
+//
+// Both are  E_c = epi1(A B1_c),  Y += E_c B2_c  over 128-column chunks c of the hidden dimension, for one
+// 128-row tile of A per CTA:
+//   tensor memory   two 128-column buffers for the chunk accumulator (the epilogue of chunk c overlaps the
+//                   first GEMM of chunk c+1) + 256 columns for Y  = all 512 columns
+//   shared memory   A tile (64 KB, resident for the whole row tile), a ring of three 32 KB weight units
+//                   (half a chunk of B1 or B2 each), two 32 KB E tiles (bf16, SWIZZLE_128B K-major: the A
+//                   operand of the second GEMM AND the source of the bulk tensor store that writes E to HBM)
+//   warps           0: TMA producer   1: tcgen05.mma issuer   2..17: epilogue (four per TMEM lane quadrant,
+//                   32 of a chunk's 128 columns each)   18: bulk tensor stores of the E tiles
+// The hidden activation therefore never returns from HBM for the second GEMM, its store costs no LSU
+// instructions, and one launch replaces two (forward) / two (backward) dl_gemm launches.
+#include <mutex>
+
+#include "../../include/druglamp_sm100.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dl {
+void count_launch(int n = 1);
+
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;   // 608
+constexpr int kD = 256;                               // model width: K of the first GEMM, N of the second
+constexpr int kCh = 128;                              // hidden columns per chunk
+constexpr int kBlk = 16384;                           // one [128 rows x 128 B] SWIZZLE_128B block
+constexpr int kUnit = 32768;                          // ring unit: half a chunk of B1 or of B2
+constexpr int kStages = 3;
+constexpr int kABytes = 4 * kBlk;                     // 128 x 256 bf16
+constexpr int kEBytes = 2 * kBlk;                     // 128 x 128 bf16
+constexpr int kBarBytes = 256;
+constexpr int kSmem = kABytes + kStages * kUnit + 2 * kEBytes + kBarBytes + 1024;
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
+
+struct FfnParams {
+  const float* bias1;            // forward: [Dh]
+  const float* bias2;            // forward: [256]
+  __nv_bfloat16* dact;           // forward: d E / d pre-activation out (or NULL); backward: multiplier in
+  const __nv_bfloat16* res;      // forward: residual (or NULL)
+  __nv_bfloat16* Y;
+  long long ldh, ldy, ldr;
+  unsigned long long seed1, seed2;
+  const long long* drop_step;
+  float drop_p;
+  int M, Dh, NC, tiles;
+  int store_e;                   // E is written to HBM (training); 0 = forward-only scoring
+  uint32_t idesc1, idesc2;
+};
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t base, int kk) {
+  // K-major operand in [rows x 128 B] blocks kBlk apart: 16 elements (32 B) per MMA, 4 MMAs per block
+  return ptx::make_smem_desc(base + (uint32_t)(kk >> 2) * kBlk + (uint32_t)(kk & 3) * 32, 16, 1024);
+}
+
+// MODE 0: forward (K-major weights, bias + GELU (+ derivative) + dropout, then bias + dropout + residual)
+// MODE 1: backward (MN-major weights, multiply by the stored derivative, plain dX)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmE,
+                 const FfnParams p) {
+  constexpr bool BMN = MODE == 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t sA = base, sRing = base + kABytes, sE = sRing + kStages * kUnit;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kStages * kUnit + 2 * kEBytes);
+  const uint32_t bar_afull = ptx::smem_u32(bars), bar_aempty = bar_afull + 8;
+  const uint32_t bar_full = bar_afull + 16;               // [3] weight unit landed
+  const uint32_t bar_empty = bar_full + 8 * kStages;      // [3] weight unit consumed
+  const uint32_t bar_sfull = bar_empty + 8 * kStages;     // [2] chunk accumulator ready
+  const uint32_t bar_sempty = bar_sfull + 16;             // [2] chunk accumulator drained
+  const uint32_t bar_efull = bar_sempty + 16;             // [2] E tile written
+  const uint32_t bar_eempty = bar_efull + 16;             // [2] E tile consumed (second GEMM + bulk store)
+  const uint32_t bar_yfull = bar_eempty + 16, bar_yempty = bar_yfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages + 8 + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB1);
+    ptx::prefetch_tmap(&tmB2);
+    if (p.store_e) ptx::prefetch_tmap(&tmE);
+    ptx::mbar_init(bar_afull, 1);
+    ptx::mbar_init(bar_aempty, 1);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_sfull + 8 * i, 1);
+      ptx::mbar_init(bar_sempty + 8 * i, kEpiWarps);
+      ptx::mbar_init(bar_efull + 8 * i, kEpiWarps);
+      ptx::mbar_init(bar_eempty + 8 * i, p.store_e ? 2 : 1);
+    }
+    ptx::mbar_init(bar_yfull, 1);
+    ptx::mbar_init(bar_yempty, kEpiWarps);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  const int NC = p.NC;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      uint32_t it = 0, ti = 0;
+      auto slot_acquire = [&]() -> uint32_t {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kUnit);
+        ++it;
+        return s;
+      };
+      auto load_b1 = [&](int c) {          // chunk c of the first GEMM's weights: two units of K = 128
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t s = slot_acquire();
+          const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
+          if constexpr (!BMN) {            // [Dh, 256] K-major: two [128 rows x 64 k] blocks
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ptx::tma_load_2d(dst + j * kBlk, &tmB1, full, (2 * u + j) * 64, c * kCh);
+          } else {                         // [256 (k), Dh] MN-major: per 64-wide MN block, 128 k rows
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+              for (int kq = 0; kq < 2; ++kq)
+                ptx::tma_load_2d(dst + blk * kBlk + kq * 8192, &tmB1, full, c * kCh + blk * 64, u * 128 + kq * 64);
+          }
+        }
+      };
+      auto load_b2 = [&](int c) {          // chunk c of the second GEMM's weights: two units of K = 64
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t s = slot_acquire();
+          const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
+          if constexpr (!BMN) {            // [256, Dh] K-major: one [256 rows x 64 k] block
+            ptx::tma_load_2d(dst, &tmB2, full, c * kCh + u * 64, 0);
+          } else {                         // [Dh (k), 256] MN-major: four 64-wide MN blocks of 64 k rows
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk) ptx::tma_load_2d(dst + blk * 8192, &tmB2, full, blk * 64, c * kCh + u * 64);
+          }
+        }
+      };
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+        ptx::mbar_wait(bar_aempty, (ti & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar_afull, kABytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ptx::tma_load_2d(sA + j * kBlk, &tmA, bar_afull, j * 64, t * 128);
+        load_b1(0);
+        if (NC > 1) load_b1(1);
+        for (int c = 0; c < NC; ++c) {          // the order the issuer consumes them in
+          if (c + 2 < NC) load_b1(c + 2);
+          load_b2(c);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      uint32_t it = 0, g1 = 0, g2 = 0, ti = 0;
+      auto unit_wait = [&]() -> uint32_t {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        ptx::mbar_wait(bar_full + 8 * s, ph);
+        ptx::tc_fence_after();
+        return s;
+      };
+      auto mma1 = [&]() {                  // chunk accumulator (g1 & 1) = A B1_chunk, K = 256
+        const uint32_t sb = g1 & 1, ph = (g1 >> 1) & 1;
+        ptx::mbar_wait(bar_sempty + 8 * sb, ph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem + sb * kCh;
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t s = unit_wait();
+          const uint32_t ub = sRing + s * kUnit;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t ad = desc_k(sA, 8 * u + kk);
+            const uint64_t bd = BMN ? ptx::make_smem_desc(ub + (uint32_t)kk * 2048, kBlk, 1024) : desc_k(ub, kk);
+            ptx::mma_ss<false>(acc, ad, bd, p.idesc1, (uint32_t)((u | kk) != 0));
+          }
+          ptx::mma_commit(bar_empty + 8 * s);
+          ++it;
+        }
+        ptx::mma_commit(bar_sfull + 8 * sb);
+        ++g1;
+      };
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+        ptx::mbar_wait(bar_afull, ti & 1);
+        ptx::tc_fence_after();
+        int issued = 0;
+        mma1(); ++issued;
+        if (NC > 1) { mma1(); ++issued; }
+        if (issued == NC) ptx::mma_commit(bar_aempty);
+        for (int c = 0; c < NC; ++c) {
+          // chunk c + 2's first GEMM goes first: its accumulator buffer is free as soon as the epilogue of
+          // chunk c has READ tensor memory, long before that epilogue hands over its E tile -- the weight
+          // ring keeps flowing instead of holding B2(c) while nothing can be issued
+          if (c + 2 < NC) {
+            mma1();
+            if (++issued == NC) ptx::mma_commit(bar_aempty);
+          }
+          const uint32_t sb = g2 & 1, ph = (g2 >> 1) & 1;
+          ptx::mbar_wait(bar_efull + 8 * sb, ph);
+          if (c == 0) ptx::mbar_wait(bar_yempty, (ti & 1) ^ 1u);      // the previous tile's Y has been read
+          ptx::tc_fence_after();
+          const uint32_t eb = sE + sb * kEBytes;
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t s = unit_wait();
+            const uint32_t ub = sRing + s * kUnit;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = ptx::make_smem_desc(eb + (uint32_t)u * kBlk + (uint32_t)kk * 32, 16, 1024);
+              const uint64_t bd = BMN ? ptx::make_smem_desc(ub + (uint32_t)kk * 2048, 8192, 1024)
+                                      : ptx::make_smem_desc(ub + (uint32_t)kk * 32, 16, 1024);
+              ptx::mma_ss<false>(tmem + 2 * kCh, ad, bd, p.idesc2, (uint32_t)((c | u | kk) != 0));
+            }
+            ptx::mma_commit(bar_empty + 8 * s);
+            ++it;
+          }
+          ptx::mma_commit(bar_eempty + 8 * sb);
+          ++g2;
+        }
+        ptx::mma_commit(bar_yfull);
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // -------------------------------------------------------------------- epilogue warps
+    const int we = warp - 2;
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = we >> 2;                     // which 32-column slice of a chunk / 64-column slice of Y
+    const int r = q * 32 + lane, xr = r & 7;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t drop_thr = drop_threshold(p.drop_p);
+    const float drop_inv = p.drop_p > 0.f ? drop_scale(drop_thr) : 1.f;
+    const unsigned long long seed1 = drop_seed_at(p.seed1, p.drop_p > 0.f ? p.drop_step : nullptr);
+    const unsigned long long seed2 = drop_seed_at(p.seed2, p.drop_p > 0.f ? p.drop_step : nullptr);
+    const bool deriv = MODE == 0 && p.dact != nullptr;
+    uint32_t g = 0, ti = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+      const int row = t * 128 + r;
+      const bool row_ok = row < p.M;
+      for (int c = 0; c < NC; ++c, ++g) {
+        const uint32_t sb = g & 1, ph = (g >> 1) & 1;
+        const int hcol = c * kCh + half * 32;     // first hidden column of this warp's slice
+        uint32_t aw[16];                          // backward: the slice of the stored derivative (32 bf16)
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) aw[i] = 0u;
+          if (row_ok) {
+            const __nv_bfloat16* ap = p.dact + (long long)row * p.ldh + hcol;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+              asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(aw[8 * h2]), "=r"(aw[8 * h2 + 1]), "=r"(aw[8 * h2 + 2]), "=r"(aw[8 * h2 + 3]),
+                             "=r"(aw[8 * h2 + 4]), "=r"(aw[8 * h2 + 5]), "=r"(aw[8 * h2 + 6]), "=r"(aw[8 * h2 + 7])
+                           : "l"(ap + 16 * h2));
+          }
+        }
+        ptx::mbar_wait(bar_sfull + 8 * sb, ph);
+        ptx::tc_fence_after();
+        uint32_t vv[32];
+        ptx::tmem_ld_32x32(tl + sb * kCh + (uint32_t)(half * 32), vv);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();                   // the accumulator buffer is free: chunk c + 2 may overwrite it
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_sempty + 8 * sb);
+        ptx::mbar_wait(bar_eempty + 8 * sb, ph ^ 1u);
+        const uint32_t erow = sE + sb * kEBytes + (uint32_t)(half >> 1) * kBlk + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t* v = vv + 16 * j;
+          float x[16];
+          if constexpr (MODE == 0) {
+            float b[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 f = reinterpret_cast<const float4*>(p.bias1 + hcol + 16 * j)[i];
+              b[4 * i] = f.x; b[4 * i + 1] = f.y; b[4 * i + 2] = f.z; b[4 * i + 3] = f.w;
+            }
+            float dv[16];
+            if (deriv) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                float2 y2, d2;
+                gelu_fwd_grad2<__nv_bfloat16>(make_float2(__uint_as_float(v[i]) + b[i], __uint_as_float(v[i + 1]) + b[i + 1]), y2, d2);
+                x[i] = y2.x; x[i + 1] = y2.y; dv[i] = d2.x; dv[i + 1] = d2.y;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const float2 y2 = gelu_fwd2<__nv_bfloat16>(make_float2(__uint_as_float(v[i]) + b[i], __uint_as_float(v[i + 1]) + b[i + 1]));
+                x[i] = y2.x; x[i + 1] = y2.y;
+              }
+            }
+            if (p.drop_p > 0.f) {
+              const unsigned long long e = (unsigned long long)row * p.Dh + (hcol + 16 * j);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t h = drop_hash(seed1, (e >> 1) + k);
+                const float2 m = make_float2((h & 0xffffu) >= drop_thr ? drop_inv : 0.f, (h >> 16) >= drop_thr ? drop_inv : 0.f);
+                const float2 xm = f2_mul(make_float2(x[2 * k], x[2 * k + 1]), m);
+                x[2 * k] = xm.x; x[2 * k + 1] = xm.y;
+                if (deriv) {
+                  const float2 dm = f2_mul(make_float2(dv[2 * k], dv[2 * k + 1]), m);
+                  dv[2 * k] = dm.x; dv[2 * k + 1] = dm.y;
+                }
+              }
+            }
+            if (deriv && row_ok) {
+              uint32_t w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) w[k] = ptx::pack_bf16(dv[2 * k], dv[2 * k + 1]);
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                           :: "l"(p.dact + (long long)row * p.ldh + hcol + 16 * j), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                              "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a2 = aw[8 * j + k];
+              x[2 * k] = __uint_as_float(v[2 * k]) * __uint_as_float(a2 << 16);
+              x[2 * k + 1] = __uint_as_float(v[2 * k + 1]) * __uint_as_float(a2 & 0xffff0000u);
+            }
+          }
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = ptx::pack_bf16(x[2 * k], x[2 * k + 1]);
+          const int ci = (half & 1) * 4 + 2 * j;       // 16-byte chunk of the row's 128-byte block
+          ptx::sts128(erow + (uint32_t)((ci ^ xr) << 4), w[0], w[1], w[2], w[3]);
+          ptx::sts128(erow + (uint32_t)(((ci + 1) ^ xr) << 4), w[4], w[5], w[6], w[7]);
+        }
+        ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the MMA and the bulk store
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_efull + 8 * sb);
+      }
+      // ---- Y: 32 rows x 64 columns per warp
+      ptx::mbar_wait(bar_yfull, ti & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int col = half * 64 + 16 * j;
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tl + (uint32_t)(2 * kCh + col), v);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float x[16];
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 f = reinterpret_cast<const float4*>(p.bias2 + col)[i];
+            x[4 * i] = __uint_as_float(v[4 * i]) + f.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + f.y;
+            x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + f.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + f.w;
+          }
+          if (p.drop_p > 0.f) {
+            const unsigned long long e = (unsigned long long)row * kD + col;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t h = drop_hash(seed2, (e >> 1) + k);
+              x[2 * k] *= (h & 0xffffu) >= drop_thr ? drop_inv : 0.f;
+              x[2 * k + 1] *= (h >> 16) >= drop_thr ? drop_inv : 0.f;
+            }
+          }
+          if (p.res != nullptr) {
+            uint32_t rw[8];
+            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
+                         : "l"(p.res + (long long)row * p.ldr + col));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              x[2 * k] += __uint_as_float(rw[k] << 16);
+              x[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = ptx::pack_bf16(x[2 * k], x[2 * k + 1]);
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p.Y + (long long)row * p.ldy + col), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                        "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_yempty);
+    }
+  } else {
+    // -------------------------------------------------------------------- E tiles -> HBM (bulk tensor stores)
+    if (lane == 0 && p.store_e) {
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        for (int c = 0; c < NC; ++c, ++g) {
+          const uint32_t sb = g & 1, ph = (g >> 1) & 1;
+          ptx::mbar_wait(bar_efull + 8 * sb, ph);
+          const uint32_t eb = sE + sb * kEBytes;
+          ptx::tma_store_2d(&tmE, eb, c * kCh, t * 128);
+          ptx::tma_store_2d(&tmE, eb + kBlk, c * kCh + 64, t * 128);
+          ptx::bulk_commit();
+          ptx::bulk_wait_read0();                 // the tile may be overwritten once it has been read
+          ptx::mbar_arrive(bar_eempty + 8 * sb);
+        }
+      }
+      ptx::bulk_wait0();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with unit column stride; box = box_c columns x box_r rows, SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* ptr, long long cols, long long rows, long long ld, int box_c, int box_r,
+             const char* name) {
+  DL_REQUIRE(((uintptr_t)ptr & 15) == 0, "dl_ffn: %s must be 16-byte aligned", name);
+  DL_REQUIRE(ld >= cols && ld % 8 == 0, "dl_ffn: %s row stride %lld must be >= %lld and a multiple of 8 elements", name, ld, cols);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+  cuuint32_t estr[2] = {1, 1};
+  EncodeTiledFn fn = encode_fn();
+  DL_REQUIRE(fn != nullptr, "dl_ffn: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(-2, "dl_ffn: cuTensorMapEncodeTiled(%s) failed with CUresult %d (cols %lld rows %lld ld %lld)",
+                     name, (int)r, cols, rows, ld);
+  return 0;
+}
+
+int check_args(const dl_ffn_args* a, const char* who) {
+  DL_REQUIRE(a != nullptr, "%s: null args", who);
+  DL_REQUIRE(a->x && a->w1 && a->w2 && a->y, "%s: x, w1, w2 and y must be non-null", who);
+  DL_REQUIRE(a->D == kD, "%s: model width must be %d (got %lld)", who, kD, (long long)a->D);
+  DL_REQUIRE(a->Dh >= kCh && a->Dh % kCh == 0 && a->Dh <= (1 << 20), "%s: hidden width %lld must be a multiple of %d", who, (long long)a->Dh, kCh);
+  DL_REQUIRE(a->M >= 0 && a->M < (1ll << 31) - 128, "%s: bad row count %lld", who, (long long)a->M);
+  DL_REQUIRE(a->ldy >= kD && a->ldy % 16 == 0 && ((uintptr_t)a->y & 31) == 0, "%s: y needs 32-byte aligned rows", who);
+  return 0;
+}
+
+template <int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const CUtensorMap& te, FfnParams& p,
+           cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(ffn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  });
+  if (attr_err != cudaSuccess)
+    return set_error((int)attr_err, "dl_ffn: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  p.idesc1 = ptx::make_idesc(false, false, MODE == 1, 128, kCh);
+  p.idesc2 = ptx::make_idesc(false, false, MODE == 1, 128, kD);
+  const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+  DL_LAUNCH((ffn_chain_kernel<MODE>), grid, kThreads, kSmem, stream, ta, tb1, tb2, te, p);
+  DL_LAUNCH_CHECK("ffn_chain_kernel");
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+}  // namespace dl
+
+extern "C" int dl_ffn_fwd(const dl_ffn_args* a, void* stream_) {
+  using namespace dl;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_args(a, "dl_ffn_fwd");
+  if (rc) return rc;
+  DL_REQUIRE(a->b1 && a->b2, "dl_ffn_fwd: b1 and b2 must be non-null");
+  DL_REQUIRE(((uintptr_t)a->b1 & 15) == 0 && ((uintptr_t)a->b2 & 15) == 0, "dl_ffn_fwd: biases must be 16-byte aligned");
+  DL_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "dl_ffn_fwd: drop_p must be in [0, 1)");
+  DL_REQUIRE(!a->dact || a->hidden, "dl_ffn_fwd: dact needs hidden (both are the backward's inputs)");
+  if (a->dact) DL_REQUIRE(a->ldh >= a->Dh && a->ldh % 16 == 0 && ((uintptr_t)a->dact & 31) == 0, "dl_ffn_fwd: dact needs 32-byte aligned rows");
+  if (a->residual) DL_REQUIRE(a->ldr >= kD && a->ldr % 16 == 0 && ((uintptr_t)a->residual & 31) == 0, "dl_ffn_fwd: residual needs 32-byte aligned rows");
+  if (a->M == 0) return 0;
+  CUtensorMap ta, tb1, tb2, te;
+  if ((rc = make_map(&ta, a->x, kD, a->M, a->ldx, 64, 128, "x"))) return rc;
+  if ((rc = make_map(&tb1, a->w1, kD, a->Dh, kD, 64, 128, "w1"))) return rc;       // [Dh, 256]: rows = hidden
+  if ((rc = make_map(&tb2, a->w2, a->Dh, kD, a->Dh, 64, 256, "w2"))) return rc;    // [256, Dh]: all rows, 64 k
+  if (a->hidden) {
+    if ((rc = make_map(&te, a->hidden, a->Dh, a->M, a->ldh, 64, 128, "hidden"))) return rc;
+  } else {
+    te = ta;
+  }
+  FfnParams p = {};
+  p.bias1 = a->b1; p.bias2 = a->b2;
+  p.dact = (__nv_bfloat16*)a->dact;
+  p.res = (const __nv_bfloat16*)a->residual;
+  p.Y = (__nv_bfloat16*)a->y;
+  p.ldh = a->ldh; p.ldy = a->ldy; p.ldr = a->ldr;
+  p.seed1 = a->seed1; p.seed2 = a->seed2; p.drop_step = (const long long*)a->drop_seed_step; p.drop_p = a->drop_p;
+  p.M = (int)a->M; p.Dh = (int)a->Dh; p.NC = (int)(a->Dh / kCh); p.tiles = ceil_div(a->M, 128);
+  p.store_e = a->hidden != nullptr;
+  return launch<0>(ta, tb1, tb2, te, p, stream);
+}
+
+extern "C" int dl_ffn_bwd(const dl_ffn_args* a, void* stream_) {
+  using namespace dl;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_args(a, "dl_ffn_bwd");
+  if (rc) return rc;
+  DL_REQUIRE(a->hidden && a->dact, "dl_ffn_bwd: hidden (out) and dact (in) must be non-null");
+  DL_REQUIRE(a->ldh >= a->Dh && a->ldh % 16 == 0 && ((uintptr_t)a->dact & 31) == 0, "dl_ffn_bwd: dact needs 32-byte aligned rows");
+  if (a->M == 0) return 0;
+  CUtensorMap ta, tb1, tb2, te;
+  if ((rc = make_map(&ta, a->x, kD, a->M, a->ldx, 64, 128, "g"))) return rc;
+  if ((rc = make_map(&tb1, a->w2, a->Dh, kD, a->Dh, 64, 64, "w2"))) return rc;     // [256 (k), Dh]: MN-major
+  if ((rc = make_map(&tb2, a->w1, kD, a->Dh, kD, 64, 64, "w1"))) return rc;        // [Dh (k), 256]: MN-major
+  if ((rc = make_map(&te, a->hidden, a->Dh, a->M, a->ldh, 64, 128, "hidden"))) return rc;
+  FfnParams p = {};
+  p.dact = (__nv_bfloat16*)a->dact;
+  p.Y = (__nv_bfloat16*)a->y;
+  p.ldh = a->ldh; p.ldy = a->ldy;
+  p.M = (int)a->M; p.Dh = (int)a->Dh; p.NC = (int)(a->Dh / kCh); p.tiles = ceil_div(a->M, 128);
+  p.store_e = 1;
+  return launch<1>(ta, tb1, tb2, te, p, stream);
+}

@@ -419,6 +419,73 @@ transpose_kernel(const T* __restrict__ x, T* __restrict__ y, int R, int Cc) {
   }
 }
 
+// 64 x 64 tiles with 16-byte global accesses both ways: y[b, c, r] = in[b, r, c].
+//   SRC 0   in[b, r, c] = x[b, r, c], optionally BatchNorm-normalised per input column c:
+//           (x - mean[c]) * rstd[c] * gamma[c] + beta[c] -- the last BatchNorm of ProteinCNN is applied
+//           while its output is laid out as the reference's (B, C, L) buffer (model/basic_model.py:178-179)
+//   SRC 1   in[b, r, c] = g[b, (f / R) % P, f % R] * scale with f = r * Cc + c: the gradient that reaches
+//           the channels-last (B, L = Cc, C = R) activation through transpose -> .view(B, L, C) ->
+//           .view(B, S, P, C).mean(1) (model/basic_model.py:179, model/DrugLAMP.py:35-37), scale = 1 / S
+template <typename T, int SRC>
+__global__ void __launch_bounds__(256)
+transpose64_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int R, int Cc, int P, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = VecWidth<T>::N;
+  constexpr int TPR = 64 / V, RPP = 256 / TPR;
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const size_t b = blockIdx.z;
+  const int tv = threadIdx.x % TPR, tr = threadIdx.x / TPR;
+  {
+    const int c = c0 + tv * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = 1.f; sh[k] = 0.f; }
+    if (SRC == 0 && mean != nullptr && c < Cc) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float a = rstd[c + k] * (gamma ? gamma[c + k] : 1.f);
+        sc[k] = a;
+        sh[k] = (beta ? beta[c + k] : 0.f) - mean[c + k] * a;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 64; i += RPP) {
+      const int r = r0 + tr + i;
+      if (r < R && c < Cc) {
+        float v[V];
+        if (SRC == 0) {
+          ldv(x + (b * R + r) * Cc + c, v);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+        } else {
+          const long long f = (long long)r * Cc + c;
+          const long long rv = f / R;
+          ldv(x + (b * P + (size_t)(rv % P)) * R + (size_t)(f - rv * R), v);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[k] *= scale;
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) tile[tv * V + k][tr + i] = v[k];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 64; i += RPP) {
+    const int c = c0 + tr + i, r = r0 + tv * V;
+    if (c < Cc && r < R) {
+      float v[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = tile[tr + i][tv * V + k];
+      stv(y + (b * Cc + c) * R + r, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ cross entropy (MLM heads)
 // logit[r, c] = x[r*ld + c] + (extra ? extra[r] * wextra[c] : 0);  rows with label == ignore are
 // skipped.  One warp per row, classes strided over lanes (C = 27 for the MLM heads).
@@ -888,6 +955,46 @@ extern "C" int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_
   else
     DL_LAUNCH((transpose_kernel<float>), grid, 256, 0, st, (const float*)x, (float*)y, R, Cc);
   DL_LAUNCH_CHECK("transpose_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_bn_transpose(const void* x, void* y, const float* mean, const float* rstd, const float* gamma,
+                               const float* beta, int64_t B, int32_t R, int32_t Cc, int32_t dtype, void* stream) {
+  DL_REQUIRE(x && y && R >= 1 && Cc >= 1 && B >= 0 && B <= 65535, "dl_bn_transpose: bad arguments");
+  DL_REQUIRE(mean == nullptr || rstd != nullptr, "dl_bn_transpose: mean needs rstd");
+  const int V = dtype == DL_BF16 ? 8 : 4;
+  DL_REQUIRE(R % V == 0 && Cc % V == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
+             "dl_bn_transpose: extents must be multiples of %d elements and the tensors 16-byte aligned", V);
+  if (B == 0) return 0;
+  dim3 grid(ceil_div(Cc, 64), ceil_div(R, 64), (unsigned)B);
+  DL_REQUIRE(grid.y <= 65535, "dl_bn_transpose: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DL_BF16)
+    DL_LAUNCH((transpose64_kernel<__nv_bfloat16, 0>), grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, R, Cc, 0, 1.f);
+  else
+    DL_LAUNCH((transpose64_kernel<float, 0>), grid, 256, 0, st, (const float*)x, (float*)y, mean, rstd, gamma, beta, R, Cc, 0, 1.f);
+  DL_LAUNCH_CHECK("transpose64_kernel");
+  count_launch();
+  return 0;
+}
+
+extern "C" int dl_site_pool_view_bwd(const void* g, void* dx, int64_t B, int32_t S, int32_t L, int32_t C,
+                                     int32_t dtype, void* stream) {
+  DL_REQUIRE(g && dx && S >= 1 && L >= 1 && C >= 1 && B >= 0 && B <= 65535, "dl_site_pool_view_bwd: bad arguments");
+  const int V = dtype == DL_BF16 ? 8 : 4;
+  DL_REQUIRE(L % S == 0 && L % V == 0 && C % V == 0 && (((uintptr_t)g | (uintptr_t)dx) & 15) == 0,
+             "dl_site_pool_view_bwd: L must be a multiple of S, L and C multiples of %d elements, tensors 16-byte aligned", V);
+  if (B == 0) return 0;
+  // the (B, C, L) gradient is never materialised: "input" rows = channels (R = C), columns = positions (Cc = L)
+  dim3 grid(ceil_div(L, 64), ceil_div(C, 64), (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = 1.f / (float)S;
+  if (dtype == DL_BF16)
+    DL_LAUNCH((transpose64_kernel<__nv_bfloat16, 1>), grid, 256, 0, st, (const __nv_bfloat16*)g, (__nv_bfloat16*)dx, nullptr, nullptr, nullptr, nullptr, C, L, L / S, scale);
+  else
+    DL_LAUNCH((transpose64_kernel<float, 1>), grid, 256, 0, st, (const float*)g, (float*)dx, nullptr, nullptr, nullptr, nullptr, C, L, L / S, scale);
+  DL_LAUNCH_CHECK("transpose64_kernel");
   count_launch();
   return 0;
 }

@@ -619,8 +619,45 @@ extern "C" int dl_batchnorm_fwd(const void* x, const float* gamma, const float* 
                                 int64_t* num_batches_tracked, double* workspace, int64_t rows,
                                 int32_t cols, float eps, float momentum, int32_t training,
                                 float last_row_weight, int32_t dtype, void* stream) {
-  DL_REQUIRE(x && y && mean && rstd, "dl_batchnorm_fwd: null pointer");
+  DL_REQUIRE(x && mean && rstd, "dl_batchnorm_fwd: null pointer");
   const bool weighted = last_row_weight > 1.f;
+  if (y == nullptr) {
+    // statistics only (mean / rstd, running buffers): the normalisation itself is fused into the
+    // consumer (dl_bn_transpose)
+    DL_REQUIRE(!weighted, "dl_batchnorm_fwd: statistics-only mode does not take last_row_weight");
+    DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_fwd: cols must be a positive multiple of 4 and rows >= 1");
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if (!training) {
+      DL_REQUIRE(running_mean && running_var, "dl_batchnorm_fwd: eval mode needs running statistics");
+      DL_LAUNCH(bn_eval_stats_kernel, ceil_div(cols, 128), 128, 0, st0, running_mean, running_var, mean, rstd, cols, eps);
+      DL_LAUNCH_CHECK("bn_eval_stats_kernel");
+      count_launch();
+      return 0;
+    }
+    DL_REQUIRE(workspace != nullptr, "dl_batchnorm_fwd: workspace required in training mode");
+    DL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st0));
+    ColSlice g0;
+    if (col_slice(x, nullptr, nullptr, rows, cols, dtype == DL_BF16 ? 8 : 4, 32, &g0)) {
+      const dim3 grid0(g0.xb, g0.yb);
+      if (dtype == DL_BF16)
+        DL_LAUNCH((bn_colstats_vec_kernel<__nv_bfloat16, false>), grid0, 256, 0, st0, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g0.rpb, g0.tpr);
+      else
+        DL_LAUNCH((bn_colstats_vec_kernel<float, false>), grid0, 256, 0, st0, (const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, g0.rpb, g0.tpr);
+      DL_LAUNCH_CHECK("bn_colstats_vec_kernel");
+    } else {
+      dim3 grid0; long long rpb0;
+      stats_grid(rows, cols, &grid0, &rpb0);
+      if (dtype == DL_BF16)
+        DL_LAUNCH((bn_colstats_kernel<__nv_bfloat16, false>), grid0, dim3(32, 8), 0, st0, (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb0);
+      else
+        DL_LAUNCH((bn_colstats_kernel<float, false>), grid0, dim3(32, 8), 0, st0, (const float*)x, nullptr, nullptr, nullptr, workspace, rows, cols, rpb0);
+      DL_LAUNCH_CHECK("bn_colstats_kernel");
+    }
+    DL_LAUNCH(bn_finalize_kernel, ceil_div(cols, 128), 128, 0, st0, workspace, mean, rstd, running_mean, running_var, (long long*)num_batches_tracked, rows, cols, eps, momentum);
+    DL_LAUNCH_CHECK("bn_finalize_kernel");
+    count_launch(2);
+    return 0;
+  }
   const double count = weighted ? (double)rows - 1.0 + (double)last_row_weight : (double)rows;
   DL_REQUIRE(cols > 0 && cols % 4 == 0 && rows >= 1, "dl_batchnorm_fwd: cols must be a positive multiple of 4 and rows >= 1");
   cudaStream_t st = (cudaStream_t)stream;

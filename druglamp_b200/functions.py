@@ -383,10 +383,20 @@ def linear(x, w, b=None, act=K.ACT_NONE, residual=None, drop_p=0.0, seed=0, keep
 
 
 # ================================================================================ FFN
+# DL_NO_FUSED_FFN=1: the two-GEMM path (A/B measurements; also what fp32 mode and other widths use)
+FUSED_FFN = os.environ.get("DL_NO_FUSED_FFN", "0") == "0"
+
+
+def _al(t, nbytes) -> bool:
+    return t is not None and t.data_ptr() % nbytes == 0
+
+
 class FFNFn(Function):
     """y = dropout(fc2(dropout(gelu(fc1(x))))) + residual  (PMMA Mlp, model/PMMA/mlp.py:44-50,
-    with the block's residual add, model/PMMA/block.py:45-47, fused into fc2's epilogue).
-    Backward fuses gelu' and the first dropout mask into the dX GEMM epilogue."""
+    with the block's residual add, model/PMMA/block.py:45-47).  bf16 rows of width 256: ONE launch
+    forward (dl_ffn_fwd: both GEMMs chained on chip, the hidden activation and its derivative stored
+    once for the backward) and ONE for (dpre, dX) backward (dl_ffn_bwd).  Otherwise two GEMMs each
+    way with gelu' and the first dropout mask fused into the dX GEMM epilogue."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, residual, p, seed1, seed2):
@@ -394,30 +404,43 @@ class FFNFn(Function):
         x2 = K.to_compute(x).view(-1, xs[-1])
         w1c, w2c = shadow(w1), shadow(w2)
         M, Dh = x2.shape[0], w1.shape[0]
-        hd = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
-        # forward-only scoring (no_grad): the pre-activation is never read, skip its store
-        pre1 = torch.empty_like(hd) if _needs_backward(ctx) else None
-        # pre1 receives d hd / d pre = gelu'(pre) * dropout factor (pre_mode 1): the backward multiplies
-        K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1), pre_mode=1)
         r2 = K.to_compute(residual).view(-1, w2.shape[0]) if residual is not None else None
-        y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
+        need = _needs_backward(ctx)
+        fused = (FUSED_FFN and K.ffn_supported(x2, w1c, w2c) and _al(b1, 16) and _al(b2, 16)
+                 and b1.dtype == torch.float32 and b2.dtype == torch.float32
+                 and (r2 is None or (_al(r2, 32) and r2.stride(0) % 16 == 0 and r2.dtype == x2.dtype)))
+        if fused:
+            y, hd, pre1 = K.ffn_fwd(x2, w1c, b1.detach(), w2c, b2.detach(), r2, (p, seed1, seed2), keep=need)
+        else:
+            hd = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device)
+            # forward-only scoring (no_grad): the pre-activation is never read, skip its store
+            pre1 = torch.empty_like(hd) if need else None
+            # pre1 receives d hd / d pre = gelu'(pre) * dropout factor (pre_mode 1): the backward multiplies
+            K.mm(x2, w1c, hd, bias=b1, act=K.ACT_GELU, pre=pre1, drop=(p, seed1), pre_mode=1)
+            y = K.mm(hd, w2c, bias=b2, res=r2, drop=(p, seed2))
         ctx.save_for_backward(x2, w1, w2, pre1, hd)
         ctx.biases = (b1, b2)
-        ctx.meta = (p, seed1, seed2, xs, x.dtype, None if residual is None else residual.dtype)
+        ctx.meta = (p, seed1, seed2, xs, x.dtype, None if residual is None else residual.dtype, fused)
         return y.view(*xs[:-1], w2.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         x2, w1, w2, pre1, hd = ctx.saved_tensors
-        p, seed1, seed2, xs, xdt, rdt = ctx.meta
+        p, seed1, seed2, xs, xdt, rdt, fused = ctx.meta
         gy2 = K.to_compute(gy).view(-1, w2.shape[0])
         g2 = K.act_bwd(gy2, None, K.ACT_NONE, (p, seed2))
         b1p, b2p = ctx.biases
         dw2, db2 = _wbgrad(w2, b2p, g2, hd)
-        dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
+        dx = None
+        if fused and ctx.needs_input_grad[0] and _al(g2, 32):
+            dpre1, dxc = K.ffn_bwd(g2, shadow(w1), shadow(w2), pre1)
+            dx = _back(dxc, xdt, xs)
+        else:
+            dpre1 = K.mm(g2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
         dw1, db1 = _wbgrad(w1, b1p, dpre1, x2)
-        dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs) if ctx.needs_input_grad[0] else None
+        if dx is None and ctx.needs_input_grad[0]:
+            dx = _back(K.mm(dpre1, shadow(w1), tb=True), xdt, xs)
         dres = _back(gy2, rdt, gy.shape) if rdt is not None else None
         return dx, dw1, db1, dw2, db2, dres, None, None, None
 
@@ -1269,6 +1292,67 @@ class TransposeFn(Function):
     @once_differentiable
     def backward(ctx, gy):
         return _back(K.transpose_last2(K.to_compute(gy)), ctx.xdt)
+
+
+class CnnTailFn(Function):
+    """The tail of ProteinCNN on the channels-last activation x (B, L, C) = relu(conv3(.)):
+    BatchNorm1d over the channels, the (B, C, L) layout of the reference and its ``.view(B, L, C)``
+    reinterpretation (model/basic_model.py:178-179) -- statistics, then ONE
+    normalise-and-transpose pass (dl_bn_transpose).  With site_len S > 0 the site mean of
+    model/DrugLAMP.py:35-37 follows inside the same Function, so the backward maps the pooled gradient
+    straight to the channels-last layout (dl_site_pool_view_bwd) instead of expanding it 9x and transposing it.
+    relu_input: x is a ReLU output whose own backward is skipped; its mask rides on the BatchNorm backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, relu_input, S):
+        xc = K.to_compute(x)
+        B, Lr, C_ = xc.shape
+        x2 = xc.view(-1, C_)
+        g_ = None if gamma is None else gamma.detach()
+        b_ = None if beta is None else beta.detach()
+        mean, rstd = K.batchnorm_stats(x2, running_mean, running_var, nbt, eps, momentum, training)
+        y = K.bn_transpose(xc, mean, rstd, g_, b_).view(B, Lr, C_)          # the reinterpreting view
+        ctx.save_for_backward(x2, gamma, beta, mean, rstd)
+        ctx.meta = (training, x.dtype, x.shape, bool(relu_input), int(S))
+        return K.site_pool_fwd(y, S) if S > 0 else y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, gamma, beta, mean, rstd = ctx.saved_tensors
+        training, xdt, xshape, relu, S = ctx.meta
+        B, Lr, C_ = xshape
+        g = _as(gy, x2.dtype)
+        if S > 0:
+            dy = K.site_pool_view_bwd(g, S)                                   # (B, L/S, C) -> (B, L, C)
+        else:
+            dy = K.bn_transpose(g.view(B, C_, Lr))                            # (B, C, L) -> (B, L, C)
+        g_ = None if gamma is None else gamma.detach()
+        tg, tb = _grad_target(gamma), _grad_target(beta)
+        nones = (None,) * 8
+        if tg is not None and tb is not None:       # straight into the flat gradient buffer
+            dx, _, _ = K.batchnorm_bwd(dy.view(x2.shape), x2, g_, mean, rstd, training, acc_into=(tg, tb),
+                                       relu_mask=relu)
+            return (_back(dx, xdt, xshape), None, None) + nones
+        dx, dg, db = K.batchnorm_bwd(dy.view(x2.shape), x2, g_, mean, rstd, training,
+                                     need_param_grads=gamma is not None, relu_mask=relu)
+        return (_back(dx, xdt, xshape), dg, db) + nones
+
+
+def cnn_tail_ok(x: torch.Tensor, S: int) -> bool:
+    """Shapes dl_bn_transpose / dl_site_pool_view_bwd serve (16-byte vectors along both tile edges)."""
+    v = 8 if K.compute_dtype() == torch.bfloat16 else 4
+    return x.is_cuda and x.dim() == 3 and x.shape[1] % v == 0 and x.shape[2] % v == 0 and (S <= 0 or x.shape[1] % S == 0)
+
+
+def cnn_tail(x, bn: torch.nn.BatchNorm1d, relu_input: bool = True, site_len: int = 0):
+    training = bn.training or bn.running_mean is None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    update = training and not _bn_frozen
+    keep = update or not training
+    return CnnTailFn.apply(x, bn.weight, bn.bias, bn.running_mean if keep else None, bn.running_var if keep else None,
+                           bn.num_batches_tracked if update else None, bn.eps, momentum, training, relu_input,
+                           site_len)
 
 
 class ActFn(Function):

@@ -312,6 +312,67 @@ def attn_bwd(d_o: torch.Tensor, q, k, v, o, lse, H: int, scale: float, dq: torch
     L.check(L.lib().dl_attn_bwd(L.C.byref(a), L.stream_ptr()), "dl_attn_bwd")
 
 
+# ----------------------------------------------------------------------------- fused FFN
+FFN_WIDTH = 256      # model width the fused feed-forward kernels are built for
+
+
+def ffn_supported(x2: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> bool:
+    """dl_ffn_fwd / dl_ffn_bwd serve bf16 rows of width 256 with a hidden width that is a multiple of 128."""
+    return (x2.is_cuda and x2.dtype == torch.bfloat16 and x2.dim() == 2 and x2.shape[1] == FFN_WIDTH
+            and x2.stride(1) == 1 and x2.stride(0) % 16 == 0 and x2.data_ptr() % 32 == 0
+            and tuple(w1.shape) == (w2.shape[1], FFN_WIDTH) and w2.shape[0] == FFN_WIDTH and w1.shape[0] % 128 == 0
+            and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16 and w1.is_contiguous() and w2.is_contiguous())
+
+
+def _ffn_args(x2, w1, w2, hidden, dact, y) -> "L.FfnArgs":
+    a = L.FfnArgs()
+    a.x, a.w1, a.w2, a.y = x2.data_ptr(), w1.data_ptr(), w2.data_ptr(), y.data_ptr()
+    a.hidden = None if hidden is None else hidden.data_ptr()
+    a.dact = None if dact is None else dact.data_ptr()
+    a.M, a.D, a.Dh = x2.shape[0], x2.shape[1], w1.shape[0]
+    a.ldx, a.ldy = x2.stride(0), y.stride(0)
+    a.ldh = w1.shape[0] if hidden is None else hidden.stride(0)
+    for t in (hidden, dact):
+        if t is not None and (t.dtype != torch.bfloat16 or t.stride(1) != 1 or t.stride(0) != a.ldh):
+            raise ValueError("dl_ffn: hidden / dact must be bf16 [M, Dh] with one row stride")
+    return a
+
+
+def ffn_fwd(x2: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+            res: Optional[torch.Tensor], drop: Tuple[float, int, int] = (0.0, 0, 0), keep: bool = True):
+    """y = dropout(dropout(gelu(x2 w1^T + b1)) w2^T + b2) + res in ONE launch (dl_ffn_fwd).
+    -> (y, hidden, dact); hidden / dact (the backward's operands) are None unless `keep`."""
+    M, Dh = x2.shape[0], w1.shape[0]
+    y = torch.empty((M, FFN_WIDTH), dtype=x2.dtype, device=x2.device)
+    hidden = torch.empty((M, Dh), dtype=x2.dtype, device=x2.device) if keep else None
+    dact = torch.empty_like(hidden) if keep else None
+    a = _ffn_args(x2, w1, w2, hidden, dact, y)
+    a.b1, a.b2 = b1.data_ptr(), b2.data_ptr()
+    if res is not None:
+        a.residual, a.ldr = res.data_ptr(), res.stride(0)
+    p, s1, s2 = drop
+    a.drop_p, a.seed1, a.seed2 = p, s1, s2
+    a.drop_seed_step = L.ptr(L.DROPOUT_STEP) if p > 0 else None
+    L.check(L.lib().dl_ffn_fwd(L.C.byref(a), L.stream_ptr()), "dl_ffn_fwd")
+    if L.PROFILE is not None:
+        L.PROFILE.append({"flops": 4.0 * M * Dh * FFN_WIDTH, "args": a, "fn": "dl_ffn_fwd",
+                          "keep": (x2, w1, b1, w2, b2, res, y, hidden, dact), "shape": ("ffn_fwd", M, Dh)})
+    return y, hidden, dact
+
+
+def ffn_bwd(g2: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, dact: torch.Tensor):
+    """-> (dpre = (g2 w2) * dact  [M, Dh],  dx = dpre w1  [M, 256]) in ONE launch (dl_ffn_bwd)."""
+    M = g2.shape[0]
+    dpre = torch.empty_like(dact)
+    dx = torch.empty((M, FFN_WIDTH), dtype=g2.dtype, device=g2.device)
+    a = _ffn_args(g2, w1, w2, dpre, dact, dx)
+    L.check(L.lib().dl_ffn_bwd(L.C.byref(a), L.stream_ptr()), "dl_ffn_bwd")
+    if L.PROFILE is not None:
+        L.PROFILE.append({"flops": 4.0 * M * w1.shape[0] * FFN_WIDTH, "args": a, "fn": "dl_ffn_bwd",
+                          "keep": (g2, w1, w2, dact, dpre, dx), "shape": ("ffn_bwd", M, w1.shape[0])})
+    return dpre, dx
+
+
 # ----------------------------------------------------------------------------- GCN
 def spmm_norm(indptr, indices, norm_src, norm_dst, h: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(h)
@@ -331,6 +392,42 @@ def batchnorm_fwd(x: torch.Tensor, gamma, beta, running_mean, running_var, nbt, 
            rstd.data_ptr(), L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt), ws.data_ptr(), rows, cols,
            eps, momentum, int(training), float(last_row_weight), L.dt(x))
     return y, mean, rstd
+
+
+def batchnorm_stats(x: torch.Tensor, running_mean, running_var, nbt, eps: float, momentum: float, training: bool):
+    """(mean, rstd) of nn.BatchNorm1d over (rows, cols) -- batch statistics in training (running buffers
+    updated), running statistics otherwise -- without normalising (dl_batchnorm_fwd, y = NULL)."""
+    rows, cols = x.shape
+    mean = torch.empty(cols, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
+    L.call("dl_batchnorm_fwd", x.data_ptr(), None, None, None, mean.data_ptr(), rstd.data_ptr(),
+           L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt), ws.data_ptr(), rows, cols, eps, momentum,
+           int(training), 1.0, L.dt(x))
+    return mean, rstd
+
+
+def bn_transpose_ok(x: torch.Tensor) -> bool:
+    v = 16 // x.element_size()
+    return x.dim() == 3 and x.is_contiguous() and x.shape[1] % v == 0 and x.shape[2] % v == 0 and x.data_ptr() % 16 == 0
+
+
+def bn_transpose(x: torch.Tensor, mean=None, rstd=None, gamma=None, beta=None) -> torch.Tensor:
+    """(B, R, C) -> (B, C, R) contiguous, normalised per column c on the way when mean / rstd are given."""
+    B, R, Cc = x.shape
+    y = torch.empty((B, Cc, R), dtype=x.dtype, device=x.device)
+    L.call("dl_bn_transpose", x.data_ptr(), y.data_ptr(), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta),
+           B, R, Cc, L.dt(x))
+    return y
+
+
+def site_pool_view_bwd(g: torch.Tensor, S: int) -> torch.Tensor:
+    """g (B, L/S, C) -> dx (B, L, C): gradient through transpose -> .view(B, L, C) -> site mean (dl_site_pool_view_bwd)."""
+    B, P, C = g.shape
+    g = g.contiguous()
+    dx = torch.empty((B, P * S, C), dtype=g.dtype, device=g.device)
+    L.call("dl_site_pool_view_bwd", g.data_ptr(), dx.data_ptr(), B, S, P * S, C, L.dt(g))
+    return dx
 
 
 def batchnorm_bwd(dy, x, gamma, mean, rstd, training: bool, need_param_grads: bool = True, acc_into=None,

@@ -121,6 +121,9 @@ class DrugLAMPBase(nn.Module):
 
     # ---- shared pieces of the three forwards ------------------------------------------------------
     def _protein_branch(self, vp, fill_bit_p):
+        from .modules import ProteinCNN
+        if isinstance(self.protein_extractor, ProteinCNN):              # site mean inside the CNN tail
+            return self.protein_extractor(vp, fill_bit_p, site_len=self.site_len)
         v = self.protein_extractor(vp, fill_bit_p)                      # (B, 2304, 128)
         return Fn.SitePoolFn.apply(v, self.site_len)                    # (B, 256, 128)   DrugLAMP.py:35-37
 

@@ -660,6 +660,10 @@ def binary_cross_entropy(pred_output, labels):
 
 
 # ================================================================================ adjacent modules
+# DL_NO_CNN_TAIL=1: BatchNorm apply, transpose and site mean as separate passes (A/B measurements)
+CNN_TAIL_FUSED = os.environ.get("DL_NO_CNN_TAIL", "0") == "0"
+
+
 class ProteinCNN(nn.Module):
     """reference ``model/basic_model.py:155-180`` -- adjacent to the hot path, on
     the dl_* kernels end to end: fused embedding gather + fill bit, implicit-GEMM convolutions,
@@ -674,20 +678,24 @@ class ProteinCNN(nn.Module):
             setattr(self, f"conv{i + 1}", nn.Conv1d(in_ch[i], in_ch[i + 1], kernel_size[i], padding='same'))
             setattr(self, f"bn{i + 1}", nn.BatchNorm1d(in_ch[i + 1]))
 
-    def forward(self, v, fill_mask):
+    def forward(self, v, fill_mask, site_len: int = 0):
         """Channels-last throughout: each Conv1d('same')+ReLU is one implicit-GEMM dl_gemm launch,
-        each BatchNorm1d runs on the (B*L, C) rows with the dl_batchnorm kernels; the result is
-        transposed once into the reference's (B, C, L) buffer and reinterpreted like its
-        ``.view(B, L, C)`` (App. A4)."""
+        each BatchNorm1d runs on the (B*L, C) rows with the dl_batchnorm kernels; the last one is
+        applied while the result is laid out as the reference's (B, C, L) buffer, which is then
+        reinterpreted like its ``.view(B, L, C)`` (App. A4).  site_len > 0 (not part of the reference
+        signature): also take the site mean of model/DrugLAMP.py:35-37 and return (B, L / site_len, C)."""
         emb = self.embedding
         x = Fn.EmbedFillFn.apply(v, fill_mask, emb.weight, emb.padding_idx)    # (B, L, 128): gather + fill bit
         for i in (1, 2, 3):
             conv, bn = getattr(self, f"conv{i}"), getattr(self, f"bn{i}")
             # conv -> ReLU -> BN: the ReLU's backward mask rides on the BatchNorm backward kernel
             x = Fn.Conv1dSameFn.apply(x, conv.weight, conv.bias, True, False)
+            if i == 3 and CNN_TAIL_FUSED and Fn.cnn_tail_ok(x, site_len):
+                return Fn.cnn_tail(x, bn, relu_input=True, site_len=site_len)
             x = Fn.batch_norm(x, bn, relu_input=True)
         y = Fn.TransposeFn.apply(x)                                         # (B, C, L) like the reference
-        return y.view(y.size(0), y.size(2), -1)
+        y = y.view(y.size(0), y.size(2), -1)
+        return Fn.SitePoolFn.apply(y, site_len) if site_len > 0 else y
 
 
 class FeedForwardLayer(nn.Module):

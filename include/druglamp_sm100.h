@@ -169,6 +169,46 @@ int dl_attn_fwd(const dl_attn_args* args, void* stream);
 int dl_attn_bwd(const dl_attn_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused position-wise feed-forward network of a PMMA block (bf16, model width D = 256):
+ * Mlp.forward (model/PMMA/mlp.py:44-50: fc1 -> GELU -> dropout -> fc2 -> dropout) together with the
+ * block's residual add (model/PMMA/block.py:45-47,59-61), two chained tcgen05 GEMMs in ONE kernel per
+ * direction; the 4x-wide hidden activation stays in shared / tensor memory between them.
+ *
+ *   dl_ffn_fwd:  hidden = dropout(gelu(x w1^T + b1), seed1)      [M, Dh]  (NULL: not stored, forward-only)
+ *                dact   = d hidden / d (x w1^T + b1)              [M, Dh]  (NULL: not stored)
+ *                y      = dropout(hidden w2^T + b2, seed2) + residual      [M, D]
+ *   dl_ffn_bwd:  x = g, the gradient of (hidden w2^T + b2) (i.e. dL/dy with the seed2 mask applied,
+ *                dl_act_bwd);  hidden (OUT) = dpre = (g w2) * dact   [M, Dh]  (the dW1 operand);
+ *                y (OUT) = dX = dpre w1                               [M, D]
+ *   The weight / bias gradients stay dl_gemm launches (dW2 = g^T hidden, dW1 = dpre^T x).
+ *
+ * x, y, residual: bf16 [M, D] with row strides ldx, ldy, ldr; hidden, dact: bf16 [M, Dh] with row
+ * stride ldh; w1: bf16 [Dh, D] contiguous, w2: bf16 [D, Dh] contiguous (nn.Linear layouts); b1, b2
+ * fp32.  Row strides are multiples of 16 elements, base pointers 32-byte aligned.  Dh is a multiple
+ * of 128.  Dropout masks are the ones dl_gemm / dl_act_bwd draw for the same (seed, element index),
+ * so either direction may be mixed with the unfused launches.
+ */
+typedef struct dl_ffn_args {
+  const void* x;
+  const void* w1;
+  const void* w2;
+  const float* b1;       /* forward */
+  const float* b2;       /* forward */
+  const void* residual;  /* forward, or NULL */
+  void* hidden;
+  void* dact;            /* forward: out (or NULL); backward: in */
+  void* y;
+  int64_t M, D, Dh;
+  int64_t ldx, ldh, ldy, ldr;
+  float drop_p;          /* forward */
+  uint64_t seed1, seed2;
+  const int64_t* drop_seed_step; /* or NULL; see dl_gemm_args.drop_seed_step */
+} dl_ffn_args;
+
+int dl_ffn_fwd(const dl_ffn_args* args, void* stream);
+int dl_ffn_bwd(const dl_ffn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound; one warp per row, 128-bit vector loads, warp-shuffle reductions).
  * `dtype` is the activation dtype (x, y, dy, dx); statistics and parameters are fp32.
  */
@@ -275,6 +315,8 @@ int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_
  * cross_modality.py:168).  training!=0: batch statistics, running buffers updated with
  * `momentum` (unbiased variance) and *num_batches_tracked += 1 when given; training==0: running
  * statistics.  mean/rstd: [cols] outputs saved for backward.  workspace: 2*cols doubles.
+ * y == NULL: statistics only (mean / rstd and the running buffers); the normalisation is then applied by
+ * the consumer (dl_bn_transpose).
  * last_row_weight w > 1 (training only): the LAST row stands for w identical rows -- the molecular
  * GCN's virtual nodes, 92 % of the 512 slots per molecule, all carry one and the same row at every
  * layer, so the layer is evaluated once for them: batch statistics count that row w
@@ -326,6 +368,20 @@ int dl_site_pool_bwd(const void* dy, void* dx, int64_t B, int32_t S, int32_t L, 
  * (B, C, L) buffer, which the reference then reinterprets with .view(B, L, C)
  * (model/basic_model.py:179). */
 int dl_transpose(const void* x, void* y, int64_t B, int32_t R, int32_t C, int32_t dtype, void* stream);
+
+/* The same layout change with ProteinCNN's last BatchNorm1d (model/basic_model.py:178) applied on the way:
+ * y[b, c, r] = (x[b, r, c] - mean[c]) * rstd[c] * gamma[c] + beta[c]  (mean == NULL: plain transpose;
+ * gamma / beta may be NULL).  mean / rstd come from dl_batchnorm_fwd called with y == NULL (statistics
+ * only).  64 x 64 tiles, 16-byte accesses both ways: R and C multiples of 8 (bf16) / 4 (fp32) elements. */
+int dl_bn_transpose(const void* x, void* y, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, int64_t B, int32_t R, int32_t C, int32_t dtype, void* stream);
+
+/* Gradient of the channels-last activation x (B, L, C) through  transpose -> (B, C, L) ->
+ * .view(B, L, C) -> .view(B, S, L/S, C).mean(1)  (model/basic_model.py:179, model/DrugLAMP.py:35-37) in one
+ * pass: dx[b, l, c] = g[b, ((c*L + l) / C) % (L/S), (c*L + l) % C] / S with g (B, L/S, C) contiguous.
+ * Replaces dl_site_pool_bwd + dl_transpose (two passes over the 9x larger tensor). */
+int dl_site_pool_view_bwd(const void* g, void* dx, int64_t B, int32_t S, int32_t L, int32_t C, int32_t dtype,
+                          void* stream);
 
 /* ProteinCNN input (model/basic_model.py:171-173: nn.Embedding(27, 127, padding_idx=0), then
  * torch.cat with the fill mask): out[r, 0:127] = table[tokens[r], :], out[r, 127] = fill[r], written

@@ -1,0 +1,115 @@
+"""GPU: the fused feed-forward kernels dl_ffn_fwd / dl_ffn_bwd (two chained tcgen05 GEMMs, hidden tile on
+chip) against (a) a float64 restatement of model/PMMA/mlp.py:44-50 + the residual add of
+model/PMMA/block.py:45-47 and (b) the two-GEMM dl_gemm path, including identical dropout masks."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+D = 256
+
+
+def _mk(M, Dh, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g, device="cuda", dtype=torch.float32)
+    x = (r(M, D) * scale).bfloat16()
+    w1 = (r(Dh, D) / 16).bfloat16()
+    w2 = (r(D, Dh) / (Dh ** 0.5)).bfloat16()
+    b1, b2 = r(Dh) * 0.1, r(D) * 0.1
+    res = r(M, D).bfloat16()
+    return x, w1, b1, w2, b2, res
+
+
+def _unfused_fwd(x, w1, b1, w2, b2, res, p, s1, s2):
+    from druglamp_b200 import kernels as K
+    hd = torch.empty((x.shape[0], w1.shape[0]), dtype=x.dtype, device=x.device)
+    dact = torch.empty_like(hd)
+    K.mm(x, w1, hd, bias=b1, act=K.ACT_GELU, pre=dact, drop=(p, s1), pre_mode=1)
+    y = K.mm(hd, w2, bias=b2, res=res, drop=(p, s2))
+    return y, hd, dact
+
+
+@pytest.mark.parametrize("M,Dh", [(128, 128), (300, 256), (1000, 384), (4096, 1024), (128 * 150 + 17, 512)])
+def test_ffn_fwd_matches_float64_and_two_gemm_path(M, Dh):
+    from druglamp_b200 import kernels as K
+    x, w1, b1, w2, b2, res = _mk(M, Dh, seed=M + Dh)
+    assert K.ffn_supported(x, w1, w2)
+    y, hd, dact = K.ffn_fwd(x, w1, b1, w2, b2, res, (0.0, 0, 0), keep=True)
+    torch.cuda.synchronize()
+    pre = x.double() @ w1.double().t() + b1.double()
+    h_ref = torch.nn.functional.gelu(pre)
+    assert (hd.double() - h_ref).abs().max() <= 2e-2 * h_ref.abs().max()          # bf16 storage + tanh-form GELU
+    y_ref = hd.double() @ w2.double().t() + b2.double() + res.double()             # second GEMM on the stored hidden
+    assert (y.double() - y_ref).abs().max() <= 1e-2 * y_ref.abs().max()
+    pr = pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    assert (dact.double() - pr.grad).abs().max() <= 2e-2
+    y2, hd2, dact2 = _unfused_fwd(x, w1, b1, w2, b2, res, 0.0, 0, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(hd, hd2) and torch.equal(dact, dact2)
+    assert (y.float() - y2.float()).abs().max() <= 2 ** -7 * y2.float().abs().max()   # at most one bf16 ulp
+    # forward-only scoring: nothing but y is written
+    y3, h3, d3 = K.ffn_fwd(x, w1, b1, w2, b2, res, (0.0, 0, 0), keep=False)
+    torch.cuda.synchronize()
+    assert h3 is None and d3 is None and torch.equal(y3, y)
+
+
+@pytest.mark.parametrize("M,Dh", [(640, 1024), (128 * 149, 256)])
+def test_ffn_fwd_dropout_masks_are_those_of_dl_gemm(M, Dh):
+    from druglamp_b200 import kernels as K
+    x, w1, b1, w2, b2, res = _mk(M, Dh, seed=7)
+    p, s1, s2 = 0.1, 0x1234567887654321, 0x0FEDCBA987654321
+    y, hd, dact = K.ffn_fwd(x, w1, b1, w2, b2, None, (p, s1, s2), keep=True)
+    y2, hd2, dact2 = _unfused_fwd(x, w1, b1, w2, b2, None, p, s1, s2)
+    torch.cuda.synchronize()
+    assert torch.equal(hd, hd2) and torch.equal(dact, dact2)
+    frac = float((hd == 0).float().mean())
+    assert 0.08 < frac < 0.12
+    assert torch.equal(y == 0, y2 == 0)
+    assert (y.float() - y2.float()).abs().max() <= 2 ** -7 * y2.float().abs().max()
+
+
+@pytest.mark.parametrize("M,Dh", [(128, 128), (333, 256), (4096, 1024), (128 * 150 + 5, 384)])
+def test_ffn_bwd_matches_float64_and_two_gemm_path(M, Dh):
+    from druglamp_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + Dh)
+    r = lambda *s: torch.randn(*s, generator=g, device="cuda", dtype=torch.float32)
+    g2 = r(M, D).bfloat16()
+    w1 = (r(Dh, D) / 16).bfloat16()
+    w2 = (r(D, Dh) / 16).bfloat16()
+    dact = r(M, Dh).bfloat16()
+    dpre, dx = K.ffn_bwd(g2, w1, w2, dact)
+    torch.cuda.synchronize()
+    dpre_ref = (g2.double() @ w2.double()) * dact.double()
+    assert (dpre.double() - dpre_ref).abs().max() <= 1e-2 * dpre_ref.abs().max()
+    dx_ref = dpre.double() @ w1.double()
+    assert (dx.double() - dx_ref).abs().max() <= 1e-2 * dx_ref.abs().max()
+    dpre2 = K.mm(g2, w2, tb=True, mul_aux=dact, mul_mode=K.MUL_VALUE)
+    dx2 = K.mm(dpre2, w1, tb=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dpre, dpre2)
+    assert (dx.float() - dx2.float()).abs().max() <= 2 ** -7 * dx2.float().abs().max()
+
+
+def test_ffn_function_fused_equals_two_gemm_function():
+    """FFNFn with and without the fused kernels: same output, same input / parameter gradients."""
+    import druglamp_b200 as Dl
+    from druglamp_b200 import functions as Fn
+    Dl.set_compute_dtype(torch.bfloat16)
+    try:
+        M, Dh = 2048, 1024
+        x, w1, b1, w2, b2, res = _mk(M, Dh, seed=11)
+        outs = []
+        for fused in (True, False):
+            Fn.FUSED_FFN = fused
+            ps = [t.float().clone().requires_grad_(True) for t in (x, w1, b1, w2, b2, res)]
+            y = Fn.FFNFn.apply(ps[0], ps[1], ps[2], ps[3], ps[4], ps[5], 0.1, 123, 456)
+            gy = torch.sin(torch.arange(y.numel(), device="cuda", dtype=torch.float32)).view_as(y)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            outs.append([y.detach().float()] + [p.grad.float() for p in ps])
+        for a, b in zip(*outs):
+            assert (a - b).abs().max() <= 1e-2 * b.abs().max() + 1e-6
+    finally:
+        Fn.FUSED_FFN = True
+        Dl.set_compute_dtype(torch.float32)

@@ -564,3 +564,75 @@ def test_decoder_head_small_kernels_equal_the_gemm_path():
         _close(p.grad, q.grad, 2e-2, n)
     for (n, p), (_, q) in zip(a.named_buffers(), b.named_buffers()):
         _close(p, q, 5e-3, n)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,R,C", [(3, 2304, 128), (2, 72, 40), (1, 64, 64)])
+def test_bn_transpose_and_site_pool_view_bwd(dtype, B, R, C):
+    """dl_bn_transpose (BatchNorm affine + (B,L,C)->(B,C,L)) and dl_site_pool_view_bwd (the gradient through
+    transpose -> .view(B,L,C) -> .view(B,S,L/S,C).mean(1), model/basic_model.py:179 + model/DrugLAMP.py:35-37)
+    against plain PyTorch on the same values."""
+    from druglamp_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + R + C)
+    x = torch.randn(B, R, C, generator=g, device="cuda").to(dtype)
+    mean = torch.randn(C, generator=g, device="cuda") * 0.2
+    rstd = torch.rand(C, generator=g, device="cuda") + 0.5
+    gamma = torch.randn(C, generator=g, device="cuda")
+    beta = torch.randn(C, generator=g, device="cuda")
+    assert K.bn_transpose_ok(x)
+    y = K.bn_transpose(x)
+    assert torch.equal(y, x.transpose(1, 2).contiguous())
+    y = K.bn_transpose(x, mean, rstd, gamma, beta)
+    ref = ((x.float() - mean) * rstd * gamma + beta).transpose(1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (y.float() - ref).abs().max() <= tol * ref.abs().max()
+    for S in (9, 4, 1):
+        if R % S:
+            continue
+        xr = x.float().clone().requires_grad_(True)
+        pooled = xr.transpose(1, 2).contiguous().view(B, R, C).view(B, S, R // S, C).mean(1)
+        gp = torch.randn(pooled.shape, generator=g, device="cuda").to(dtype)
+        pooled.backward(gp.float())
+        dx = K.site_pool_view_bwd(gp, S)
+        assert dx.shape == x.shape
+        assert (dx.float() - xr.grad).abs().max() <= (1e-6 if dtype == torch.float32 else 1e-2) * xr.grad.abs().max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("site_len", [0, 9])
+def test_protein_cnn_fused_tail_equals_separate_passes(dtype, site_len):
+    """ProteinCNN with the fused tail (statistics -> normalise-and-transpose -> site mean, gradient mapped
+    straight back) against the separate BatchNorm / transpose / site-pool passes: outputs, BN buffers and
+    every parameter gradient."""
+    import druglamp_b200 as D
+    from druglamp_b200 import modules as M
+    D.set_compute_dtype(dtype)
+    try:
+        torch.manual_seed(3)
+        B, Lr = 3, 2304
+        tok = torch.randint(0, 27, (B, Lr), device="cuda")
+        fill = (tok == 0).float()
+        res = []
+        for fused in (True, False):
+            M.CNN_TAIL_FUSED = fused
+            torch.manual_seed(4)
+            cnn = M.ProteinCNN(128, [128, 128, 128], [3, 6, 9]).cuda().train(True)
+            out = cnn(tok, fill, site_len=site_len)
+            w = torch.cos(torch.arange(out.numel(), device="cuda", dtype=torch.float32)).view_as(out)
+            (out.float() * w).sum().backward()
+            torch.cuda.synchronize()
+            res.append((out.detach().float(), {k: p.grad.float().clone() for k, p in cnn.named_parameters()},
+                        {k: v.clone() for k, v in cnn.state_dict().items() if "running" in k}))
+        (o1, g1, s1), (o2, g2, s2) = res
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        assert o1.shape == (B, Lr // site_len if site_len else Lr, 128)
+        assert (o1 - o2).abs().max() <= tol * o2.abs().max()
+        for k in s1:
+            assert (s1[k] - s2[k]).abs().max() <= 1e-5 * s2[k].abs().max() + 1e-7, k
+        for k in g1:
+            a, b = g1[k].double().flatten(), g2[k].double().flatten()
+            cos = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+            assert cos >= (0.99999 if dtype == torch.float32 else 0.995), (k, cos)
+    finally:
+        M.CNN_TAIL_FUSED = True
+        D.set_compute_dtype(torch.float32)

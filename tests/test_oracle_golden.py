@@ -67,3 +67,18 @@ def test_cm_losses_and_margin_schedule(model_shapes):
         l = R.cross_modality(sd2, "cm_model.", o["vp"].detach(), o["xp"].detach(), o["vd"].detach(),
                              o["xd"].detach(), b.meta, m, True)
         assert abs(l.item() - fx["cm_losses"][step]) < 2e-4 * max(abs(fx["cm_losses"][step]), 1e-3), step
+
+
+def _nt_xent_inputs():
+    """Closed-form (RNG-free) inputs of the NT-Xent known-answer test."""
+    b, d = 6, 16
+    i = torch.arange(b * d, dtype=torch.float64)
+    return torch.sin(0.37 * i + 0.1).view(b, d).float(), torch.cos(0.23 * i - 0.4).view(b, d).float()
+
+
+def test_nt_xent_known_answer_from_the_reference():
+    """model/self_supervised_learning.py:168-182 (`nt_xent_loss`) evaluated by the unmodified reference on
+    the closed-form inputs above returned 61.0732421875 (generated in the build container through
+    oracle/ref_shim.py; tests/test_oracle_vs_reference.py re-checks it live)."""
+    q, k = _nt_xent_inputs()
+    assert abs(float(R.nt_xent(q, k, 0.1)) - 61.0732421875) <= 1e-4

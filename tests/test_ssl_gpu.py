@@ -79,3 +79,51 @@ def test_ssl_losses_and_grads_match_reference_fixture(dtype, tol, gtol):
             assert errs[0][0] <= gtol, errs[0]
     finally:
         D.set_compute_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 3e-2)])
+def test_drug_simclr_nt_xent_matches_oracle(dtype, tol):
+    """SSL(drug_ssl_type='simclr').drug_simclr (model/self_supervised_learning.py:35-41,168-182: both
+    projectors, then NT-Xent over the 2b x 2b similarity matrix without its diagonal) against the oracle:
+    loss, input gradients and projector weight gradients."""
+    import druglamp_b200 as D
+    from druglamp_b200.ssl import SSL
+    from oracle import restatement as R
+    D.set_compute_dtype(dtype)
+    try:
+        B, Ld, C = 4, 6, 128
+        g = torch.Generator().manual_seed(21)
+        vd, xd = torch.randn(B, Ld, C, generator=g), torch.randn(B, Ld, C, generator=g)
+        ssl = SSL(torch.nn.Identity(), 640, drug_ssl_type="simclr").cuda().train(True)
+        with torch.no_grad():
+            ssl.drug_simclr(vd.cuda(), xd.cuda())              # materialises the lazy projectors
+        shapes = {k: tuple(v.shape) for k, v in ssl.state_dict().items()}
+        sd = R.deterministic_state(shapes)
+        ssl.load_state_dict(sd, strict=True)
+        a, b = vd.cuda().requires_grad_(True), xd.cuda().requires_grad_(True)
+        ssl.zero_grad()
+        loss = ssl.drug_simclr(a, b)
+        loss.backward()
+        torch.cuda.synchronize()
+        sdr = {"ssl_model." + k: v.clone() for k, v in sd.items()}
+        for k, v in sdr.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(True)
+        ar, br = vd.clone().requires_grad_(True), xd.clone().requires_grad_(True)
+        q = R._simsiam_mlp(sdr, "ssl_model.net.projector.", ar.reshape(-1, C), True)
+        k_ = R._simsiam_mlp(sdr, "ssl_model.llm_net.projector.", br.reshape(-1, C), True)
+        ref = R.nt_xent(q, k_, 0.1)
+        ref.backward()
+        assert abs(float(loss) - float(ref)) <= tol * abs(float(ref)), (float(loss), float(ref))
+
+        def cos(x, y):
+            x, y = x.detach().double().flatten().cpu(), y.detach().double().flatten()
+            return float((x * y).sum() / (x.norm() * y.norm()).clamp_min(1e-30))
+        # bf16: logits of magnitude ~100 (temperature 0.1) carry ~0.5 of rounding, the softmax is that sharp
+        bar = 0.9999 if dtype == torch.float32 else 0.95
+        assert cos(a.grad, ar.grad) >= bar and cos(b.grad, br.grad) >= bar
+        for name in ("net.projector.0.weight", "net.projector.6.weight", "llm_net.projector.3.weight"):
+            p = dict(ssl.named_parameters())[name]
+            assert cos(p.grad, sdr["ssl_model." + name].grad) >= bar, name
+    finally:
+        D.set_compute_dtype(torch.float32)
