@@ -65,6 +65,26 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// the same with thread-block clusters of `cluster_x` CTAs along x (CTA pairs for cta_group::2 kernels)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster_x,
+                                    cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // DL_LAUNCH((kernel<T>), grid, block, smem, stream, args...): parenthesise templated kernel names
 #define DL_LAUNCH(kernel, grid, block, smem, stream, ...) \
   (void)dl::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)

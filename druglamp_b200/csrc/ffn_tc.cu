@@ -57,11 +57,6 @@ struct FfnParams {
   uint32_t idesc1, idesc2;
 };
 
-__device__ __forceinline__ uint64_t desc_k(uint32_t base, int kk) {
-  // K-major operand in [rows x 128 B] blocks kBlk apart: 16 elements (32 B) per MMA, 4 MMAs per block
-  return ptx::make_smem_desc(base + (uint32_t)(kk >> 2) * kBlk + (uint32_t)(kk & 3) * 32, 16, 1024);
-}
-
 // MODE 0: forward (K-major weights, bias + GELU (+ derivative) + dropout, then bias + dropout + residual)
 // MODE 1: backward (MN-major weights, multiply by the stored derivative, plain dX)
 template <int MODE>
@@ -118,50 +113,60 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_wait();
   const int NC = p.NC;
 
+  // Producer and issuer loops run warp-uniformly (all lanes wait and keep the loop state in uniform registers,
+  // one elected lane issues): as single-lane divergent regions every tcgen05.mma paid an R2UR + ELECT sequence.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------------ TMA producer
-      uint32_t it = 0, ti = 0;
-      auto slot_acquire = [&]() -> uint32_t {
-        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-        ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kUnit);
-        ++it;
-        return s;
-      };
+      const bool leader = ptx::elect_one();
+      uint32_t s = 0, ph = 0, ti = 0;
+      auto slot_next = [&]() { if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; } };
       auto load_b1 = [&](int c) {          // chunk c of the first GEMM's weights: two units of K = 128
         for (int u = 0; u < 2; ++u) {
-          const uint32_t s = slot_acquire();
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
-          if constexpr (!BMN) {            // [Dh, 256] K-major: two [128 rows x 64 k] blocks
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(full, kUnit);
+            if constexpr (!BMN) {          // [Dh, 256] K-major: two [128 rows x 64 k] blocks
 #pragma unroll
-            for (int j = 0; j < 2; ++j) ptx::tma_load_2d(dst + j * kBlk, &tmB1, full, (2 * u + j) * 64, c * kCh);
-          } else {                         // [256 (k), Dh] MN-major: per 64-wide MN block, 128 k rows
+              for (int j = 0; j < 2; ++j) ptx::tma_load_2d(dst + j * kBlk, &tmB1, full, (2 * u + j) * 64, c * kCh);
+            } else {                       // [256 (k), Dh] MN-major: per 64-wide MN block, 128 k rows
 #pragma unroll
-            for (int blk = 0; blk < 2; ++blk)
+              for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
-              for (int kq = 0; kq < 2; ++kq)
-                ptx::tma_load_2d(dst + blk * kBlk + kq * 8192, &tmB1, full, c * kCh + blk * 64, u * 128 + kq * 64);
+                for (int kq = 0; kq < 2; ++kq)
+                  ptx::tma_load_2d(dst + blk * kBlk + kq * 8192, &tmB1, full, c * kCh + blk * 64, u * 128 + kq * 64);
+            }
           }
+          __syncwarp();
+          slot_next();
         }
       };
       auto load_b2 = [&](int c) {          // chunk c of the second GEMM's weights: two units of K = 64
         for (int u = 0; u < 2; ++u) {
-          const uint32_t s = slot_acquire();
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
-          if constexpr (!BMN) {            // [256, Dh] K-major: one [256 rows x 64 k] block
-            ptx::tma_load_2d(dst, &tmB2, full, c * kCh + u * 64, 0);
-          } else {                         // [Dh (k), 256] MN-major: four 64-wide MN blocks of 64 k rows
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(full, kUnit);
+            if constexpr (!BMN) {          // [256, Dh] K-major: one [256 rows x 64 k] block
+              ptx::tma_load_2d(dst, &tmB2, full, c * kCh + u * 64, 0);
+            } else {                       // [Dh (k), 256] MN-major: four 64-wide MN blocks of 64 k rows
 #pragma unroll
-            for (int blk = 0; blk < 4; ++blk) ptx::tma_load_2d(dst + blk * 8192, &tmB2, full, blk * 64, c * kCh + u * 64);
+              for (int blk = 0; blk < 4; ++blk) ptx::tma_load_2d(dst + blk * 8192, &tmB2, full, blk * 64, c * kCh + u * 64);
+            }
           }
+          __syncwarp();
+          slot_next();
         }
       };
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
         ptx::mbar_wait(bar_aempty, (ti & 1) ^ 1u);
-        ptx::mbar_arrive_expect_tx(bar_afull, kABytes);
+        if (leader) {
+          ptx::mbar_arrive_expect_tx(bar_afull, kABytes);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ptx::tma_load_2d(sA + j * kBlk, &tmA, bar_afull, j * 64, t * 128);
+          for (int j = 0; j < 4; ++j) ptx::tma_load_2d(sA + j * kBlk, &tmA, bar_afull, j * 64, t * 128);
+        }
+        __syncwarp();
         load_b1(0);
         if (NC > 1) load_b1(1);
         for (int c = 0; c < NC; ++c) {          // the order the issuer consumes them in
@@ -171,33 +176,40 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------------ MMA issuer
-      uint32_t it = 0, g1 = 0, g2 = 0, ti = 0;
-      auto unit_wait = [&]() -> uint32_t {
-        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-        ptx::mbar_wait(bar_full + 8 * s, ph);
-        ptx::tc_fence_after();
-        return s;
-      };
+      // descriptor templates: only the 14-bit start-address field (16-byte units) changes per unit / K step
+      const uint64_t k_tmpl = ptx::make_smem_desc(0, 16, 1024);                        // K-major operands
+      const uint64_t b1_tmpl = BMN ? ptx::make_smem_desc(0, kBlk, 1024) : k_tmpl;      // first GEMM's weights
+      const uint64_t b2_tmpl = BMN ? ptx::make_smem_desc(0, 8192, 1024) : k_tmpl;      // second GEMM's weights
+      constexpr uint32_t kStepMn = 2048 >> 4, kStepK = 32 >> 4, kBlkU = kBlk >> 4;
+      auto addr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFF) >> 4); };
+      const bool leader = ptx::elect_one();
+      uint32_t s = 0, ph = 0, g1 = 0, g2 = 0, ti = 0;
+      auto slot_next = [&]() { if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; } };
       auto mma1 = [&]() {                  // chunk accumulator (g1 & 1) = A B1_chunk, K = 256
-        const uint32_t sb = g1 & 1, ph = (g1 >> 1) & 1;
-        ptx::mbar_wait(bar_sempty + 8 * sb, ph ^ 1u);
+        const uint32_t sb = g1 & 1, sph = (g1 >> 1) & 1;
+        ptx::mbar_wait(bar_sempty + 8 * sb, sph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t acc = tmem + sb * kCh;
         for (int u = 0; u < 2; ++u) {
-          const uint32_t s = unit_wait();
-          const uint32_t ub = sRing + s * kUnit;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint64_t a0 = k_tmpl | addr(sA + (uint32_t)u * 2 * kBlk), b0 = b1_tmpl | addr(sRing + s * kUnit);
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t ad = desc_k(sA, 8 * u + kk);
-            const uint64_t bd = BMN ? ptx::make_smem_desc(ub + (uint32_t)kk * 2048, kBlk, 1024) : desc_k(ub, kk);
-            ptx::mma_ss<false>(acc, ad, bd, p.idesc1, (uint32_t)((u | kk) != 0));
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t ad = a0 + (uint64_t)((kk >> 2) * kBlkU + (kk & 3) * kStepK);
+              const uint64_t bd = b0 + (uint64_t)(BMN ? kk * kStepMn : (kk >> 2) * kBlkU + (kk & 3) * kStepK);
+              ptx::mma_ss<false>(acc, ad, bd, p.idesc1, (uint32_t)((u | kk) != 0));
+            }
+            ptx::mma_commit(bar_empty + 8 * s);
           }
-          ptx::mma_commit(bar_empty + 8 * s);
-          ++it;
+          __syncwarp();
+          slot_next();
         }
-        ptx::mma_commit(bar_sfull + 8 * sb);
+        if (leader) ptx::mma_commit(bar_sfull + 8 * sb);
+        __syncwarp();
         ++g1;
       };
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
@@ -206,37 +218,40 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int issued = 0;
         mma1(); ++issued;
         if (NC > 1) { mma1(); ++issued; }
-        if (issued == NC) ptx::mma_commit(bar_aempty);
+        if (issued == NC && leader) ptx::mma_commit(bar_aempty);
         for (int c = 0; c < NC; ++c) {
           // chunk c + 2's first GEMM goes first: its accumulator buffer is free as soon as the epilogue of
           // chunk c has READ tensor memory, long before that epilogue hands over its E tile -- the weight
           // ring keeps flowing instead of holding B2(c) while nothing can be issued
           if (c + 2 < NC) {
             mma1();
-            if (++issued == NC) ptx::mma_commit(bar_aempty);
+            if (++issued == NC && leader) ptx::mma_commit(bar_aempty);
           }
-          const uint32_t sb = g2 & 1, ph = (g2 >> 1) & 1;
-          ptx::mbar_wait(bar_efull + 8 * sb, ph);
+          const uint32_t sb = g2 & 1, eph = (g2 >> 1) & 1;
+          ptx::mbar_wait(bar_efull + 8 * sb, eph);
           if (c == 0) ptx::mbar_wait(bar_yempty, (ti & 1) ^ 1u);      // the previous tile's Y has been read
           ptx::tc_fence_after();
           const uint32_t eb = sE + sb * kEBytes;
           for (int u = 0; u < 2; ++u) {
-            const uint32_t s = unit_wait();
-            const uint32_t ub = sRing + s * kUnit;
+            ptx::mbar_wait(bar_full + 8 * s, ph);
+            ptx::tc_fence_after();
+            const uint64_t a0 = k_tmpl | addr(eb + (uint32_t)u * kBlk), b0 = b2_tmpl | addr(sRing + s * kUnit);
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = ptx::make_smem_desc(eb + (uint32_t)u * kBlk + (uint32_t)kk * 32, 16, 1024);
-              const uint64_t bd = BMN ? ptx::make_smem_desc(ub + (uint32_t)kk * 2048, 8192, 1024)
-                                      : ptx::make_smem_desc(ub + (uint32_t)kk * 32, 16, 1024);
-              ptx::mma_ss<false>(tmem + 2 * kCh, ad, bd, p.idesc2, (uint32_t)((c | u | kk) != 0));
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::mma_ss<false>(tmem + 2 * kCh, a0 + (uint64_t)(kk * kStepK), b0 + (uint64_t)(kk * (BMN ? kStepMn : kStepK)),
+                                   p.idesc2, (uint32_t)((c | u | kk) != 0));
+              ptx::mma_commit(bar_empty + 8 * s);
             }
-            ptx::mma_commit(bar_empty + 8 * s);
-            ++it;
+            __syncwarp();
+            slot_next();
           }
-          ptx::mma_commit(bar_eempty + 8 * sb);
+          if (leader) ptx::mma_commit(bar_eempty + 8 * sb);
+          __syncwarp();
           ++g2;
         }
-        ptx::mma_commit(bar_yfull);
+        if (leader) ptx::mma_commit(bar_yfull);
+        __syncwarp();
       }
     }
   } else if (warp < 2 + kEpiWarps) {

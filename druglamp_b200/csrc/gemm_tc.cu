@@ -97,18 +97,27 @@ struct GemmParams {
 // every load / store instruction touch 32 different 128-byte lines (the L1 retires about one per
 // cycle: 2048 cycles per 128 x 256 tile and operand, as long as the tile's MMAs at K = 256); through
 // shared memory the same bytes cost a few hundred cycles and no LSU address traffic at all.
-template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false>
+// CTA2 (bf16 operands, BN >= 128): a pair of CTAs (a cluster of two, one TPC) works on two vertically
+// adjacent 128-row tiles as ONE 256 x BN tcgen05.mma.cta_group::2 tile.  Each CTA loads its own 128 rows of A
+// but only HALF of the B tile (BN/2 columns); the leader CTA's thread issues every MMA for both, reading the
+// operands out of both shared memories and writing both tensor memories.  The L2 -> SM operand traffic per
+// output tile drops by a third (256-wide tiles: 48 -> 32 KB per K-block and CTA) and the smaller stages make
+// the ring deeper -- the K <= 512 forward shapes and the split-K weight gradients are bound by exactly that feed.
+template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false, bool CTA2 = false>
 struct Cfg {
   static_assert(!TMAEPI || (BN == 256 && !TF32), "TMA epilogue: bf16 operands, 256-wide tiles");
+  static_assert(!CTA2 || (!TF32 && !SPLIT && BN >= 128), "CTA pairs: bf16 operands, tiles at least 128 wide");
   static constexpr int ELEM = TF32 ? 4 : 2;
   static constexpr int KE = 128 / ELEM;   // K elements per K-block
   static constexpr int UK = 32 / ELEM;    // K elements per tcgen05.mma
   static constexpr int MNB = 128 / ELEM;  // MN elements per 128-byte block (MN-major operands)
+  static constexpr int BNL = CTA2 ? BN / 2 : BN;                   // B columns this CTA holds
   static constexpr int A_BYTES = BM * 128;
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;             // what TMA delivers per stage
+  static constexpr int B_BYTES = BNL * 128;
+  static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;             // what TMA delivers per stage (and CTA)
   static constexpr int STAGE_BYTES = SPLIT ? 2 * LOAD_BYTES : LOAD_BYTES;
-  static constexpr int STAGES = TMAEPI ? 3 : SPLIT ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4))
+  static constexpr int STAGES = CTA2 ? (TMAEPI ? 4 : (BN == 256 ? 6 : 8))
+                                : TMAEPI ? 3 : SPLIT ? ((BN == 256) ? 2 : (BN == 128 ? 3 : 4))
                                                : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int EPI_BYTES = TMAEPI ? kEpiWarps * 4096 : 0;   // per-warp staging slabs
   static constexpr int BAR_BYTES = 512;
@@ -123,12 +132,13 @@ struct Tile {
   unsigned zb;
 };
 
+// mrank / mstep: CTA pairs decode a tile PAIR index; CTA `mrank` of the pair owns its mrank-th 128 rows
 template <int BN, int KE>
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t, int mrank = 0, int mstep = 1) {
   Tile T;
   const uint32_t z = p.fd_perz.div((uint32_t)t), r = (uint32_t)t - z * p.fd_perz.d;
   const uint32_t mi = p.fd_nt.div(r), ni = r - mi * p.fd_nt.d;
-  T.m0 = (int)mi * BM;
+  T.m0 = ((int)mi * mstep + mrank) * BM;
   T.n0 = (int)ni * BN;
   T.zb = p.fd_splits.div(z);
   const uint32_t ks = z - T.zb * p.fd_splits.d;
@@ -578,12 +588,12 @@ __device__ __forceinline__ void tma_chunk16(const GemmParams& p, const EpiFlags&
   ptx::sts128(a1, w[4], w[5], w[6], w[7]);
 }
 
-template <int BN, bool TF32, bool SPLIT, bool TMAEPI>
+template <int BN, bool TF32, bool SPLIT, bool TMAEPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmIn,
                const GemmParams p) {
-  using C = Cfg<BN, TF32, SPLIT, TMAEPI>;
+  using C = Cfg<BN, TF32, SPLIT, TMAEPI, CTA2>;
   static_assert(!SPLIT || TF32, "SPLIT applies to fp32 operands");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -599,19 +609,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 4 + kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pairs: both CTAs walk the same sequence of tile pairs; `rank` picks the 128 rows (and the half of B)
+  const int rank = CTA2 ? (int)ptx::cluster_ctarank() : 0;
+  const int tile_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kMStep = CTA2 ? 2 : 1;
   pdl_trigger();
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
+      // pair: the leader's barrier takes its own expect_tx arrival and the peer producer's remote arrival
+      ptx::mbar_init(bar_full + 8 * s, CTA2 ? 2 : 1);
       ptx::mbar_init(bar_empty + 8 * s, p.colsum_a ? 1 + kColsumWarps : 1);
-      ptx::mbar_init(bar_conv + 8 * s, 32 * kEpiWarps);
+      // pair: "stage landed" forwarded by the leader's issuer to the peer's column-sum warps (colsum_a)
+      ptx::mbar_init(bar_conv + 8 * s, CTA2 ? 1 : 32 * kEpiWarps);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_tfull + 8 * i, 1);
-      ptx::mbar_init(bar_tempty + 8 * i, kEpiWarps);
+      // pair: the leader issues for both, so it waits for the epilogue warps of both CTAs
+      ptx::mbar_init(bar_tempty + 8 * i, CTA2 ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < kEpiWarps; ++i) ptx::mbar_init(bar_in + 8 * i, 1);
     if constexpr (TMAEPI) {
@@ -620,30 +638,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::TMEM_COLS>(ptx::smem_u32(tmem_slot));
+  if (warp == 1) {
+    if constexpr (CTA2) ptx::tmem_alloc_2sm<C::TMEM_COLS>(ptx::smem_u32(tmem_slot));
+    else ptx::tmem_alloc<C::TMEM_COLS>(ptx::smem_u32(tmem_slot));
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync_all();      // the peer's barriers exist before anything arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // everything above overlaps the tail of the previous kernel; nothing below (TMA loads, epilogue
   // reads and writes) may start before that kernel's results are visible
   pdl_wait();
 
+  // Producer and issuer run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers and keep the loop
+  // state; one elected lane issues the TMA / tcgen05 instructions).  As single-lane divergent regions the
+  // compiler kept every descriptor in per-thread registers and paid R2UR + ELECT for each tcgen05.mma: ~130
+  // dependent instructions = ~790 cycles per K-block of four 128-cycle MMAs, which bounded every long-K GEMM.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------ TMA producer
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const Tile T = decode_tile<BN, C::KE>(p, t);
+      // pair: every load of either CTA is counted on the LEADER's barrier (shared::cluster address)
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int x0, int x1, int x2, int x3, int x4) {
+        if constexpr (CTA2) ptx::tma_load_5d_2sm(dst, m, bar, x0, x1, x2, x3, x4);
+        else ptx::tma_load_5d(dst, m, bar, x0, x1, x2, x3, x4);
+      };
+      const int nb_off = rank * C::BNL;             // this CTA's columns of the B tile
+      const bool leader_lane = ptx::elect_one();
+      uint32_t s = 0, ph = 0;
+      for (int t = tile_first; t < p.total_tiles; t += tile_step) {
+        const Tile T = decode_tile<BN, C::KE>(p, t, rank, kMStep);
         const int a2 = p.a_on[0] ? T.b0 : 0, a3 = p.a_on[1] ? T.b1 : 0, a4 = p.a_on[2] ? T.b2 : 0;
         const int c2 = p.b_on[0] ? T.b0 : 0, c3 = p.b_on[1] ? T.b1 : 0, c4 = p.b_on[2] ? T.b2 : 0;
-        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
+        for (int kb = 0; kb < T.nkb; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t full = bar_full + 8 * s;
-          ptx::mbar_arrive_expect_tx(full, C::LOAD_BYTES);
+          uint32_t full = bar_full + 8 * s;
           const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
+          if (++s == (uint32_t)C::STAGES) { s = 0; ph ^= 1u; }
+          if (p.dbg == 5) {                     // bring-up: barrier protocol only, no loads (results are garbage)
+            if (leader_lane) {
+              if (!CTA2 || rank == 0) ptx::mbar_arrive_expect_tx(full, 0);
+              else ptx::mbar_arrive_remote(ptx::mapa(full, 0));
+            }
+            continue;
+          }
           const int k0 = (T.kb_begin + kb) * C::KE;
           int ka = k0, kbb = k0, a_row = T.m0, a4r = a4, c4r = c4;
           if (p.conv_cin) {
@@ -662,58 +700,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             kbb = ka + (p.kred_tap ? T.b0 : 0) + p.kred_shift;
             a4r = c4r = rb;
           }
-          if (!p.a_mn) {
-            ptx::tma_load_5d(sA, &tmA, full, ka, a_row, a2, a3, a4r);
-          } else {
+          if (leader_lane) {
+            if constexpr (CTA2) {
+              const uint32_t lfull = ptx::mapa(full, 0);
+              if (rank == 0) ptx::mbar_arrive_expect_tx(full, 2 * C::LOAD_BYTES);
+              else ptx::mbar_arrive_remote(lfull);
+              full = lfull;
+            } else {
+              ptx::mbar_arrive_expect_tx(full, C::LOAD_BYTES);
+            }
+            if (!p.a_mn) {
+              load(sA, &tmA, full, ka, a_row, a2, a3, a4r);
+            } else {
 #pragma unroll
-            for (int blk = 0; blk < BM / C::MNB; ++blk)
-              ptx::tma_load_5d(sA + blk * C::KE * 128, &tmA, full, T.m0 + blk * C::MNB, ka, a2, a3, a4r);
-          }
-          if (!p.b_mn) {
-            ptx::tma_load_5d(sB, &tmB, full, kbb, T.n0, c2, c3, c4r);
-          } else {
+              for (int blk = 0; blk < BM / C::MNB; ++blk)
+                load(sA + blk * C::KE * 128, &tmA, full, T.m0 + blk * C::MNB, ka, a2, a3, a4r);
+            }
+            if (!p.b_mn) {
+              load(sB, &tmB, full, kbb, T.n0 + nb_off, c2, c3, c4r);
+            } else {
 #pragma unroll
-            for (int blk = 0; blk < BN / C::MNB; ++blk)
-              ptx::tma_load_5d(sB + blk * C::KE * 128, &tmB, full, T.n0 + blk * C::MNB, kbb, c2, c3, c4r);
+              for (int blk = 0; blk < C::BNL / C::MNB; ++blk)
+                load(sB + blk * C::KE * 128, &tmB, full, T.n0 + nb_off + blk * C::MNB, kbb, c2, c3, c4r);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      uint32_t it = 0, ti = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
-        const Tile T = decode_tile<BN, C::KE>(p, t);
+    if (rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (pair: the leader, for both)
+      // Launch-invariant halves of the shared-memory descriptors: only the 14-bit start-address field
+      // changes per stage and per K step.  MN-major: bf16 uses SWIZZLE_128B (8-row K atom), tf32 must use
+      // 128B_BASE32B (4-row).
+      constexpr uint32_t kMnSbo = TF32 ? 512 : 1024, kMnType = TF32 ? 1 : 2;
+      const uint64_t a_tmpl = p.a_mn ? ptx::make_smem_desc(0, C::KE * 128, kMnSbo, kMnType) : ptx::make_smem_desc(0, 16, 1024);
+      const uint64_t b_tmpl = p.b_mn ? ptx::make_smem_desc(0, C::KE * 128, kMnSbo, kMnType) : ptx::make_smem_desc(0, 16, 1024);
+      const uint32_t a_kstep = (p.a_mn ? C::UK * 128 : 32) >> 4, b_kstep = (p.b_mn ? C::UK * 128 : 32) >> 4;   // 16-byte units
+      const bool leader_lane = ptx::elect_one();
+      uint32_t s = 0, ph = 0, ti = 0;
+      for (int t = tile_first; t < p.total_tiles; t += tile_step, ++ti) {
+        const Tile T = decode_tile<BN, C::KE>(p, t, rank, kMStep);
         const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
         ptx::mbar_wait(bar_tempty + 8 * ab, aph ^ 1u);     // epilogue has drained this buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem + ab * BN;
-        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
+        for (int kb = 0; kb < T.nkb; ++kb) {
           ptx::mbar_wait((SPLIT ? bar_conv : bar_full) + 8 * s, ph);
           ptx::tc_fence_after();
           const uint32_t sA = base_addr + s * C::STAGE_BYTES, sB = sA + C::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // MN-major: bf16 uses SWIZZLE_128B (8-row K atom), tf32 must use 128B_BASE32B (4-row)
-            constexpr uint32_t kMnSbo = TF32 ? 512 : 1024, kMnType = TF32 ? 1 : 2;
-            const uint64_t ad = p.a_mn ? ptx::make_smem_desc(sA + k * C::UK * 128, C::KE * 128, kMnSbo, kMnType)
-                                       : ptx::make_smem_desc(sA + k * 32, 16, 1024);
-            const uint64_t bd = p.b_mn ? ptx::make_smem_desc(sB + k * C::UK * 128, C::KE * 128, kMnSbo, kMnType)
-                                       : ptx::make_smem_desc(sB + k * 32, 16, 1024);
-            ptx::mma_ss<TF32>(acc, ad, bd, p.idesc, (uint32_t)((kb | k) != 0));
-            if constexpr (SPLIT) {
-              // descriptors address 16-byte units: the lo copies sit LOAD_BYTES above the hi ones
-              constexpr uint64_t kLo = (uint64_t)(C::LOAD_BYTES >> 4);
-              ptx::mma_ss<TF32>(acc, ad + kLo, bd, p.idesc, 1u);
-              ptx::mma_ss<TF32>(acc, ad, bd + kLo, p.idesc, 1u);
+          const uint64_t ad0 = a_tmpl | (uint64_t)((sA & 0x3FFFF) >> 4), bd0 = b_tmpl | (uint64_t)((sB & 0x3FFFF) >> 4);
+          if (leader_lane) {
+            if constexpr (CTA2) {
+              // only the leader's barrier sees the loads complete: tell the peer's column-sum warps.  (Plain
+              // remote arrive: a .release.cluster one compiles to MEMBAR.ALL.GPU, which -- even predicated off for
+              // launches without colsum_a -- cost ~250 cycles per K-block in this loop: 8192^3 1.23 -> 1.46 PFLOP/s.)
+              if (p.colsum_a != nullptr) ptx::mbar_arrive_remote(ptx::mapa(bar_conv + 8 * s, 1));
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ad0 + (uint64_t)(k * a_kstep), bd = bd0 + (uint64_t)(k * b_kstep);
+              if constexpr (CTA2) ptx::mma_ss_2sm(acc, ad, bd, p.idesc, (uint32_t)((kb | k) != 0));
+              else ptx::mma_ss<TF32>(acc, ad, bd, p.idesc, (uint32_t)((kb | k) != 0));
+              if constexpr (SPLIT) {
+                // descriptors address 16-byte units: the lo copies sit LOAD_BYTES above the hi ones
+                constexpr uint64_t kLo = (uint64_t)(C::LOAD_BYTES >> 4);
+                ptx::mma_ss<TF32>(acc, ad + kLo, bd, p.idesc, 1u);
+                ptx::mma_ss<TF32>(acc, ad, bd + kLo, p.idesc, 1u);
+              }
+            }
+            // frees the stage once these MMAs have read it (pair: in both CTAs)
+            if constexpr (CTA2) ptx::mma_commit_2sm(bar_empty + 8 * s);
+            else ptx::mma_commit(bar_empty + 8 * s);
           }
-          ptx::mma_commit(bar_empty + 8 * s);   // frees the stage once these MMAs have read it
+          __syncwarp();
+          if (++s == (uint32_t)C::STAGES) { s = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(bar_tfull + 8 * ab);
+        if (leader_lane) {
+          if constexpr (CTA2) ptx::mma_commit_2sm(bar_tfull + 8 * ab);
+          else ptx::mma_commit(bar_tfull + 8 * ab);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -723,8 +791,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = we >> 2;                     // which column slice of the tile
     const EpiFlags ef = p.c_bf16 ? make_epi_flags<__nv_bfloat16>(p) : make_epi_flags<float>(p);
     uint32_t it = 0, ti = 0, in_phase = 0;
-    for (int tl = blockIdx.x; tl < p.total_tiles; tl += gridDim.x, ++ti) {
-      const Tile T = decode_tile<BN, C::KE>(p, tl);
+    // the accumulator buffer is handed back to the issuing CTA (pair: the leader's barrier, from both CTAs)
+    auto release_acc = [&](uint32_t ab_) {
+      if constexpr (CTA2) ptx::mbar_arrive_remote(ptx::mapa(bar_tempty + 8 * ab_, 0));
+      else ptx::mbar_arrive(bar_tempty + 8 * ab_);
+    };
+    for (int tl = tile_first; tl < p.total_tiles; tl += tile_step, ++ti) {
+      const Tile T = decode_tile<BN, C::KE>(p, tl, rank, kMStep);
       if constexpr (SPLIT) {
         const int tid = threadIdx.x - 64;         // 0 .. 32*kEpiWarps-1
         for (int kb = 0; kb < T.nkb; ++kb, ++it) {
@@ -759,13 +832,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int t = threadIdx.x - 64;
           const int blk = t >> 6, ch = (t >> 3) & 7, rcls = t & 7;
           const bool active = T.n0 == 0;
+          const uint32_t bar_landed = (CTA2 && rank != 0) ? bar_conv : bar_full;
           float acc[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = 0.f;
           for (int kb = 0; kb < T.nkb; ++kb, ++it) {
             const int s = it % C::STAGES;
             const uint32_t ph = (it / C::STAGES) & 1;
-            ptx::mbar_wait(bar_full + 8 * s, ph);
+            ptx::mbar_wait(bar_landed + 8 * s, ph);
             if (active) {
               const uint8_t* src = smem + s * C::STAGE_BYTES + blk * (C::KE * 128) + ((ch ^ rcls) << 4) + rcls * 128;
 #pragma unroll
@@ -838,7 +912,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tma_store_5d(&tmC, slab, T.n0 + cb, row0, T.b0, T.b1, T.b2);
             ptx::bulk_commit();
           }
-          ptx::mbar_arrive(bar_tempty + 8 * ab);
+          release_acc(ab);
         }
         continue;
       }
@@ -860,17 +934,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * ab);
+      if (lane == 0) release_acc(ab);
     }
     if constexpr (TMAEPI) {
       if (lane == 0) ptx::bulk_wait0();          // the slabs must outlive the stores that read them
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync_all();      // neither CTA's shared / tensor memory may go while the other uses it
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<C::TMEM_COLS>(tmem);
+    if constexpr (CTA2) ptx::tmem_dealloc_2sm<C::TMEM_COLS>(tmem);
+    else ptx::tmem_dealloc<C::TMEM_COLS>(tmem);
   }
 }
 
@@ -947,20 +1023,48 @@ int make_epi_map(CUtensorMap* m, const void* ptr, long long cols, long long rows
   return 0;
 }
 
-template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false>
+// CTA pairs: the persistent loop assumes every launched pair is resident at once.  How many pairs the
+// device co-schedules (GPC / TPC floor-sweeping can leave fewer than sm_count / 2) is asked once, for the
+// largest pair configuration (every variant needs one whole SM per CTA).
+int max_cta_pairs() {
+  static int max_pairs = [] {
+    using K = Cfg<256, false, false, false, true>;
+    auto kern = gemm_tc_kernel<256, false, false, false, true>;
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (sm_count() / 2));
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = K::SMEM;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    if (n <= 0 || n > sm_count() / 2) n = sm_count() / 2;
+    if (getenv("DL_GEMM_VERBOSE")) fprintf(stderr, "dl_gemm: %d co-resident CTA pairs on %d SMs\n", n, sm_count());
+    return n;
+  }();
+  return max_pairs;
+}
+
+template <int BN, bool TF32, bool SPLIT = false, bool TMAEPI = false, bool CTA2 = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long long batch,
            cudaStream_t stream, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmIn = nullptr) {
-  using C = Cfg<BN, TF32, SPLIT, TMAEPI>;
+  using C = Cfg<BN, TF32, SPLIT, TMAEPI, CTA2>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI>,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI, CTA2>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   });
   if (attr_err != cudaSuccess)
     return set_error((int)attr_err, "dl_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-  p.idesc = ptx::make_idesc(TF32, p.a_mn != 0, p.b_mn != 0, BM, BN);
-  p.mt = ceil_div(p.M, BM);
+  p.idesc = ptx::make_idesc(TF32, p.a_mn != 0, p.b_mn != 0, CTA2 ? 2 * BM : BM, BN);
+  p.mt = ceil_div(ceil_div(p.M, BM), CTA2 ? 2 : 1);        // CTA pairs: tile PAIRS along M
   p.nt = ceil_div(p.N, BN);
   const long long total = (long long)p.mt * p.nt * batch * p.splits;
   DL_REQUIRE(total < (1ll << 31), "dl_gemm: too many tiles");
@@ -974,9 +1078,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long l
   p.fd_conv.init((uint32_t)(p.conv_cin > 0 ? p.conv_cin : 1));
   p.fd_kred.init((uint32_t)(p.kred_kpb > 0 ? p.kred_kpb : 1));
   p.total_tiles = (int)total;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  DL_LAUNCH((gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI>), grid, kGemmThreads, C::SMEM, stream, tmA, tmB,
-            tmC ? *tmC : tmA, tmIn ? *tmIn : tmA, p);
+  if constexpr (CTA2) {
+    const int pairs = max_cta_pairs();
+    const int grid = 2 * (int)(total < pairs ? total : pairs);
+    (void)launch_cluster_k(gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI, CTA2>, dim3(grid), dim3(kGemmThreads),
+                           (size_t)C::SMEM, 2u, stream, tmA, tmB, tmC ? *tmC : tmA, tmIn ? *tmIn : tmA, p);
+  } else {
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    DL_LAUNCH((gemm_tc_kernel<BN, TF32, SPLIT, TMAEPI, CTA2>), grid, kGemmThreads, C::SMEM, stream, tmA, tmB,
+              tmC ? *tmC : tmA, tmIn ? *tmIn : tmA, p);
+  }
   DL_LAUNCH_CHECK("gemm_tc_kernel");
   count_launch();
   return 0;
@@ -1061,9 +1172,30 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   // split-K: weight-gradient shaped problems (few output tiles, very long K) would otherwise
   // occupy a handful of SMs.  Only for plain fp32 outputs: slices are accumulated with atomics
   // into a zero-initialised C.
-  int splits = 1;
-  const long long tiles = (long long)ceil_div(a->N, bn) * ceil_div(a->M, BM) * batch;
+  // CTA pairs (cta_group::2, see Cfg): bf16 operands, tiles at least 128 wide, at least two row tiles.
+  // DL_GEMM_CTA2: 0 = never, 1 = where it measured faster (default), 2 = wherever it is legal.
+  static const int cta2_mode = [] { const char* e = getenv("DL_GEMM_CTA2"); return e ? atoi(e) : 1; }();
+  static const int dbg_mode0 = [] { const char* e = getenv("DL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  const int mt_all = ceil_div(a->M, BM);
+  bool cta2 = cta2_mode != 0 && !f32 && bn >= 128 && mt_all >= 2 && (dbg_mode0 == 0 || dbg_mode0 == 5) && a->tile_n >= 0;
   const int nkb = ceil_div(k_total, KE_);
+  if (cta2 && cta2_mode == 1) {
+    // Measured on B200 over the step's shapes (profiles/r2t_gemm_cta_pairs.txt): a pair launch costs ~1 us more
+    // (cluster scheduling, two cluster barriers) and saves a third of the operand traffic per K-block, so it
+    // pays for 256-wide tiles once the launch runs more than one wave of tiles or a unit is at least 24
+    // K-blocks long (16384 x 512 x 2048: 35.7 -> 33.1 us, 8192^3: 1.29 -> 1.46 PFLOP/s); the 1-wave, K <= 1024
+    // launches and the short split-K slices stay single-CTA.
+    const long long tiles1 = (long long)ceil_div(a->N, bn) * mt_all * batch;
+    long long splits1 = a->split_k > 1 ? a->split_k : 1;
+    if (a->split_k == 0 && tiles1 * 2 <= sms && nkb >= 16) {
+      splits1 = sms / tiles1;
+      if (splits1 > nkb / 4) splits1 = nkb / 4;
+    }
+    cta2 = bn == 256 && ((mt_all % 2 == 0) || mt_all >= 9) && (tiles1 > sms || nkb / splits1 >= 24);
+  }
+  const int unit_sms = cta2 ? max_cta_pairs() : sms;     // schedulable units: CTAs, or co-resident CTA pairs
+  int splits = 1;
+  const long long tiles = (long long)ceil_div(a->N, bn) * (cta2 ? ceil_div(mt_all, 2) : mt_all) * batch;
   // batched outputs can be split too when C is one dense [batch, M, N] block (a single memset)
   const bool dense_c = batch == 1 || (a->ldc == a->N && a->sc[0] == a->M * a->N &&
                                       (a->batch[1] == 1 || a->sc[1] == a->M * a->N * a->batch[0]) &&
@@ -1073,12 +1205,12 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   if (a->split_k > 1) {
     DL_REQUIRE(plain, "dl_gemm: split_k needs a plain fp32 output (no epilogue operands; batched C must be dense)");
     splits = a->split_k;
-  } else if (a->split_k == 0 && plain && tiles * 2 <= sms && nkb >= 16) {
+  } else if (a->split_k == 0 && plain && tiles * 2 <= unit_sms && nkb >= 16) {
     // one (tile, K-slice) unit per CTA and never more units than SMs: a 149th unit would run as a second
     // wave on its own (measured, 1024 x 256 x 16384: 19 slices = 152 units 20.1 us, 18 slices = 144 units
     // 14.7 us).  More, shorter slices do not pay either: every unit ends in a 128 x BN fp32 reduction
     // into L2 (~5 us per wave of 128 KB tiles), the same L2 the operand feed is bound by.
-    splits = (int)(sms / tiles);
+    splits = (int)(unit_sms / tiles);
     if (splits > nkb / 4) splits = nkb / 4;
   }
   if (splits > nkb) splits = nkb;
@@ -1096,7 +1228,7 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, a->A, f32, a->trans_a != 0, a->M, conv ? conv_cin : a->K, a->lda, a->batch, a->sa, BM, "A");
   if (rc) return rc;
-  rc = make_operand_map(&tmB, a->B, f32, a->trans_b != 0, a->N, a->K, a->ldb, a->batch, a->sb, bn, "B");
+  rc = make_operand_map(&tmB, a->B, f32, a->trans_b != 0, a->N, a->K, a->ldb, a->batch, a->sb, cta2 ? bn / 2 : bn, "B");
   if (rc) return rc;
 
   GemmParams p;
@@ -1146,7 +1278,7 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
   // launches keep them.
   const bool tma_epi = !tma_epi_off && (a->mul_aux || a->residual) && !(a->preact_out && a->pre_mode == 1) &&
                        !f32 && p.c_bf16 && bn == 256 && splits == 1 && !conv && !kred &&
-                       dbg_mode == 0 && nkb <= 16 && ((uintptr_t)a->C & 15) == 0 && al8(a->ldc) && al8(a->sc[0]) &&
+                       (dbg_mode == 0 || dbg_mode == 5) && nkb <= 16 && ((uintptr_t)a->C & 15) == 0 && al8(a->ldc) && al8(a->sc[0]) &&
                        al8(a->sc[1]) && al8(a->sc[2]) && !(a->mul_aux && a->residual) &&
                        (!a->mul_aux || ((uintptr_t)a->mul_aux & 15) == 0) &&
                        (!a->residual || (((uintptr_t)a->residual & 15) == 0 && al8(p.ldr) && al8(p.sr[0]) &&
@@ -1165,7 +1297,12 @@ extern "C" int dl_gemm(const dl_gemm_args* a, void* stream_) {
       rc = make_epi_map(&tmIn, a->residual, a->N, a->M, p.ldr, a->batch, p.sr, "residual");
     }
     if (rc) return rc;
+    if (cta2) return launch<256, false, false, true, true>(tmA, tmB, p, batch, stream, &tmC, p.tma_in ? &tmIn : nullptr);
     return launch<256, false, false, true>(tmA, tmB, p, batch, stream, &tmC, p.tma_in ? &tmIn : nullptr);
+  }
+  if (cta2) {
+    if (bn == 128) return launch<128, false, false, false, true>(tmA, tmB, p, batch, stream);
+    return launch<256, false, false, false, true>(tmA, tmB, p, batch, stream);
   }
   if (f32 && a->precise) {
     if (bn == 64) return launch<64, true, true>(tmA, tmB, p, batch, stream);
