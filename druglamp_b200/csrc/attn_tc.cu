@@ -139,9 +139,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
 
+  // Producer / issuer warps run warp-uniformly; one elected lane issues the TMA / tcgen05 instructions (as
+  // single-lane divergent regions every tcgen05.mma paid an R2UR + ELECT sequence).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+    const bool leader = ptx::elect_one();
+    // ---------------------------------------------------------------- TMA producer
+    if (leader) {
       ptx::mbar_arrive_expect_tx(bar_qk, (uint32_t)(C::CH + p.nkc * C::CH));
 #pragma unroll
       for (int j = 0; j < C::NB; ++j) ptx::tma_load_4d(sQ + j * kBlk, &tmQ, bar_qk, h * D + 64 * j, q0, b, set);
@@ -149,38 +152,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < C::NB; ++j)
           ptx::tma_load_4d(sKV + c * C::CH + j * kBlk, &tmK, bar_qk, h * D + 64 * j, c * 128, b, 0);
-      // V replaces K once every score MMA has read it
-      ptx::mbar_wait(bar_s, 0);
+    }
+    __syncwarp();
+    // V replaces K once every score MMA has read it
+    ptx::mbar_wait(bar_s, 0);
+    if (leader) {
       ptx::mbar_arrive_expect_tx(bar_v, (uint32_t)(p.nkc * C::CH));
       for (int c = 0; c < p.nkc; ++c)
 #pragma unroll
         for (int j = 0; j < C::NB; ++j)
           ptx::tma_load_4d(sKV + c * C::CH + j * kBlk, &tmV, bar_v, h * D + 64 * j, c * 128, b, 0);
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      ptx::mbar_wait(bar_qk, 0);
-      ptx::tc_fence_after();
+    const bool leader = ptx::elect_one();
+    // ---------------------------------------------------------------- MMA issuer
+    ptx::mbar_wait(bar_qk, 0);
+    ptx::tc_fence_after();
+    if (leader) {
       for (int c = 0; c < p.nkc; ++c)
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           ptx::mma_ss<false>(tmem + c * 128, desc_k(sQ, kk), desc_k(sKV + c * C::CH, kk), p.idesc_a,
                              (uint32_t)(kk != 0));
       ptx::mma_commit(bar_s);
-      ptx::mbar_wait(bar_v, 0);
-      for (int c = 0; c < p.nkc; ++c) {
-        ptx::mbar_wait(bar_p + 8 * c, 0);
-        ptx::tc_fence_after();
-        const uint32_t sPc = sP + (c & 1) * 2 * kBlk;
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar_v, 0);
+    for (int c = 0; c < p.nkc; ++c) {
+      ptx::mbar_wait(bar_p + 8 * c, 0);
+      ptx::tc_fence_after();
+      const uint32_t sPc = sP + (c & 1) * 2 * kBlk;
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           ptx::mma_ss<false>(tmem, desc_k(sPc, kk), desc_mn(sKV + c * C::CH, kk), p.idesc_b,
                              (uint32_t)((c | kk) != 0));
         ptx::mma_commit(bar_pf + 8 * (c & 1));
       }
-      ptx::mma_commit(bar_o);
+      __syncwarp();
     }
+    if (leader) ptx::mma_commit(bar_o);
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax / epilogue warps
     const int quad = warp & 3, hh = (warp - 2) >> 2;
@@ -404,36 +417,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+    {
+      // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane)
+      const bool leader = ptx::elect_one();
       uint32_t n = 0;
       for (int t = 0; t < p.nkc; ++t) {
         if (t > 0) ptx::mbar_wait(bar_dkv, (uint32_t)((t - 1) & 1));   // previous tile's MMAs are done with K/V
-        ptx::mbar_arrive_expect_tx(bar_kv, 2 * C::CH);
+        if (leader) {
+          ptx::mbar_arrive_expect_tx(bar_kv, 2 * C::CH);
 #pragma unroll
-        for (int j = 0; j < C::NB; ++j) {
-          ptx::tma_load_4d(sK + j * kBlk, &tmK, bar_kv, h * D + 64 * j, t * 128, b, 0);
-          ptx::tma_load_4d(sV + j * kBlk, &tmV, bar_kv, h * D + 64 * j, t * 128, b, 0);
+          for (int j = 0; j < C::NB; ++j) {
+            ptx::tma_load_4d(sK + j * kBlk, &tmK, bar_kv, h * D + 64 * j, t * 128, b, 0);
+            ptx::tma_load_4d(sV + j * kBlk, &tmV, bar_kv, h * D + 64 * j, t * 128, b, 0);
+          }
         }
+        __syncwarp();
         for (int it = 0; it < nit; ++it, ++n) {
           const int st = (int)(n % C::NST);
           const uint32_t ph = (n / C::NST) & 1;
           ptx::mbar_wait(bar_qempty + 8 * st, ph ^ 1u);
           const uint32_t full = bar_qfull + 8 * st;
-          ptx::mbar_arrive_expect_tx(full, 2 * C::CH);
           const int set = it / p.nqt, q0 = (it % p.nqt) * 128;
           const uint32_t sQ = base + C::OFF_Q + st * 2 * C::CH, sdO = sQ + C::CH;
+          if (leader) {
+            ptx::mbar_arrive_expect_tx(full, 2 * C::CH);
 #pragma unroll
-          for (int j = 0; j < C::NB; ++j) {
-            ptx::tma_load_4d(sQ + j * kBlk, &tmQ, full, h * D + 64 * j, q0, b, set);
-            ptx::tma_load_4d(sdO + j * kBlk, &tmdO, full, h * D + 64 * j, q0, b, set);
+            for (int j = 0; j < C::NB; ++j) {
+              ptx::tma_load_4d(sQ + j * kBlk, &tmQ, full, h * D + 64 * j, q0, b, set);
+              ptx::tma_load_4d(sdO + j * kBlk, &tmdO, full, h * D + 64 * j, q0, b, set);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+    {
+      // ---------------------------------------------------------------- MMA issuer (warp-uniform, elected lane)
+      const bool leader = ptx::elect_one();
       uint32_t n = 0;
       for (int t = 0; t < p.nkc; ++t) {
         ptx::mbar_wait(bar_kv, (uint32_t)(t & 1));
@@ -445,30 +466,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (n > 0) ptx::mbar_wait(bar_tfree, (n - 1) & 1);    // S^T / dP^T / dQ columns drained
           ptx::tc_fence_after();
           const uint32_t sQ = base + C::OFF_Q + st * 2 * C::CH, sdO = sQ + C::CH;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk)          // S^T = K Q^T
-            ptx::mma_ss<false>(tmem + C::T_ST, desc_k(sK, kk), desc_k(sQ, kk), p.idesc_a, (uint32_t)(kk != 0));
+            for (int kk = 0; kk < D / 16; ++kk)          // S^T = K Q^T
+              ptx::mma_ss<false>(tmem + C::T_ST, desc_k(sK, kk), desc_k(sQ, kk), p.idesc_a, (uint32_t)(kk != 0));
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk)          // dP^T = V dO^T
-            ptx::mma_ss<false>(tmem + C::T_DPT, desc_k(sV, kk), desc_k(sdO, kk), p.idesc_a, (uint32_t)(kk != 0));
-          ptx::mma_commit(bar_st);
+            for (int kk = 0; kk < D / 16; ++kk)          // dP^T = V dO^T
+              ptx::mma_ss<false>(tmem + C::T_DPT, desc_k(sV, kk), desc_k(sdO, kk), p.idesc_a, (uint32_t)(kk != 0));
+            ptx::mma_commit(bar_st);
+          }
+          __syncwarp();
           ptx::mbar_wait(bar_pds, n & 1);
           ptx::tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)               // dV += P^T dO
-            ptx::mma_ss<false>(tmem + C::T_DV, desc_k(sPT, kk), desc_mn(sdO, kk), p.idesc_b,
-                               (uint32_t)((it | kk) != 0));
+            for (int kk = 0; kk < 8; ++kk)               // dV += P^T dO
+              ptx::mma_ss<false>(tmem + C::T_DV, desc_k(sPT, kk), desc_mn(sdO, kk), p.idesc_b,
+                                 (uint32_t)((it | kk) != 0));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)               // dK += dS^T Q
-            ptx::mma_ss<false>(tmem + C::T_DK, desc_k(sDST, kk), desc_mn(sQ, kk), p.idesc_b,
-                               (uint32_t)((it | kk) != 0));
+            for (int kk = 0; kk < 8; ++kk)               // dK += dS^T Q
+              ptx::mma_ss<false>(tmem + C::T_DK, desc_k(sDST, kk), desc_mn(sQ, kk), p.idesc_b,
+                                 (uint32_t)((it | kk) != 0));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)               // dQ tile = dS K
-            ptx::mma_ss<false>(tmem + C::T_DQ, desc_mn(sDST, kk), desc_mn(sK, kk), p.idesc_c, (uint32_t)(kk != 0));
-          ptx::mma_commit(bar_qempty + 8 * st);
-          ptx::mma_commit(bar_dq);
+            for (int kk = 0; kk < 8; ++kk)               // dQ tile = dS K
+              ptx::mma_ss<false>(tmem + C::T_DQ, desc_mn(sDST, kk), desc_mn(sK, kk), p.idesc_c, (uint32_t)(kk != 0));
+            ptx::mma_commit(bar_qempty + 8 * st);
+            ptx::mma_commit(bar_dq);
+          }
+          __syncwarp();
         }
-        ptx::mma_commit(bar_dkv);
+        if (leader) ptx::mma_commit(bar_dkv);
+        __syncwarp();
       }
     }
   } else {
