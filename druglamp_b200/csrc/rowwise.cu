@@ -4,6 +4,7 @@
 // reduced with warp shuffles.  Column reductions finish with one fp32 atomic per block.
 #include "../../include/druglamp_sm100.h"
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dl {
 void count_launch(int n = 1);
@@ -131,7 +132,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
-template <typename T, int C>
+template <typename T, int C, int CL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, C <= 512 ? 2 : 1)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
@@ -212,7 +213,11 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
       }
     }
   }
-  // block-reduce the per-warp column partials, then one atomic per column per block
+  // Column partials: per-warp registers -> per-block sums in shared memory -> (CL > 1) summed over the CL
+  // blocks of a cluster through distributed shared memory -> ONE 16-byte vector reduction per four columns
+  // per cluster.  One atomicAdd per column per block was the kernel's tail: 296 blocks x 512 same-address
+  // atomics serialise in L2 for longer than the 25 MB of row traffic take (12.5 us at 2.0 TB/s).
+  __shared__ __align__(16) float tot[2][C];
   for (int pass = 0; pass < 2; ++pass) {
     __syncthreads();
 #pragma unroll
@@ -221,16 +226,40 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
       for (int e = 0; e < V; ++e) red[w][k * 32 * V + lane * V + e] = pass == 0 ? ag[k * V + e] : ab[k * V + e];
     }
     __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (dst) {
-      for (int c = threadIdx.x; c < C; c += kWarpsPerBlock * 32) {
-        float t = 0.f;
+    for (int c = threadIdx.x; c < C; c += kWarpsPerBlock * 32) {
+      float t = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < kWarpsPerBlock; ++ww) t += red[ww][c];
-        atomicAdd(dst + c, t);
+      for (int ww = 0; ww < kWarpsPerBlock; ++ww) t += red[ww][c];
+      tot[pass][c] = t;
+    }
+  }
+  if constexpr (CL > 1) ptx::cluster_sync_all();
+  else __syncthreads();
+  if (CL == 1 || ptx::cluster_ctarank() == 0) {
+    for (int i = threadIdx.x; i < 2 * (C / 4); i += kWarpsPerBlock * 32) {
+      const int pass = i / (C / 4), c = (i % (C / 4)) * 4;
+      float* dst = pass == 0 ? dgamma : dbeta;
+      if (!dst) continue;
+      float4 t = *reinterpret_cast<const float4*>(&tot[pass][c]);
+      if constexpr (CL > 1) {
+        const uint32_t a = ptx::smem_u32(&tot[pass][c]);
+#pragma unroll
+        for (int r = 1; r < CL; ++r) {
+          float4 u;
+          asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w) : "r"(ptx::mapa(a, (uint32_t)r)));
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+      }
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                     :: "l"(dst + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+      } else {
+        atomicAdd(dst + c, t.x); atomicAdd(dst + c + 1, t.y); atomicAdd(dst + c + 2, t.z); atomicAdd(dst + c + 3, t.w);
       }
     }
   }
+  if constexpr (CL > 1) ptx::cluster_sync_all();     // the other blocks' partials stay alive until block 0 has read them
 }
 
 // ------------------------------------------------------------------ row softmax
@@ -574,14 +603,24 @@ colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long ro
 #pragma unroll
   for (int j = 0; j < V; ++j) red[threadIdx.x][j] = acc[j];
   __syncthreads();
-  // thread t finishes column (t % tpr) * V + (t / tpr) when that sub-index is a vector lane
-  for (int o = threadIdx.x; o < tpr * V; o += 256) {
-    const int vc = o / V, j = o % V;
+  // four consecutive columns per thread: one 16-byte vector reduction instead of four scalar atomics (every
+  // block of a column slice adds to the same addresses, and same-address atomics serialise in L2)
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int o = threadIdx.x; o < tpr * V / 4; o += 256) {
+    const int vc = (o * 4) / V, j = (o * 4) % V;
     const int col = (blockIdx.x * tpr + vc) * V + j;
-    if (col < cols) {
-      float t = 0.f;
-      for (int i = 0; i < rpp; ++i) t += red[i * tpr + vc][j];
-      atomicAdd(out + col, t);
+    if (col < cols) {                     // cols % V == 0, so the four columns are valid together
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < rpp; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] += red[i * tpr + vc][j + q];
+      if (vec_ok) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                     :: "l"(out + col), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(out + col + q, t[q]);
+      }
     }
   }
 }
@@ -864,21 +903,43 @@ int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* y, floa
   return 0;
 }
 
+// cluster size for the column-partial reduction: 8 blocks share one set of atomics (1 = no cluster)
+constexpr int kLnBwdCluster = 8;
+
+template <typename T, int C>
+int ln_bwd_launch(const T* dy, const T* x, const float* g, const float* mean, const float* rstd, T* dx, const T* add,
+                  float* dg, float* db, long long rows, cudaStream_t st) {
+  // two blocks per SM (as many as fit with 8 x C floats of shared memory and ~100 registers), a whole number of
+  // clusters; rows are strided over all warps
+  int grid = row_grid(rows);
+  if (grid > sm_count() * 2) grid = sm_count() * 2;
+  const int th = kWarpsPerBlock * 32;
+  // Measured on B200 (tools/ln_bench.py, 16384 x 256 bf16): one atomicAdd per column per block 12.5 us; 16-byte
+  // vector reductions per block 7.0 us; the same per 8-block cluster 11.8 us (cluster scheduling + two cluster
+  // barriers cost more than the 8x fewer reductions save) -- so clusters are opt-in (DL_LN_CLUSTER=1).
+  static const bool use_cluster = [] { const char* e = getenv("DL_LN_CLUSTER"); return e && atoi(e) != 0; }();
+  if (use_cluster && grid >= kLnBwdCluster && (dg || db)) {
+    grid -= grid % kLnBwdCluster;
+    (void)launch_cluster_k(layernorm_bwd_kernel<T, C, kLnBwdCluster>, dim3(grid), dim3(th), (size_t)0, (unsigned)kLnBwdCluster,
+                           st, dy, x, g, mean, rstd, dx, add, dg, db, rows);
+  } else {
+    DL_LAUNCH((layernorm_bwd_kernel<T, C, 1>), grid, th, 0, st, dy, x, g, mean, rstd, dx, add, dg, db, rows);
+  }
+  return 0;
+}
+
 template <typename T>
 int ln_bwd_dispatch(const void* dy, const void* x, const float* g, const float* mean,
                     const float* rstd, void* dx, const void* dx_add, float* dg, float* db, long long rows,
                     int cols, cudaStream_t st) {
-  int grid = row_grid(rows);
-  if (grid > sm_count() * 2) grid = sm_count() * 2;   // fewer blocks -> fewer atomics
-  const int th = kWarpsPerBlock * 32;
   const T *dyy = (const T*)dy, *xx = (const T*)x;
   T* dxx = (T*)dx;
   const T* add = (const T*)dx_add;
   switch (cols / 128) {
-    case 1: DL_LAUNCH((layernorm_bwd_kernel<T, 128>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 2: DL_LAUNCH((layernorm_bwd_kernel<T, 256>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 4: DL_LAUNCH((layernorm_bwd_kernel<T, 512>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
-    case 8: DL_LAUNCH((layernorm_bwd_kernel<T, 1024>), grid, th, 0, st, dyy, xx, g, mean, rstd, dxx, add, dg, db, rows); break;
+    case 1: ln_bwd_launch<T, 128>(dyy, xx, g, mean, rstd, dxx, add, dg, db, rows, st); break;
+    case 2: ln_bwd_launch<T, 256>(dyy, xx, g, mean, rstd, dxx, add, dg, db, rows, st); break;
+    case 4: ln_bwd_launch<T, 512>(dyy, xx, g, mean, rstd, dxx, add, dg, db, rows, st); break;
+    case 8: ln_bwd_launch<T, 1024>(dyy, xx, g, mean, rstd, dxx, add, dg, db, rows, st); break;
     default: return set_error(-1, "dl_layernorm_bwd: cols must be 128, 256, 512 or 1024 (got %d)", cols);
   }
   DL_LAUNCH_CHECK("layernorm_bwd_kernel");
