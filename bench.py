@@ -419,7 +419,7 @@ def run_gpu(args):
                 del g1
             os.makedirs(os.path.dirname(os.environ["DL_BENCH_DUMP"]) or ".", exist_ok=True)
             with open(os.environ["DL_BENCH_DUMP"], "w") as f:
-                f.write(f"# {len(prof)} dl_gemm launches per step, {flops / 1e9:.1f} GFLOP, {gemm_ms:.3f} ms back-to-back\n")
+                f.write(f"# {len(prof)} tensor-core launches per step (dl_gemm + fused dl_ffn_fwd / dl_ffn_bwd), {flops / 1e9:.1f} GFLOP, {gemm_ms:.3f} ms back-to-back\n")
                 f.write("# total_us  n  us/launch  TFLOP/s  (M,N,K,batch,ta,tb)\n")
                 for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["n"] * kv[1]["us"]):
                     f.write(f"{d['n'] * d['us']:9.1f}  n={d['n']:3d}  {d['us']:8.1f}  {d['flops'] / d['n'] / d['us'] / 1e6:7.1f}  {k}\n")
@@ -433,14 +433,15 @@ def run_gpu(args):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        roof = {"kernel": "gemm_tc_kernel (dl_gemm: TMA + tcgen05.mma, bf16 in / fp32 TMEM accumulate)",
+        roof = {"kernel": "gemm_tc_kernel (dl_gemm: TMA + tcgen05.mma, CTA pairs per shape, bf16 in / fp32 TMEM accumulate) "
+                          "+ ffn_chain_kernel (dl_ffn_fwd / dl_ffn_bwd: the two FFN GEMMs chained on chip)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean)",
                 "traffic_source": traffic_src, "peak_source": pk["source"] + " bf16_tflops_sustained",
                 "launches_per_step": len(prof), "flops_per_launch_avg": flops / max(len(prof), 1),
                 "gemm_flops_per_step": flops, "avg_launch_us": 1000.0 * gemm_ms / max(len(prof), 1),
                 "gemm_ms_per_step": gemm_ms,
-                "how": "all dl_gemm launches of one step re-issued back to back in a CUDA graph, CUDA events, mean of 5 replays",
+                "how": "all dl_gemm / dl_ffn launches of one step re-issued back to back in a CUDA graph, CUDA events, mean of 5 replays",
                 "share_of_step": min(1.0, gemm_ms / step_ms) if step_ms > 0 else None,
                 "whole_step_tflops": FLOP_PER_PAIR_FWD_BWD * BATCH / (step_ms * 1e-3) / 1e12,
                 "whole_step_frac": FLOP_PER_PAIR_FWD_BWD * BATCH / (step_ms * 1e-3) / 1e12 / peak}

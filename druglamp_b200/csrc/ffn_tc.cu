@@ -19,6 +19,7 @@
 // The hidden activation therefore never returns from HBM for the second GEMM, its store costs no LSU
 // instructions, and one launch replaces two (forward) / two (backward) dl_gemm launches.
 #include <mutex>
+#include <stdlib.h>
 
 #include "../../include/druglamp_sm100.h"
 #include "common.cuh"
@@ -59,12 +60,19 @@ struct FfnParams {
 
 // MODE 0: forward (K-major weights, bias + GELU (+ derivative) + dropout, then bias + dropout + residual)
 // MODE 1: backward (MN-major weights, multiply by the stored derivative, plain dX)
-template <int MODE>
+// PAIR: two CTAs (a cluster of two) own two adjacent 128-row tiles as ONE 256-row tcgen05.mma.cta_group::2
+// problem.  Each CTA keeps its own A and E tiles but loads only HALF of every weight chunk (64 of the 128
+// hidden columns of B1, 128 of the 256 output columns of B2); the leader CTA's warp issues every MMA for both.
+// The weight traffic per CTA -- what bounds this kernel: 1 MB for a 128-row tile through a 96 KB ring -- halves,
+// and a 32 KB ring unit now holds a whole chunk operand (two units per chunk instead of four).
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmE,
                  const FfnParams p) {
   constexpr bool BMN = MODE == 1;
+  constexpr int UPC = PAIR ? 1 : 2;                      // ring units per chunk operand
+  constexpr int NM1 = 16 / UPC, NM2 = 8 / UPC;           // MMAs per unit: first / second GEMM
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -79,9 +87,16 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bar_efull = bar_sempty + 16;             // [2] E tile written
   const uint32_t bar_eempty = bar_efull + 16;             // [2] E tile consumed (second GEMM + bulk store)
   const uint32_t bar_yfull = bar_eempty + 16, bar_yempty = bar_yfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages + 8 + 2);
+  const uint32_t bar_efullm = bar_yempty + 8;             // [2] pair: E tiles of BOTH CTAs written (leader's issuer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages + 8 + 2 + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)ptx::cluster_ctarank() : 0;
+  // pair: both CTAs walk the same sequence of tile pairs; this CTA's rows are tile 2 * pair + rank
+  const int tile_first = PAIR ? 2 * (int)(blockIdx.x >> 1) + rank : (int)blockIdx.x;
+  const int tile_step = (int)gridDim.x;
+  const int tile_end = PAIR ? 2 * ((p.tiles + 1) / 2) : p.tiles;     // a phantom last tile keeps the pair in step
+  constexpr uint32_t kArr = PAIR ? 2 : 1;                 // arrivals per barrier that both CTAs feed
   pdl_trigger();
 
   if (threadIdx.x == 0) {
@@ -89,25 +104,30 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tmap(&tmB1);
     ptx::prefetch_tmap(&tmB2);
     if (p.store_e) ptx::prefetch_tmap(&tmE);
-    ptx::mbar_init(bar_afull, 1);
+    ptx::mbar_init(bar_afull, kArr);                      // pair: leader's expect_tx + the peer producer's arrival
     ptx::mbar_init(bar_aempty, 1);
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_full + 8 * s, kArr);
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_sfull + 8 * i, 1);
-      ptx::mbar_init(bar_sempty + 8 * i, kEpiWarps);
-      ptx::mbar_init(bar_efull + 8 * i, kEpiWarps);
+      ptx::mbar_init(bar_sempty + 8 * i, kArr * kEpiWarps);   // pair: the epilogue warps of both CTAs, at the leader
+      ptx::mbar_init(bar_efull + 8 * i, kEpiWarps);           // this CTA's E tile (its bulk-store warp)
+      ptx::mbar_init(bar_efullm + 8 * i, kArr * kEpiWarps);
       ptx::mbar_init(bar_eempty + 8 * i, p.store_e ? 2 : 1);
     }
     ptx::mbar_init(bar_yfull, 1);
-    ptx::mbar_init(bar_yempty, kEpiWarps);
+    ptx::mbar_init(bar_yempty, kArr * kEpiWarps);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  if (warp == 1) {
+    if constexpr (PAIR) ptx::tmem_alloc_2sm<512>(ptx::smem_u32(tmem_slot));
+    else ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
@@ -121,50 +141,81 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool leader = ptx::elect_one();
       uint32_t s = 0, ph = 0, ti = 0;
       auto slot_next = [&]() { if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; } };
-      auto load_b1 = [&](int c) {          // chunk c of the first GEMM's weights: two units of K = 128
-        for (int u = 0; u < 2; ++u) {
+      // pair: every load of either CTA is counted on the LEADER CTA's barrier
+      auto ld = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int x0, int x1) {
+        if constexpr (PAIR) ptx::tma_load_2d_2sm(dst, m, bar, x0, x1);
+        else ptx::tma_load_2d(dst, m, bar, x0, x1);
+      };
+      auto begin_fill = [&](uint32_t bar, uint32_t bytes) -> uint32_t {       // -> the barrier the loads signal
+        if constexpr (PAIR) {
+          const uint32_t lbar = ptx::mapa(bar, 0);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar, 2 * bytes);
+          else ptx::mbar_arrive_remote(lbar);
+          return lbar;
+        } else {
+          ptx::mbar_arrive_expect_tx(bar, bytes);
+          return bar;
+        }
+      };
+      auto load_b1 = [&](int c) {          // chunk c of the first GEMM's weights
+        for (int u = 0; u < UPC; ++u) {
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
+          const uint32_t dst = sRing + s * kUnit;
           if (leader) {
-            ptx::mbar_arrive_expect_tx(full, kUnit);
-            if constexpr (!BMN) {          // [Dh, 256] K-major: two [128 rows x 64 k] blocks
+            const uint32_t full = begin_fill(bar_full + 8 * s, kUnit);
+            if constexpr (!BMN && !PAIR) {        // [Dh, 256] K-major: K half u as two [128 rows x 64 k] blocks
 #pragma unroll
-              for (int j = 0; j < 2; ++j) ptx::tma_load_2d(dst + j * kBlk, &tmB1, full, (2 * u + j) * 64, c * kCh);
-            } else {                       // [256 (k), Dh] MN-major: per 64-wide MN block, 128 k rows
+              for (int j = 0; j < 2; ++j) ld(dst + j * kBlk, &tmB1, full, (2 * u + j) * 64, c * kCh);
+            } else if constexpr (!BMN) {          // pair: this CTA's 64 hidden columns, four [64 rows x 64 k] blocks
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ld(dst + j * 8192, &tmB1, full, j * 64, c * kCh + rank * 64);
+            } else if constexpr (!PAIR) {         // [256 (k), Dh] MN-major: per 64-wide MN block, 128 k rows
 #pragma unroll
               for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
                 for (int kq = 0; kq < 2; ++kq)
-                  ptx::tma_load_2d(dst + blk * kBlk + kq * 8192, &tmB1, full, c * kCh + blk * 64, u * 128 + kq * 64);
-            }
-          }
-          __syncwarp();
-          slot_next();
-        }
-      };
-      auto load_b2 = [&](int c) {          // chunk c of the second GEMM's weights: two units of K = 64
-        for (int u = 0; u < 2; ++u) {
-          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t dst = sRing + s * kUnit, full = bar_full + 8 * s;
-          if (leader) {
-            ptx::mbar_arrive_expect_tx(full, kUnit);
-            if constexpr (!BMN) {          // [256, Dh] K-major: one [256 rows x 64 k] block
-              ptx::tma_load_2d(dst, &tmB2, full, c * kCh + u * 64, 0);
-            } else {                       // [Dh (k), 256] MN-major: four 64-wide MN blocks of 64 k rows
+                  ld(dst + blk * kBlk + kq * 8192, &tmB1, full, c * kCh + blk * 64, u * 128 + kq * 64);
+            } else {                              // pair: this CTA's 64-wide MN block, all 256 k rows
 #pragma unroll
-              for (int blk = 0; blk < 4; ++blk) ptx::tma_load_2d(dst + blk * 8192, &tmB2, full, blk * 64, c * kCh + u * 64);
+              for (int kq = 0; kq < 4; ++kq) ld(dst + kq * 8192, &tmB1, full, c * kCh + rank * 64, kq * 64);
             }
           }
           __syncwarp();
           slot_next();
         }
       };
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+      auto load_b2 = [&](int c) {          // chunk c of the second GEMM's weights
+        for (int u = 0; u < UPC; ++u) {
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t dst = sRing + s * kUnit;
+          if (leader) {
+            const uint32_t full = begin_fill(bar_full + 8 * s, kUnit);
+            if constexpr (!BMN && !PAIR) {        // [256, Dh] K-major: one [256 rows x 64 k] block
+              ld(dst, &tmB2, full, c * kCh + u * 64, 0);
+            } else if constexpr (!BMN) {          // pair: this CTA's 128 output rows, two [128 rows x 64 k] blocks
+#pragma unroll
+              for (int j = 0; j < 2; ++j) ld(dst + j * kBlk, &tmB2, full, c * kCh + j * 64, rank * 128);
+            } else if constexpr (!PAIR) {         // [Dh (k), 256] MN-major: four 64-wide MN blocks of 64 k rows
+#pragma unroll
+              for (int blk = 0; blk < 4; ++blk) ld(dst + blk * 8192, &tmB2, full, blk * 64, c * kCh + u * 64);
+            } else {                              // pair: this CTA's two 64-wide MN blocks of 128 k rows
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                for (int kq = 0; kq < 2; ++kq)
+                  ld(dst + blk * kBlk + kq * 8192, &tmB2, full, rank * 128 + blk * 64, c * kCh + kq * 64);
+            }
+          }
+          __syncwarp();
+          slot_next();
+        }
+      };
+      for (int t = tile_first; t < tile_end; t += tile_step, ++ti) {
         ptx::mbar_wait(bar_aempty, (ti & 1) ^ 1u);
         if (leader) {
-          ptx::mbar_arrive_expect_tx(bar_afull, kABytes);
+          const uint32_t afull = begin_fill(bar_afull, kABytes);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ptx::tma_load_2d(sA + j * kBlk, &tmA, bar_afull, j * 64, t * 128);
+          for (int j = 0; j < 4; ++j) ld(sA + j * kBlk, &tmA, afull, j * 64, t * 128);
         }
         __syncwarp();
         load_b1(0);
@@ -176,14 +227,23 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    {
-      // ------------------------------------------------------------------ MMA issuer
+    if (rank == 0) {
+      // ------------------------------------------------------------------ MMA issuer (pair: the leader, for both)
       // descriptor templates: only the 14-bit start-address field (16-byte units) changes per unit / K step
-      const uint64_t k_tmpl = ptx::make_smem_desc(0, 16, 1024);                        // K-major operands
-      const uint64_t b1_tmpl = BMN ? ptx::make_smem_desc(0, kBlk, 1024) : k_tmpl;      // first GEMM's weights
-      const uint64_t b2_tmpl = BMN ? ptx::make_smem_desc(0, 8192, 1024) : k_tmpl;      // second GEMM's weights
+      const uint64_t k_tmpl = ptx::make_smem_desc(0, 16, 1024);                                      // K-major operands
+      const uint64_t b1_tmpl = BMN ? ptx::make_smem_desc(0, kBlk, 1024) : k_tmpl;                    // first GEMM's weights
+      const uint64_t b2_tmpl = BMN ? ptx::make_smem_desc(0, PAIR ? kBlk : 8192, 1024) : k_tmpl;      // second GEMM's weights
       constexpr uint32_t kStepMn = 2048 >> 4, kStepK = 32 >> 4, kBlkU = kBlk >> 4;
+      constexpr uint32_t kB1BlkU = (PAIR ? 8192 : kBlk) >> 4;       // K-major B1: [64 | 128 rows x 128 B] blocks
       auto addr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFF) >> 4); };
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if constexpr (PAIR) ptx::mma_ss_2sm(d, ad, bd, idesc, acc);
+        else ptx::mma_ss<false>(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {                              // pair: arrives in both CTAs
+        if constexpr (PAIR) ptx::mma_commit_2sm(bar);
+        else ptx::mma_commit(bar);
+      };
       const bool leader = ptx::elect_one();
       uint32_t s = 0, ph = 0, g1 = 0, g2 = 0, ti = 0;
       auto slot_next = [&]() { if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; } };
@@ -192,65 +252,69 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_wait(bar_sempty + 8 * sb, sph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t acc = tmem + sb * kCh;
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < UPC; ++u) {
           ptx::mbar_wait(bar_full + 8 * s, ph);
           ptx::tc_fence_after();
-          const uint64_t a0 = k_tmpl | addr(sA + (uint32_t)u * 2 * kBlk), b0 = b1_tmpl | addr(sRing + s * kUnit);
+          const uint64_t a0 = k_tmpl | addr(sA + (uint32_t)u * (NM1 / 4) * kBlk), b0 = b1_tmpl | addr(sRing + s * kUnit);
           if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
+            for (int kk = 0; kk < NM1; ++kk) {
               const uint64_t ad = a0 + (uint64_t)((kk >> 2) * kBlkU + (kk & 3) * kStepK);
-              const uint64_t bd = b0 + (uint64_t)(BMN ? kk * kStepMn : (kk >> 2) * kBlkU + (kk & 3) * kStepK);
-              ptx::mma_ss<false>(acc, ad, bd, p.idesc1, (uint32_t)((u | kk) != 0));
+              const uint64_t bd = b0 + (uint64_t)(BMN ? kk * kStepMn : (kk >> 2) * kB1BlkU + (kk & 3) * kStepK);
+              mma(acc, ad, bd, p.idesc1, (uint32_t)((u | kk) != 0));
             }
-            ptx::mma_commit(bar_empty + 8 * s);
+            commit(bar_empty + 8 * s);
           }
           __syncwarp();
           slot_next();
         }
-        if (leader) ptx::mma_commit(bar_sfull + 8 * sb);
+        if (leader) commit(bar_sfull + 8 * sb);
         __syncwarp();
         ++g1;
       };
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+      for (int t = tile_first; t < tile_end; t += tile_step, ++ti) {
         ptx::mbar_wait(bar_afull, ti & 1);
         ptx::tc_fence_after();
         int issued = 0;
         mma1(); ++issued;
         if (NC > 1) { mma1(); ++issued; }
-        if (issued == NC && leader) ptx::mma_commit(bar_aempty);
+        if (issued == NC && leader) commit(bar_aempty);
         for (int c = 0; c < NC; ++c) {
           // chunk c + 2's first GEMM goes first: its accumulator buffer is free as soon as the epilogue of
           // chunk c has READ tensor memory, long before that epilogue hands over its E tile -- the weight
           // ring keeps flowing instead of holding B2(c) while nothing can be issued
           if (c + 2 < NC) {
             mma1();
-            if (++issued == NC && leader) ptx::mma_commit(bar_aempty);
+            if (++issued == NC && leader) commit(bar_aempty);
           }
           const uint32_t sb = g2 & 1, eph = (g2 >> 1) & 1;
-          ptx::mbar_wait(bar_efull + 8 * sb, eph);
+          ptx::mbar_wait((PAIR ? bar_efullm : bar_efull) + 8 * sb, eph);     // pair: the E tiles of both CTAs
           if (c == 0) ptx::mbar_wait(bar_yempty, (ti & 1) ^ 1u);      // the previous tile's Y has been read
           ptx::tc_fence_after();
           const uint32_t eb = sE + sb * kEBytes;
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < UPC; ++u) {
             ptx::mbar_wait(bar_full + 8 * s, ph);
             ptx::tc_fence_after();
-            const uint64_t a0 = k_tmpl | addr(eb + (uint32_t)u * kBlk), b0 = b2_tmpl | addr(sRing + s * kUnit);
+            const uint64_t a0 = k_tmpl | addr(eb + (uint32_t)u * (PAIR ? 0u : (uint32_t)kBlk)), b0 = b2_tmpl | addr(sRing + s * kUnit);
             if (leader) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                ptx::mma_ss<false>(tmem + 2 * kCh, a0 + (uint64_t)(kk * kStepK), b0 + (uint64_t)(kk * (BMN ? kStepMn : kStepK)),
-                                   p.idesc2, (uint32_t)((c | u | kk) != 0));
-              ptx::mma_commit(bar_empty + 8 * s);
+              for (int kk = 0; kk < NM2; ++kk) {
+                // A: the E tile, two [128 rows x 128 B] blocks of 64 hidden columns each
+                const uint64_t ad = a0 + (uint64_t)((kk >> 2) * kBlkU + (kk & 3) * kStepK);
+                // B: K-major [rows x 128 B] blocks (kBlk apart in pair mode) or MN-major 16-row K steps
+                const uint64_t bd = b0 + (uint64_t)(BMN ? kk * kStepMn : (kk >> 2) * kBlkU + (kk & 3) * kStepK);
+                mma(tmem + 2 * kCh, ad, bd, p.idesc2, (uint32_t)((c | u | kk) != 0));
+              }
+              commit(bar_empty + 8 * s);
             }
             __syncwarp();
             slot_next();
           }
-          if (leader) ptx::mma_commit(bar_eempty + 8 * sb);
+          if (leader) commit(bar_eempty + 8 * sb);
           __syncwarp();
           ++g2;
         }
-        if (leader) ptx::mma_commit(bar_yfull);
+        if (leader) commit(bar_yfull);
         __syncwarp();
       }
     }
@@ -266,8 +330,13 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const unsigned long long seed1 = drop_seed_at(p.seed1, p.drop_p > 0.f ? p.drop_step : nullptr);
     const unsigned long long seed2 = drop_seed_at(p.seed2, p.drop_p > 0.f ? p.drop_step : nullptr);
     const bool deriv = MODE == 0 && p.dact != nullptr;
+    // barriers the issuer waits on live in the leader CTA (pair: the peer's warps arrive remotely)
+    auto arrive_issuer = [&](uint32_t bar) {
+      if constexpr (PAIR) ptx::mbar_arrive_remote(ptx::mapa(bar, 0));
+      else ptx::mbar_arrive(bar);
+    };
     uint32_t g = 0, ti = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++ti) {
+    for (int t = tile_first; t < tile_end; t += tile_step, ++ti) {
       const int row = t * 128 + r;
       const bool row_ok = row < p.M;
       for (int c = 0; c < NC; ++c, ++g) {
@@ -287,6 +356,11 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            : "l"(ap + 16 * h2));
           }
         }
+        if constexpr (MODE == 0) {
+          // the next chunk's 32 bias values (one 128-byte line per warp) on their way into L1 while this chunk is
+          // processed: their L2 latency sat exposed in front of every chunk's GELU
+          if (lane == 0 && c + 1 < NC) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.bias1 + hcol + kCh));
+        }
         ptx::mbar_wait(bar_sfull + 8 * sb, ph);
         ptx::tc_fence_after();
         uint32_t vv[32];
@@ -294,7 +368,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();                   // the accumulator buffer is free: chunk c + 2 may overwrite it
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_sempty + 8 * sb);
+        if (lane == 0) arrive_issuer(bar_sempty + 8 * sb);
         ptx::mbar_wait(bar_eempty + 8 * sb, ph ^ 1u);
         const uint32_t erow = sE + sb * kEBytes + (uint32_t)(half >> 1) * kBlk + (uint32_t)r * 128u;
 #pragma unroll
@@ -362,12 +436,32 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the MMA and the bulk store
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_efull + 8 * sb);
+        if (lane == 0) {
+          ptx::mbar_arrive(bar_efull + 8 * sb);                       // this CTA's bulk-store warp (and the single-CTA issuer)
+          if constexpr (PAIR) arrive_issuer(bar_efullm + 8 * sb);    // the leader's issuer reads both CTAs' E tiles
+        }
       }
       // ---- Y: 32 rows x 64 columns per warp
+      // the four residual segments of this thread's row (one 128-byte line) are requested before the wait for
+      // the last GEMM: their HBM latency hides behind it instead of sitting in front of every 16 columns
+      uint32_t rw4[4][8];
+      if constexpr (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rw4[j][k] = 0u;
+        if (p.res != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rw4[j][0]), "=r"(rw4[j][1]), "=r"(rw4[j][2]), "=r"(rw4[j][3]), "=r"(rw4[j][4]), "=r"(rw4[j][5]),
+                           "=r"(rw4[j][6]), "=r"(rw4[j][7])
+                         : "l"(p.res + (long long)row * p.ldr + half * 64 + 16 * j));
+        }
+      }
       ptx::mbar_wait(bar_yfull, ti & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = half * 64 + 16 * j;
         uint32_t v[16];
@@ -392,14 +486,10 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.res != nullptr) {
-            uint32_t rw[8];
-            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
-                         : "l"(p.res + (long long)row * p.ldr + col));
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              x[2 * k] += __uint_as_float(rw[k] << 16);
-              x[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+              x[2 * k] += __uint_as_float(rw4[j][k] << 16);
+              x[2 * k + 1] += __uint_as_float(rw4[j][k] & 0xffff0000u);
             }
           }
         } else {
@@ -415,13 +505,13 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_yempty);
+      if (lane == 0) arrive_issuer(bar_yempty);
     }
   } else {
     // -------------------------------------------------------------------- E tiles -> HBM (bulk tensor stores)
     if (lane == 0 && p.store_e) {
       uint32_t g = 0;
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int t = tile_first; t < tile_end; t += tile_step) {
         for (int c = 0; c < NC; ++c, ++g) {
           const uint32_t sb = g & 1, ph = (g >> 1) & 1;
           ptx::mbar_wait(bar_efull + 8 * sb, ph);
@@ -437,10 +527,12 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();      // neither CTA's shared / tensor memory may go while the other uses it
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem);
+    if constexpr (PAIR) ptx::tmem_dealloc_2sm<512>(tmem);
+    else ptx::tmem_dealloc<512>(tmem);
   }
 }
 
@@ -488,20 +580,36 @@ int check_args(const dl_ffn_args* a, const char* who) {
   return 0;
 }
 
-template <int MODE>
+// CTA pairs are opt-in (DL_FFN_PAIR=1; they need at least two row tiles).  Measured on B200 at 16384 x 256 ->
+// 1024 -> 256 (tools/ffn_probe.py): forward 45.1 us single-CTA / 47.1 us as pairs, backward 31.7 / 32.8 --
+// halving the weight traffic per CTA buys nothing because the kernel is bound by the serial chain of its
+// epilogue warps (tensor-memory load -> bias / GELU -> shared-memory store -> barrier, eight chunks per tile),
+// not by the weight feed; the pair variant stays for the shapes where that changes (wider hidden layers).
+bool use_pairs(long long M) {
+  static const bool on = [] { const char* e = getenv("DL_FFN_PAIR"); return e && atoi(e) != 0; }();
+  return on && M > 128;
+}
+
+template <int MODE, bool PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const CUtensorMap& te, FfnParams& p,
            cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(ffn_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    attr_err = cudaFuncSetAttribute(ffn_chain_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   });
   if (attr_err != cudaSuccess)
     return set_error((int)attr_err, "dl_ffn: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-  p.idesc1 = ptx::make_idesc(false, false, MODE == 1, 128, kCh);
-  p.idesc2 = ptx::make_idesc(false, false, MODE == 1, 128, kD);
-  const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
-  DL_LAUNCH((ffn_chain_kernel<MODE>), grid, kThreads, kSmem, stream, ta, tb1, tb2, te, p);
+  p.idesc1 = ptx::make_idesc(false, false, MODE == 1, PAIR ? 256 : 128, kCh);
+  p.idesc2 = ptx::make_idesc(false, false, MODE == 1, PAIR ? 256 : 128, kD);
+  if constexpr (PAIR) {
+    const int pairs = (p.tiles + 1) / 2, max_pairs = sm_count() / 2;       // one CTA per SM: sm_count / 2 co-resident pairs
+    const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    (void)launch_cluster_k(ffn_chain_kernel<MODE, PAIR>, dim3(grid), dim3(kThreads), (size_t)kSmem, 2u, stream, ta, tb1, tb2, te, p);
+  } else {
+    const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+    DL_LAUNCH((ffn_chain_kernel<MODE, PAIR>), grid, kThreads, kSmem, stream, ta, tb1, tb2, te, p);
+  }
   DL_LAUNCH_CHECK("ffn_chain_kernel");
   count_launch();
   return 0;
@@ -524,8 +632,10 @@ extern "C" int dl_ffn_fwd(const dl_ffn_args* a, void* stream_) {
   if (a->M == 0) return 0;
   CUtensorMap ta, tb1, tb2, te;
   if ((rc = make_map(&ta, a->x, kD, a->M, a->ldx, 64, 128, "x"))) return rc;
-  if ((rc = make_map(&tb1, a->w1, kD, a->Dh, kD, 64, 128, "w1"))) return rc;       // [Dh, 256]: rows = hidden
-  if ((rc = make_map(&tb2, a->w2, a->Dh, kD, a->Dh, 64, 256, "w2"))) return rc;    // [256, Dh]: all rows, 64 k
+  const bool pair = use_pairs(a->M);
+  // [Dh, 256]: rows = hidden (pair: this CTA's 64 of a chunk's 128);  [256, Dh]: output rows (pair: 128 of the 256)
+  if ((rc = make_map(&tb1, a->w1, kD, a->Dh, kD, 64, pair ? 64 : 128, "w1"))) return rc;
+  if ((rc = make_map(&tb2, a->w2, a->Dh, kD, a->Dh, 64, pair ? 128 : 256, "w2"))) return rc;
   if (a->hidden) {
     if ((rc = make_map(&te, a->hidden, a->Dh, a->M, a->ldh, 64, 128, "hidden"))) return rc;
   } else {
@@ -540,7 +650,8 @@ extern "C" int dl_ffn_fwd(const dl_ffn_args* a, void* stream_) {
   p.seed1 = a->seed1; p.seed2 = a->seed2; p.drop_step = (const long long*)a->drop_seed_step; p.drop_p = a->drop_p;
   p.M = (int)a->M; p.Dh = (int)a->Dh; p.NC = (int)(a->Dh / kCh); p.tiles = ceil_div(a->M, 128);
   p.store_e = a->hidden != nullptr;
-  return launch<0>(ta, tb1, tb2, te, p, stream);
+  if (pair) return launch<0, true>(ta, tb1, tb2, te, p, stream);
+  return launch<0, false>(ta, tb1, tb2, te, p, stream);
 }
 
 extern "C" int dl_ffn_bwd(const dl_ffn_args* a, void* stream_) {
@@ -562,5 +673,6 @@ extern "C" int dl_ffn_bwd(const dl_ffn_args* a, void* stream_) {
   p.ldh = a->ldh; p.ldy = a->ldy;
   p.M = (int)a->M; p.Dh = (int)a->Dh; p.NC = (int)(a->Dh / kCh); p.tiles = ceil_div(a->M, 128);
   p.store_e = 1;
-  return launch<1>(ta, tb1, tb2, te, p, stream);
+  if (use_pairs(a->M)) return launch<1, true>(ta, tb1, tb2, te, p, stream);
+  return launch<1, false>(ta, tb1, tb2, te, p, stream);
 }

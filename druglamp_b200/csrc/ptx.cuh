@@ -164,6 +164,12 @@ __device__ __forceinline__ void tma_load_5d_2sm(uint32_t smem_dst, const CUtenso
       "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_slot) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "n"(kCols)

@@ -113,3 +113,20 @@ def test_ffn_function_fused_equals_two_gemm_function():
     finally:
         Fn.FUSED_FFN = True
         Dl.set_compute_dtype(torch.float32)
+
+
+def test_ffn_cta_pairs_opt_in():
+    """DL_FFN_PAIR=1 runs the fused kernels as CTA pairs (tcgen05.mma.cta_group::2: each CTA loads half of every
+    weight chunk).  Measured neutral at the model's shape, so it is opt-in; this child run (the switch is read
+    once per process) keeps the variant correct: odd tile counts (a phantom tile), several tiles per pair, and
+    dropout masks identical to dl_gemm's."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DL_FFN_PAIR_CHILD"):
+        pytest.skip("already the child run")
+    env = dict(os.environ, DL_FFN_PAIR="1", DL_FFN_PAIR_CHILD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

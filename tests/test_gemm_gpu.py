@@ -230,3 +230,22 @@ def test_tma_epilogue_residual_in_place_and_broadcast():
               sc=(M * N, 0, 0), residual=C0, ldr=N, sr=(0, 0, 0))
     ref3 = A3.double() @ B.double().t() + C0.double()
     assert torch.equal(out.double(), ref3.to(torch.bfloat16).double())
+
+
+def test_cta_pairs_forced_everywhere():
+    """dl_gemm picks CTA pairs (tcgen05.mma.cta_group::2: 256 x BN tiles over a cluster of two CTAs, each
+    loading half of B) only for the shapes where they measured faster; DL_GEMM_CTA2=2 forces them wherever
+    they are legal.  The whole module is re-run that way in a child process (the switch is read once per
+    process): bit-exact integer cases, split-K, fused bias gradients (colsum_a), the shared-memory epilogue
+    and the implicit-GEMM convolutions all go through the pair kernels."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DL_GEMM_CTA2_CHILD"):
+        pytest.skip("already the forced child run")
+    env = dict(os.environ, DL_GEMM_CTA2="2", DL_GEMM_CTA2_CHILD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gemm_gpu.py"),
+                        os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
