@@ -90,6 +90,7 @@ SIGNATURES = {
     "dl_gemm": [C.POINTER(GemmArgs), _P],
     "dl_attn_fwd": [C.POINTER(AttnArgs), _P],
     "dl_attn_bwd": [C.POINTER(AttnArgs), _P],
+    "dl_smallk_mul": [_P, _P, _P, _P, _I64, _I32, _I32, _I64, _P],
     "dl_ffn_fwd": [C.POINTER(FfnArgs), _P],
     "dl_ffn_bwd": [C.POINTER(FfnArgs), _P],
     "dl_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _P],

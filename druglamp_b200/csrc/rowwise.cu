@@ -1088,6 +1088,83 @@ extern "C" int dl_dropout(const void* x, void* y, int64_t n, float p, uint64_t s
   return 0;
 }
 
+// out[m, n] = aux[m, n] * sum_{k < K} g[m, k] * w[k, n]   (bf16, K <= 16): the input gradient of a layer with a
+// handful of outputs -- MHLA's lin2 (model/PMMA/encoder.py:130: 1024 -> 8 heads) -- times the stored
+// activation derivative.  As a K = 8 tensor-core GEMM it was a 64-wide K-block of zeros behind a TMA epilogue
+// (24 us for 67 MB of aux + out); here each thread keeps its 8 columns of w in registers and streams rows.
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+smallk_mul_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ w,
+                  const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ out, long long M, int N, int K,
+                  long long ldg, long long rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
+  const int nv = blockIdx.x * 128 + threadIdx.x;          // 8-column vector of the row
+  if (nv * 8 >= N) return;
+  float wr[KMAX][8];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) ldv(w + (long long)k * N + nv * 8, wr[k]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wr[k][j] = 0.f;
+    }
+  }
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (long long r = r0; r < r1; r += 2) {
+    float a[2][8], gv[2][KMAX];
+    const bool two = r + 1 < r1;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || two) {
+        ldv(aux + (r + u) * N + nv * 8, a[u]);
+#pragma unroll
+        for (int k0 = 0; k0 < KMAX; k0 += 8) ldv(g + (r + u) * ldg + k0, *reinterpret_cast<float(*)[8]>(&gv[u][k0]));
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k >= K) gv[u][k] = 0.f;             // padding columns of g may hold anything
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(gv[u][k], wr[k][j], o[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= a[u][j];
+      stv(out + (r + u) * N + nv * 8, o);
+    }
+  }
+}
+
+extern "C" int dl_smallk_mul(const void* g, const void* w, const void* aux, void* out, int64_t M, int32_t N, int32_t K,
+                             int64_t ldg, void* stream) {
+  DL_REQUIRE(g && w && aux && out && M >= 0 && N >= 8 && N % 8 == 0 && K >= 1 && K <= 16, "dl_smallk_mul: bad shape (N %% 8 == 0, K <= 16)");
+  DL_REQUIRE(ldg % 8 == 0 && ldg >= (K <= 8 ? 8 : 16), "dl_smallk_mul: g rows must be whole 16-byte vectors (ldg %% 8 == 0, padded to 8 / 16 columns)");
+  DL_REQUIRE((((uintptr_t)g | (uintptr_t)w | (uintptr_t)aux | (uintptr_t)out) & 15) == 0, "dl_smallk_mul: tensors must be 16-byte aligned");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int xb = ceil_div(N / 8, 128);
+  long long yb = (long long)sm_count() * 8 / xb;
+  if (yb > (M + 7) / 8) yb = (M + 7) / 8;
+  if (yb < 1) yb = 1;
+  const long long rpb = (M + yb - 1) / yb;
+  dim3 grid(xb, (unsigned)yb);
+  if (K <= 8)
+    DL_LAUNCH((smallk_mul_kernel<8>), grid, 128, 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)w, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, (long long)M, N, K, (long long)ldg, rpb);
+  else
+    DL_LAUNCH((smallk_mul_kernel<16>), grid, 128, 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)w, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, (long long)M, N, K, (long long)ldg, rpb);
+  DL_LAUNCH_CHECK("smallk_mul_kernel");
+  count_launch();
+  return 0;
+}
+
 extern "C" int dl_act_fwd(const void* x, void* y, int64_t n, int32_t act, int32_t dtype, void* stream) {
   DL_REQUIRE(x && y && act >= 0 && act <= 2, "dl_act_fwd: bad arguments");
   if (n <= 0) return 0;

@@ -978,7 +978,11 @@ class MHLAFn(Function):
         dl2 = dlogits.view(-1, Hh)
         b1, b2 = ctx.biases
         dw2, db2 = _wbgrad(w2, b2, dl2, h)
-        dpre1 = K.mm(dl2, shadow(w2), tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
+        w2c = shadow(w2)
+        if K.smallk_mul_ok(dl2, w2c, pre1):          # 8 heads: a K = 8 contraction, HBM-bound (dl_smallk_mul)
+            dpre1 = K.smallk_mul(dl2, w2c, pre1)
+        else:
+            dpre1 = K.mm(dl2, w2c, tb=True, mul_aux=pre1, mul_mode=K.MUL_VALUE)
         dw1, db1 = _wbgrad(w1, b1, dpre1, vc.view(-1, E))
         dv = K.mm(dpre1, shadow(w1), tb=True, res=dv_direct.view(-1, E)).view(Bn, Lr, E)
         return _back(dv, ctx.vdt), dw1, db1, dw2, db2, dg, db, None

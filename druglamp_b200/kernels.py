@@ -312,6 +312,22 @@ def attn_bwd(d_o: torch.Tensor, q, k, v, o, lse, H: int, scale: float, dq: torch
     L.check(L.lib().dl_attn_bwd(L.C.byref(a), L.stream_ptr()), "dl_attn_bwd")
 
 
+def smallk_mul_ok(g: torch.Tensor, w: torch.Tensor, aux: torch.Tensor) -> bool:
+    K_, N = w.shape
+    return (g.is_cuda and g.dtype == w.dtype == aux.dtype == torch.bfloat16 and K_ <= 16 and N % 8 == 0
+            and g.dim() == 2 and g.shape[1] == K_ and g.stride(1) == 1 and g.stride(0) % 8 == 0
+            and g.stride(0) >= (8 if K_ <= 8 else 16) and w.is_contiguous() and aux.is_contiguous()
+            and all(t.data_ptr() % 16 == 0 for t in (g, w, aux)))
+
+
+def smallk_mul(g: torch.Tensor, w: torch.Tensor, aux: torch.Tensor) -> torch.Tensor:
+    """(g [M, K] @ w [K, N]) * aux [M, N] for K <= 16 (dl_smallk_mul): HBM-bound, no tensor cores."""
+    out = torch.empty_like(aux)
+    L.call("dl_smallk_mul", g.data_ptr(), w.data_ptr(), aux.data_ptr(), out.data_ptr(), g.shape[0], w.shape[1],
+           w.shape[0], g.stride(0))
+    return out
+
+
 # ----------------------------------------------------------------------------- fused FFN
 FFN_WIDTH = 256      # model width the fused feed-forward kernels are built for
 

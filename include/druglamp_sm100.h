@@ -165,6 +165,13 @@ typedef struct dl_attn_args {
   int32_t dq_accumulate;
 } dl_attn_args;
 
+/* out[m, n] = aux[m, n] * sum_{k < K} g[m, k] * w[k, n]  (bf16; K <= 16; N a multiple of 8; g rows padded to
+ * 8 (K <= 8) or 16 columns, row stride ldg; w [K, N] and aux / out [M, N] contiguous).  The input gradient of a
+ * layer with a handful of outputs times the stored activation derivative: MultiHeadLinearAttention's lin2
+ * (model/PMMA/encoder.py:128-131, 1024 -> 8 heads) in its backward -- HBM-bound, no tensor cores. */
+int dl_smallk_mul(const void* g, const void* w, const void* aux, void* out, int64_t M, int32_t N, int32_t K,
+                  int64_t ldg, void* stream);
+
 int dl_attn_fwd(const dl_attn_args* args, void* stream);
 int dl_attn_bwd(const dl_attn_args* args, void* stream);
 

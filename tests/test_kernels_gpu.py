@@ -636,3 +636,26 @@ def test_protein_cnn_fused_tail_equals_separate_passes(dtype, site_len):
     finally:
         M.CNN_TAIL_FUSED = True
         D.set_compute_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,Kc", [(16384, 1024, 8), (333, 64, 5), (1000, 2048, 16), (7, 8, 1)])
+def test_smallk_mul(M, N, Kc):
+    """dl_smallk_mul: (g [M, K] @ w [K, N]) * aux for K <= 16 -- the input gradient of MHLA's 8-head lin2 times
+    the stored GELU derivative (model/PMMA/encoder.py:128-131) -- against float64, and against dl_gemm."""
+    from druglamp_b200 import kernels as K
+    gen = torch.Generator(device="cuda").manual_seed(M + N + Kc)
+    ld = 8 if Kc <= 8 else 16
+    gbuf = torch.full((M, ld), float("nan"), device="cuda", dtype=torch.bfloat16)     # padding columns: NaN
+    gbuf[:, :Kc] = torch.randn(M, Kc, generator=gen, device="cuda").bfloat16()
+    g = gbuf[:, :Kc]
+    w = torch.randn(Kc, N, generator=gen, device="cuda").bfloat16()
+    aux = torch.randn(M, N, generator=gen, device="cuda").bfloat16()
+    assert K.smallk_mul_ok(g, w, aux)
+    out = K.smallk_mul(g, w, aux)
+    torch.cuda.synchronize()
+    ref = (g.double() @ w.double()) * aux.double()
+    assert torch.isfinite(out.float()).all()
+    assert (out.double() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    if Kc == 8:
+        out2 = K.mm(g.contiguous(), w, tb=True, mul_aux=aux, mul_mode=K.MUL_VALUE)
+        assert (out.float() - out2.float()).abs().max() <= 2 ** -7 * out2.float().abs().max()
