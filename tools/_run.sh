@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q -x -k "smallk or mhla or MHLA or Multi" 2>&1 | grep -v "^$" | tail -4
-timeout 300 python bench.py --steps 100 --no-cpu-baseline > gpurun_out/bench_A.json 2> gpurun_out/bench_A.err
-python -c "
-import json;d=json.load(open('gpurun_out/bench_A.json'));print('A', d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['gemm_ms_per_step'], d['loss'])" || tail -5 gpurun_out/bench_A.err
+timeout 1700 python -m pytest tests -m gpu -q -x > gpurun_out/r2w_pytest_gpu.txt 2>&1; tail -2 gpurun_out/r2w_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err; python -c "
+import json;d=json.load(open('gpurun_out/r2w_bench.json'));print('bench', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['whole_step_frac'])" || tail -5 gpurun_out/r2w_bench.err
