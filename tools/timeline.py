@@ -1,7 +1,10 @@
 """Offline view of a chrome trace written by tools/graph_profile.py: per stream busy time, the
 time no kernel runs at all, and the longest kernels of the last replay in launch order.
 
-    python tools/timeline.py gpurun_out/trace.json [--list]
+    python tools/timeline.py gpurun_out/trace.json [--list] [--alone]
+
+--alone: per kernel name, the time during which it is the ONLY kernel running (a proxy for its share of the
+critical path of the multi-stream step), next to its total time.
 """
 import collections
 import json
@@ -41,6 +44,27 @@ def main(path):
         depth += d
         last = t
     print(f"no kernel running: {idle:.1f} us; two or more kernels in flight: {multi:.1f} us")
+    if "--alone" in sys.argv:
+        import re
+        ev2 = sorted([(e["ts"], 1, i) for i, e in enumerate(k)] + [(e["ts"] + e["dur"], -1, i) for i, e in enumerate(k)])
+        active, last, alone = set(), t0, collections.defaultdict(float)
+        for t, d, i in ev2:
+            if len(active) == 1:
+                alone[next(iter(active))] += t - last
+            last = t
+            if d == 1:
+                active.add(i)
+            else:
+                active.discard(i)
+        by = collections.defaultdict(lambda: [0.0, 0, 0.0])
+        for i, e in enumerate(k):
+            n = re.sub(r"dl::\(anonymous namespace\)::|dl::<unnamed>::|dl::", "", e["name"].replace("void ", ""))
+            b = by[re.sub(r"\(.*", "", n)[:70]]
+            b[0] += alone.get(i, 0.0); b[1] += 1; b[2] += e["dur"]
+        print(f"# single-kernel time {sum(v[0] for v in by.values()):.1f} us of the span")
+        print("alone_us    n  total_us  kernel")
+        for n, (a, c, t) in sorted(by.items(), key=lambda kv: -kv[1][0])[:30]:
+            print(f"{a:8.1f} {c:4d} {t:9.1f}  {n}")
     if "--list" in sys.argv:
         main_tid = max(per, key=per.get)
         for e in k:
